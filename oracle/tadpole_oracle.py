@@ -1,0 +1,571 @@
+"""CPU oracle for the TADpole hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+import this module.  The product (tadpole_b200/) never does.
+
+This is a numpy restatement of the reference's algorithm (reference = pure R,
+/root/reference/R/TADpole.R and R/DiffT.R).  R is not installed here or on the GPU box, so
+the reference itself cannot be run.  Each function cites the reference lines it follows.
+The arithmetic of stages 1-5 lives in CRAN packages that are NOT under /root/reference
+(lower-bound pins only, DESCRIPTION:14-29): rioja >= 0.9-21 (chclust/bstick), fpc >=
+2.1-11.1 (calinhara), Matrix >= 1.2-15, base/stats of R >= 3.5.2 (prcomp, dist, cutree,
+quantile, rowMeans, crossprod) and vegan::bstick.default reached through rioja.  Their
+published algorithms are restated from their documentation.
+
+PARITY PINNING
+  * diffT (stage 6) is PINNED by the reference's own fixture pair inst/extdata/control.bed
+    x case.bed and the curve drawn in misc/DiffT_score.png (tests/golden/difft_*.json).
+  * stages 1-5 (filter, correlation, PCA, CONISS sweep, broken stick + CH): PARITY UNPINNED.
+    The reference has no tests, no golden outputs and its example matrix is missing from
+    the checkout.  Cross-checks used instead: numpy SVD, scipy pdist, sklearn structured
+    Ward, and two independent CONISS restatements (Lance-Williams on squared distances,
+    as rioja's C++ does, and the centroid form) that must agree on merge order.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+# ----------------------------------------------------------------------------------------
+# stage 1: load_mat numeric core
+# ----------------------------------------------------------------------------------------
+
+
+def quantile_type7(x, p):
+    """stats::quantile(x, p) default type 7 (R/TADpole.R:37).
+
+    index = 1 + (n-1)p; lo = floor, hi = ceiling; q = x_(lo), and if index > lo and
+    x_(hi) != x_(lo): q = (1-h) x_(lo) + h x_(hi), h = index - lo.
+    """
+    xs = np.sort(np.asarray(x, dtype=np.float64))
+    n = xs.size
+    index = 1.0 + max(n - 1, 0) * p
+    lo = int(np.floor(index))
+    hi = int(np.ceil(index))
+    q = xs[lo - 1]
+    if index > lo and xs[hi - 1] != q:
+        h = index - lo
+        q = (1.0 - h) * q + h * xs[hi - 1]
+    return float(q)
+
+
+def symmetrise_upper(mat):
+    """NA->0 then Matrix::forceSymmetric(uplo='U') (R/TADpole.R:19-20)."""
+    m = np.array(mat, dtype=np.float64, copy=True)
+    m[np.isnan(m)] = 0.0
+    u = np.triu(m)
+    return u + np.triu(m, 1).T
+
+
+def bad_columns(sym, bad_frac):
+    """diag == 0 | rowMeans < quantile(rowMeans, bad_frac) (R/TADpole.R:35-37).
+
+    seq(0, 1, by=bad_frac)[2] is bad_frac itself.  Strict '<'.  Skipped when bad_frac == 0.
+    Returns (bad bool[N], rowmeans[N], threshold or nan).
+    """
+    n = sym.shape[0]
+    # R accumulates rowMeans in long double; np.longdouble is x87 extended here
+    r = (sym.astype(np.longdouble).sum(axis=1) / n).astype(np.float64)
+    bad = np.diag(sym) == 0
+    thr = float("nan")
+    if bad_frac:
+        thr = quantile_type7(r, bad_frac)
+        bad = bad | (r < thr)
+    return bad, r, thr
+
+
+@dataclass
+class LoadedMat:
+    """What load_mat returns (R/TADpole.R:85,88-90): a filtered matrix carrying the
+    'bad_columns' attribute, or for a split chromosome the list(p, q, centromere)."""
+    mat: np.ndarray | None = None
+    names: np.ndarray | None = None          # original 1-based bin index of every kept row
+    bad_columns: np.ndarray | None = None    # 1-based bin indices (R: character names)
+    p: "LoadedMat | None" = None
+    q: "LoadedMat | None" = None
+    centromere: np.ndarray | None = None     # 1-based cs..ce
+    n_bins: int = 0
+
+
+def load_mat_numeric(mat, bad_frac=0.01, centromere_search=False):
+    """Numeric part of load_mat (R/TADpole.R:17-22,35-37,55-91); plots are out of scope."""
+    sym = symmetrise_upper(mat)
+    n = sym.shape[0]
+    bad, _, _ = bad_columns(sym, bad_frac)
+    idx = np.flatnonzero(bad) + 1  # 1-based
+    if bad.any() and centromere_search:
+        # longest run of consecutive bad indices, first on ties (R/TADpole.R:62-64)
+        brk = np.flatnonzero(np.diff(idx) > 1) + 1
+        runs = np.split(idx, brk)
+        longest = runs[int(np.argmax([len(r) for r in runs]))]
+        cs, ce = int(longest[0]), int(longest[-1])
+        if cs == 1 or ce == n:  # R/TADpole.R:66-71
+            keep = ~bad
+            return LoadedMat(mat=sym[np.ix_(keep, keep)], names=np.flatnonzero(keep) + 1,
+                             bad_columns=idx, n_bins=n)
+        idx_p = np.arange(1, cs)            # R/TADpole.R:73
+        idx_q = np.arange(ce + 1, n + 1)    # R/TADpole.R:74
+        mat_p = sym[np.ix_(idx_p - 1, idx_p - 1)]
+        mat_q = sym[np.ix_(idx_q - 1, idx_q - 1)]
+        bad_p = idx[idx < cs]
+        bad_q = idx[idx > ce]
+        names_p, names_q = idx_p.copy(), idx_q.copy()
+        if bad_p.size:
+            keep = np.ones(mat_p.shape[0], bool)
+            keep[bad_p - 1] = False
+            mat_p, names_p = mat_p[np.ix_(keep, keep)], names_p[keep]
+        if bad_q.size:
+            # Quirk Q3 (R/TADpole.R:80): original-coordinate indices used as negative
+            # positional indices into the re-based q arm; out-of-range ones are ignored.
+            keep = np.ones(mat_q.shape[0], bool)
+            inr = bad_q[bad_q <= mat_q.shape[0]]
+            keep[inr - 1] = False
+            mat_q, names_q = mat_q[np.ix_(keep, keep)], names_q[keep]
+        return LoadedMat(p=LoadedMat(mat=mat_p, names=names_p, bad_columns=bad_p if bad_p.size else None),
+                         q=LoadedMat(mat=mat_q, names=names_q, bad_columns=bad_q if bad_q.size else None),
+                         centromere=np.arange(cs, ce + 1), n_bins=n)
+    keep = ~bad
+    return LoadedMat(mat=sym[np.ix_(keep, keep)], names=np.flatnonzero(keep) + 1,
+                     bad_columns=idx, n_bins=n)
+
+
+# ----------------------------------------------------------------------------------------
+# stage 2: sparse_cor
+# ----------------------------------------------------------------------------------------
+
+
+def sparse_cor(x):
+    """Pearson correlation of columns, one-pass covariance (R/TADpole.R:94-100), then the
+    caller's NaN -> 0 (R/TADpole.R:363,449)."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.shape[0]
+    cm = x.mean(axis=0)
+    cov = (x.T @ x - n * np.outer(cm, cm)) / (n - 1)
+    sd = np.sqrt(np.diag(cov))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cor = cov / np.outer(sd, sd)
+    cor[np.isnan(cor)] = 0.0
+    return cor
+
+
+# ----------------------------------------------------------------------------------------
+# stage 3: prcomp
+# ----------------------------------------------------------------------------------------
+
+
+def prcomp_scores(cor, k):
+    """stats::prcomp(cor, rank.=k)$x (R/TADpole.R:367,453): centre columns, SVD,
+    x = Xc V[:, :k].  Signs are LAPACK-dependent; every consumer is sign-invariant."""
+    xc = cor - cor.mean(axis=0, keepdims=True)
+    _, _, vt = np.linalg.svd(xc, full_matrices=False)
+    return xc @ vt[:k].T
+
+
+# ----------------------------------------------------------------------------------------
+# stage 4: dist + rioja::chclust(method='coniss')
+# ----------------------------------------------------------------------------------------
+
+
+def coniss_centroid(pcs):
+    """CONISS in centroid form: adjacent-only Ward, increase = na nb/(na+nb) |ca-cb|^2,
+    strict '<' scan (lowest boundary index wins ties), seqdist[j] = running total of
+    increases at the merge that removed boundary j|j+1.  Pure python; small n only.
+    Returns (seqdist[n-1], order[n-1] = boundary removed at each step)."""
+    x = np.asarray(pcs, dtype=np.float64)
+    if x.ndim == 1:
+        x = x[:, None]
+    n = x.shape[0]
+    sums = [x[i].copy() for i in range(n)]
+    cnt = [1] * n
+    left = list(range(-1, n - 1))   # previous live cluster head
+    right = list(range(1, n + 1))   # next live cluster head (n = none)
+    inc = np.full(n, np.inf)        # inc[h] = increase of merging cluster h with its right neighbour
+
+    def delta(a, b):
+        d = sums[a] / cnt[a] - sums[b] / cnt[b]
+        return cnt[a] * cnt[b] / (cnt[a] + cnt[b]) * float(d @ d)
+
+    for h in range(n - 1):
+        inc[h] = delta(h, h + 1)
+    last = list(range(n))           # last bin of cluster with head h
+    seq = np.zeros(n - 1)
+    order = np.zeros(n - 1, dtype=np.int64)
+    total = 0.0
+    for step in range(n - 1):
+        a = int(np.argmin(inc))     # first minimum == strict '<' scan
+        b = right[a]
+        total += inc[a]
+        seq[last[a]] = total        # boundary between bin last[a] and last[a]+1
+        order[step] = last[a]
+        sums[a] = sums[a] + sums[b]
+        cnt[a] += cnt[b]
+        last[a] = last[b]
+        right[a] = right[b]
+        if right[b] < n:
+            left[right[b]] = a
+        inc[b] = np.inf
+        inc[a] = delta(a, right[a]) if right[a] < n else np.inf
+        if left[a] >= 0:
+            inc[left[a]] = delta(left[a], a)
+    return seq, order
+
+
+_LIB = None
+
+
+def _oracle_lib():
+    """Build (if needed) and load oracle/liboracle.so (plain C, oracle/coniss_lw.c)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "coniss_lw.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    lib = ctypes.CDLL(so)
+    dp = ctypes.POINTER(ctypes.c_double)
+    ip = ctypes.POINTER(ctypes.c_int)
+    lib.oracle_coniss_lw.argtypes = [dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, ip]
+    lib.oracle_coniss_lw.restype = ctypes.c_int
+    lib.oracle_difft.argtypes = [ip, ip, ctypes.c_int, dp]
+    lib.oracle_difft.restype = ctypes.c_int
+    _LIB = lib
+    return lib
+
+
+def coniss_lw(pcs):
+    """dist(pcs) -> rioja::chclust(method='coniss') (R/TADpole.R:108,374,460) in the
+    reference's algorithmic shape: full Euclidean distance matrix, squared, adjacent-pair
+    scan, Lance-Williams/Ward update of the whole row (oracle/coniss_lw.c).
+    Returns (seqdist, order)."""
+    x = np.ascontiguousarray(np.asarray(pcs, dtype=np.float64))
+    if x.ndim == 1:
+        x = x[:, None]
+    n, p = x.shape
+    seq = np.zeros(n - 1)
+    order = np.zeros(n - 1, dtype=np.int32)
+    rc = _oracle_lib().oracle_coniss_lw(
+        x.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n, p, p,
+        seq.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+        order.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    if rc != 0:
+        raise MemoryError("oracle_coniss_lw failed")
+    return seq, order.astype(np.int64)
+
+
+def find_groups(seqdist):
+    """rioja's .find.groups: hclust merge matrix from seqdist by repeated which.min
+    (first index on ties).  Returns (merge[(n-1),2] R-style signed ints, height)."""
+    x = np.array(seqdist, dtype=np.float64)
+    n1 = x.size
+    merge = np.zeros((n1, 2), dtype=np.int64)
+    owner = np.zeros(n1 + 1, dtype=np.int64)  # 0 = singleton, else merge step that absorbed it
+    # union-find over objects so that "the merge step that last absorbed object j" is O(alpha)
+    parent = np.arange(n1 + 1)
+
+    def root(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+
+    idx = np.lexsort((np.arange(n1), x))  # ascending value, first index on ties
+    for step, j in enumerate(idx, start=1):
+        ra, rb = root(j), root(j + 1)
+        merge[step - 1, 0] = -(j + 1) if owner[ra] == 0 else owner[ra]
+        merge[step - 1, 1] = -(j + 2) if owner[rb] == 0 else owner[rb]
+        parent[rb] = ra
+        owner[ra] = step
+    return merge, np.sort(x)
+
+
+def cutree_boundaries(seqdist, k):
+    """Boundaries (0-based j: split between object j and j+1) left after stats::cutree(k):
+    the k-1 boundaries merged last under the (value, index) order of find_groups."""
+    x = np.asarray(seqdist)
+    idx = np.lexsort((np.arange(x.size), x))
+    return np.sort(idx[x.size - (k - 1):]) if k > 1 else np.zeros(0, dtype=np.int64)
+
+
+def cutree(seqdist, k):
+    """stats::cutree(clust, k) labels 1..k (R/TADpole.R:118,382,411,471); clusters are
+    contiguous so labels increase left to right."""
+    n = len(seqdist) + 1
+    lab = np.ones(n, dtype=np.int64)
+    for b in cutree_boundaries(seqdist, k):
+        lab[b + 1:] += 1
+    return lab
+
+
+# ----------------------------------------------------------------------------------------
+# stage 5: broken stick + Calinski-Harabasz
+# ----------------------------------------------------------------------------------------
+
+
+def bstick_table(seqdist):
+    """rioja::bstick(clust, ng = n-1, plot=FALSE) (R/TADpole.R:111): dispersion =
+    |diff(rev(height))|, bstick = vegan::bstick.default(nobj, tot) = rev(cumsum(tot/n:1)/n).
+    Returns (dispersion[n-2], bstick[n-2])."""
+    height = np.sort(np.asarray(seqdist, dtype=np.float64))
+    disp = height[::-1]
+    tot = disp[0]
+    d = np.abs(np.diff(disp))
+    nobj = height.size
+    bs = (np.cumsum(tot / np.arange(nobj, 0, -1.0)) / nobj)[::-1]
+    ng = nobj  # called with ng = nrow(pcs) - 1 = nobj
+    return d[: ng - 1], bs[: ng - 1]
+
+
+def first_true_run(flags):
+    """r <- rle(x); r$lengths[r$values][1] (R/TADpole.R:112-113): length of the first
+    run of TRUE wherever it starts (quirk Q1); None when there is no TRUE."""
+    f = np.asarray(flags, dtype=bool)
+    t = np.flatnonzero(f)
+    if t.size == 0:
+        return None
+    s = t[0]
+    e = s
+    while e + 1 < f.size and f[e + 1]:
+        e += 1
+    return int(e - s + 1)
+
+
+def calinhara(x, labels, cn):
+    """fpc::calinhara(x, clustering, cn) (R/TADpole.R:119): W = sum_c (n_c-1) cov(x[c,]),
+    S = (n-1) cov(x), B = S - W, (n-cn) tr(B) / ((cn-1) tr(W)).  Only traces are used."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.shape[0]
+    trw = 0.0
+    for c in range(1, cn + 1):
+        xc = x[labels == c]
+        if xc.shape[0] >= 2:
+            trw += float(((xc - xc.mean(axis=0)) ** 2).sum())
+    trs = float(((x - x.mean(axis=0)) ** 2).sum())
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return float(np.float64(n - cn) * np.float64(trs - trw) / (np.float64(cn - 1) * np.float64(trw)))
+
+
+def candidate_scores(scores_all, i, min_clusters, coniss=coniss_lw):
+    """Body of the foreach in find_params for one candidate i (R/TADpole.R:105-122).
+    Returns (score vector with NaN for NA, n_cluster, seqdist)."""
+    seq, _ = coniss(scores_all[:, :i])
+    disp, bs = bstick_table(seq)
+    n_cluster = first_true_run(disp > bs)
+    if n_cluster is None:
+        raise ValueError("no broken-stick level is significant (reference errors here, quirk Q1)")
+    score = np.full(n_cluster, np.nan)
+    mc = min(min_clusters, n_cluster)
+    for n in range(mc, n_cluster + 1):
+        score[n - 1] = calinhara(scores_all, cutree(seq, n), n)
+    return score, n_cluster, seq
+
+
+def reduce_scores(score_list):
+    """NA-padded score matrix and the two which.max (R/TADpole.R:125-135).
+    Returns (scores[k, maxlev] NaN padded, optimal_PCs, optimal_n_clusters), 1-based."""
+    width = max(len(s) for s in score_list)
+    scores = np.full((len(score_list), width), np.nan)
+    for r, s in enumerate(score_list):
+        scores[r, : len(s)] = s
+    with np.errstate(invalid="ignore"):
+        cnt = (~np.isnan(scores)).sum(axis=1)
+        rm = np.where(cnt > 0, np.nansum(scores, axis=1) / np.maximum(cnt, 1), np.nan)
+    opt_pcs = int(np.nanargmax(rm)) + 1          # which.max ignores NaN, first max
+    opt_k = int(np.nanargmax(scores[opt_pcs - 1])) + 1
+    return scores, opt_pcs, opt_k
+
+
+# ----------------------------------------------------------------------------------------
+# result assembly
+# ----------------------------------------------------------------------------------------
+
+
+def fix_values(values):
+    """fix_values on rle values (R/TADpole.R:503-510): interior zero runs flanked by the
+    same id take that id; sequential, left to right, in place on a copy."""
+    v = list(values)
+    for i in range(1, len(v) - 1):
+        if v[i] == 0 and v[i - 1] == v[i + 1]:
+            v[i] = v[i - 1]
+    return v
+
+
+def _rle(a):
+    a = np.asarray(a)
+    if a.size == 0:
+        return np.zeros(0, a.dtype), np.zeros(0, np.int64)
+    brk = np.flatnonzero(a[1:] != a[:-1]) + 1
+    starts = np.concatenate(([0], brk))
+    lens = np.diff(np.concatenate((starts, [a.size])))
+    return a[starts], lens
+
+
+def fixed_labels(good_labels, names, bad_cols):
+    """Interleave bad bins as 0 by numeric name order, fix_values, inverse.rle
+    (R/TADpole.R:384-394,473-483).  names: 1-based original index per good bin."""
+    if bad_cols is None:
+        return np.asarray(good_labels, dtype=np.int64)
+    allnames = np.concatenate((np.asarray(names, dtype=np.float64), np.asarray(bad_cols, dtype=np.float64)))
+    lab = np.concatenate((np.asarray(good_labels, dtype=np.int64), np.zeros(len(bad_cols), dtype=np.int64)))
+    lab = lab[np.argsort(allnames, kind="stable")]   # order() is stable
+    vals, lens = _rle(lab)
+    vals = np.array(fix_values(vals), dtype=np.int64)
+    return np.repeat(vals, lens)
+
+
+def coords_from_labels(fixed, drop_zero=True):
+    """start/end table from run lengths (R/TADpole.R:396-399,485-488); rle is taken again
+    on the fixed vector, so runs merged by fix_values collapse."""
+    vals, lens = _rle(fixed)
+    eb = np.cumsum(lens)
+    start = np.concatenate(([1], eb[:-1] + 1))
+    tab = np.stack([start, eb], axis=1)
+    if drop_zero:
+        tab = tab[vals != 0]
+    return tab
+
+
+@dataclass
+class OracleResult:
+    n_pcs: int = 0
+    optimal_n_clusters: int = 0
+    seqdist: np.ndarray | None = None       # dendro of the optimal n_pcs
+    clusters: dict = field(default_factory=dict)
+    scores: np.ndarray | None = None
+    arms: dict = field(default_factory=dict)
+    merging_arms: np.ndarray | None = None
+    pcs: np.ndarray | None = None
+    cor: np.ndarray | None = None
+
+
+def _call_one(lm, max_pcs, min_clusters, coniss):
+    cor = sparse_cor(lm.mat)
+    k = min(max_pcs, lm.mat.shape[0])
+    pcs = prcomp_scores(cor, k)
+    per = [candidate_scores(pcs, i, min_clusters, coniss) for i in range(1, k + 1)]
+    scores, opt_pcs, opt_k = reduce_scores([p[0] for p in per])
+    seq = per[opt_pcs - 1][2]
+    clusters = {}
+    for kk in np.flatnonzero(~np.isnan(scores[opt_pcs - 1])) + 1:
+        good = cutree(seq, int(kk))
+        if lm.bad_columns is not None:
+            clusters[int(kk)] = coords_from_labels(fixed_labels(good, lm.names, lm.bad_columns))
+        else:
+            _, lens = _rle(good)    # table(good_clusters)
+            eb = np.cumsum(lens)
+            clusters[int(kk)] = np.stack([np.concatenate(([1], eb[:-1] + 1)), eb], axis=1)
+    return OracleResult(n_pcs=opt_pcs, optimal_n_clusters=opt_k, seqdist=seq, clusters=clusters,
+                        scores=scores, pcs=pcs, cor=cor)
+
+
+def tadpole(mat, max_pcs=200, min_clusters=2, bad_frac=0.01, centromere_search=False,
+            coniss=coniss_lw):
+    """TADpole() (R/TADpole.R:344-501) from an in-memory matrix."""
+    lm = load_mat_numeric(mat, bad_frac, centromere_search)
+    if centromere_search:
+        if lm.p is None:
+            raise ValueError("centromere_search=TRUE but the matrix was not split (reference errors, quirk Q4)")
+        res = OracleResult()
+        fixed_arms = []
+        ncen = len(lm.centromere)
+        for arm in ("p", "q"):
+            la = getattr(lm, arm)
+            r = _call_one(la, max_pcs, min_clusters, coniss)
+            res.arms[arm] = r
+            good = cutree(r.seqdist, r.optimal_n_clusters)
+            if la.bad_columns is not None:
+                fx = fixed_labels(good, la.names, la.bad_columns)
+            else:
+                vals, lens = _rle(good)
+                fx = np.repeat(np.array(fix_values(vals), dtype=np.int64), lens)
+            fixed_arms.append(fx)
+            fixed_arms.append(np.zeros(ncen, dtype=np.int64))
+        allv = np.concatenate(fixed_arms)
+        allv = allv[: allv.size - ncen]          # R/TADpole.R:438
+        res.merging_arms = coords_from_labels(allv)
+        return res
+    return _call_one(lm, max_pcs, min_clusters, coniss)
+
+
+# ----------------------------------------------------------------------------------------
+# stage 6: diffT
+# ----------------------------------------------------------------------------------------
+
+
+def bin_index(bed, size):
+    """bin_index (R/DiffT.R:1-9): label per bin, offset by the first row's start; later
+    rows overwrite; uncovered bins stay 0.  bed: [T, 2] (start, end) in bins."""
+    bed = np.asarray(bed, dtype=np.int64)
+    tad = np.zeros(size, dtype=np.int64)
+    for t in range(bed.shape[0]):
+        for b in range(bed[t, 0], bed[t, 1] + 1):
+            pos = b - bed[0, 0] + 1
+            tad[pos - 1] = t + 1
+    return tad
+
+
+def difft_labels(bed_x, bed_y):
+    """Padding to a common extent (R/DiffT.R:20-38)."""
+    bed_x = np.asarray(bed_x, dtype=np.int64)
+    bed_y = np.asarray(bed_y, dtype=np.int64)
+    if bed_x.shape[0] != bed_y.shape[0]:
+        raise ValueError("Both calls must have the same number of TADs.")
+    sx, sy = bed_x[0, 0], bed_y[0, 0]
+    ex, ey = bed_x[-1, 1], bed_y[-1, 1]
+    tx = bin_index(bed_x, ex - sx + 1)
+    ty = bin_index(bed_y, ey - sy + 1)
+    tx = np.concatenate((np.ones(max(0, sx - sy), np.int64), tx, np.full(max(0, ey - ex), tx.max(), np.int64)))
+    ty = np.concatenate((np.ones(max(0, sy - sx), np.int64), ty, np.full(max(0, ex - ey), ty.max(), np.int64)))
+    if tx.size != ty.size:
+        raise AssertionError("length(tad_x) == length(tad_y) is not TRUE")
+    return tx, ty
+
+
+def difft_from_labels(tx, ty, raw=False):
+    """The O(L^2) loop of diffT (R/DiffT.R:41-49), literally."""
+    tx = np.asarray(tx)
+    ty = np.asarray(ty)
+    scores = np.zeros(tx.size, dtype=np.int64)
+    for b in range(tx.size):
+        x = (tx[b] != tx) | (tx[b] == 0)
+        y = (ty[b] != ty) | (ty[b] == 0)
+        scores[b] = np.count_nonzero(x ^ y)
+    cs = np.cumsum(scores)
+    if raw:
+        return cs
+    if scores.max() == 0:
+        return cs.astype(np.float64)
+    return cs.astype(np.float64) / float(cs.max())
+
+
+def difft(bed_x, bed_y, raw=False):
+    """diffT(bed_x, bed_y) (R/DiffT.R:19-50)."""
+    return difft_from_labels(*difft_labels(bed_x, bed_y), raw=raw)
+
+
+def difft_from_labels_c(tx, ty):
+    """Same loop in C (oracle/coniss_lw.c: oracle_difft) for the timed CPU baseline."""
+    tx = np.ascontiguousarray(tx, dtype=np.int32)
+    ty = np.ascontiguousarray(ty, dtype=np.int32)
+    out = np.zeros(tx.size)
+    ip = ctypes.POINTER(ctypes.c_int)
+    _oracle_lib().oracle_difft(tx.ctypes.data_as(ip), ty.ctypes.data_as(ip), tx.size,
+                               out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    return out
+
+
+def read_bed(path):
+    """read.table on a 3-column BED; returns [T,2] (start,end)."""
+    rows = []
+    with open(path) as fh:
+        for line in fh:
+            f = line.split()
+            if len(f) >= 3:
+                rows.append((int(f[1]), int(f[2])))
+    return np.array(rows, dtype=np.int64)
