@@ -1,0 +1,147 @@
+/* tadpole_b200.h -- C ABI of libtadpole_b200 (CUDA sm_100a implementation of the TADpole hot path).
+ *
+ * The reference (3DGenomes/TADpole) is pure R and has no native interface: the hot path sits
+ * behind the exported R functions TADpole() (R/TADpole.R:344), load_mat() (R/TADpole.R:15) and
+ * diffT() (R/DiffT.R:19).  These entry points are what an R .Call shim or the
+ * Python host in tadpole_b200/api.py binds.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 (TP_OK) or an error code; tp_last_error() gives the message of the
+ *     last failure on the calling thread.
+ *   - "host" pointers are ordinary process memory; "dev" pointers are CUDA device pointers on the
+ *     context's device.  Functions taking `on_device` accept either.
+ *   - matrices handed in by the caller are N x N doubles.  `colmajor` = 1 is R's layout
+ *     (element (i,j) at i + j*N), 0 is C / numpy layout (i*N + j).  Only the upper triangle
+ *     (i <= j) is ever read, as Matrix::forceSymmetric(uplo='U') does (R/TADpole.R:20).
+ *   - bins, candidates and levels are 0-based here; the R shim / Python host add 1.
+ *   - internal device state (filtered matrix, correlation, PC scores, per-candidate dendrograms)
+ *     lives in the context between calls, so stages can be driven one by one (parity tests) or
+ *     all at once (tp_call).
+ */
+#ifndef TADPOLE_B200_H
+#define TADPOLE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tp_ctx tp_ctx;
+
+enum {
+    TP_OK = 0,
+    TP_ERR_ARG = 1,        /* bad argument / call order */
+    TP_ERR_CUDA = 2,       /* CUDA runtime failure */
+    TP_ERR_NOLEVEL = 3,    /* a candidate has no significant broken-stick level: the reference
+                              errors inside the worker here (R/TADpole.R:113-115, n_cluster = NA) */
+    TP_ERR_NOCONV = 4,     /* eigensolver did not reach the residual tolerance */
+    TP_ERR_NOMEM = 5
+};
+
+const char *tp_last_error(void);
+int tp_version(void);
+
+/* ---- context --------------------------------------------------------------------------- */
+int tp_ctx_create(int device, tp_ctx **out);
+int tp_ctx_destroy(tp_ctx *ctx);
+int tp_ctx_sync(tp_ctx *ctx);
+/* cudaStream_t every kernel of this context is launched on (for CUDA-event timing by callers) */
+void *tp_ctx_stream(tp_ctx *ctx);
+/* number of kernels this context has launched so far */
+long long tp_ctx_launches(tp_ctx *ctx);
+/* tunables: "pca_block" (subspace width, 0 = auto), "pca_tol" (x1e-16), "pca_maxit",
+ * "jacobi_direct_max", "level_cap" */
+int tp_ctx_set(tp_ctx *ctx, const char *key, double value);
+/* per-stage device milliseconds of the last tp_call / stage call, measured with CUDA events on
+ * the context stream: [0] filter [1] compact [2] correlation [3] pca [4] sweep (CONISS) [5] CH
+ * [6] total; and counters [7] pca iterations [8] pca operator applications [9] jacobi sweeps */
+int tp_ctx_timings(tp_ctx *ctx, double *out10);
+
+/* per-kernel-class device time: when enabled, every launch of the classes below is bracketed by
+ * CUDA events on the context stream; reading sums them since the last enable/reset.
+ * classes: [0] rowmean (filter) [1] compact [2] dgemm [3] jacobi [4] coniss_sweep [5] ch [6] difft
+ * [7] spare.  enable: 1 = start/reset, 0 = stop, -1 = just read. */
+int tp_ctx_profile(tp_ctx *ctx, int enable, double *ms_out8, long long *count_out8);
+
+/* ---- stage 1: load_mat numeric core (R/TADpole.R:19-22,35-37) ----------------------------- */
+/* Uploads (or adopts, when on_device) the N x N matrix, computes rowMeans of the symmetrised
+ * matrix, diag == 0, and, when bad_frac != 0, the type-7 quantile threshold; writes the bad flag
+ * per bin (host, n bytes), the row means (host, n doubles, may be NULL) and the threshold
+ * (may be NULL; NaN when bad_frac == 0).  The matrix stays in the context for tp_compact. */
+int tp_filter(tp_ctx *ctx, const double *mat, int n, int colmajor, int on_device, double bad_frac,
+              uint8_t *bad_out, double *rowmeans_out, double *thr_out);
+
+/* mat[keep, keep] with NA -> 0 and lower := upper^T (R/TADpole.R:19-20,75-80,88): `keep` (host) lists
+ * nf ascending 0-based original bin indices.  Result becomes the context's filtered matrix. */
+int tp_compact(tp_ctx *ctx, const int *keep, int nf);
+
+/* test / pipeline hooks: install or read back the context's matrices (row-major n x n, host) */
+int tp_set_filtered(tp_ctx *ctx, const double *x, int nf);
+int tp_get_filtered(tp_ctx *ctx, double *x_out);
+
+/* ---- stage 2: sparse_cor()$cor + NaN -> 0 (R/TADpole.R:94-100,363,449) -------------------------- */
+int tp_correlation(tp_ctx *ctx);
+int tp_get_correlation(tp_ctx *ctx, double *cor_out);      /* nf x nf row-major, host */
+int tp_set_correlation(tp_ctx *ctx, const double *cor, int nf);
+
+/* ---- stage 3: prcomp(cor, rank. = k)$x (R/TADpole.R:366-367,452-453) ---------------------------- */
+/* k = min(max_pcs, nf).  Consumes the context's correlation matrix (it is centred in place). */
+int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out);
+int tp_get_scores(tp_ctx *ctx, double *scores_out);         /* nf x k row-major, host */
+int tp_set_scores(tp_ctx *ctx, const double *scores, int nf, int k);
+
+/* ---- stages 4+5: the find_params sweep (R/TADpole.R:104-123) --------------------------------------
+ * For candidates i = cand_begin + t*cand_stride < k (0-based: candidate i clusters on the first
+ * i+1 score columns): CONISS dendrogram (seqdist), broken-stick level count n_cluster, and the
+ * Calinski-Harabasz score of every level min(min_clusters, n_cluster)..n_cluster on ALL k columns.
+ * Outputs (host, may be NULL): n_cluster[k] (0 for candidates not run); scores[k * ld_scores]
+ * row-major NaN padded (row = candidate, column = n_clusters-1); ld_scores is chosen by the
+ * caller and must be >= the largest n_cluster, otherwise *maxlev_out tells the width needed and
+ * TP_ERR_ARG is returned. */
+int tp_sweep(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stride,
+             int *n_cluster_out, double *scores_out, int ld_scores, int *maxlev_out);
+/* seqdist (nf-1 doubles) and merge order (nf-1 ints: boundary removed at each step) of one
+ * candidate of the last sweep; either pointer may be NULL */
+int tp_get_dendro(tp_ctx *ctx, int cand, double *seqdist_out, int *order_out);
+
+/* which.max(rowMeans(scores, na.rm=TRUE)) then which.max(scores[opt,]) (R/TADpole.R:134-135);
+ * host-side reduction over a k x ld NaN-padded matrix; results 0-based */
+int tp_select(const double *scores, int k, int ld, int maxlev, int *opt_cand, int *opt_level);
+
+/* ---- one-shot: filter -> compact -> correlation -> PCA -> sweep -> selection -------------------
+ * The non-centromere path of TADpole() (R/TADpole.R:444-468) from an in-memory matrix.
+ * bad_out[n]; scores_out[k * ld_scores] (k = min(max_pcs, nf)); seqdist_out[nf-1] of the optimal
+ * candidate.  nf_out/k_out/maxlev_out report the sizes actually used. */
+int tp_call(tp_ctx *ctx, const double *mat, int n, int colmajor, int on_device,
+            int max_pcs, int min_clusters, double bad_frac,
+            uint8_t *bad_out, int *nf_out, int *k_out,
+            int *n_pcs_out, int *n_clusters_out,
+            double *scores_out, int ld_scores, int *maxlev_out,
+            double *seqdist_out);
+/* same, starting from an explicit keep list (chromosome arms, R/TADpole.R:357-374) on the matrix
+ * already held by the context after tp_filter */
+int tp_call_arm(tp_ctx *ctx, const int *keep, int nf, int max_pcs, int min_clusters,
+                int *k_out, int *n_pcs_out, int *n_clusters_out,
+                double *scores_out, int ld_scores, int *maxlev_out, double *seqdist_out);
+
+/* ---- stage 6: diffT (R/DiffT.R:41-49) on padded label vectors -------------------------------------
+ * labels_x / labels_y: npairs x L int32 row-major (0 = uncovered bin); out: npairs x L doubles =
+ * cumulative score, normalised by its last value unless every per-bin score is 0. */
+int tp_difft_batch(tp_ctx *ctx, const int32_t *labels_x, const int32_t *labels_y, int L, int npairs,
+                   int on_device, double *out);
+
+/* ---- result assembly (host integer logic, R/TADpole.R:470-497 and fix_values :503-510) ----------
+ * Cuts the dendrogram `seqdist` (nf-1) into n_clusters contiguous clusters, re-inserts the bad bins
+ * as 0 by original position, absorbs interior 0 runs flanked by the same id, and writes the
+ * start/end table (1-based, inclusive) of the non-zero runs.  names[nf] = original 1-based bin of
+ * each kept row; bad[nbad] = original 1-based bad bins (may contain names again, quirk Q3);
+ * nbad < 0 means "bad_columns attribute is NULL".  start/end need room for n_clusters + nbad + 1
+ * rows.  Also returns the fixed label vector when labels_out != NULL (nf + max(nbad,0) ints). */
+int tp_assemble(const double *seqdist, int nf, int n_clusters, const int *names, const int *bad,
+                int nbad, int *start_out, int *end_out, int *nrows_out, int *labels_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

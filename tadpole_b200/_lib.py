@@ -1,0 +1,318 @@
+"""ctypes binding of libtadpole_b200.so (include/tadpole_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no B200 is visible the
+product fails loudly.  Nothing under oracle/ is imported here.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_longlong, c_uint8, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtadpole_b200.so")
+
+TP_OK, TP_ERR_ARG, TP_ERR_CUDA, TP_ERR_NOLEVEL, TP_ERR_NOCONV, TP_ERR_NOMEM = range(6)
+
+# every symbol include/tadpole_b200.h declares
+EXPORTED = [
+    "tp_last_error", "tp_version", "tp_ctx_create", "tp_ctx_destroy", "tp_ctx_sync", "tp_ctx_stream",
+    "tp_ctx_launches", "tp_ctx_set", "tp_ctx_timings", "tp_ctx_profile", "tp_filter", "tp_compact", "tp_set_filtered",
+    "tp_get_filtered", "tp_correlation", "tp_get_correlation", "tp_set_correlation", "tp_pca",
+    "tp_get_scores", "tp_set_scores", "tp_sweep", "tp_get_dendro", "tp_select", "tp_call", "tp_call_arm",
+    "tp_difft_batch", "tp_assemble",
+]
+
+
+class TadpoleError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libtadpole_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (building is __graft_entry__.build()'s job, not ours)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m tadpole_b200.build` "
+            "(nvcc, sm_100a). tadpole_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    dp, ip, u8p, vp = POINTER(c_double), POINTER(c_int), POINTER(c_uint8), c_void_p
+    sig = {
+        "tp_last_error": (c_char_p, []),
+        "tp_version": (c_int, []),
+        "tp_ctx_create": (c_int, [c_int, POINTER(vp)]),
+        "tp_ctx_destroy": (c_int, [vp]),
+        "tp_ctx_sync": (c_int, [vp]),
+        "tp_ctx_stream": (vp, [vp]),
+        "tp_ctx_launches": (c_longlong, [vp]),
+        "tp_ctx_set": (c_int, [vp, c_char_p, c_double]),
+        "tp_ctx_timings": (c_int, [vp, dp]),
+        "tp_ctx_profile": (c_int, [vp, c_int, dp, POINTER(c_longlong)]),
+        "tp_filter": (c_int, [vp, vp, c_int, c_int, c_int, c_double, u8p, dp, dp]),
+        "tp_compact": (c_int, [vp, ip, c_int]),
+        "tp_set_filtered": (c_int, [vp, dp, c_int]),
+        "tp_get_filtered": (c_int, [vp, dp]),
+        "tp_correlation": (c_int, [vp]),
+        "tp_get_correlation": (c_int, [vp, dp]),
+        "tp_set_correlation": (c_int, [vp, dp, c_int]),
+        "tp_pca": (c_int, [vp, c_int, ip]),
+        "tp_get_scores": (c_int, [vp, dp]),
+        "tp_set_scores": (c_int, [vp, dp, c_int, c_int]),
+        "tp_sweep": (c_int, [vp, c_int, c_int, c_int, ip, dp, c_int, ip]),
+        "tp_get_dendro": (c_int, [vp, c_int, dp, ip]),
+        "tp_select": (c_int, [dp, c_int, c_int, c_int, ip, ip]),
+        "tp_call": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, c_double, u8p, ip, ip, ip, ip, dp, c_int, ip, dp]),
+        "tp_call_arm": (c_int, [vp, ip, c_int, c_int, c_int, ip, ip, ip, dp, c_int, ip, dp]),
+        "tp_difft_batch": (c_int, [vp, vp, vp, c_int, c_int, c_int, vp]),
+        "tp_assemble": (c_int, [dp, c_int, c_int, ip, ip, c_int, ip, ip, ip, ip]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != TP_OK:
+        raise TadpoleError(rc, load().tp_last_error().decode("utf-8", "replace"))
+
+
+def _dp(a):
+    return a.ctypes.data_as(POINTER(c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(POINTER(c_int))
+
+
+class Context:
+    """One GPU context (device buffers, stream).  Thin wrapper over tp_ctx."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        self._h = c_void_p()
+        check(self.lib.tp_ctx_create(int(device), ctypes.byref(self._h)))
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.tp_ctx_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- plumbing ----
+    def set(self, key, value):
+        check(self.lib.tp_ctx_set(self._h, key.encode(), float(value)))
+
+    def sync(self):
+        check(self.lib.tp_ctx_sync(self._h))
+
+    @property
+    def stream(self):
+        return self.lib.tp_ctx_stream(self._h) or 0
+
+    @property
+    def launches(self):
+        return int(self.lib.tp_ctx_launches(self._h))
+
+    def timings(self):
+        out = np.zeros(10)
+        check(self.lib.tp_ctx_timings(self._h, _dp(out)))
+        keys = ["filter_ms", "compact_ms", "correlation_ms", "pca_ms", "sweep_ms", "ch_ms", "total_ms",
+                "pca_iterations", "pca_applications", "jacobi_sweeps"]
+        return dict(zip(keys, out.tolist()))
+
+    PROFILE_CLASSES = ["rowmean", "compact", "dgemm", "jacobi", "coniss_sweep", "ch", "difft", "spare"]
+
+    def profile(self, enable=-1):
+        """enable: 1 start/reset, 0 stop, -1 read.  Returns {class: (ms, launches)} accumulated so far."""
+        ms = np.zeros(8)
+        cnt = np.zeros(8, dtype=np.int64)
+        check(self.lib.tp_ctx_profile(self._h, int(enable), _dp(ms), cnt.ctypes.data_as(POINTER(c_longlong))))
+        return {k: (float(m), int(c)) for k, m, c in zip(self.PROFILE_CLASSES, ms, cnt)}
+
+    # ---- stage 1 ----
+    def filter(self, mat, bad_frac=0.01, colmajor=None, device_ptr=None, n=None):
+        """mat: numpy n x n float64 (C or F order), or device_ptr + n (+ colmajor)."""
+        if device_ptr is None:
+            mat = np.asarray(mat)
+            if mat.dtype != np.float64 or not (mat.flags.c_contiguous or mat.flags.f_contiguous):
+                mat = np.ascontiguousarray(mat, dtype=np.float64)
+            assert mat.ndim == 2 and mat.shape[0] == mat.shape[1], "square matrix expected"
+            n = mat.shape[0]
+            colmajor = 0 if mat.flags.c_contiguous else 1
+            ptr, ondev = mat.ctypes.data, 0
+        else:
+            ptr, ondev, colmajor = int(device_ptr), 1, int(bool(colmajor))
+        bad = np.zeros(n, dtype=np.uint8)
+        rm = np.zeros(n)
+        thr = np.zeros(1)
+        check(self.lib.tp_filter(self._h, ptr, n, colmajor, ondev, float(bad_frac),
+                                 bad.ctypes.data_as(POINTER(c_uint8)), _dp(rm), _dp(thr)))
+        return bad.astype(bool), rm, float(thr[0])
+
+    def compact(self, keep):
+        keep = np.ascontiguousarray(keep, dtype=np.int32)
+        check(self.lib.tp_compact(self._h, _ip(keep), keep.size))
+        return keep.size
+
+    def set_filtered(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        check(self.lib.tp_set_filtered(self._h, _dp(x), x.shape[0]))
+
+    def get_filtered(self, nf):
+        out = np.zeros((nf, nf))
+        check(self.lib.tp_get_filtered(self._h, _dp(out)))
+        return out
+
+    # ---- stage 2 ----
+    def correlation(self):
+        check(self.lib.tp_correlation(self._h))
+
+    def get_correlation(self, nf):
+        out = np.zeros((nf, nf))
+        check(self.lib.tp_get_correlation(self._h, _dp(out)))
+        return out
+
+    def set_correlation(self, cor):
+        cor = np.ascontiguousarray(cor, dtype=np.float64)
+        check(self.lib.tp_set_correlation(self._h, _dp(cor), cor.shape[0]))
+
+    # ---- stage 3 ----
+    def pca(self, max_pcs=200):
+        k = c_int(0)
+        check(self.lib.tp_pca(self._h, int(max_pcs), ctypes.byref(k)))
+        return k.value
+
+    def get_scores(self, nf, k):
+        out = np.zeros((nf, k))
+        check(self.lib.tp_get_scores(self._h, _dp(out)))
+        return out
+
+    def set_scores(self, scores):
+        scores = np.ascontiguousarray(scores, dtype=np.float64)
+        check(self.lib.tp_set_scores(self._h, _dp(scores), scores.shape[0], scores.shape[1]))
+
+    # ---- stages 4 + 5 ----
+    def sweep(self, k, min_clusters=2, cand_begin=0, cand_stride=1, ld=256):
+        """Returns (n_cluster[k], scores[k, maxlev] NaN padded)."""
+        ncl = np.zeros(k, dtype=np.int32)
+        maxlev = c_int(0)
+        while True:
+            sc = np.empty((k, ld))
+            rc = self.lib.tp_sweep(self._h, int(min_clusters), int(cand_begin), int(cand_stride),
+                                   _ip(ncl), _dp(sc), ld, ctypes.byref(maxlev))
+            if rc == TP_ERR_ARG and maxlev.value > ld:
+                ld = maxlev.value
+                continue
+            check(rc)
+            return ncl, sc[:, :max(maxlev.value, 1)].copy() if maxlev.value else sc[:, :0]
+
+    def dendro(self, cand, nf):
+        seq = np.zeros(nf - 1)
+        order = np.zeros(nf - 1, dtype=np.int32)
+        check(self.lib.tp_get_dendro(self._h, int(cand), _dp(seq), _ip(order)))
+        return seq, order
+
+    def select(self, scores):
+        scores = np.ascontiguousarray(scores, dtype=np.float64)
+        oc, ol = c_int(0), c_int(0)
+        check(self.lib.tp_select(_dp(scores), scores.shape[0], scores.shape[1], scores.shape[1],
+                                 ctypes.byref(oc), ctypes.byref(ol)))
+        return oc.value, ol.value
+
+    # ---- one-shot ----
+    def call(self, mat=None, max_pcs=200, min_clusters=2, bad_frac=0.01, device_ptr=None, n=None, colmajor=None,
+             ld=256, want_scores=True):
+        if device_ptr is None:
+            mat = np.asarray(mat)
+            if mat.dtype != np.float64 or not (mat.flags.c_contiguous or mat.flags.f_contiguous):
+                mat = np.ascontiguousarray(mat, dtype=np.float64)
+            n = mat.shape[0]
+            colmajor = 0 if mat.flags.c_contiguous else 1
+            ptr, ondev = mat.ctypes.data, 0
+        else:
+            ptr, ondev, colmajor = int(device_ptr), 1, int(bool(colmajor))
+        bad = np.zeros(n, dtype=np.uint8)
+        nf, k, npcs, ncl, maxlev = c_int(0), c_int(0), c_int(0), c_int(0), c_int(0)
+        kmax = min(int(max_pcs), n)
+        seq = np.zeros(max(n - 1, 1))
+        while True:
+            sc = np.empty((kmax, ld)) if want_scores else None
+            rc = self.lib.tp_call(self._h, ptr, n, colmajor, ondev, int(max_pcs), int(min_clusters), float(bad_frac),
+                                  bad.ctypes.data_as(POINTER(c_uint8)), ctypes.byref(nf), ctypes.byref(k),
+                                  ctypes.byref(npcs), ctypes.byref(ncl),
+                                  _dp(sc) if want_scores else None, ld, ctypes.byref(maxlev), _dp(seq))
+            if rc == TP_ERR_ARG and maxlev.value > ld:
+                ld = maxlev.value
+                continue
+            check(rc)
+            break
+        return dict(bad=bad.astype(bool), nf=nf.value, k=k.value, n_pcs=npcs.value, n_clusters=ncl.value,
+                    scores=sc[:k.value, :maxlev.value].copy() if want_scores else None,
+                    seqdist=seq[:nf.value - 1].copy())
+
+    def call_arm(self, keep, max_pcs=200, min_clusters=2, ld=256):
+        keep = np.ascontiguousarray(keep, dtype=np.int32)
+        nf = keep.size
+        k, npcs, ncl, maxlev = c_int(0), c_int(0), c_int(0), c_int(0)
+        kmax = min(int(max_pcs), nf)
+        seq = np.zeros(nf - 1)
+        while True:
+            sc = np.empty((kmax, ld))
+            rc = self.lib.tp_call_arm(self._h, _ip(keep), nf, int(max_pcs), int(min_clusters), ctypes.byref(k),
+                                      ctypes.byref(npcs), ctypes.byref(ncl), _dp(sc), ld, ctypes.byref(maxlev), _dp(seq))
+            if rc == TP_ERR_ARG and maxlev.value > ld:
+                ld = maxlev.value
+                continue
+            check(rc)
+            break
+        return dict(nf=nf, k=k.value, n_pcs=npcs.value, n_clusters=ncl.value,
+                    scores=sc[:k.value, :maxlev.value].copy(), seqdist=seq)
+
+    # ---- stage 6 ----
+    def difft_batch(self, lx, ly):
+        lx = np.ascontiguousarray(lx, dtype=np.int32)
+        ly = np.ascontiguousarray(ly, dtype=np.int32)
+        assert lx.shape == ly.shape and lx.ndim == 2
+        out = np.empty(lx.shape, dtype=np.float64)
+        check(self.lib.tp_difft_batch(self._h, lx.ctypes.data, ly.ctypes.data, lx.shape[1], lx.shape[0], 0,
+                                      out.ctypes.data))
+        return out
+
+    def difft_batch_dev(self, lx_ptr, ly_ptr, L, npairs, out_ptr):
+        check(self.lib.tp_difft_batch(self._h, int(lx_ptr), int(ly_ptr), int(L), int(npairs), 1, int(out_ptr)))
+
+
+def assemble(seqdist, n_clusters, names, bad):
+    """tp_assemble: start/end table (1-based) and fixed labels for one hierarchical level."""
+    lib = load()
+    seqdist = np.ascontiguousarray(seqdist, dtype=np.float64)
+    names = np.ascontiguousarray(names, dtype=np.int32)
+    nf = names.size
+    nbad = -1 if bad is None else len(bad)
+    badarr = np.ascontiguousarray(bad if bad is not None else [], dtype=np.int32)
+    cap = n_clusters + max(nbad, 0) + 2
+    start = np.zeros(cap, dtype=np.int32)
+    end = np.zeros(cap, dtype=np.int32)
+    labels = np.zeros(nf + max(nbad, 0), dtype=np.int32)
+    nrows = c_int(0)
+    check(lib.tp_assemble(_dp(seqdist), nf, int(n_clusters), _ip(names), _ip(badarr), nbad, _ip(start), _ip(end),
+                          ctypes.byref(nrows), _ip(labels)))
+    return np.stack([start[:nrows.value], end[:nrows.value]], axis=1).astype(np.int64), labels

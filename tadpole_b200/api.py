@@ -1,0 +1,288 @@
+"""Host-side mirror of the reference's R API (NAMESPACE:3-8) over the C ABI.
+
+    TADpole(mat_file, max_pcs=200, min_clusters=2, bad_frac=0.01, chr, start, end, resol,
+            centromere_search=False)                                  R/TADpole.R:344
+    load_mat(mat_file, chr, start, end, resol, bad_frac=0.01, centromere_search=False)   :15
+    diffT(bed_x, bed_y)                                               R/DiffT.R:19
+    random_bed(bed, bad_columns=None)                                 R/DiffT.R:61
+
+R is not available in the build image, so the host language is Python (the reference is an
+interpreted-language package; this file plays the role of R/*.R in INTEGRATION.md).  Same
+argument names, defaults, messages and error behaviour; chr/start/end/resol are accepted and
+ignored exactly as in the reference, where they only label plots.  All numeric work happens in
+libtadpole_b200 on the GPU; this file only does what the R wrapper would do: read the file,
+integer bookkeeping of bad columns / centromere, and packing the result object.
+"""
+from __future__ import annotations
+
+import sys
+
+import numpy as np
+
+from . import _lib
+from .hclust import Dendro
+
+__all__ = ["TADpole", "load_mat", "diffT", "random_bed", "bin_index", "Tadpole", "LoadedMatrix", "get_context"]
+
+_CTX = {}
+QUIET = False
+
+
+def message(text):
+    """R's message(): diagnostics on stderr."""
+    if not QUIET:
+        print(text, file=sys.stderr)
+
+
+def get_context(device=0):
+    ctx = _CTX.get(device)
+    if ctx is None:
+        ctx = _CTX[device] = _lib.Context(device)
+    return ctx
+
+
+def read_matrix(mat_file):
+    """bigmemory::read.big.matrix(mat_file, type='double', sep='\\t') (R/TADpole.R:17): header-less
+    tab-separated numeric matrix.  An in-memory square array is accepted as well."""
+    if isinstance(mat_file, np.ndarray):
+        return mat_file
+    import pandas as pd
+    return pd.read_csv(mat_file, sep="\t", header=None, dtype=np.float64, na_values=["NA", "NaN"]).to_numpy()
+
+
+class LoadedMatrix:
+    """What load_mat returns: the filtered matrix with its 'bad_columns' attribute
+    (R/TADpole.R:88-90), or, when the chromosome was split, the list(p, q, centromere)
+    (R/TADpole.R:85).  The matrix itself stays on the GPU; to_numpy() fetches it."""
+
+    def __init__(self, ctx, n_bins, keep, bad_columns, split=None):
+        self._ctx = ctx
+        self.n_bins = n_bins
+        self.keep = keep                    # 0-based original indices of kept bins
+        self.names = None if keep is None else keep + 1
+        self.bad_columns = bad_columns      # R: character names for the whole matrix, numeric for arms
+        self.p = self.q = self.centromere = None
+        if split is not None:
+            self.p, self.q, self.centromere = split
+
+    @property
+    def is_split(self):
+        return self.p is not None
+
+    def to_numpy(self):
+        self._ctx.compact(self.keep)
+        return self._ctx.get_filtered(self.keep.size)
+
+    @property
+    def shape(self):
+        return (self.keep.size, self.keep.size)
+
+
+def _split_centromere(bad):
+    """R/TADpole.R:58-86 on the bad flags.  Returns None when the matrix is not split."""
+    n = bad.size
+    idx = np.flatnonzero(bad) + 1
+    brk = np.flatnonzero(np.diff(idx) > 1) + 1
+    runs = np.split(idx, brk)
+    longest = runs[int(np.argmax([len(r) for r in runs]))]       # which.max: first on ties
+    cs, ce = int(longest[0]), int(longest[-1])
+    message(f"centromere position: {cs} {ce}")
+    if cs == 1 or ce == n:
+        message("longest stretch of bad rows/columns at the ends, not splitting the matrix.")
+        return None
+    idx_p = np.arange(1, cs)
+    idx_q = np.arange(ce + 1, n + 1)
+    bad_p = idx[idx < cs]
+    bad_q = idx[idx > ce]
+    keep_p = np.ones(idx_p.size, bool)
+    keep_p[bad_p - 1] = False
+    keep_q = np.ones(idx_q.size, bool)
+    # R/TADpole.R:80 applies the ORIGINAL indices of the q-arm bad columns as negative positional
+    # indices to the re-based q matrix; out-of-range ones are silently ignored.
+    inr = bad_q[bad_q <= idx_q.size]
+    keep_q[inr - 1] = False
+    return (idx_p[keep_p] - 1, bad_p if bad_p.size else None), (idx_q[keep_q] - 1, bad_q if bad_q.size else None), \
+        np.arange(cs, ce + 1)
+
+
+def load_mat(mat_file, chr=None, start=None, end=None, resol=None, bad_frac=0.01, centromere_search=False,
+             ctx=None):
+    """Load a Hi-C matrix, flag bad columns, optionally split at the centromere (R/TADpole.R:15-92).
+    Plots (R/TADpole.R:24-53) are out of scope."""
+    ctx = ctx or get_context()
+    mat = read_matrix(mat_file)
+    bad, _, _ = ctx.filter(mat, bad_frac=bad_frac)
+    return _loaded_from_flags(ctx, bad, centromere_search)
+
+
+def _loaded_from_flags(ctx, bad, centromere_search):
+    n = bad.size
+    bad_names = [str(i) for i in np.flatnonzero(bad) + 1]
+    message(f"{int(bad.sum())} bad columns found at position(s):")
+    message(" ".join(bad_names))
+    if bad.any() and centromere_search:
+        split = _split_centromere(bad)
+        if split is not None:
+            (kp, bp), (kq, bq), cen = split
+            return LoadedMatrix(ctx, n, None, None, split=(LoadedMatrix(ctx, n, kp.astype(np.int32), bp),
+                                                           LoadedMatrix(ctx, n, kq.astype(np.int32), bq), cen))
+    keep = np.flatnonzero(~bad).astype(np.int32)
+    return LoadedMatrix(ctx, n, keep, np.flatnonzero(bad) + 1)
+
+
+class _Obj(dict):
+    """R list semantics: x$name and x[['name']]."""
+    __getattr__ = dict.get
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+class Tadpole(_Obj):
+    """The returned 'tadpole' object (R/TADpole.R:463-468; arms :354,376-378,407,442):
+    n_pcs, optimal_n_clusters, dendro, clusters (dict keyed by str(k) -> [rows, 2] start/end),
+    scores; with centromere_search: p, q (each n_pcs, optimal_n_clusters, dendro, cluster) and
+    merging_arms."""
+
+
+def _levels_table(res, names, bad_cols):
+    """for (k in which(!is.na(scores[n_PCs, ]))) ... (R/TADpole.R:381-408,470-497)."""
+    out = {}
+    row = res["scores"][res["n_pcs"] - 1]
+    for k in np.flatnonzero(~np.isnan(row)) + 1:
+        tab, _ = _lib.assemble(res["seqdist"], int(k), names, bad_cols)
+        out[str(int(k))] = tab
+    return out
+
+
+def _messages_optimal(res):
+    message(f"Optimal number of PCs: {res['n_pcs']}")
+    message(f"Optimal number of clusters: {res['n_clusters']}")
+
+
+def TADpole(mat_file, max_pcs=200, min_clusters=2, bad_frac=0.01, chr=None, start=None, end=None, resol=None,
+            centromere_search=False, ctx=None):
+    """Call hierarchical TADs (R/TADpole.R:344-501)."""
+    ctx = ctx or get_context()
+    mat = read_matrix(mat_file)
+    if not centromere_search:
+        res = ctx.call(mat, max_pcs=max_pcs, min_clusters=min_clusters, bad_frac=bad_frac)
+        bad = res["bad"]
+        message(f"{int(bad.sum())} bad columns found at position(s):")
+        message(" ".join(str(i) for i in np.flatnonzero(bad) + 1))
+        _messages_optimal(res)
+        names = (np.flatnonzero(~bad) + 1).astype(np.int32)
+        bad_cols = (np.flatnonzero(bad) + 1).astype(np.int32)
+        tp = Tadpole()
+        tp.n_pcs = res["n_pcs"]
+        tp.optimal_n_clusters = res["n_clusters"]
+        tp.dendro = Dendro(res["seqdist"], labels=names)
+        tp.clusters = _levels_table(res, names, bad_cols)
+        tp.scores = res["scores"]
+        return tp
+
+    bad, _, _ = ctx.filter(mat, bad_frac=bad_frac)
+    lm = _loaded_from_flags(ctx, bad, True)
+    if not lm.is_split:
+        # R/TADpole.R:356-359 then does mat$centromer / mat[['p']] on a plain matrix and errors (quirk Q4)
+        raise ValueError("centromere_search=TRUE but load_mat did not split the matrix "
+                         "(no bad columns, or the longest bad stretch touches an end); the reference errors here")
+    tp = Tadpole()
+    fixed_arms = []
+    ncen = len(lm.centromere)
+    for arm in ("p", "q"):
+        message(f"Processing arm {arm}")
+        la = getattr(lm, arm)
+        res = ctx.call_arm(la.keep, max_pcs=max_pcs, min_clusters=min_clusters)
+        _messages_optimal(res)
+        a = _Obj()
+        a.n_pcs = res["n_pcs"]
+        a.optimal_n_clusters = res["n_clusters"]
+        a.dendro = Dendro(res["seqdist"], labels=la.names)
+        a.cluster = _levels_table(res, la.names.astype(np.int32), la.bad_columns)
+        tp[arm] = a
+        # optimal level of this arm, bad columns re-inserted, fix_values applied (R/TADpole.R:411-431)
+        bad_for_merge = la.bad_columns if la.bad_columns is not None else np.zeros(0, np.int32)
+        _, labels = _lib.assemble(res["seqdist"], res["n_clusters"], la.names.astype(np.int32), bad_for_merge)
+        fixed_arms.append(labels.astype(np.int64))
+        fixed_arms.append(np.zeros(ncen, dtype=np.int64))
+    allv = np.concatenate(fixed_arms)
+    allv = allv[: allv.size - ncen]                      # R/TADpole.R:438
+    brk = np.flatnonzero(allv[1:] != allv[:-1]) + 1
+    starts = np.concatenate(([0], brk))
+    ends = np.concatenate((brk, [allv.size]))
+    keep = allv[starts] != 0
+    tp.merging_arms = np.stack([starts[keep] + 1, ends[keep]], axis=1)
+    return tp
+
+
+# ---- diffT -------------------------------------------------------------------------------------------
+
+def _bed_rows(bed):
+    """Accepts a [T,3] table (chrom, start, end), a [T,2] array (start, end) or a path."""
+    if isinstance(bed, str):
+        rows = []
+        with open(bed) as fh:
+            for line in fh:
+                f = line.split()
+                if len(f) >= 3:
+                    rows.append((int(f[1]), int(f[2])))
+        return np.array(rows, dtype=np.int64)
+    if hasattr(bed, "iloc"):
+        return bed.iloc[:, 1:3].to_numpy(dtype=np.int64)
+    arr = np.asarray(bed)
+    if arr.ndim == 2 and arr.shape[1] >= 3:
+        return arr[:, 1:3].astype(np.int64)
+    return arr.astype(np.int64)
+
+
+def bin_index(bed, size):
+    """bin_index (R/DiffT.R:1-9): TAD label per bin, offsets relative to the first row's start,
+    later rows overwrite earlier ones, uncovered bins stay 0."""
+    bed = np.asarray(bed, dtype=np.int64)
+    tad = np.zeros(int(size), dtype=np.int32)
+    off = bed[0, 0]
+    for t in range(bed.shape[0]):
+        tad[bed[t, 0] - off: bed[t, 1] - off + 1] = t + 1
+    return tad
+
+
+def _difft_labels(bed_x, bed_y):
+    bx, by = _bed_rows(bed_x), _bed_rows(bed_y)
+    if bx.shape[0] != by.shape[0]:
+        raise ValueError("Both calls must have the same number of TADs.")       # R/DiffT.R:20
+    sx, sy, ex, ey = bx[0, 0], by[0, 0], bx[-1, 1], by[-1, 1]
+    tx = bin_index(bx, ex - sx + 1)
+    ty = bin_index(by, ey - sy + 1)
+    tx = np.concatenate((np.ones(max(0, sx - sy), np.int32), tx, np.full(max(0, ey - ex), tx.max(), np.int32)))
+    ty = np.concatenate((np.ones(max(0, sy - sx), np.int32), ty, np.full(max(0, ex - ey), ty.max(), np.int32)))
+    if tx.size != ty.size:
+        raise AssertionError("length(tad_x) == length(tad_y) is not TRUE")       # stopifnot, R/DiffT.R:38
+    return tx, ty
+
+
+def diffT(bed_x, bed_y, ctx=None):
+    """diffT score between two TAD calls (R/DiffT.R:19-50)."""
+    ctx = ctx or get_context()
+    tx, ty = _difft_labels(bed_x, bed_y)
+    return ctx.difft_batch(tx[None, :], ty[None, :])[0]
+
+
+def diffT_batch(labels_x, labels_y, ctx=None):
+    """Many comparisons at once on padded label vectors ([npairs, L] int32 each)."""
+    ctx = ctx or get_context()
+    return ctx.difft_batch(labels_x, labels_y)
+
+
+def random_bed(bed, bad_columns=None, rng=None):
+    """Random partition with the same number of TADs (R/DiffT.R:61-73).  Uses numpy's RNG, so
+    draws differ from R's sample(); the distribution is the same."""
+    rows = _bed_rows(bed)
+    rng = rng or np.random.default_rng()
+    start, end = int(rows[0, 0]), int(rows[-1, 1])
+    size = end - start + 1
+    bins = np.arange(start, end + 1)
+    if bad_columns is not None:
+        bins = np.delete(bins, np.asarray(bad_columns, dtype=np.int64) - 1)
+    borders = np.sort(rng.choice(bins[1:], size=rows.shape[0] - 1, replace=False))
+    return np.stack([np.concatenate(([start], borders - 1)), np.concatenate((borders - 2, [start + size - 1]))], axis=1)

@@ -1,0 +1,444 @@
+// api.cu -- context management, one-shot pipeline, host-side reductions and result assembly.
+#include "common.cuh"
+#include <stdarg.h>
+#include <algorithm>
+#include <numeric>
+
+int tp_sweep_device(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stride, int *ncand_out);
+int tp_ch_device(tp_ctx *ctx, int min_clusters, int ncand, int ld_chs);
+
+static thread_local char g_err[1024] = "";
+
+void tp_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *tp_last_error(void) { return g_err; }
+extern "C" int tp_version(void) { return 100; }
+
+int tp_pin_reserve(tp_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->pin_cap) return TP_OK;
+    if (ctx->pin) cudaFreeHost(ctx->pin);
+    ctx->pin = nullptr; ctx->pin_cap = 0;
+    TP_CUDA(cudaMallocHost(&ctx->pin, bytes));
+    ctx->pin_cap = bytes;
+    return TP_OK;
+}
+
+extern "C" int tp_ctx_create(int device, tp_ctx **out) {
+    TP_ARG(out, "tp_ctx_create: null output pointer");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        tp_set_error("tp_ctx_create: no CUDA device available (%s); this library has no CPU fallback",
+                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return TP_ERR_CUDA;
+    }
+    TP_ARG(device >= 0 && device < ndev, "tp_ctx_create: device index out of range");
+    TP_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    TP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        tp_set_error("tp_ctx_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                     device, prop.major, prop.minor);
+        return TP_ERR_CUDA;
+    }
+    tp_ctx *ctx = new tp_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    TP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < EV_COUNT; i++) TP_CUDA(cudaEventCreate(&ctx->ev[i]));
+    TP_TRY(tp_pin_reserve(ctx, 1 << 16));
+    *out = ctx;
+    return TP_OK;
+}
+
+extern "C" int tp_ctx_destroy(tp_ctx *ctx) {
+    if (!ctx) return TP_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->raw_own, &ctx->rowmean, &ctx->ranks, &ctx->flags, &ctx->qtmp, &ctx->keep, &ctx->X, &ctx->C,
+                      &ctx->colstat, &ctx->scores, &ctx->M, &ctx->Y0, &ctx->Y1, &ctx->Y2, &ctx->W, &ctx->G, &ctx->T,
+                      &ctx->Q, &ctx->Jw, &ctx->Jv, &ctx->Jt, &ctx->small1, &ctx->small2, &ctx->part, &ctx->resid,
+                      &ctx->P, &ctx->Qp, &ctx->d0, &ctx->seqdist, &ctx->order, &ctx->ncl, &ctx->chs, &ctx->bsbuf,
+                      &ctx->links, &ctx->harm, &ctx->lx, &ctx->ly, &ctx->dout, &ctx->dhash, &ctx->lhash};
+    for (DevBuf *b : bufs) b->release();
+    for (int i = 0; i < EV_COUNT; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+    if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return TP_OK;
+}
+
+extern "C" int tp_ctx_sync(tp_ctx *ctx) {
+    TP_ARG(ctx, "tp_ctx_sync: null context");
+    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return TP_OK;
+}
+
+extern "C" void *tp_ctx_stream(tp_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" long long tp_ctx_launches(tp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int tp_ctx_set(tp_ctx *ctx, const char *key, double value) {
+    TP_ARG(ctx && key, "tp_ctx_set: null argument");
+    std::string k(key);
+    if (k == "pca_block") ctx->pca_block = (int)value;
+    else if (k == "pca_tol") ctx->pca_tol = value;
+    else if (k == "pca_maxit") ctx->pca_maxit = (int)value;
+    else if (k == "jacobi_direct_max") ctx->jacobi_direct_max = (int)value;
+    else if (k == "level_cap") ctx->level_cap = (int)value;
+    else { tp_set_error("tp_ctx_set: unknown key '%s'", key); return TP_ERR_ARG; }
+    return TP_OK;
+}
+
+static double ev_ms(tp_ctx *ctx, int a, int b) {
+    if (!ctx->ev_set[a] || !ctx->ev_set[b]) return 0.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]) != cudaSuccess) { (void)cudaGetLastError(); return 0.0; }
+    return ms;
+}
+
+extern "C" int tp_ctx_timings(tp_ctx *ctx, double *out10) {
+    TP_ARG(ctx && out10, "tp_ctx_timings: null argument");
+    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    out10[0] = ev_ms(ctx, EV_FILTER0, EV_FILTER1);
+    out10[1] = ev_ms(ctx, EV_COMPACT0, EV_COMPACT1);
+    out10[2] = ev_ms(ctx, EV_CORR0, EV_CORR1);
+    out10[3] = ev_ms(ctx, EV_PCA0, EV_PCA1);
+    out10[4] = ev_ms(ctx, EV_SWEEP0, EV_SWEEP1);
+    out10[5] = ev_ms(ctx, EV_SWEEP1, EV_CH1);
+    out10[6] = ev_ms(ctx, EV_TOTAL0, EV_TOTAL1);
+    out10[7] = ctx->timing[7]; out10[8] = ctx->timing[8]; out10[9] = ctx->timing[9];
+    return TP_OK;
+}
+
+void tp_prof_begin(tp_ctx *ctx, int cls) {
+    if (!ctx->prof) return;
+    if (ctx->prof_used + 2 > ctx->prof_ev.size()) {
+        for (int i = 0; i < 512; i++) { cudaEvent_t e; cudaEventCreate(&e); ctx->prof_ev.push_back(e); }
+    }
+    ctx->prof_cls.resize(ctx->prof_ev.size() / 2);
+    ctx->prof_cls[ctx->prof_used / 2] = cls;
+    cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream);
+}
+void tp_prof_end(tp_ctx *ctx) {
+    if (!ctx->prof) return;
+    cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], ctx->stream);
+    ctx->prof_used += 2;
+}
+
+extern "C" int tp_ctx_profile(tp_ctx *ctx, int enable, double *ms_out8, long long *count_out8) {
+    TP_ARG(ctx, "tp_ctx_profile: null context");
+    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ms_out8 || count_out8) {
+        double ms[PC_COUNT] = {};
+        long long cnt[PC_COUNT] = {};
+        for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, ctx->prof_ev[i], ctx->prof_ev[i + 1]) == cudaSuccess) {
+                ms[ctx->prof_cls[i / 2]] += t;
+                cnt[ctx->prof_cls[i / 2]]++;
+            } else (void)cudaGetLastError();
+        }
+        for (int c = 0; c < PC_COUNT; c++) { if (ms_out8) ms_out8[c] = ms[c]; if (count_out8) count_out8[c] = cnt[c]; }
+    }
+    if (enable == 1) { ctx->prof = true; ctx->prof_used = 0; }
+    else if (enable == 0) ctx->prof = false;
+    return TP_OK;
+}
+
+// ---- set / get hooks ----------------------------------------------------------------------------
+static int upload_square(tp_ctx *ctx, DevBuf &buf, const double *h, int n, int ld) {
+    TP_TRY(buf.reserve((size_t)n * ld * sizeof(double)));
+    TP_CUDA(cudaMemsetAsync(buf.p, 0, (size_t)n * ld * sizeof(double), ctx->stream));
+    TP_CUDA(cudaMemcpy2DAsync(buf.p, (size_t)ld * sizeof(double), h, (size_t)n * sizeof(double),
+                              (size_t)n * sizeof(double), n, cudaMemcpyHostToDevice, ctx->stream));
+    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return TP_OK;
+}
+static int download(tp_ctx *ctx, const DevBuf &buf, double *h, int rows, int cols, int ld) {
+    TP_CUDA(cudaMemcpy2DAsync(h, (size_t)cols * sizeof(double), buf.p, (size_t)ld * sizeof(double),
+                              (size_t)cols * sizeof(double), rows, cudaMemcpyDeviceToHost, ctx->stream));
+    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return TP_OK;
+}
+
+extern "C" int tp_set_filtered(tp_ctx *ctx, const double *x, int nf) {
+    TP_ARG(ctx && x && nf >= 2, "tp_set_filtered: bad arguments");
+    TP_CUDA(cudaSetDevice(ctx->device));
+    ctx->nf = nf; ctx->ldx = round_up(nf, 8);
+    TP_TRY(upload_square(ctx, ctx->X, x, nf, ctx->ldx));
+    ctx->have_X = true; ctx->have_C = ctx->have_scores = ctx->have_sweep = false;
+    return TP_OK;
+}
+extern "C" int tp_get_filtered(tp_ctx *ctx, double *x_out) {
+    TP_ARG(ctx && x_out && ctx->have_X, "tp_get_filtered: no filtered matrix");
+    return download(ctx, ctx->X, x_out, ctx->nf, ctx->nf, ctx->ldx);
+}
+extern "C" int tp_set_correlation(tp_ctx *ctx, const double *cor, int nf) {
+    TP_ARG(ctx && cor && nf >= 2, "tp_set_correlation: bad arguments");
+    TP_CUDA(cudaSetDevice(ctx->device));
+    ctx->nf = nf; ctx->ldx = round_up(nf, 8);
+    TP_TRY(upload_square(ctx, ctx->C, cor, nf, ctx->ldx));
+    ctx->have_C = true; ctx->have_scores = ctx->have_sweep = false;
+    return TP_OK;
+}
+extern "C" int tp_get_correlation(tp_ctx *ctx, double *cor_out) {
+    TP_ARG(ctx && cor_out && ctx->have_C, "tp_get_correlation: no correlation matrix (tp_pca consumes it)");
+    return download(ctx, ctx->C, cor_out, ctx->nf, ctx->nf, ctx->ldx);
+}
+extern "C" int tp_set_scores(tp_ctx *ctx, const double *scores, int nf, int k) {
+    TP_ARG(ctx && scores && nf >= 3 && k >= 1 && k <= nf, "tp_set_scores: bad arguments");
+    TP_CUDA(cudaSetDevice(ctx->device));
+    ctx->nf = nf; ctx->k = k; ctx->ldk = round_up(k, 8);
+    TP_TRY(ctx->scores.reserve((size_t)nf * ctx->ldk * sizeof(double)));
+    TP_CUDA(cudaMemsetAsync(ctx->scores.p, 0, (size_t)nf * ctx->ldk * sizeof(double), ctx->stream));
+    TP_CUDA(cudaMemcpy2DAsync(ctx->scores.p, (size_t)ctx->ldk * sizeof(double), scores, (size_t)k * sizeof(double),
+                              (size_t)k * sizeof(double), nf, cudaMemcpyHostToDevice, ctx->stream));
+    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->have_scores = true; ctx->have_sweep = false;
+    return TP_OK;
+}
+extern "C" int tp_get_scores(tp_ctx *ctx, double *scores_out) {
+    TP_ARG(ctx && scores_out && ctx->have_scores, "tp_get_scores: no scores");
+    return download(ctx, ctx->scores, scores_out, ctx->nf, ctx->k, ctx->ldk);
+}
+
+// ---- stages 4 + 5 ---------------------------------------------------------------------------------
+static int sweep_impl(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stride,
+                      int *n_cluster_out, double *scores_out, int ld_scores, int *maxlev_out) {
+    int ncand = 0;
+    TP_TRY(tp_sweep_device(ctx, min_clusters, cand_begin, cand_stride, &ncand));
+    const int k = ctx->k;
+    if (maxlev_out) *maxlev_out = 0;
+    if (ncand == 0) {
+        if (n_cluster_out) std::fill(n_cluster_out, n_cluster_out + k, 0);
+        return TP_OK;
+    }
+    int ld = ctx->level_cap > 8 ? ctx->level_cap : 8;
+    TP_TRY(tp_pin_reserve(ctx, (size_t)k * sizeof(int) + 64));
+    int *h_ncl = (int *)ctx->pin;
+    int maxlev = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        TP_TRY(tp_ch_device(ctx, min_clusters, ncand, ld));
+        TP_CUDA(cudaMemcpyAsync(h_ncl, ctx->ncl.p, (size_t)k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        TP_CUDA(cudaStreamSynchronize(ctx->stream));
+        maxlev = 0;
+        for (int c = 0; c < k; c++) {
+            if (h_ncl[c] < 0) {
+                tp_set_error("candidate %d PCs: no broken-stick level is significant (the reference fails here too: "
+                             "n_cluster is NA at R/TADpole.R:113)", c + 1);
+                return TP_ERR_NOLEVEL;
+            }
+            maxlev = std::max(maxlev, h_ncl[c]);
+        }
+        if (maxlev <= ld) break;
+        ld = round_up(maxlev, 8);          // rare: more levels than the cap; redo the cheap CH pass wider
+    }
+    if (maxlev_out) *maxlev_out = maxlev;
+    if (n_cluster_out) memcpy(n_cluster_out, h_ncl, (size_t)k * sizeof(int));
+    if (scores_out) {
+        if (ld_scores < maxlev) {
+            tp_set_error("tp_sweep: ld_scores = %d is smaller than the %d levels found", ld_scores, maxlev);
+            return TP_ERR_ARG;
+        }
+        // NaN-fill, then copy the first maxlev columns of every row
+        for (size_t i = 0; i < (size_t)k * ld_scores; i++) scores_out[i] = NAN;
+        if (maxlev > 0)
+            TP_CUDA(cudaMemcpy2DAsync(scores_out, (size_t)ld_scores * sizeof(double), ctx->chs.p,
+                                      (size_t)ctx->ld_chs * sizeof(double), (size_t)maxlev * sizeof(double), k,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+        TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return TP_OK;
+}
+
+extern "C" int tp_sweep(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stride,
+                        int *n_cluster_out, double *scores_out, int ld_scores, int *maxlev_out) {
+    TP_ARG(ctx, "tp_sweep: null context");
+    TP_CUDA(cudaSetDevice(ctx->device));
+    return sweep_impl(ctx, min_clusters, cand_begin, cand_stride, n_cluster_out, scores_out, ld_scores, maxlev_out);
+}
+
+extern "C" int tp_get_dendro(tp_ctx *ctx, int cand, double *seqdist_out, int *order_out) {
+    TP_ARG(ctx && ctx->have_sweep, "tp_get_dendro: run tp_sweep first");
+    TP_ARG(cand >= 0 && cand < ctx->k, "tp_get_dendro: candidate out of range");
+    const int n1 = ctx->nf - 1, ldd = round_up(n1, 8);
+    if (seqdist_out)
+        TP_CUDA(cudaMemcpyAsync(seqdist_out, ctx->seqdist.as<double>() + (size_t)cand * ldd, (size_t)n1 * sizeof(double),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<int> tmp;
+    if (order_out) {
+        tmp.resize((size_t)n1 * 4);
+        TP_CUDA(cudaMemcpyAsync(tmp.data(), ctx->order.as<int4>() + (size_t)cand * ldd, (size_t)n1 * sizeof(int4),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (order_out) for (int t = 0; t < n1; t++) order_out[t] = tmp[(size_t)t * 4];
+    return TP_OK;
+}
+
+// which.max(rowMeans(scores, na.rm = TRUE)); which.max(scores[opt, ])  (R/TADpole.R:134-135)
+extern "C" int tp_select(const double *scores, int k, int ld, int maxlev, int *opt_cand, int *opt_level) {
+    TP_ARG(scores && opt_cand && opt_level && k >= 1 && maxlev >= 1 && ld >= maxlev, "tp_select: bad arguments");
+    int best = -1;
+    long double bestv = 0;
+    for (int r = 0; r < k; r++) {
+        long double s = 0;   // R accumulates rowMeans in long double
+        int cnt = 0;
+        for (int c = 0; c < maxlev; c++) {
+            const double v = scores[(size_t)r * ld + c];
+            if (v == v) { s += v; cnt++; }
+        }
+        if (!cnt) continue;                       // mean of nothing is NaN: ignored by which.max
+        const double m = (double)(s / cnt);
+        if (m != m) continue;
+        if (best < 0 || m > (double)bestv) { best = r; bestv = m; }
+    }
+    if (best < 0) { tp_set_error("tp_select: every candidate row is NA"); return TP_ERR_NOLEVEL; }
+    int bl = -1;
+    double blv = 0;
+    for (int c = 0; c < maxlev; c++) {
+        const double v = scores[(size_t)best * ld + c];
+        if (v == v && (bl < 0 || v > blv)) { bl = c; blv = v; }
+    }
+    if (bl < 0) { tp_set_error("tp_select: optimal row has no score"); return TP_ERR_NOLEVEL; }
+    *opt_cand = best;
+    *opt_level = bl;
+    return TP_OK;
+}
+
+// ---- one-shot -----------------------------------------------------------------------------------------
+static int call_from_compacted(tp_ctx *ctx, int max_pcs, int min_clusters, int *k_out, int *n_pcs_out,
+                               int *n_clusters_out, double *scores_out, int ld_scores, int *maxlev_out,
+                               double *seqdist_out) {
+    int k = 0, maxlev = 0;
+    TP_TRY(tp_correlation(ctx));
+    TP_TRY(tp_pca(ctx, max_pcs, &k));
+    if (k_out) *k_out = k;
+    std::vector<double> local;
+    double *sc = scores_out;
+    int ld = ld_scores;
+    if (!sc) { ld = std::max(ctx->level_cap, 8); }
+    // first try with the caller's width; when scores_out is NULL use a local buffer
+    int rc;
+    if (sc) {
+        rc = sweep_impl(ctx, min_clusters, 0, 1, nullptr, sc, ld, &maxlev);
+    } else {
+        local.assign((size_t)k * ld, NAN);
+        rc = sweep_impl(ctx, min_clusters, 0, 1, nullptr, local.data(), ld, &maxlev);
+        if (rc == TP_ERR_ARG && maxlev > ld) {
+            ld = maxlev;
+            local.assign((size_t)k * ld, NAN);
+            rc = sweep_impl(ctx, min_clusters, 0, 1, nullptr, local.data(), ld, &maxlev);
+        }
+        sc = local.data();
+    }
+    if (maxlev_out) *maxlev_out = maxlev;
+    TP_TRY(rc);
+    int oc = 0, ol = 0;
+    TP_TRY(tp_select(sc, k, ld, maxlev, &oc, &ol));
+    if (n_pcs_out) *n_pcs_out = oc + 1;
+    if (n_clusters_out) *n_clusters_out = ol + 1;
+    if (seqdist_out) TP_TRY(tp_get_dendro(ctx, oc, seqdist_out, nullptr));
+    TP_MARK(ctx, EV_TOTAL1);
+    return TP_OK;
+}
+
+extern "C" int tp_call(tp_ctx *ctx, const double *mat, int n, int colmajor, int on_device,
+                       int max_pcs, int min_clusters, double bad_frac,
+                       uint8_t *bad_out, int *nf_out, int *k_out, int *n_pcs_out, int *n_clusters_out,
+                       double *scores_out, int ld_scores, int *maxlev_out, double *seqdist_out) {
+    TP_ARG(ctx && mat && bad_out, "tp_call: null argument");
+    TP_CUDA(cudaSetDevice(ctx->device));
+    TP_MARK(ctx, EV_TOTAL0);
+    TP_TRY(tp_filter(ctx, mat, n, colmajor, on_device, bad_frac, bad_out, nullptr, nullptr));
+    std::vector<int> keep;
+    keep.reserve(n);
+    for (int i = 0; i < n; i++) if (!bad_out[i]) keep.push_back(i);
+    if (nf_out) *nf_out = (int)keep.size();
+    TP_ARG(keep.size() >= 3, "tp_call: fewer than 3 good bins left after filtering");
+    TP_TRY(tp_compact(ctx, keep.data(), (int)keep.size()));
+    return call_from_compacted(ctx, max_pcs, min_clusters, k_out, n_pcs_out, n_clusters_out, scores_out, ld_scores,
+                               maxlev_out, seqdist_out);
+}
+
+extern "C" int tp_call_arm(tp_ctx *ctx, const int *keep, int nf, int max_pcs, int min_clusters,
+                           int *k_out, int *n_pcs_out, int *n_clusters_out,
+                           double *scores_out, int ld_scores, int *maxlev_out, double *seqdist_out) {
+    TP_ARG(ctx && keep, "tp_call_arm: null argument");
+    TP_CUDA(cudaSetDevice(ctx->device));
+    TP_MARK(ctx, EV_TOTAL0);
+    TP_TRY(tp_compact(ctx, keep, nf));
+    return call_from_compacted(ctx, max_pcs, min_clusters, k_out, n_pcs_out, n_clusters_out, scores_out, ld_scores,
+                               maxlev_out, seqdist_out);
+}
+
+// ---- result assembly (host integer logic) ------------------------------------------------------------
+extern "C" int tp_assemble(const double *seqdist, int nf, int n_clusters, const int *names, const int *bad,
+                           int nbad, int *start_out, int *end_out, int *nrows_out, int *labels_out) {
+    TP_ARG(seqdist && names && start_out && end_out && nrows_out, "tp_assemble: null argument");
+    TP_ARG(nf >= 2 && n_clusters >= 1 && n_clusters <= nf, "tp_assemble: bad sizes");
+    const int n1 = nf - 1;
+    // stats::cutree(k): undo the k-1 merges that come last in rioja's .find.groups order
+    // (ascending value, first index on ties)
+    std::vector<int> idx(n1);
+    std::iota(idx.begin(), idx.end(), 0);
+    const int kb = n_clusters - 1;
+    if (kb > 0)
+        std::partial_sort(idx.begin(), idx.begin() + kb, idx.end(), [&](int a, int b) {
+            return seqdist[a] > seqdist[b] || (seqdist[a] == seqdist[b] && a > b);
+        });
+    std::vector<char> cut(n1, 0);
+    for (int i = 0; i < kb; i++) cut[idx[i]] = 1;
+    std::vector<int> good(nf);
+    int lab = 1;
+    for (int i = 0; i < nf; i++) {
+        good[i] = lab;
+        if (i < n1 && cut[i]) lab++;
+    }
+    std::vector<int> fixed;
+    if (nbad >= 0) {
+        // c(good, bad) ordered by as.numeric(names) (stable): merge two sorted lists, good first on ties
+        TP_ARG(nbad == 0 || bad, "tp_assemble: null bad list");
+        fixed.reserve((size_t)nf + nbad);
+        int i = 0, j = 0;
+        while (i < nf || j < nbad) {
+            if (j >= nbad || (i < nf && names[i] <= bad[j])) fixed.push_back(good[i++]);
+            else { fixed.push_back(0); j++; }
+        }
+        // fix_values on the run values, left to right
+        std::vector<int> vals, lens;
+        for (size_t p = 0; p < fixed.size(); p++) {
+            if (p == 0 || fixed[p] != fixed[p - 1]) { vals.push_back(fixed[p]); lens.push_back(1); }
+            else lens.back()++;
+        }
+        for (size_t r = 1; r + 1 < vals.size(); r++)
+            if (vals[r] == 0 && vals[r - 1] == vals[r + 1]) vals[r] = vals[r - 1];
+        size_t p = 0;
+        for (size_t r = 0; r < vals.size(); r++) for (int t = 0; t < lens[r]; t++) fixed[p++] = vals[r];
+    } else {
+        fixed = good;
+    }
+    if (labels_out) memcpy(labels_out, fixed.data(), fixed.size() * sizeof(int));
+    // rle again -> start / end of the non-zero runs (1-based, inclusive)
+    int rows = 0;
+    size_t p = 0;
+    while (p < fixed.size()) {
+        size_t q = p;
+        while (q + 1 < fixed.size() && fixed[q + 1] == fixed[p]) q++;
+        if (fixed[p] != 0 || nbad < 0) {
+            start_out[rows] = (int)p + 1;
+            end_out[rows] = (int)q + 1;
+            rows++;
+        }
+        p = q + 1;
+    }
+    *nrows_out = rows;
+    return TP_OK;
+}

@@ -1,0 +1,146 @@
+// common.cuh -- context, error plumbing and small device helpers shared by every translation unit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+#include "../../include/tadpole_b200.h"
+
+void tp_set_error(const char *fmt, ...);
+
+#define TP_CUDA(call)                                                                     \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            tp_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return TP_ERR_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+
+#define TP_TRY(call)                   \
+    do {                               \
+        int rc_ = (call);              \
+        if (rc_ != TP_OK) return rc_;  \
+    } while (0)
+
+#define TP_ARG(cond, msg)                               \
+    do {                                                \
+        if (!(cond)) {                                  \
+            tp_set_error("%s (%s)", msg, #cond);        \
+            return TP_ERR_ARG;                          \
+        }                                               \
+    } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return TP_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + (bytes >> 3);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();   // clear the sticky-free error state
+            tp_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+            return TP_ERR_NOMEM;
+        }
+        cap = want;
+        return TP_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+enum { EV_FILTER0 = 0, EV_FILTER1, EV_COMPACT0, EV_COMPACT1, EV_CORR0, EV_CORR1, EV_PCA0, EV_PCA1,
+       EV_SWEEP0, EV_SWEEP1, EV_CH1, EV_TOTAL0, EV_TOTAL1, EV_DIFFT0, EV_DIFFT1, EV_COUNT };
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct tp_ctx {
+    int device = 0;
+    int sm_count = 148;
+    int max_smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_COUNT] = {};
+    bool ev_set[EV_COUNT] = {};
+    long long launches = 0;
+
+    // tunables
+    int pca_block = 0;
+    double pca_tol = 2e-13;
+    int pca_maxit = 16;
+    int jacobi_direct_max = 512;
+    int level_cap = 256;
+
+    // stage 1 state
+    DevBuf raw_own;              // uploaded copy of the caller's matrix (when it came from the host)
+    const double *raw = nullptr; // device pointer to the N x N input (raw_own.p or caller's)
+    int n = 0;
+    int colmajor = 0;
+    DevBuf rowmean, ranks, flags, qtmp, keep;
+    // filtered matrix / correlation (nf x ldx row-major, ldx multiple of 8)
+    int nf = 0, ldx = 0;
+    DevBuf X, C, colstat;
+    bool have_X = false, have_C = false;
+    // PCA
+    int k = 0, ldk = 0;          // scores: nf x ldk row-major
+    DevBuf scores, M, Y0, Y1, Y2, W, G, T, Q, Jw, Jv, Jt, small1, small2, part, resid;
+    bool have_scores = false;
+    // sweep
+    DevBuf P, Qp, d0, seqdist, order, ncl, chs, bsbuf, links, harm;
+    int ld_chs = 0;
+    bool have_sweep = false;
+    // diffT
+    DevBuf lx, ly, dout, dhash, lhash;
+    // pinned staging for small read-backs
+    void *pin = nullptr;
+    size_t pin_cap = 0;
+
+    double timing[10] = {};
+
+    // per-kernel-class profiling (tp_ctx_profile)
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_ev;      // pool, pairs
+    std::vector<int> prof_cls;             // class of pair i
+    size_t prof_used = 0;                  // events used
+};
+
+enum { PC_ROWMEAN = 0, PC_COMPACT, PC_GEMM, PC_JACOBI, PC_SWEEP, PC_CH, PC_DIFFT, PC_SPARE, PC_COUNT };
+void tp_prof_begin(tp_ctx *ctx, int cls);
+void tp_prof_end(tp_ctx *ctx);
+
+int tp_pin_reserve(tp_ctx *ctx, size_t bytes);
+// record a timing event on the context stream
+#define TP_MARK(ctx, id)                                              \
+    do {                                                              \
+        TP_CUDA(cudaEventRecord((ctx)->ev[id], (ctx)->stream));       \
+        (ctx)->ev_set[id] = true;                                     \
+    } while (0)
+
+// ---- device helpers ------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// min over the warp of non-negative doubles (or +inf); IEEE bit patterns of non-negative doubles
+// order like unsigned integers, so two 32-bit REDUX ops do it.
+__device__ __forceinline__ double warp_min_nonneg(double v) {
+    unsigned hi = (unsigned)__double2hiint(v);
+    unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    unsigned lo = (hi == mh) ? (unsigned)__double2loint(v) : 0xffffffffu;
+    unsigned ml = __reduce_min_sync(0xffffffffu, lo);
+    return __hiloint2double((int)mh, (int)ml);
+}
+__device__ __forceinline__ double nan_to_zero(double x) { return x == x ? x : 0.0; }
+#endif

@@ -1,0 +1,257 @@
+// filter.cu -- stage 1: the numeric core of load_mat (reference R/TADpole.R:19-22,35-37,88).
+//
+//   mat[is.na(mat)] <- 0 ; mat <- forceSymmetric(mat, uplo='U')          (:19-20)
+//   r <- rowMeans(mat) ; bad <- diag(mat) == 0 | r < quantile(r, bad_frac)  (:35-37)
+//   mat <- mat[!bad, !bad]                                                  (:88)
+//
+// The symmetrised matrix is never materialised: only the upper triangle U(i,j), i <= j, of the
+// caller's buffer is read.  With A the row-major view of the buffer, U(i,j) = A[i][j] for a C /
+// numpy buffer (upper triangle of A) and U(i,j) = A[j][i] for an R column-major buffer (lower
+// triangle of A).  Row i of the symmetric matrix is then one contiguous row segment of A plus one
+// column segment of A; a CTA owning R consecutive rows streams an R-row horizontal strip and an
+// R-column vertical strip, both in full 32-byte sectors, so the pass reads N^2 doubles in total
+// (every off-diagonal element of the triangle twice, once per incident row) with a fixed
+// summation order -- no atomics, bit-reproducible.  HBM-bound: 8 N^2 bytes.
+#include "common.cuh"
+
+#define FT_THREADS 256
+
+// upper == true : valid triangle is c >= r of A ; row i = A[i][i..n) + A[0..i)[i]
+// upper == false: valid triangle is c <= r of A ; row i = A[i][0..i] + A(i..n)[i]
+template <int R>
+__global__ void __launch_bounds__(FT_THREADS)
+rowmean_kernel(const double *__restrict__ A, int n, int upper, double *__restrict__ rowmean,
+               unsigned char *__restrict__ diag0) {
+    __shared__ double s_h[R];
+    __shared__ double s_v[FT_THREADS / R][R];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int i0 = blockIdx.x * R;
+    // horizontal segments: one warp per row, lanes along the row
+    for (int rr = wid; rr < R; rr += FT_THREADS / 32) {
+        const int i = i0 + rr;
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+        if (i < n) {
+            const double *row = A + (size_t)i * n;
+            const int c0 = upper ? i : 0, c1 = upper ? n : i + 1;
+            int c = c0 + lane;
+            for (; c + 96 < c1; c += 128) {
+                acc0 += nan_to_zero(row[c]);
+                acc1 += nan_to_zero(row[c + 32]);
+                acc2 += nan_to_zero(row[c + 64]);
+                acc3 += nan_to_zero(row[c + 96]);
+            }
+            for (; c < c1; c += 32) acc0 += nan_to_zero(row[c]);
+        }
+        double acc = warp_sum((acc0 + acc1) + (acc2 + acc3));
+        if (lane == 0) s_h[rr] = acc;
+    }
+    // vertical strip: thread (g, cc) walks rows g, g+G, ... of column i0+cc
+    {
+        const int G = FT_THREADS / R;
+        const int cc = tid % R, g = tid / R;
+        const int i = i0 + cc;
+        double acc0 = 0.0, acc1 = 0.0;
+        if (i < n) {
+            const int r0 = upper ? 0 : i + 1, r1 = upper ? i : n;
+            // start every column of the strip at the same row so that warps stay coalesced
+            const int rs = upper ? 0 : i0 + 1;
+            int r = rs + g;
+            for (; r + G < r1; r += 2 * G) {
+                double a = (r >= r0) ? nan_to_zero(A[(size_t)r * n + i]) : 0.0;
+                double b = (r + G >= r0) ? nan_to_zero(A[(size_t)(r + G) * n + i]) : 0.0;
+                acc0 += a; acc1 += b;
+            }
+            for (; r < r1; r += G) if (r >= r0) acc0 += nan_to_zero(A[(size_t)r * n + i]);
+        }
+        s_v[g][cc] = acc0 + acc1;
+    }
+    __syncthreads();
+    if (tid < R) {
+        const int i = i0 + tid;
+        if (i < n) {
+            double v = 0.0;
+            for (int g = 0; g < FT_THREADS / R; g++) v += s_v[g][tid];
+            rowmean[i] = (s_h[tid] + v) / (double)n;
+            diag0[i] = nan_to_zero(A[(size_t)i * n + i]) == 0.0;
+        }
+    }
+}
+
+// rank by counting: rank[i] = #{j : v_j < v_i} + #{j < i : v_j == v_i}; the two order statistics the
+// type-7 quantile needs are the values whose rank is lo-1 and hi-1.
+__global__ void __launch_bounds__(256)
+order_stat_kernel(const double *__restrict__ v, int n, int rank_lo, int rank_hi, double *__restrict__ out2) {
+    __shared__ double tile[256];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const double vi = (i < n) ? v[i] : 0.0;
+    int rank = 0;
+    for (int j0 = 0; j0 < n; j0 += 256) {
+        const int j = j0 + threadIdx.x;
+        tile[threadIdx.x] = (j < n) ? v[j] : 0.0;
+        __syncthreads();
+        const int m = min(256, n - j0);
+        for (int t = 0; t < m; t++) {
+            const double vj = tile[t];
+            rank += (vj < vi) || (vj == vi && (j0 + t) < i);
+        }
+        __syncthreads();
+    }
+    if (i < n) {
+        if (rank == rank_lo) out2[0] = vi;
+        if (rank == rank_hi) out2[1] = vi;
+    }
+}
+
+// stats::quantile type 7 on the two order statistics, then the flags (R/TADpole.R:36-37)
+__global__ void flags_kernel(const double *__restrict__ rowmean, const unsigned char *__restrict__ diag0, int n,
+                             int use_q, double index, int lo, const double *__restrict__ xs,
+                             unsigned char *__restrict__ bad, double *__restrict__ thr_out) {
+    double q = __longlong_as_double(0x7ff8000000000000LL);
+    if (use_q) {
+        q = xs[0];
+        const double xhi = xs[1];
+        if (index > (double)lo && xhi != q) {
+            const double h = index - (double)lo;
+            q = (1.0 - h) * q + h * xhi;
+        }
+    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *thr_out = q;
+    if (i < n) bad[i] = diag0[i] | (use_q ? (rowmean[i] < q) : 0);
+}
+
+// mat[keep, keep] with NA -> 0 and the lower triangle mirrored from the upper one.
+// 32 x 32 tiles of the output's upper triangle; each tile is read once from the valid triangle of
+// A and written twice (as is, and transposed through shared memory).
+__global__ void __launch_bounds__(256)
+compact_kernel(const double *__restrict__ A, int n, int upper, const int *__restrict__ keep, int nf,
+               double *__restrict__ X, int ldx) {
+    __shared__ double tile[32][33];
+    const int ta = blockIdx.y, tb = blockIdx.x;
+    if (tb < ta) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int a0 = ta * 32, b0 = tb * 32;
+    // tile[y][x] = S(keep[a0+y], keep[b0+x]); choose the thread mapping so that the fast thread index
+    // runs along the contiguous direction of A
+    for (int s = ty; s < 32; s += 8) {
+        int ya, xb;
+        if (upper) { ya = s; xb = tx; } else { ya = tx; xb = s; }
+        const int a = a0 + ya, b = b0 + xb;
+        double v = 0.0;
+        if (a < nf && b < nf) {
+            int ia = keep[a], ib = keep[b];
+            int lo = min(ia, ib), hi = max(ia, ib);
+            // U(lo, hi): upper -> A[lo][hi], lower -> A[hi][lo]
+            v = upper ? A[(size_t)lo * n + hi] : A[(size_t)hi * n + lo];
+            v = nan_to_zero(v);
+        }
+        tile[ya][xb] = v;
+    }
+    __syncthreads();
+    for (int s = ty; s < 32; s += 8) {
+        const int a = a0 + s, b = b0 + tx;
+        if (a < nf && b < nf) X[(size_t)a * ldx + b] = tile[s][tx];
+        if (ta != tb) {
+            const int bb = b0 + s, aa = a0 + tx;
+            if (bb < nf && aa < nf) X[(size_t)bb * ldx + aa] = tile[tx][s];
+        }
+    }
+}
+
+// zero the padding columns [nf, ldx) of an nf x ldx matrix
+__global__ void zero_pad_kernel(double *__restrict__ X, int nf, int ldx) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nf) for (int c = nf; c < ldx; c++) X[(size_t)r * ldx + c] = 0.0;
+}
+
+template <int R>
+static void launch_rowmean(tp_ctx *ctx, const double *A, int n, int upper, double *rm, unsigned char *d0) {
+    rowmean_kernel<R><<<(n + R - 1) / R, FT_THREADS, 0, ctx->stream>>>(A, n, upper, rm, d0);
+}
+
+int tp_filter(tp_ctx *ctx, const double *mat, int n, int colmajor, int on_device, double bad_frac,
+              uint8_t *bad_out, double *rowmeans_out, double *thr_out) {
+    TP_ARG(ctx && mat && bad_out, "tp_filter: null argument");
+    TP_ARG(n >= 2, "tp_filter: matrix must be at least 2 x 2");
+    TP_ARG(bad_frac >= 0.0 && bad_frac <= 1.0, "tp_filter: bad_frac must be in [0, 1]");
+    TP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t bytes = (size_t)n * n * sizeof(double);
+    if (on_device) {
+        ctx->raw = mat;
+    } else {
+        TP_TRY(ctx->raw_own.reserve(bytes));
+        TP_CUDA(cudaMemcpyAsync(ctx->raw_own.p, mat, bytes, cudaMemcpyHostToDevice, st));
+        ctx->raw = ctx->raw_own.as<double>();
+    }
+    ctx->n = n;
+    ctx->colmajor = colmajor ? 1 : 0;
+    ctx->have_X = ctx->have_C = ctx->have_scores = ctx->have_sweep = false;
+    const int upper = colmajor ? 0 : 1;
+    TP_TRY(ctx->rowmean.reserve((size_t)n * sizeof(double)));
+    TP_TRY(ctx->flags.reserve((size_t)2 * n));
+    TP_TRY(ctx->qtmp.reserve(4 * sizeof(double)));
+    double *rm = ctx->rowmean.as<double>();
+    unsigned char *diag0 = ctx->flags.as<unsigned char>();
+    unsigned char *bad = diag0 + n;
+    double *xs = ctx->qtmp.as<double>();
+
+    TP_MARK(ctx, EV_FILTER0);
+    // rows per CTA: keep the grid at >= ~2 waves of 148 SMs when the matrix allows it
+    const int want = 2 * ctx->sm_count;
+    tp_prof_begin(ctx, PC_ROWMEAN);
+    if (n / 64 >= want) launch_rowmean<64>(ctx, ctx->raw, n, upper, rm, diag0);
+    else if (n / 32 >= want) launch_rowmean<32>(ctx, ctx->raw, n, upper, rm, diag0);
+    else if (n / 16 >= want) launch_rowmean<16>(ctx, ctx->raw, n, upper, rm, diag0);
+    else launch_rowmean<8>(ctx, ctx->raw, n, upper, rm, diag0);
+    tp_prof_end(ctx);
+    ctx->launches += 1;
+    int use_q = bad_frac != 0.0;
+    double index = 1.0;
+    int lo = 1, hi = 1;
+    if (use_q) {
+        index = 1.0 + (double)(n - 1) * bad_frac;      // R: 1 + max(n - 1, 0) * probs
+        lo = (int)floor(index);
+        hi = (int)ceil(index);
+        order_stat_kernel<<<(n + 255) / 256, 256, 0, st>>>(rm, n, lo - 1, hi - 1, xs);
+        ctx->launches += 1;
+    }
+    flags_kernel<<<(n + 255) / 256, 256, 0, st>>>(rm, diag0, n, use_q, index, lo, xs, bad, xs + 2);
+    ctx->launches += 1;
+    TP_CUDA(cudaGetLastError());
+    TP_MARK(ctx, EV_FILTER1);
+    TP_CUDA(cudaMemcpyAsync(bad_out, bad, n, cudaMemcpyDeviceToHost, st));
+    if (rowmeans_out) TP_CUDA(cudaMemcpyAsync(rowmeans_out, rm, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (thr_out) TP_CUDA(cudaMemcpyAsync(thr_out, xs + 2, sizeof(double), cudaMemcpyDeviceToHost, st));
+    TP_CUDA(cudaStreamSynchronize(st));
+    return TP_OK;
+}
+
+int tp_compact(tp_ctx *ctx, const int *keep, int nf) {
+    TP_ARG(ctx && keep, "tp_compact: null argument");
+    TP_ARG(ctx->raw && ctx->n > 0, "tp_compact: call tp_filter first");
+    TP_ARG(nf >= 2 && nf <= ctx->n, "tp_compact: bad keep count");
+    for (int i = 0; i < nf; i++)
+        TP_ARG(keep[i] >= 0 && keep[i] < ctx->n, "tp_compact: keep index out of range");
+    TP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int ldx = round_up(nf, 8);
+    TP_TRY(ctx->keep.reserve((size_t)nf * sizeof(int)));
+    TP_TRY(ctx->X.reserve((size_t)nf * ldx * sizeof(double)));
+    TP_CUDA(cudaMemcpyAsync(ctx->keep.p, keep, (size_t)nf * sizeof(int), cudaMemcpyHostToDevice, st));
+    TP_MARK(ctx, EV_COMPACT0);
+    const int nt = (nf + 31) / 32;
+    tp_prof_begin(ctx, PC_COMPACT);
+    compact_kernel<<<dim3(nt, nt), 256, 0, st>>>(ctx->raw, ctx->n, ctx->colmajor ? 0 : 1, ctx->keep.as<int>(), nf,
+                                                 ctx->X.as<double>(), ldx);
+    tp_prof_end(ctx);
+    if (ldx > nf) zero_pad_kernel<<<(nf + 127) / 128, 128, 0, st>>>(ctx->X.as<double>(), nf, ldx);
+    ctx->launches += (ldx > nf) ? 2 : 1;
+    TP_CUDA(cudaGetLastError());
+    TP_MARK(ctx, EV_COMPACT1);
+    ctx->nf = nf;
+    ctx->ldx = ldx;
+    ctx->have_X = true;
+    ctx->have_C = ctx->have_scores = ctx->have_sweep = false;
+    return TP_OK;
+}

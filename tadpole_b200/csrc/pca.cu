@@ -1,0 +1,388 @@
+// pca.cu -- stage 2 (sparse_cor, reference R/TADpole.R:94-100 + NaN->0 :363,449) and
+//           stage 3 (prcomp(cor, rank.=k)$x, R/TADpole.R:366-367,452-453).
+//
+// Stage 2: colMeans and diag(cov) come from one row pass over the (symmetric) filtered matrix; the
+// Gram matrix X^T X = X X^T runs on the FP64 tensor path (gemm.cu) and the covariance ->
+// correlation -> NaN->0 arithmetic is the GEMM epilogue, in the reference's order of operations.
+//
+// Stage 3: prcomp centres the columns of C and takes the SVD; the scores are x = Xc V = U S.  U and
+// S^2 are the eigenpairs of M = Xc Xc^T (n x n, PSD), so the first k score columns are
+// u_j sqrt(lambda_j).  Small problems (n <= jacobi_direct_max) are solved directly by the cluster
+// Jacobi solver.  Larger ones use Chebyshev-filtered subspace iteration on a block of b > k vectors:
+// the filter is a three-term recurrence of GEMMs with M (fused alpha/beta/gamma epilogue),
+// orthonormalisation and Rayleigh-Ritz are done together as a generalised b x b problem
+// (G = Y^T Y, T = Y^T M Y) solved with two Jacobi eigen-decompositions, and convergence is tested
+// on residuals ||M y - theta y|| computed from a fresh product.  Signs of the components are
+// arbitrary, as they are in LAPACK; every consumer downstream is sign-invariant.
+#include "common.cuh"
+#include "gemm.cuh"
+
+int tp_jacobi(tp_ctx *ctx, double *A, int b, int ld, double *w, double *Vs, int lds, int ncols_out, int *sweeps_out);
+
+// ---- small kernels -------------------------------------------------------------------------------
+// per row: mean and sd of the one-pass formula (columns == rows: the matrix is symmetric)
+__global__ void rowstats_kernel(const double *__restrict__ X, int n, int ld, double *__restrict__ mean,
+                                double *__restrict__ sd) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const double *row = X + (size_t)w * ld;
+    double s = 0.0, q = 0.0;
+    for (int c = lane; c < n; c += 32) { const double v = row[c]; s += v; q += v * v; }
+    s = warp_sum(s); q = warp_sum(q);
+    if (lane == 0) {
+        const double dn = (double)n;
+        const double m = s / dn;
+        mean[w] = m;
+        // diag(covmat) = (crossprod_ii - nrow * m_i * m_i) / (nrow - 1)
+        sd[w] = sqrt((q - dn * (m * m)) / (dn - 1.0));
+    }
+}
+
+// column means of an n x n matrix: 32 columns per CTA, 8 row groups, fixed summation order
+__global__ void __launch_bounds__(256)
+colmean_kernel(const double *__restrict__ C, int n, int ld, double *__restrict__ mu) {
+    __shared__ double s[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    double a0 = 0.0, a1 = 0.0;
+    if (c < n) {
+        int r = ty;
+        for (; r + 8 < n; r += 16) { a0 += C[(size_t)r * ld + c]; a1 += C[(size_t)(r + 8) * ld + c]; }
+        for (; r < n; r += 8) a0 += C[(size_t)r * ld + c];
+    }
+    s[ty][tx] = a0 + a1;
+    __syncthreads();
+    if (ty == 0 && c < n) {
+        double v = 0.0;
+        for (int g = 0; g < 8; g++) v += s[g][tx];
+        mu[c] = v / (double)n;
+    }
+}
+
+__global__ void center_cols_kernel(double *__restrict__ C, int n, int ld, const double *__restrict__ mu) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = (int)(idx / ld), c = (int)(idx % ld);
+    if (r < n) C[idx] = (c < n) ? C[idx] - mu[c] : 0.0;
+}
+
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9e3779b97f4a7c15ULL;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebULL;
+    return x ^ (x >> 31);
+}
+// deterministic start block: uniform(-1, 1)
+__global__ void random_block_kernel(double *__restrict__ Y, int n, int b, int ld) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = (int)(idx / ld), c = (int)(idx % ld);
+    if (r >= n) return;
+    double v = 0.0;
+    if (c < b) {
+        unsigned long long h = splitmix64(((unsigned long long)r << 20) ^ (unsigned long long)c ^ 0x5851f42d4c957f2dULL);
+        v = (double)(h >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
+    }
+    Y[idx] = v;
+}
+
+// Gs = D G D, Ts = D (T + T^T)/2 D with D = diag(G)^-1/2 (0 where the diagonal is not positive)
+__global__ void scale_gram_kernel(const double *__restrict__ G, const double *__restrict__ T, int b, int ld,
+                                  double *__restrict__ Gs, double *__restrict__ Ts, double *__restrict__ dvec) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= b * b) return;
+    const int i = idx / b, j = idx % b;
+    const double gi = G[(size_t)i * ld + i], gj = G[(size_t)j * ld + j];
+    const double di = gi > 0.0 ? 1.0 / sqrt(gi) : 0.0, dj = gj > 0.0 ? 1.0 / sqrt(gj) : 0.0;
+    Gs[(size_t)i * ld + j] = 0.5 * (G[(size_t)i * ld + j] + G[(size_t)j * ld + i]) * di * dj;
+    Ts[(size_t)i * ld + j] = 0.5 * (T[(size_t)i * ld + j] + T[(size_t)j * ld + i]) * di * dj;
+    if (j == 0) dvec[i] = di;
+}
+
+// X = S diag(g^-1/2), directions with g_i <= eps * g_0 dropped (zero column)
+__global__ void whiten_kernel(const double *__restrict__ S, const double *__restrict__ g, int b, int ld,
+                              double *__restrict__ X) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= b * b) return;
+    const int i = idx / b, j = idx % b;
+    const double gj = g[j];
+    const double sc = (gj > 1e-14 * g[0] && gj > 0.0) ? 1.0 / sqrt(gj) : 0.0;
+    X[(size_t)i * ld + j] = S[(size_t)i * ld + j] * sc;
+}
+
+__global__ void symmetrize_kernel(double *__restrict__ A, int b, int ld) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= b * b) return;
+    const int i = idx / b, j = idx % b;
+    if (i < j) {
+        const double v = 0.5 * (A[(size_t)i * ld + j] + A[(size_t)j * ld + i]);
+        A[(size_t)i * ld + j] = v;
+        A[(size_t)j * ld + i] = v;
+    }
+}
+
+__global__ void scale_rows_kernel(double *__restrict__ Q, int b, int ld, const double *__restrict__ d) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= b * b) return;
+    const int i = idx / b, j = idx % b;
+    Q[(size_t)i * ld + j] *= d[i];
+}
+
+// residual_j = || MY_j - theta_j Y_j ||_2 where MY = (e / sigma1) Y1 + c Y0 (first filter step)
+__global__ void __launch_bounds__(256)
+residual_kernel(const double *__restrict__ Y0, const double *__restrict__ Y1, int n, int ld, int k,
+                const double *__restrict__ theta, double e_over_sig, double c, double *__restrict__ res) {
+    __shared__ double s[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + tx;
+    double a = 0.0;
+    if (j < k) {
+        const double th = theta[j];
+        for (int r = ty; r < n; r += 8) {
+            const double y0 = Y0[(size_t)r * ld + j];
+            const double v = e_over_sig * Y1[(size_t)r * ld + j] + (c - th) * y0;
+            a += v * v;
+        }
+    }
+    s[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && j < k) {
+        double v = 0.0;
+        for (int g = 0; g < 8; g++) v += s[g][tx];
+        res[j] = sqrt(v);
+    }
+}
+
+// scores[:, j] = U[:, j] * sqrt(max(w_j, 0)), j < k; padding columns zero
+__global__ void scores_kernel(const double *__restrict__ U, int ldu, const double *__restrict__ w, int n, int k,
+                              double *__restrict__ S, int lds) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = (int)(idx / lds), c = (int)(idx % lds);
+    if (r >= n) return;
+    S[idx] = (c < k) ? U[(size_t)r * ldu + c] * sqrt(fmax(w[c], 0.0)) : 0.0;
+}
+
+// ---- stage 2 -------------------------------------------------------------------------------------
+int tp_correlation(tp_ctx *ctx) {
+    TP_ARG(ctx && ctx->have_X, "tp_correlation: no filtered matrix in the context");
+    TP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int n = ctx->nf, ld = ctx->ldx;
+    TP_TRY(ctx->C.reserve((size_t)n * ld * sizeof(double)));
+    TP_TRY(ctx->colstat.reserve((size_t)3 * n * sizeof(double)));
+    double *mean = ctx->colstat.as<double>(), *sd = mean + n;
+    TP_MARK(ctx, EV_CORR0);
+    rowstats_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(ctx->X.as<double>(), n, ld, mean, sd);
+    ctx->launches += 1;
+    GemmArgs g;
+    g.A = ctx->X.as<double>(); g.lda = ld; g.a_kc = 1;
+    g.B = ctx->X.as<double>(); g.ldb = ld; g.b_kc = 1;     // B = X^T: (k, n) at X[n*ld + k]
+    g.D = ctx->C.as<double>(); g.ldd = ld;
+    g.M = n; g.N = n; g.K = n;
+    g.sym = 1; g.epi = EPI_CORR; g.mean = mean; g.sd = sd; g.nrows = (double)n;
+    TP_TRY(tp_gemm(ctx, g));
+    TP_MARK(ctx, EV_CORR1);
+    ctx->have_C = true;
+    ctx->have_scores = ctx->have_sweep = false;
+    return TP_OK;
+}
+
+// ---- stage 3 -------------------------------------------------------------------------------------
+struct PcaOp {
+    tp_ctx *ctx;
+    int n, ld;            // Xc is n x n (ld)
+    const double *Xc;
+    const double *M;      // explicit M (n x ld) or nullptr
+    double *Z;            // scratch n x ldb for the two-GEMM form
+    int b, ldb;
+    long applications = 0;
+    // Yout = alpha * M * Yin + beta * E1 + gamma * E2
+    int apply(const double *Yin, double *Yout, double alpha, const double *E1, double beta, const double *E2,
+              double gamma) {
+        GemmArgs g;
+        g.M = n; g.N = b; g.D = Yout; g.ldd = ldb; g.alpha = alpha;
+        g.E1 = E1; g.lde1 = ldb; g.beta = beta; g.E2 = E2; g.lde2 = ldb; g.gamma = gamma;
+        applications++;
+        if (M) {
+            g.A = M; g.lda = ld; g.a_kc = 1; g.B = Yin; g.ldb = ldb; g.b_kc = 0; g.K = n;
+            return tp_gemm(ctx, g);
+        }
+        GemmArgs z;   // Z = Xc^T Yin
+        z.A = Xc; z.lda = ld; z.a_kc = 0; z.B = Yin; z.ldb = ldb; z.b_kc = 0;
+        z.D = Z; z.ldd = ldb; z.M = n; z.N = b; z.K = n;
+        TP_TRY(tp_gemm(ctx, z));
+        g.A = Xc; g.lda = ld; g.a_kc = 1; g.B = Z; g.ldb = ldb; g.b_kc = 0; g.K = n;
+        return tp_gemm(ctx, g);
+    }
+};
+
+static int small_gemm(tp_ctx *ctx, const double *A, int a_kc, const double *B, int b_kc, double *D, int b, int ld) {
+    GemmArgs g;
+    g.A = A; g.lda = ld; g.a_kc = a_kc; g.B = B; g.ldb = ld; g.b_kc = b_kc;
+    g.D = D; g.ldd = ld; g.M = b; g.N = b; g.K = b;
+    return tp_gemm(ctx, g);
+}
+
+int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
+    TP_ARG(ctx && ctx->have_C, "tp_pca: no correlation matrix in the context");
+    TP_ARG(max_pcs >= 1, "tp_pca: max_pcs must be >= 1");
+    TP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int n = ctx->nf, ld = ctx->ldx;
+    const int k = max_pcs < n ? max_pcs : n;       // number_pca <- min(max_pcs, nrow(mat))
+    const int ldk = round_up(k, 8);
+    if (k_out) *k_out = k;
+    TP_MARK(ctx, EV_PCA0);
+    TP_TRY(ctx->scores.reserve((size_t)n * ldk * sizeof(double)));
+    TP_TRY(ctx->colstat.reserve((size_t)3 * n * sizeof(double)));
+    double *mu = ctx->colstat.as<double>() + 2 * n;
+    double *C = ctx->C.as<double>();
+    colmean_kernel<<<(n + 31) / 32, 256, 0, st>>>(C, n, ld, mu);
+    center_cols_kernel<<<(unsigned)(((size_t)n * ld + 255) / 256), 256, 0, st>>>(C, n, ld, mu);
+    ctx->launches += 2;
+    ctx->have_C = false;                               // C now holds Xc
+    ctx->timing[7] = ctx->timing[8] = ctx->timing[9] = 0.0;
+
+    int b = ctx->pca_block > 0 ? ctx->pca_block : round_up(k + (k / 4 > 32 ? k / 4 : 32), 32);
+    const bool direct = n <= ctx->jacobi_direct_max || b >= n;
+    const bool explicitM = direct || n <= 12288;
+    double *M = nullptr;
+    if (explicitM) {
+        TP_TRY(ctx->M.reserve((size_t)n * ld * sizeof(double)));
+        M = ctx->M.as<double>();
+        GemmArgs g;
+        g.A = C; g.lda = ld; g.a_kc = 1; g.B = C; g.ldb = ld; g.b_kc = 1;
+        g.D = M; g.ldd = ld; g.M = n; g.N = n; g.K = n; g.sym = 1;
+        TP_TRY(tp_gemm(ctx, g));
+    }
+    if (direct) {
+        TP_ARG(n <= 1024, "tp_pca: direct eigensolver limited to 1024 bins; lower pca_block");
+        TP_TRY(ctx->W.reserve((size_t)n * ld * sizeof(double)));
+        TP_TRY(ctx->Jw.reserve((size_t)n * sizeof(double)));
+        int sweeps = 0;
+        TP_TRY(tp_jacobi(ctx, M, n, ld, ctx->Jw.as<double>(), ctx->W.as<double>(), ld, n, &sweeps));
+        ctx->timing[9] = sweeps;
+        scores_kernel<<<(unsigned)(((size_t)n * ldk + 255) / 256), 256, 0, st>>>(ctx->W.as<double>(), ld,
+                                                                               ctx->Jw.as<double>(), n, k,
+                                                                               ctx->scores.as<double>(), ldk);
+        ctx->launches += 1;
+    } else {
+        const int ldb = round_up(b, 8);
+        const size_t blk = (size_t)n * ldb * sizeof(double);
+        const size_t sm = (size_t)b * ldb * sizeof(double);
+        TP_TRY(ctx->Y0.reserve(blk)); TP_TRY(ctx->Y1.reserve(blk)); TP_TRY(ctx->Y2.reserve(blk));
+        TP_TRY(ctx->W.reserve(blk));
+        TP_TRY(ctx->G.reserve(sm)); TP_TRY(ctx->T.reserve(sm)); TP_TRY(ctx->Q.reserve(sm));
+        TP_TRY(ctx->small1.reserve(sm)); TP_TRY(ctx->small2.reserve(sm)); TP_TRY(ctx->Jv.reserve(sm));
+        TP_TRY(ctx->Jw.reserve((size_t)4 * b * sizeof(double)));
+        TP_TRY(ctx->resid.reserve((size_t)(k + b) * sizeof(double)));
+        TP_TRY(tp_pin_reserve(ctx, (size_t)(k + b + 8) * sizeof(double)));
+        double *Ya = ctx->Y0.as<double>(), *Yb = ctx->Y1.as<double>(), *Yc = ctx->Y2.as<double>();
+        double *W = ctx->W.as<double>();
+        double *G = ctx->G.as<double>(), *T = ctx->T.as<double>(), *Q = ctx->Q.as<double>();
+        double *S1 = ctx->small1.as<double>(), *S2 = ctx->small2.as<double>(), *JV = ctx->Jv.as<double>();
+        double *gval = ctx->Jw.as<double>(), *theta = gval + b, *dvec = theta + b;
+        double *res = ctx->resid.as<double>();
+        double *hbuf = (double *)ctx->pin;
+        PcaOp op{ctx, n, ld, C, M, nullptr, b, ldb};
+        DevBuf zbuf;   // scratch for the two-GEMM operator
+        if (!M) { TP_TRY(zbuf.reserve(blk)); op.Z = zbuf.as<double>(); }
+
+        const unsigned gb = (unsigned)((b * b + 255) / 256);
+        const int splitk = n >= 4096 ? 32 : (n >= 1024 ? 8 : 1);
+        random_block_kernel<<<(unsigned)(((size_t)n * ldb + 255) / 256), 256, 0, st>>>(Ya, n, b, ldb);
+        ctx->launches += 1;
+        double *Y = Ya, *F1 = Yb, *F2 = Yc;      // Y: current block; F1/F2: filter scratch
+        TP_TRY(op.apply(Y, W, 1.0, nullptr, 0.0, nullptr, 0.0));
+        int it = 0, sweeps_total = 0, rc = TP_OK;
+        bool converged = false;
+        double last_res = 0.0;
+        for (; it < ctx->pca_maxit * 4; it++) {
+            // ---- orthonormalise + Rayleigh-Ritz as one generalised problem ----------------------
+            GemmArgs gg;
+            gg.A = Y; gg.lda = ldb; gg.a_kc = 0; gg.B = Y; gg.ldb = ldb; gg.b_kc = 0;
+            gg.D = G; gg.ldd = ldb; gg.M = b; gg.N = b; gg.K = n; gg.splitk = splitk;
+            if ((rc = tp_gemm(ctx, gg)) != TP_OK) break;
+            gg.B = W; gg.D = T;
+            if ((rc = tp_gemm(ctx, gg)) != TP_OK) break;
+            scale_gram_kernel<<<gb, 256, 0, st>>>(G, T, b, ldb, S1, S2, dvec);       // S1 = Gs, S2 = Ts
+            ctx->launches += 1;
+            int sw = 0;
+            if ((rc = tp_jacobi(ctx, S1, b, ldb, gval, JV, ldb, b, &sw)) != TP_OK) break;   // Gs = JV diag(gval) JV^T
+            sweeps_total += sw;
+            whiten_kernel<<<gb, 256, 0, st>>>(JV, gval, b, ldb, S1);                 // S1 = X
+            ctx->launches += 1;
+            if ((rc = small_gemm(ctx, S2, 1, S1, 0, G, b, ldb)) != TP_OK) break;     // G  = Ts X
+            if ((rc = small_gemm(ctx, S1, 0, G, 0, T, b, ldb)) != TP_OK) break;      // T  = X^T Ts X
+            symmetrize_kernel<<<gb, 256, 0, st>>>(T, b, ldb);
+            ctx->launches += 1;
+            if ((rc = tp_jacobi(ctx, T, b, ldb, theta, JV, ldb, b, &sw)) != TP_OK) break;   // T = JV diag(theta) JV^T
+            sweeps_total += sw;
+            if ((rc = small_gemm(ctx, S1, 1, JV, 0, Q, b, ldb)) != TP_OK) break;     // Q = X Z
+            scale_rows_kernel<<<gb, 256, 0, st>>>(Q, b, ldb, dvec);                  // Q = D X Z
+            ctx->launches += 1;
+            {   // Y <- Y Q  (into F1), then F1 becomes the current block
+                GemmArgs r;
+                r.A = Y; r.lda = ldb; r.a_kc = 1; r.B = Q; r.ldb = ldb; r.b_kc = 0;
+                r.D = F1; r.ldd = ldb; r.M = n; r.N = b; r.K = b;
+                if ((rc = tp_gemm(ctx, r)) != TP_OK) break;
+                double *t = Y; Y = F1; F1 = t;
+            }
+            // ---- first filter step doubles as the residual check ---------------------------------
+            if ((rc = (cudaMemcpyAsync(hbuf, theta, (size_t)b * sizeof(double), cudaMemcpyDeviceToHost, st) == cudaSuccess
+                           ? TP_OK : TP_ERR_CUDA)) != TP_OK) break;
+            if (cudaStreamSynchronize(st) != cudaSuccess) { rc = TP_ERR_CUDA; break; }
+            const double top = hbuf[0], thk = hbuf[k - 1];
+            double cut = hbuf[b - 1];
+            if (!(cut > 0.0)) { for (int j = b - 1; j >= k; j--) if (hbuf[j] > 0.0) { cut = hbuf[j]; break; } }
+            if (!(cut > 0.0) || !(thk > cut)) cut = 0.5 * thk > 0.0 ? 0.5 * thk : 1e-300;
+            const double e = 0.5 * cut, c = 0.5 * cut;
+            const double sig1 = e / (top - c);
+            // Y1 = (sig1 / e) (M Y - c Y)
+            if ((rc = op.apply(Y, F1, sig1 / e, Y, -sig1 * c / e, nullptr, 0.0)) != TP_OK) break;
+            residual_kernel<<<(k + 31) / 32, 256, 0, st>>>(Y, F1, n, ldb, k, theta, e / sig1, c, res);
+            ctx->launches += 1;
+            cudaMemcpyAsync(hbuf, res, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, st);
+            if (cudaStreamSynchronize(st) != cudaSuccess) { rc = TP_ERR_CUDA; break; }
+            double rmax = 0.0;
+            for (int j = 0; j < k; j++) rmax = hbuf[j] > rmax || hbuf[j] != hbuf[j] ? hbuf[j] : rmax;
+            last_res = rmax / top;
+            if (rmax <= ctx->pca_tol * top) { converged = true; it++; break; }
+            // ---- remaining filter steps: degree bounded by the conditioning of the filtered block
+            const double xk = (thk - c) / e, x1 = (top - c) / e;
+            int deg = 1;
+            for (int mdeg = 2; mdeg <= 24; mdeg++) {
+                const double ratio = cosh(mdeg * acosh(x1)) / cosh(mdeg * acosh(xk));
+                if (ratio <= 1e5) deg = mdeg; else break;
+            }
+            double sig = sig1;
+            double *P0 = Y, *P1 = F1, *P2 = F2;
+            for (int j = 2; j <= deg; j++) {
+                const double sig2 = 1.0 / (2.0 / sig1 - sig);
+                // P2 = 2 (sig2/e) (M P1 - c P1) - sig sig2 P0
+                if ((rc = op.apply(P1, P2, 2.0 * sig2 / e, P1, -2.0 * sig2 * c / e, P0, -sig * sig2)) != TP_OK) break;
+                double *t = P0; P0 = P1; P1 = P2; P2 = t;
+                sig = sig2;
+            }
+            if (rc != TP_OK) break;
+            Y = P1; F1 = P0; F2 = P2;
+            if ((rc = op.apply(Y, W, 1.0, nullptr, 0.0, nullptr, 0.0)) != TP_OK) break;
+        }
+        zbuf.release();
+        TP_TRY(rc);
+        ctx->timing[7] = it;
+        ctx->timing[8] = (double)op.applications;
+        ctx->timing[9] = sweeps_total;
+        if (!converged) {
+            tp_set_error("tp_pca: subspace iteration stopped at relative residual %.3e after %d iterations", last_res, it);
+            return TP_ERR_NOCONV;
+        }
+        scores_kernel<<<(unsigned)(((size_t)n * ldk + 255) / 256), 256, 0, st>>>(Y, ldb, theta, n, k,
+                                                                               ctx->scores.as<double>(), ldk);
+        ctx->launches += 1;
+    }
+    TP_CUDA(cudaGetLastError());
+    TP_MARK(ctx, EV_PCA1);
+    ctx->k = k; ctx->ldk = ldk;
+    ctx->have_scores = true;
+    ctx->have_sweep = false;
+    return TP_OK;
+}
