@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- TADpole calls/sec on synthetic Hi-C matrices (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference
+
+A "step" is one full TADpole() call on one synthetic matrix: bad-column filter, Pearson
+correlation, PCA to max_pcs = 200 components, the n_pcs sweep (CONISS per candidate), broken
+stick + Calinski-Harabasz, selection.  Workload at N = 1: BASELINE.json configs[1], a 2,000-bin
+matrix with nested block TADs and power-law decay.  With N > 1 every rank calls its own
+matrices (multi-chromosome batch, no data-path collective): weak scaling.
+
+value  : calls/s with the input matrices already resident in HBM (device pointers through the
+         C ABI), timed with CUDA events on the library's stream, max over ranks.
+e2e    : the same through the public API TADpole(matrix) with the matrix in pinned HOST memory;
+         H2D copy of the matrix and D2H of the results are inside the timed region.
+A pool of different matrices larger than L2 (5 x 32 MB) is cycled, so no step re-reads a warm input.
+
+The reference is a pure-R package and R is not installed here or on the GPU box, so
+`--impl reference` and `cpu_baseline` time oracle/ (numpy + C restatement in the reference's
+algorithmic shape: full LAPACK SVD, per-candidate O(N^2) dist + Lance-Williams CONISS, per-level
+Calinski-Harabasz) on the host cores, on a bounded sample of candidates extrapolated to all 200.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_BINS = 2000
+MAX_PCS = 200
+POOL = 5
+METRIC = "tadpole_calls_per_sec"
+UNIT = "calls/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--bins", type=int, default=N_BINS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="candidates timed per CPU sample")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle, timed (the only place besides tests/ and smoke() that touches oracle/)
+# ---------------------------------------------------------------------------------------------
+def cpu_sample(mat, ncand_sample, threads):
+    """One bounded sample of the reference-shaped CPU path.  Returns (estimated seconds for the
+    full call, detail dict)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import tadpole_oracle as O
+    t0 = time.perf_counter()
+    lm = O.load_mat_numeric(mat)
+    cor = O.sparse_cor(lm.mat)
+    k = min(MAX_PCS, lm.mat.shape[0])
+    pcs = O.prcomp_scores(cor, k)
+    t_front = time.perf_counter() - t0
+    cands = np.unique(np.linspace(1, k, ncand_sample).round().astype(int))
+    t1 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:      # foreach %dopar% over candidates
+        list(ex.map(lambda i: O.candidate_scores(pcs, int(i), 2), cands))
+    t_sweep = time.perf_counter() - t1
+    est = t_front + t_sweep * (k / len(cands))
+    return est, dict(front_s=round(t_front, 3), sweep_sample_s=round(t_sweep, 3), candidates=len(cands), k=int(k))
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from tadpole_b200.synth import synth_hic
+    threads = os.cpu_count() or 1
+    mats = [synth_hic(args.bins, seed=1 + s) for s in range(min(POOL, max(1, args.steps)))]
+    for w in range(min(args.warmup, 1)):
+        cpu_sample(mats[0], 2, threads)
+    ests, detail = [], None
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        est, detail = cpu_sample(mats[s % len(mats)], args.cpu_sample, threads)
+        ests.append(est)
+    wall = time.perf_counter() - t0
+    sec = float(np.mean(ests))
+    val = 1.0 / sec
+    sample = (f"per step: filter+correlation+full SVD timed in full, {detail['candidates']} of {detail['k']} candidates "
+              f"(dist + Lance-Williams CONISS + broken stick + per-level CH) on {threads} threads, sweep time "
+              f"scaled by k/candidates; wall for {args.steps} sampled steps {wall:.1f} s")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic {args.bins}-bin Hi-C matrix, nested block TADs, power-law decay, max_pcs=200 "
+                               "(BASELINE.json configs[1])", "bins": args.bins, "max_pcs": MAX_PCS,
+                   "note": "reference is pure R and R is not installed: CPU restatement (oracle/) in the "
+                           "reference's algorithmic shape, runs on rank 0 only"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(device), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def measure_fp64_peak(torch):
+    """cuBLAS DGEMM TFLOP/s on this box (library GEMM used only as the roofline denominator)."""
+    a = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
+    b = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
+    best = 0.0
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+        best = max(best, 2 * 4096 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from tadpole_b200 import Context, TADpole, api
+    from tadpole_b200.synth import synth_hic
+
+    api.QUIET = True
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = Context(local_rank)
+    n = args.bins
+
+    # synthetic inputs: POOL different matrices per rank; pinned host copies for e2e, device copies for value
+    host = []
+    for s in range(POOL):
+        m = synth_hic(n, seed=1000 * rank + 1 + s)
+        t = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
+        t.numpy()[:] = m
+        host.append(t)
+    dev = [t.cuda(non_blocking=False) for t in host]
+    torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_dev(i):
+        d = dev[i % POOL]
+        return ctx.call(device_ptr=d.data_ptr(), n=n, colmajor=0, max_pcs=MAX_PCS)
+
+    def step_e2e(i):
+        return TADpole(host[i % POOL].numpy(), max_pcs=MAX_PCS, ctx=ctx)
+
+    # ---- value: inputs resident in HBM, CUDA events on the library's stream --------------------
+    for i in range(args.warmup):
+        step_dev(i)
+    barrier()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    ctx.profile(1)
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        res = step_dev(args.warmup + i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launches - l0
+    prof = ctx.profile(0)
+    stage = ctx.timings()
+    clk = clocks.stop() if clocks else None
+
+    # ---- e2e: public API, pinned host input, copies inside the timed region --------------------
+    for i in range(min(args.warmup, 3)):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        tp = step_e2e(args.warmup + i)
+    ctx.sync()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    d2h = int(n + tp.scores.size * 8 + (res["nf"] - 1) * 8)
+
+    tmax = torch.tensor([ms, t_e2e * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_all, e2e_ms_all = float(tmax[0]), float(tmax[1])
+
+    if rank == 0:
+        value = world * args.steps / (ms_all * 1e-3)
+        e2e_val = world * args.steps / (e2e_ms_all * 1e-3)
+        # roofline of the dominant kernel class (device time measured live with CUDA events around
+        # every launch of the class, in the timed region above)
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
+        nf, k = res["nf"], res["k"]
+        fp64_peak = measure_fp64_peak(torch)
+        top = max(("jacobi", "dgemm", "coniss_sweep", "ch", "rowmean"), key=lambda c: prof[c][0])
+        t_ms, cnt = prof[top]
+        per_launch_ms = t_ms / max(cnt, 1)
+        if top == "coniss_sweep":
+            # 8*Nf*k(k+1)/2 read + 8*k*(Nf-1) written per sweep launch
+            alg = 8.0 * nf * k * (k + 1) / 2 + 8.0 * k * (nf - 1)
+            roof = {"kernel": "coniss_sweep_kernel", "bound": "hbm", "achieved": alg / (per_launch_ms * 1e-3) / 1e9,
+                    "peak": hbm_peak, "unit": "GB/s", "traffic": None,
+                    "merges_per_s": k * (nf - 1) / (per_launch_ms * 1e-3)}
+        elif top == "dgemm":
+            # algorithmic flops summed by the library per launch (2MNK; one triangle for SYRK shapes);
+            # denominator: cuBLAS DGEMM measured in this same run (no FP64 peak in MEASURED_PEAKS.json)
+            gflop = prof["gemm_gflop"][0]
+            roof = {"kernel": "dgemm_kernel (FP64 DMMA mma.sync m8n8k4)", "bound": "tensor",
+                    "achieved": gflop / t_ms, "peak": fp64_peak, "unit": "TFLOP/s", "traffic": None}
+            peak_src = "cuBLAS DGEMM 4096^3 via torch.matmul, best of 5, measured in this run"
+        else:
+            # Jacobi eigensolver on a b x b L2-resident matrix: algorithmic bytes = read A, write V (2 b^2 doubles)
+            b = -(-(k + max(32, k // 4)) // 32) * 32 if nf > 512 else nf
+            alg = 2.0 * 8.0 * b * b
+            roof = {"kernel": f"{top}_kernel", "bound": "hbm", "achieved": alg / (per_launch_ms * 1e-3) / 1e9,
+                    "peak": hbm_peak, "unit": "GB/s", "traffic": None,
+                    "note": "latency-bound: serial rotation steps on an L2-resident matrix"}
+        if roof.get("achieved") is not None and roof.get("peak"):
+            roof["frac"] = roof["achieved"] / roof["peak"]
+        roof["peak_source"] = peak_src
+        roof["share_of_step"] = t_ms / ms
+        roof["avg_launch_ms"] = per_launch_ms
+
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic {n}-bin Hi-C matrix, nested block TADs, power-law decay, max_pcs=200 "
+                                   "(BASELINE.json configs[1]); one TADpole() call per step",
+                       "bins": n, "good_bins": nf, "max_pcs": MAX_PCS, "n_pcs_found": res["n_pcs"],
+                       "optimal_n_clusters": res["n_clusters"],
+                       "l2": f"pool of {POOL} different {n}x{n} f64 matrices per rank ({POOL * n * n * 8 >> 20} MiB > L2) "
+                             "cycled, no step re-reads a warm input",
+                       "parallelism": f"{world} independent calls (one per GPU), no collective on the data path"},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * n * 8, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms_all / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": roof,
+            "fp64_dgemm_peak_tflops_measured": fp64_peak,
+            "stage_ms_last_step": {k_: round(v, 4) for k_, v in stage.items()},
+            "kernel_ms_per_step": {c: round(v[0] / args.steps, 4) for c, v in prof.items() if v[1]},
+            "kernel_launches_per_step": {c: v[1] / args.steps for c, v in prof.items() if v[1]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            est, detail = cpu_sample(host[0].numpy().copy(), args.cpu_sample, threads)
+            line["cpu_baseline"] = {
+                "value": 1.0 / est, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": (f"oracle/ (numpy + C restatement; R unavailable): filter+correlation+full SVD timed in full "
+                           f"({detail['front_s']} s), {detail['candidates']} of {detail['k']} candidates on {threads} "
+                           f"threads ({detail['sweep_sample_s']} s) scaled by k/candidates")}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

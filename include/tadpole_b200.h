@@ -61,7 +61,7 @@ int tp_ctx_timings(tp_ctx *ctx, double *out10);
 /* per-kernel-class device time: when enabled, every launch of the classes below is bracketed by
  * CUDA events on the context stream; reading sums them since the last enable/reset.
  * classes: [0] rowmean (filter) [1] compact [2] dgemm [3] jacobi [4] coniss_sweep [5] ch [6] difft
- * [7] spare.  enable: 1 = start/reset, 0 = stop, -1 = just read. */
+ * [7] in ms_out8: GFLOP (algorithmic) of the profiled dgemm launches.  enable: 1 = start/reset, 0 = stop, -1 = just read. */
 int tp_ctx_profile(tp_ctx *ctx, int enable, double *ms_out8, long long *count_out8);
 
 /* ---- stage 1: load_mat numeric core (R/TADpole.R:19-22,35-37) ----------------------------- */

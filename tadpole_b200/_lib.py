@@ -138,7 +138,7 @@ class Context:
                 "pca_iterations", "pca_applications", "jacobi_sweeps"]
         return dict(zip(keys, out.tolist()))
 
-    PROFILE_CLASSES = ["rowmean", "compact", "dgemm", "jacobi", "coniss_sweep", "ch", "difft", "spare"]
+    PROFILE_CLASSES = ["rowmean", "compact", "dgemm", "jacobi", "coniss_sweep", "ch", "difft", "gemm_gflop"]
 
     def profile(self, enable=-1):
         """enable: 1 start/reset, 0 stop, -1 read.  Returns {class: (ms, launches)} accumulated so far."""

@@ -145,9 +145,10 @@ extern "C" int tp_ctx_profile(tp_ctx *ctx, int enable, double *ms_out8, long lon
                 cnt[ctx->prof_cls[i / 2]]++;
             } else (void)cudaGetLastError();
         }
+        ms[PC_SPARE] = ctx->prof_gemm_flop * 1e-9;   // slot 7: GFLOP of the profiled GEMM launches
         for (int c = 0; c < PC_COUNT; c++) { if (ms_out8) ms_out8[c] = ms[c]; if (count_out8) count_out8[c] = cnt[c]; }
     }
-    if (enable == 1) { ctx->prof = true; ctx->prof_used = 0; }
+    if (enable == 1) { ctx->prof = true; ctx->prof_used = 0; ctx->prof_gemm_flop = 0.0; }
     else if (enable == 0) ctx->prof = false;
     return TP_OK;
 }

@@ -112,6 +112,7 @@ struct tp_ctx {
     std::vector<cudaEvent_t> prof_ev;      // pool, pairs
     std::vector<int> prof_cls;             // class of pair i
     size_t prof_used = 0;                  // events used
+    double prof_gemm_flop = 0.0;           // algorithmic flops of the GEMM launches profiled
 };
 
 enum { PC_ROWMEAN = 0, PC_COMPACT, PC_GEMM, PC_JACOBI, PC_SWEEP, PC_CH, PC_DIFFT, PC_SPARE, PC_COUNT };

@@ -165,6 +165,8 @@ __global__ void splitk_reduce_kernel(GemmArgs g, const double *__restrict__ part
     g.D[(size_t)m * g.ldd + n] = v;
 }
 
+static inline bool blockIdx_z_first(int) { return true; }
+
 template <bool A_KC, bool B_KC, int BM, int BN, int WM, int WN>
 static int launch_cfg(tp_ctx *ctx, const GemmArgs &g, double *partial, int splits, int kt_per_split) {
     constexpr size_t smem = (size_t)GEMM_STAGES * (tile_doubles<BM, A_KC>() + tile_doubles<BN, B_KC>()) * sizeof(double);
@@ -172,6 +174,8 @@ static int launch_cfg(tp_ctx *ctx, const GemmArgs &g, double *partial, int split
     TP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, splits);
     tp_prof_begin(ctx, PC_GEMM);
+    // algorithmic flops: 2 M N K, or M N (K + 1) ~ SYRK count when only one triangle is computed
+    if (ctx->prof && blockIdx_z_first(splits)) ctx->prof_gemm_flop += g.sym ? (double)g.M * g.N * g.K : 2.0 * g.M * g.N * g.K;
     kern<<<grid, WM * WN * 32, smem, ctx->stream>>>(g, partial, kt_per_split);
     tp_prof_end(ctx);
     ctx->launches += 1;

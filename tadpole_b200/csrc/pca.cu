@@ -16,8 +16,11 @@
 // arbitrary, as they are in LAPACK; every consumer downstream is sign-invariant.
 #include "common.cuh"
 #include "gemm.cuh"
+#include <stdlib.h>
 
-int tp_jacobi(tp_ctx *ctx, double *A, int b, int ld, double *w, double *Vs, int lds, int ncols_out, int *sweeps_out);
+int tp_jacobi(tp_ctx *ctx, double *A, int b, int ld, double *w, double *Vs, int lds, int ncols_out, int *sweeps_out,
+              double tol);
+int tp_chol_inv(tp_ctx *ctx, double *G, double *Linv, int b, int ld, int *bad_out);
 
 // ---- small kernels -------------------------------------------------------------------------------
 // per row: mean and sd of the one-pass formula (columns == rows: the matrix is symmetric)
@@ -258,7 +261,7 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
         TP_TRY(ctx->W.reserve((size_t)n * ld * sizeof(double)));
         TP_TRY(ctx->Jw.reserve((size_t)n * sizeof(double)));
         int sweeps = 0;
-        TP_TRY(tp_jacobi(ctx, M, n, ld, ctx->Jw.as<double>(), ctx->W.as<double>(), ld, n, &sweeps));
+        TP_TRY(tp_jacobi(ctx, M, n, ld, ctx->Jw.as<double>(), ctx->W.as<double>(), ld, n, &sweeps, 1e-14));
         ctx->timing[9] = sweeps;
         scores_kernel<<<(unsigned)(((size_t)n * ldk + 255) / 256), 256, 0, st>>>(ctx->W.as<double>(), ld,
                                                                                ctx->Jw.as<double>(), n, k,
@@ -275,97 +278,155 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
         TP_TRY(ctx->Jw.reserve((size_t)4 * b * sizeof(double)));
         TP_TRY(ctx->resid.reserve((size_t)(k + b) * sizeof(double)));
         TP_TRY(tp_pin_reserve(ctx, (size_t)(k + b + 8) * sizeof(double)));
-        double *Ya = ctx->Y0.as<double>(), *Yb = ctx->Y1.as<double>(), *Yc = ctx->Y2.as<double>();
         double *W = ctx->W.as<double>();
         double *G = ctx->G.as<double>(), *T = ctx->T.as<double>(), *Q = ctx->Q.as<double>();
         double *S1 = ctx->small1.as<double>(), *S2 = ctx->small2.as<double>(), *JV = ctx->Jv.as<double>();
         double *gval = ctx->Jw.as<double>(), *theta = gval + b, *dvec = theta + b;
         double *res = ctx->resid.as<double>();
-        double *hbuf = (double *)ctx->pin;
         PcaOp op{ctx, n, ld, C, M, nullptr, b, ldb};
         DevBuf zbuf;   // scratch for the two-GEMM operator
         if (!M) { TP_TRY(zbuf.reserve(blk)); op.Z = zbuf.as<double>(); }
 
         const unsigned gb = (unsigned)((b * b + 255) / 256);
         const int splitk = n >= 4096 ? 32 : (n >= 1024 ? 8 : 1);
-        random_block_kernel<<<(unsigned)(((size_t)n * ldb + 255) / 256), 256, 0, st>>>(Ya, n, b, ldb);
-        ctx->launches += 1;
-        double *Y = Ya, *F1 = Yb, *F2 = Yc;      // Y: current block; F1/F2: filter scratch
-        TP_TRY(op.apply(Y, W, 1.0, nullptr, 0.0, nullptr, 0.0));
-        int it = 0, sweeps_total = 0, rc = TP_OK;
+        // three rotating n x b buffers: Y = current block, F1 / F2 = scratch
+        double *Y = ctx->Y0.as<double>(), *F1 = ctx->Y1.as<double>(), *F2 = ctx->Y2.as<double>();
+        int sweeps_total = 0, rc = TP_OK, it = 0;
         bool converged = false;
-        double last_res = 0.0;
-        for (; it < ctx->pca_maxit * 4; it++) {
-            // ---- orthonormalise + Rayleigh-Ritz as one generalised problem ----------------------
+        double last_res = 1.0;
+
+        // D = Ysrc^T Bsrc  (b x b, long reduction over the bins: deterministic split-K)
+        auto gram = [&](const double *Ysrc, const double *Bsrc, double *D) {
             GemmArgs gg;
-            gg.A = Y; gg.lda = ldb; gg.a_kc = 0; gg.B = Y; gg.ldb = ldb; gg.b_kc = 0;
-            gg.D = G; gg.ldd = ldb; gg.M = b; gg.N = b; gg.K = n; gg.splitk = splitk;
-            if ((rc = tp_gemm(ctx, gg)) != TP_OK) break;
-            gg.B = W; gg.D = T;
-            if ((rc = tp_gemm(ctx, gg)) != TP_OK) break;
+            gg.A = Ysrc; gg.lda = ldb; gg.a_kc = 0; gg.B = Bsrc; gg.ldb = ldb; gg.b_kc = 0;
+            gg.D = D; gg.ldd = ldb; gg.M = b; gg.N = b; gg.K = n; gg.splitk = splitk;
+            return tp_gemm(ctx, gg);
+        };
+        // F1 = Y * R (R: b x b, (k,n) at R[k*ldb+n] or transposed), then F1 becomes the block
+        auto rotate = [&](const double *R, int r_kc) {
+            GemmArgs r;
+            r.A = Y; r.lda = ldb; r.a_kc = 1; r.B = R; r.ldb = ldb; r.b_kc = r_kc;
+            r.D = F1; r.ldd = ldb; r.M = n; r.N = b; r.K = b;
+            int e = tp_gemm(ctx, r);
+            double *t = Y; Y = F1; F1 = t;
+            return e;
+        };
+        // Cholesky QR, two passes: Y <- Y L^-T.  Returns 1 in *bad when the Gram matrix is not PD.
+        auto cholqr2 = [&](int *bad) {
+            *bad = 0;
+            for (int pass = 0; pass < 2; pass++) {
+                TP_TRY(gram(Y, Y, G));
+                TP_TRY(tp_chol_inv(ctx, G, S1, b, ldb, bad));
+                if (*bad) return (int)TP_OK;
+                TP_TRY(rotate(S1, 1));          // B = Linv^T: (k, n) at Linv[n*ldb + k]
+            }
+            return (int)TP_OK;
+        };
+        // Rayleigh-Ritz on an orthonormal block: T = Y^T W, T = Z diag(theta) Z^T, Y <- Y Z
+        auto rr_orthonormal = [&](double jtol) {
+            TP_TRY(gram(Y, W, T));
+            symmetrize_kernel<<<gb, 256, 0, st>>>(T, b, ldb);
+            ctx->launches += 1;
+            int sw = 0;
+            TP_TRY(tp_jacobi(ctx, T, b, ldb, theta, JV, ldb, b, &sw, jtol));
+            sweeps_total += sw;
+            return rotate(JV, 0);
+        };
+        // orthonormalisation and Rayleigh-Ritz together as the generalised problem (G = Y^T Y,
+        // T = Y^T W) through two eigen-decompositions: robust for ill-conditioned blocks
+        auto rr_general = [&](double jtol) {
+            TP_TRY(gram(Y, Y, G));
+            TP_TRY(gram(Y, W, T));
             scale_gram_kernel<<<gb, 256, 0, st>>>(G, T, b, ldb, S1, S2, dvec);       // S1 = Gs, S2 = Ts
             ctx->launches += 1;
             int sw = 0;
-            if ((rc = tp_jacobi(ctx, S1, b, ldb, gval, JV, ldb, b, &sw)) != TP_OK) break;   // Gs = JV diag(gval) JV^T
+            TP_TRY(tp_jacobi(ctx, S1, b, ldb, gval, JV, ldb, b, &sw, jtol));          // Gs = JV diag(gval) JV^T
             sweeps_total += sw;
             whiten_kernel<<<gb, 256, 0, st>>>(JV, gval, b, ldb, S1);                 // S1 = X
             ctx->launches += 1;
-            if ((rc = small_gemm(ctx, S2, 1, S1, 0, G, b, ldb)) != TP_OK) break;     // G  = Ts X
-            if ((rc = small_gemm(ctx, S1, 0, G, 0, T, b, ldb)) != TP_OK) break;      // T  = X^T Ts X
+            TP_TRY(small_gemm(ctx, S2, 1, S1, 0, G, b, ldb));                        // G  = Ts X
+            TP_TRY(small_gemm(ctx, S1, 0, G, 0, T, b, ldb));                         // T  = X^T Ts X
             symmetrize_kernel<<<gb, 256, 0, st>>>(T, b, ldb);
             ctx->launches += 1;
-            if ((rc = tp_jacobi(ctx, T, b, ldb, theta, JV, ldb, b, &sw)) != TP_OK) break;   // T = JV diag(theta) JV^T
+            TP_TRY(tp_jacobi(ctx, T, b, ldb, theta, JV, ldb, b, &sw, jtol));          // T = JV diag(theta) JV^T
             sweeps_total += sw;
-            if ((rc = small_gemm(ctx, S1, 1, JV, 0, Q, b, ldb)) != TP_OK) break;     // Q = X Z
+            TP_TRY(small_gemm(ctx, S1, 1, JV, 0, Q, b, ldb));                        // Q = X Z
             scale_rows_kernel<<<gb, 256, 0, st>>>(Q, b, ldb, dvec);                  // Q = D X Z
             ctx->launches += 1;
-            {   // Y <- Y Q  (into F1), then F1 becomes the current block
-                GemmArgs r;
-                r.A = Y; r.lda = ldb; r.a_kc = 1; r.B = Q; r.ldb = ldb; r.b_kc = 0;
-                r.D = F1; r.ldd = ldb; r.M = n; r.N = b; r.K = b;
-                if ((rc = tp_gemm(ctx, r)) != TP_OK) break;
-                double *t = Y; Y = F1; F1 = t;
-            }
-            // ---- first filter step doubles as the residual check ---------------------------------
-            if ((rc = (cudaMemcpyAsync(hbuf, theta, (size_t)b * sizeof(double), cudaMemcpyDeviceToHost, st) == cudaSuccess
-                           ? TP_OK : TP_ERR_CUDA)) != TP_OK) break;
-            if (cudaStreamSynchronize(st) != cudaSuccess) { rc = TP_ERR_CUDA; break; }
-            const double top = hbuf[0], thk = hbuf[k - 1];
-            double cut = hbuf[b - 1];
-            if (!(cut > 0.0)) { for (int j = b - 1; j >= k; j--) if (hbuf[j] > 0.0) { cut = hbuf[j]; break; } }
-            if (!(cut > 0.0) || !(thk > cut)) cut = 0.5 * thk > 0.0 ? 0.5 * thk : 1e-300;
-            const double e = 0.5 * cut, c = 0.5 * cut;
-            const double sig1 = e / (top - c);
-            // Y1 = (sig1 / e) (M Y - c Y)
-            if ((rc = op.apply(Y, F1, sig1 / e, Y, -sig1 * c / e, nullptr, 0.0)) != TP_OK) break;
-            residual_kernel<<<(k + 31) / 32, 256, 0, st>>>(Y, F1, n, ldb, k, theta, e / sig1, c, res);
-            ctx->launches += 1;
-            cudaMemcpyAsync(hbuf, res, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, st);
-            if (cudaStreamSynchronize(st) != cudaSuccess) { rc = TP_ERR_CUDA; break; }
-            double rmax = 0.0;
-            for (int j = 0; j < k; j++) rmax = hbuf[j] > rmax || hbuf[j] != hbuf[j] ? hbuf[j] : rmax;
-            last_res = rmax / top;
-            if (rmax <= ctx->pca_tol * top) { converged = true; it++; break; }
-            // ---- remaining filter steps: degree bounded by the conditioning of the filtered block
-            const double xk = (thk - c) / e, x1 = (top - c) / e;
-            int deg = 1;
-            for (int mdeg = 2; mdeg <= 24; mdeg++) {
-                const double ratio = cosh(mdeg * acosh(x1)) / cosh(mdeg * acosh(xk));
-                if (ratio <= 1e5) deg = mdeg; else break;
-            }
-            double sig = sig1;
+            return rotate(Q, 0);
+        };
+        // Chebyshev filter steps 2..deg on P0 = Y, P1 = F1 (step 1 already done); result becomes Y
+        struct Bounds { double top, thk, cut, e, c, sig1; int deg; } bd{};
+        auto filter_rest = [&]() {
+            double sig = bd.sig1;
             double *P0 = Y, *P1 = F1, *P2 = F2;
-            for (int j = 2; j <= deg; j++) {
-                const double sig2 = 1.0 / (2.0 / sig1 - sig);
+            for (int j = 2; j <= bd.deg; j++) {
+                const double sig2 = 1.0 / (2.0 / bd.sig1 - sig);
                 // P2 = 2 (sig2/e) (M P1 - c P1) - sig sig2 P0
-                if ((rc = op.apply(P1, P2, 2.0 * sig2 / e, P1, -2.0 * sig2 * c / e, P0, -sig * sig2)) != TP_OK) break;
+                TP_TRY(op.apply(P1, P2, 2.0 * sig2 / bd.e, P1, -2.0 * sig2 * bd.c / bd.e, P0, -sig * sig2));
                 double *t = P0; P0 = P1; P1 = P2; P2 = t;
                 sig = sig2;
             }
-            if (rc != TP_OK) break;
             Y = P1; F1 = P0; F2 = P2;
-            if ((rc = op.apply(Y, W, 1.0, nullptr, 0.0, nullptr, 0.0)) != TP_OK) break;
-        }
+            return (int)TP_OK;
+        };
+        auto filter_step1 = [&]() {   // F1 = (sig1 / e) (M Y - c Y)
+            return op.apply(Y, F1, bd.sig1 / bd.e, Y, -bd.sig1 * bd.c / bd.e, nullptr, 0.0);
+        };
+
+        auto body = [&]() -> int {
+            random_block_kernel<<<(unsigned)(((size_t)n * ldb + 255) / 256), 256, 0, st>>>(Y, n, b, ldb);
+            ctx->launches += 1;
+            TP_TRY(op.apply(Y, W, 1.0, nullptr, 0.0, nullptr, 0.0));
+            TP_TRY(rr_general(1e-5));
+            double *hbuf = (double *)ctx->pin;
+            const int inner = 2;             // filter + CholQR rounds between two Rayleigh-Ritz steps
+            for (it = 1; it <= ctx->pca_maxit * 2; it++) {
+                // ---- bounds from the current Ritz values -----------------------------------------
+                TP_CUDA(cudaMemcpyAsync(hbuf, theta, (size_t)b * sizeof(double), cudaMemcpyDeviceToHost, st));
+                TP_CUDA(cudaStreamSynchronize(st));
+                hbuf = (double *)ctx->pin;
+                bd.top = hbuf[0]; bd.thk = hbuf[k - 1];
+                double cut = hbuf[b - 1];
+                if (!(cut > 0.0)) { for (int j = b - 1; j >= k; j--) if (hbuf[j] > 0.0) { cut = hbuf[j]; break; } }
+                if (!(cut > 0.0) || !(bd.thk > cut)) cut = 0.5 * bd.thk > 0.0 ? 0.5 * bd.thk : 1e-300;
+                bd.cut = cut; bd.e = 0.5 * cut; bd.c = 0.5 * cut;
+                bd.sig1 = bd.e / (bd.top - bd.c);
+                const double xk = (bd.thk - bd.c) / bd.e, x1 = (bd.top - bd.c) / bd.e;
+                bd.deg = 1;      // degree bounded by the conditioning of the filtered block
+                for (int mdeg = 2; mdeg <= 24; mdeg++) {
+                    const double ratio = cosh(mdeg * acosh(x1)) / cosh(mdeg * acosh(xk));
+                    if (ratio <= 1e5) bd.deg = mdeg; else break;
+                }
+                // ---- first filter step doubles as the residual check ---------------------------------
+                TP_TRY(filter_step1());
+                residual_kernel<<<(k + 31) / 32, 256, 0, st>>>(Y, F1, n, ldb, k, theta, bd.e / bd.sig1, bd.c, res);
+                ctx->launches += 1;
+                TP_CUDA(cudaMemcpyAsync(hbuf, res, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, st));
+                TP_CUDA(cudaStreamSynchronize(st));
+                double rmax = 0.0;
+                for (int j = 0; j < k; j++) rmax = (hbuf[j] > rmax || hbuf[j] != hbuf[j]) ? hbuf[j] : rmax;
+                last_res = rmax / bd.top;
+                if (getenv("TADPOLE_DEBUG"))
+                    fprintf(stderr, "[tadpole] pca it=%d res=%.3e top=%.4e thk=%.4e cut=%.4e deg=%d\n", it, last_res,
+                            bd.top, bd.thk, bd.cut, bd.deg);
+                if (rmax <= ctx->pca_tol * bd.top) { converged = true; return TP_OK; }
+                // ---- filter / orthonormalise rounds, then one Rayleigh-Ritz ------------------------
+                bool general = false;
+                for (int r = 0; r < inner; r++) {
+                    if (r > 0) TP_TRY(filter_step1());
+                    TP_TRY(filter_rest());
+                    int bad = 0;
+                    TP_TRY(cholqr2(&bad));
+                    if (bad) { general = true; break; }
+                }
+                TP_TRY(op.apply(Y, W, 1.0, nullptr, 0.0, nullptr, 0.0));
+                const double jtol = fmin(1e-6, fmax(1e-14, last_res * 1e-9));
+                if (general) TP_TRY(rr_general(jtol)); else TP_TRY(rr_orthonormal(jtol));
+            }
+            return TP_OK;
+        };
+        rc = body();
         zbuf.release();
         TP_TRY(rc);
         ctx->timing[7] = it;

@@ -14,4 +14,8 @@ for rep in range(4):
     tm = ctx.timings()
     print(f"N={n} rep={rep} wall={wall:.2f} ms n_pcs={r['n_pcs']} ncl={r['n_clusters']} nf={r['nf']} "
           + " ".join(f"{k}={v:.3f}" for k, v in tm.items()), flush=True)
+ctx.profile(1)
+r = ctx.call(m)
+prof = ctx.profile(0)
+print("profile (ms, launches):", {k: (round(v[0], 3), v[1]) for k, v in prof.items()})
 print("launches", ctx.launches)

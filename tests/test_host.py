@@ -1,0 +1,144 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, and
+the pure-host entry points (tp_select, tp_assemble) and Python wrappers agree with the oracle.
+No CUDA compute is called here."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import tadpole_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from tadpole_b200 import _lib
+    return _lib
+
+
+def test_library_exports_every_header_symbol(lib):
+    with open(os.path.join(ROOT, "include", "tadpole_b200.h")) as fh:
+        text = fh.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    declared = set(re.findall(r"\b(tp_[a-z_0-9]+)\s*\(", text))
+    declared.discard("tp_ctx")
+    l = lib.load()
+    missing = [s for s in sorted(declared) if not hasattr(l, s)]
+    assert not missing, missing
+    assert declared == set(lib.EXPORTED)
+    assert l.tp_version() >= 100
+
+
+def test_no_gpu_is_a_loud_error(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(lib.TadpoleError) as e:
+        lib.Context(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "tadpole_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(dirpath, f)) as fh:
+                    src = fh.read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_tp_select_matches_oracle(lib):
+    import ctypes
+    rng = np.random.default_rng(0)
+    l = lib.load()
+    for _ in range(20):
+        k, w = int(rng.integers(1, 12)), int(rng.integers(2, 9))
+        rows = []
+        for r in range(k):
+            ncl = int(rng.integers(2, w + 1))
+            row = np.full(ncl, np.nan)
+            row[1:] = rng.integers(1, 6, ncl - 1).astype(float)     # small ints: plenty of ties
+            rows.append(row)
+        scores, opcs, ok = O.reduce_scores(rows)
+        oc, ol = ctypes.c_int(), ctypes.c_int()
+        sc = np.ascontiguousarray(scores)
+        rc = l.tp_select(sc.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), sc.shape[0], sc.shape[1], sc.shape[1],
+                         ctypes.byref(oc), ctypes.byref(ol))
+        assert rc == 0 and (oc.value + 1, ol.value + 1) == (opcs, ok)
+
+
+def test_tp_assemble_matches_oracle(lib):
+    rng = np.random.default_rng(1)
+    for trial in range(30):
+        n = int(rng.integers(8, 60))
+        bad_mask = rng.random(n) < 0.2
+        bad_mask[rng.integers(0, n)] = False
+        names = np.flatnonzero(~bad_mask) + 1
+        nf = names.size
+        if nf < 3:
+            continue
+        seq = rng.integers(1, 5, nf - 1).astype(float).cumsum()[rng.permutation(nf - 1)]
+        seq[rng.integers(0, nf - 1)] = seq[0]                       # a tie
+        for k in (1, 2, min(5, nf)):
+            good = O.cutree(seq, k)
+            for bad in (np.flatnonzero(bad_mask) + 1, None):
+                tab, labels = lib.assemble(seq, k, names, bad)
+                if bad is None:
+                    ref_fixed = good
+                    _, lens = O._rle(good)
+                    eb = np.cumsum(lens)
+                    ref_tab = np.stack([np.concatenate(([1], eb[:-1] + 1)), eb], axis=1)
+                else:
+                    ref_fixed = O.fixed_labels(good, names, bad)
+                    ref_tab = O.coords_from_labels(ref_fixed)
+                assert labels[: ref_fixed.size].tolist() == ref_fixed.tolist()
+                assert tab.tolist() == ref_tab.tolist()
+
+
+def test_assemble_q_arm_quirk_duplicate_names(lib):
+    """Quirk Q3: bad columns that were never removed appear both as good rows and as bad names."""
+    names = np.array([11, 12, 13, 14, 15, 16])
+    bad = np.array([13, 15])                                         # still present among names
+    seq = np.array([1.0, 5.0, 2.0, 9.0, 3.0])
+    good = O.cutree(seq, 3)
+    ref = O.fixed_labels(good, names, bad)
+    tab, labels = lib.assemble(seq, 3, names, bad)
+    assert labels[: ref.size].tolist() == ref.tolist() and ref.size == 8
+    assert tab.tolist() == O.coords_from_labels(ref).tolist()
+
+
+def test_python_host_helpers_match_oracle():
+    from tadpole_b200 import api, hclust
+    rng = np.random.default_rng(2)
+    seq = rng.random(40)
+    assert hclust.find_groups(seq).tolist() == O.find_groups(seq)[0].tolist()
+    for k in (1, 2, 7, 41):
+        assert hclust.cutree(seq, k).tolist() == O.cutree(seq, k).tolist()
+    bed = np.array([[5, 9], [10, 20], [18, 25]])
+    assert api.bin_index(bed, 21).tolist() == O.bin_index(bed, 21).tolist()
+    bx, by = np.array([[3, 8], [9, 15]]), np.array([[1, 6], [7, 12]])
+    tx, ty = api._difft_labels(bx, by)
+    ox, oy = O.difft_labels(bx, by)
+    assert tx.tolist() == ox.tolist() and ty.tolist() == oy.tolist()
+    with pytest.raises(ValueError):
+        api._difft_labels(bx, by[:1])
+    rb = api.random_bed(np.array([[1, 10], [11, 30], [31, 40]]), rng=np.random.default_rng(0))
+    assert rb.shape == (3, 2) and rb[0, 0] == 1 and rb[-1, 1] == 40
+
+
+def test_centromere_split_host_logic_matches_oracle():
+    from tadpole_b200 import api
+    from tadpole_b200.synth import synth_hic
+    api.QUIET = True
+    m = synth_hic(400, seed=2, centromere=True)
+    sym = O.symmetrise_upper(m)
+    bad, _, _ = O.bad_columns(sym, 0.01)
+    (kp, bp), (kq, bq), cen = api._split_centromere(bad)
+    lm = O.load_mat_numeric(m, centromere_search=True)
+    assert (kp + 1).tolist() == lm.p.names.tolist() and (kq + 1).tolist() == lm.q.names.tolist()
+    assert cen.tolist() == lm.centromere.tolist()
+    assert (bq is None) == (lm.q.bad_columns is None)

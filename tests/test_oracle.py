@@ -1,0 +1,192 @@
+"""CPU tests of the oracle: golden vectors, cross-checks against independent implementations, and
+properties.  The reference has no tests; the diffT fixture pair is its only known-answer case."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import tadpole_oracle as O
+from tadpole_b200.synth import synth_hic, synth_partition_pairs
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_difft_golden_pins_oracle():
+    """inst/extdata/control.bed x case.bed: L = 194, un-normalised total 1777 and the kinks of
+    misc/DiffT_score.png."""
+    with open(os.path.join(GOLD, "difft_control_case.json")) as fh:
+        g = json.load(fh)
+    control, case = np.array(g["control"]), np.array(g["case"])
+    raw = O.difft(control, case, raw=True)
+    assert raw.size == 194 and raw[-1] == 1777
+    assert raw.tolist() == g["raw_cumulative"]
+    norm = O.difft(control, case)
+    for pos, val in [(1, 0.002814), (23, 0.064716), (28, 0.168824), (42, 0.208216), (54, 0.230726), (72, 0.240855),
+                     (100, 0.288126), (103, 0.367473), (122, 0.399550), (134, 0.446820), (141, 0.576815),
+                     (156, 0.686550), (162, 0.797974), (174, 0.881823), (179, 0.957794), (194, 1.0)]:
+        assert round(norm[pos - 1], 6) == val
+    tx, ty = O.difft_labels(control, case)
+    assert tx[173] == 0 or ty[173] == 0                 # the 1-bin gap at bin 466 (control.bed:9-10)
+    assert (O.difft_from_labels_c(tx, ty) == norm).all()
+    # first per-bin raw scores: 5 x 23, 37 x 5, ...
+    per_bin = np.diff(np.concatenate(([0], raw)))
+    assert (per_bin[:23] == 5).all() and (per_bin[23:28] == 37).all()
+
+
+def test_difft_errors_and_edge_cases():
+    with pytest.raises(ValueError):
+        O.difft(np.array([[1, 5], [6, 9]]), np.array([[1, 9]]))
+    same = O.difft(np.array([[1, 5], [6, 9]]), np.array([[1, 5], [6, 9]]))
+    assert (same == 0).all()                            # max(scores) == 0: returned un-normalised (Q10)
+    # later rows overwrite earlier ones, offsets relative to the first start (Q11)
+    assert O.bin_index(np.array([[10, 15], [13, 14]]), 6).tolist() == [1, 1, 1, 2, 2, 1]
+
+
+def test_quantile_type7_matches_numpy():
+    rng = np.random.default_rng(0)
+    for n in (5, 198, 2000):
+        x = rng.random(n)
+        for p in (0.01, 0.05, 0.5, 1.0):
+            assert O.quantile_type7(x, p) == pytest.approx(np.quantile(x, p, method="linear"), rel=1e-15)
+
+
+def test_bad_columns_and_symmetrise():
+    m = synth_hic(300, seed=9)
+    m[np.tril_indices(300, -1)] = 77.0                 # lower triangle ignored
+    m[5, 9] = np.nan
+    sym = O.symmetrise_upper(m)
+    assert (sym == sym.T).all() and sym[9, 5] == 0 and sym[5, 9] == 0
+    bad, r, thr = O.bad_columns(sym, 0.01)
+    assert bad[np.diag(sym) == 0].all()
+    assert ((r < thr) <= bad).all()
+    bad0, _, thr0 = O.bad_columns(sym, 0.0)
+    assert np.isnan(thr0) and (bad0 == (np.diag(sym) == 0)).all()
+
+
+def test_load_mat_centromere_split_and_quirks():
+    m = synth_hic(400, seed=2, centromere=True)
+    lm = O.load_mat_numeric(m, centromere_search=True)
+    assert lm.p is not None and lm.q is not None
+    cs, ce = lm.centromere[0], lm.centromere[-1]
+    assert lm.p.mat.shape[0] == cs - 1 - (0 if lm.p.bad_columns is None else len(lm.p.bad_columns))
+    # quirk Q3: q-arm bad columns carry ORIGINAL indices; only those <= arm length delete rows
+    nq = 400 - ce
+    if lm.q.bad_columns is not None:
+        removed = int((lm.q.bad_columns <= nq).sum())
+        assert lm.q.mat.shape[0] == nq - removed
+    # longest bad run at the end: not split (R/TADpole.R:66-71)
+    m2 = synth_hic(200, seed=3, zero_frac=0.0)
+    m2[190:, :] = 0; m2[:, 190:] = 0
+    lm2 = O.load_mat_numeric(m2, centromere_search=True)
+    assert lm2.p is None and lm2.mat.shape[0] <= 190
+
+
+def test_sparse_cor_matches_numpy_corrcoef():
+    x = O.load_mat_numeric(synth_hic(200, seed=1)).mat
+    np.testing.assert_allclose(O.sparse_cor(x), np.corrcoef(x, rowvar=False), atol=1e-12)
+
+
+def test_prcomp_matches_eigh():
+    cor = O.sparse_cor(O.load_mat_numeric(synth_hic(200, seed=1)).mat)
+    pcs = O.prcomp_scores(cor, 20)
+    xc = cor - cor.mean(0)
+    w = np.linalg.eigvalsh(xc @ xc.T)[::-1]
+    np.testing.assert_allclose((pcs ** 2).sum(0), w[:20], rtol=1e-10)
+    assert np.abs(pcs.mean(0)).max() < 1e-12
+
+
+@pytest.mark.parametrize("n,seed", [(120, 1), (200, 2), (333, 3)])
+def test_coniss_two_restatements_agree(n, seed):
+    """Lance-Williams on squared distances (rioja's shape, C) vs centroid form (python): identical
+    merge order; cumulative dispersion ends at the total sum of squares."""
+    cor = O.sparse_cor(O.load_mat_numeric(synth_hic(n, seed=seed)).mat)
+    pcs = O.prcomp_scores(cor, 40)
+    for i in (1, 3, 17, 40):
+        s1, o1 = O.coniss_centroid(pcs[:, :i])
+        s2, o2 = O.coniss_lw(pcs[:, :i])
+        assert (o1 == o2).all()
+        np.testing.assert_allclose(s1, s2, rtol=1e-12)
+        x = pcs[:, :i]
+        assert s2.max() == pytest.approx(((x - x.mean(0)) ** 2).sum(), rel=1e-12)
+        h = s2[o2]
+        assert (np.diff(h) >= 0).all()                 # cumulative heights are monotone
+
+
+def test_coniss_matches_sklearn_structured_ward():
+    from scipy.sparse import diags
+    from sklearn.cluster import AgglomerativeClustering
+    cor = O.sparse_cor(O.load_mat_numeric(synth_hic(200, seed=5)).mat)
+    pcs = O.prcomp_scores(cor, 30)
+    n = pcs.shape[0]
+    chain = diags([np.ones(n - 1), np.ones(n - 1)], [-1, 1])
+    seq, _ = O.coniss_lw(pcs)
+    for k in (2, 5, 13):
+        sk = AgglomerativeClustering(n_clusters=k, linkage="ward", connectivity=chain).fit(pcs).labels_
+        ours = O.cutree(seq, k)
+        # same partition up to label names
+        assert (np.diff(sk) != 0).tolist() == (np.diff(ours) != 0).tolist()
+
+
+def test_find_groups_and_cutree():
+    seq = np.array([3.0, 1.0, 7.0, 1.0, 5.0])
+    merge, height = O.find_groups(seq)
+    assert height.tolist() == [1.0, 1.0, 3.0, 5.0, 7.0]
+    assert merge.tolist() == [[-2, -3], [-4, -5], [-1, 1], [2, -6], [3, 4]]   # first index on ties
+    assert O.cutree(seq, 1).tolist() == [1] * 6
+    assert O.cutree(seq, 2).tolist() == [1, 1, 1, 2, 2, 2]
+    assert O.cutree(seq, 3).tolist() == [1, 1, 1, 2, 2, 3]
+
+
+def test_bstick_and_first_true_run():
+    seq = np.cumsum(np.arange(1.0, 11.0))               # heights 1,3,6,...,55
+    disp, bs = O.bstick_table(seq)
+    n = 10
+    assert disp.tolist() == [10, 9, 8, 7, 6, 5, 4, 3, 2]
+    expect = [(55.0 / n) * sum(1.0 / m for m in range(j, n + 1)) for j in range(1, n)]
+    np.testing.assert_allclose(bs, expect, rtol=1e-14)
+    assert O.first_true_run([True, True, False, True]) == 2
+    assert O.first_true_run([False, True, True, True, False]) == 3      # quirk Q1: first TRUE run wherever it starts
+    assert O.first_true_run([False, False]) is None
+
+
+def test_calinhara_matches_sklearn():
+    from sklearn.metrics import calinski_harabasz_score
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((90, 7))
+    lab = np.repeat([1, 2, 3], 30)
+    assert O.calinhara(x, lab, 3) == pytest.approx(calinski_harabasz_score(x, lab), rel=1e-12)
+
+
+def test_fix_values_and_assembly():
+    assert O.fix_values([1, 0, 1, 0, 2, 0]) == [1, 1, 1, 0, 2, 0]
+    assert O.fix_values([0, 1, 0, 1]) == [0, 1, 1, 1]
+    good = np.array([1, 1, 2, 2, 2, 3])
+    names = np.array([1, 2, 4, 5, 7, 8])
+    fx = O.fixed_labels(good, names, np.array([3, 6, 9]))
+    assert fx.tolist() == [1, 1, 0, 2, 2, 2, 2, 3, 0]    # bin 6 absorbed (2|0|2), bins 3 and 9 stay 0
+    assert O.coords_from_labels(fx).tolist() == [[1, 2], [4, 7], [8, 8]]
+
+
+def test_reduce_scores_which_max_semantics():
+    a = [np.array([np.nan, 3.0, 5.0]), np.array([np.nan, 4.0, 4.0, 4.0]), np.array([np.nan, 4.0])]
+    scores, pcs, k = O.reduce_scores(a)
+    assert scores.shape == (3, 4) and pcs == 1 and k == 3    # rows tie at mean 4: first wins
+    scores, pcs, k = O.reduce_scores([np.array([np.nan]), np.array([np.nan, 2.0])])
+    assert pcs == 2 and k == 2                                # an all-NA row is ignored
+
+
+def test_full_oracle_is_deterministic_and_sane():
+    m = synth_hic(200, seed=1)
+    r1, r2 = O.tadpole(m), O.tadpole(m)
+    assert r1.n_pcs == r2.n_pcs and r1.optimal_n_clusters == r2.optimal_n_clusters
+    tab = r1.clusters[r1.optimal_n_clusters]
+    assert tab[0, 0] == 1 and (tab[1:, 0] > tab[:-1, 1]).all()
+    assert np.isnan(r1.scores[:, 0]).all()                    # min_clusters = 2: level 1 is NA
+
+
+def test_synth_generators():
+    m = synth_hic(150, seed=4, centromere=True)
+    assert (m == m.T).all() and m.dtype == np.float64 and (m >= 0).all()
+    lx, ly = synth_partition_pairs(3, 500, 20, seed=1)
+    assert lx.shape == (3, 500) and lx.max() == 20 and ly.max() == 20 and (lx == 0).any()
