@@ -90,6 +90,7 @@ extern "C" int tp_ctx_set(tp_ctx *ctx, const char *key, double value) {
     if (k == "pca_block") ctx->pca_block = (int)value;
     else if (k == "pca_tol") ctx->pca_tol = value;
     else if (k == "pca_maxit") ctx->pca_maxit = (int)value;
+    else if (k == "pca_inner") ctx->pca_inner = (int)value < 1 ? 1 : (int)value;
     else if (k == "jacobi_direct_max") ctx->jacobi_direct_max = (int)value;
     else if (k == "level_cap") ctx->level_cap = (int)value;
     else { tp_set_error("tp_ctx_set: unknown key '%s'", key); return TP_ERR_ARG; }

@@ -76,8 +76,9 @@ struct tp_ctx {
 
     // tunables
     int pca_block = 0;
-    double pca_tol = 2e-13;
+    double pca_tol = 1e-12;
     int pca_maxit = 16;
+    int pca_inner = 4;
     int jacobi_direct_max = 512;
     int level_cap = 256;
 

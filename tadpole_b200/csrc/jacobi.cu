@@ -12,11 +12,12 @@
 namespace cg = cooperative_groups;
 
 #define JC_CLUSTER 8
-#define JC_THREADS 512
+#define JC_THREADS 1024
 #define JC_MAXPAIRS 512
 
+// round-robin tournament over m (even) players: player m-1 is fixed, the others rotate.
+// slot 0 pairs (m-1, step); slot J pairs ((step+J) mod (m-1), (step-J) mod (m-1)).
 __device__ __forceinline__ void jc_pair(int slot, int step, int m, int &p, int &q) {
-    // round-robin tournament over m (even) players: player m-1 is fixed, the others rotate
     int a, b;
     if (slot == 0) { a = m - 1; b = step; }
     else {
@@ -26,29 +27,47 @@ __device__ __forceinline__ void jc_pair(int slot, int step, int m, int &p, int &
     p = min(a, b); q = max(a, b);
 }
 
-// One step = (A) rotations of this step from the old matrix, (V) eigenvector update with the
-// rotations of the PREVIOUS step (so it overlaps the latency of A), (B) all 2x2 blocks of A.
-// Everything a thread needs from global memory for (B) is loaded before the rotations are known.
-#define JC_TA 4    // A tasks loaded per batch
+__device__ __forceinline__ double fast_rcp(double x) {       // ~1e-11 relative: MUFU + one Newton step
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    return fma(r, fma(-x, r, 1.0), r);
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {     // full precision after two Newton steps
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = r * fma(-0.5 * x * r, r, 1.5);
+    r = r * fma(-0.5 * x * r, r, 1.5);
+    return r * fma(-0.5 * x * r, r, 1.5);
+}
+
+// One step: (A) rotations of this step from the old matrix, (B) every 2 x 2 block (I, J) of the
+// pair-permuted matrix becomes J_I^T * block * J_J.  The rotations (c, s) of every step are logged
+// to global memory; the eigenvectors are accumulated afterwards by vapply_kernel, which is
+// embarrassingly parallel over rows, so the serial loop here only carries the matrix itself.
+// TA = 2 x 2 blocks per thread.
+template <int TA>
 __global__ void __cluster_dims__(JC_CLUSTER, 1, 1) __launch_bounds__(JC_THREADS, 1)
-jacobi_kernel(double *A0, double *A1, double *V0, double *V1,
+jacobi_kernel(double *A0, double *A1, double2 *__restrict__ rotlog,
               int b, int ld, int max_sweeps, double tol, int *info) {
     cg::cluster_group cluster = cg::this_cluster();
-    __shared__ double s_c[2][JC_MAXPAIRS], s_s[2][JC_MAXPAIRS], s_t[JC_MAXPAIRS];
-    __shared__ short s_p[2][JC_MAXPAIRS], s_q[2][JC_MAXPAIRS];
+    __shared__ double s_c[JC_MAXPAIRS], s_s[JC_MAXPAIRS];
+    __shared__ short s_p[JC_MAXPAIRS], s_q[JC_MAXPAIRS];
     __shared__ double s_red[JC_THREADS / 32];
     __shared__ double s_anorm;
     __shared__ double s_off;               // max |a_pq| seen in the sweep
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int gtid = cluster.block_rank() * JC_THREADS + tid;
+    const int crank = cluster.block_rank();
+    const int gtid = crank * JC_THREADS + tid;
     const int GT = JC_CLUSTER * JC_THREADS;
     const int m = (b + 1) & ~1;          // even number of players; index b (if any) is a bye
     const int np = m / 2;
-
-    // V = I; anorm = max |diag(A)|
-    for (int idx = gtid; idx < b * b; idx += GT) {
-        int r = idx / b, c = idx % b;
-        V0[(size_t)r * ld + c] = (r == c) ? 1.0 : 0.0;
+    // this thread's blocks: task t = gtid + u * GT  <->  (I, J) = (t / np, t % np), fixed for the whole run
+    int tI[TA], tJ[TA];
+#pragma unroll
+    for (int u = 0; u < TA; u++) {
+        const int t = gtid + u * GT;
+        tI[u] = t / np; tJ[u] = t % np;       // tI >= np marks an empty slot
     }
     {
         double mx = 0.0;
@@ -67,122 +86,89 @@ jacobi_kernel(double *A0, double *A1, double *V0, double *V1,
     const double tolabs = tol * s_anorm;
     cluster.sync();
 
-    double *Ao = A0, *An = A1, *Vo = V0, *Vn = V1;
-    int sweeps = 0, cur = 0;
-    bool have_prev = false;              // rotations of the previous step still to be applied to V
+    const double *Ao = A0;
+    double *An = A1;
+    int sweeps = 0;
+    long logpos = 0;                       // step counter across sweeps
     bool converged = (b < 2);
-    const int tasksA = np * np, tasksV = b * np;
-
-    // V <- V * J(previous step): reads Vo, writes Vn with the rotation table `tb`
-    auto apply_v = [&](int tb) {
-        for (int t0 = gtid; t0 < tasksV; t0 += GT * 4) {
-            double v0[4], v1[4];
-            int rr[4], r1[4], r2[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int tv = t0 + u * GT;
-                rr[u] = -1;
-                if (tv < tasksV) {
-                    rr[u] = tv / np;
-                    const int J = tv % np;
-                    r1[u] = s_p[tb][J]; r2[u] = s_q[tb][J];
-                    v0[u] = __ldcg(&Vo[(size_t)rr[u] * ld + r1[u]]);
-                    v1[u] = (r2[u] < b) ? __ldcg(&Vo[(size_t)rr[u] * ld + r2[u]]) : 0.0;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (rr[u] < 0) continue;
-                const int J = (t0 + u * GT) % np;
-                const double cJ = s_c[tb][J], sJ = s_s[tb][J];
-                Vn[(size_t)rr[u] * ld + r1[u]] = cJ * v0[u] - sJ * v1[u];
-                if (r2[u] < b) Vn[(size_t)rr[u] * ld + r2[u]] = sJ * v0[u] + cJ * v1[u];
-            }
-        }
-    };
-
     while (!converged && sweeps < max_sweeps) {
         double offmax = 0.0;               // per thread; reduced once per sweep (no atomics in the step loop)
+        // pair of slot `tid`, advanced incrementally from step to step
+        int pa = 0, pb = 0;
+        if (tid < np) { if (tid == 0) { pa = m - 1; pb = 0; } else { pa = tid % (m - 1); pb = (m - 1 - tid) % (m - 1); } }
         for (int step = 0; step < m - 1; step++) {
-            // ---- (A) loads for this step's rotations ---------------------------------------------
+            // ---- pair table of this step + loads for its rotations --------------------------------
             int p = 0, q = 0;
             double app = 0.0, aqq = 0.0, apq = 0.0;
             if (tid < np) {
-                jc_pair(tid, step, m, p, q);
+                p = min(pa, pb); q = max(pa, pb);
+                s_p[tid] = (short)p; s_q[tid] = (short)q;
                 if (q < b) {
-                    app = __ldcg(&Ao[(size_t)p * ld + p]);
-                    aqq = __ldcg(&Ao[(size_t)q * ld + q]);
-                    apq = __ldcg(&Ao[(size_t)p * ld + q]);
+                    app = __ldcg(&Ao[p * ld + p]);
+                    aqq = __ldcg(&Ao[q * ld + q]);
+                    apq = __ldcg(&Ao[p * ld + q]);
+                }
+                // next step: every rotating player moves on by one
+                if (tid == 0) pb = pb + 1;
+                else { pa = (pa + 1 == m - 1) ? 0 : pa + 1; pb = (pb + 1 == m - 1) ? 0 : pb + 1; }
+            }
+            __syncthreads();
+            // ---- (B) loads: they do not depend on the rotations -----------------------------------
+            double b00[TA], b01[TA], b10[TA], b11[TA];
+            int opr[TA], ops[TA], oqr[TA], oqs[TA];     // element offsets, -1 = bye
+#pragma unroll
+            for (int u = 0; u < TA; u++) {
+                opr[u] = ops[u] = oqr[u] = oqs[u] = -1;
+                if (tI[u] < np) {
+                    const int pi = s_p[tI[u]], qi = s_q[tI[u]], ri = s_p[tJ[u]], si = s_q[tJ[u]];
+                    opr[u] = pi * ld + ri;
+                    if (si < b) ops[u] = pi * ld + si;
+                    if (qi < b) oqr[u] = qi * ld + ri;
+                    if (qi < b && si < b) oqs[u] = qi * ld + si;
+                    b00[u] = __ldcg(Ao + opr[u]);
+                    b01[u] = ops[u] >= 0 ? __ldcg(Ao + ops[u]) : 0.0;
+                    b10[u] = oqr[u] >= 0 ? __ldcg(Ao + oqr[u]) : 0.0;
+                    b11[u] = oqs[u] >= 0 ? __ldcg(Ao + oqs[u]) : 0.0;
                 }
             }
-            // ---- (V) eigenvectors catch up with the previous step while those loads fly ---------
-            if (have_prev) {
-                apply_v(cur ^ 1);
-                double *tV = Vo; Vo = Vn; Vn = tV;
-            }
-            // ---- (A) rotations -------------------------------------------------------------------
+            // ---- (A) rotations, published through shared memory and logged for vapply_kernel ------
             if (tid < np) {
-                double c = 1.0, s = 0.0, t = 0.0;
+                double c = 1.0, s = 0.0;
                 if (q < b) {
                     const double aoff = fabs(apq);
                     offmax = fmax(offmax, aoff);
-                    if (aoff > 1e-300 && aoff > 1e-18 * sqrt(fabs(app) * fabs(aqq))) {
-                        const double tau = (aqq - app) / (2.0 * apq);
-                        t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                        c = rsqrt(1.0 + t * t);
+                    const double dd = aqq - app;
+                    // rotate unless a_pq is negligible against both the diagonal gap and the diagonal
+                    if (aoff > 1e-300 && aoff > 1e-20 * (fabs(dd) + fabs(app) + fabs(aqq))) {
+                        // t = sgn(tau) / (|tau| + sqrt(1 + tau^2)), tau = dd / (2 a_pq), written without
+                        // the division:  t = 2 a_pq sgn / (|dd| + sqrt(dd^2 + 4 a_pq^2))
+                        const double h = sqrt(fma(dd, dd, 4.0 * apq * apq));
+                        double t = 2.0 * apq * fast_rcp(fabs(dd) + h);
+                        if (dd < 0.0) t = -t;
+                        // c^2 + s^2 = 1 to working precision whatever the accuracy of t
+                        c = fast_rsqrt(fma(t, t, 1.0));
                         s = t * c;
                     }
                 }
-                s_c[cur][tid] = c; s_s[cur][tid] = s; s_t[tid] = t; s_p[cur][tid] = (short)p; s_q[cur][tid] = (short)q;
+                s_c[tid] = c; s_s[tid] = s;
+                if (crank == 0) rotlog[logpos * np + tid] = make_double2(c, s);
             }
-            // ---- (B) 2x2 blocks: loads first (they do not depend on the rotations) -------------
-            bool synced = false;
-            for (int base = 0; base < tasksA; base += GT * JC_TA) {      // uniform trip count: barrier inside
-                const int t0 = base + gtid;
-                double b00[JC_TA], b01[JC_TA], b10[JC_TA], b11[JC_TA];
-                int pi[JC_TA], qi[JC_TA], ri[JC_TA], si[JC_TA];
-                // pair indices come from the schedule, not from shared memory, so no barrier is needed yet
+            __syncthreads();
 #pragma unroll
-                for (int u = 0; u < JC_TA; u++) {
-                    const int task = t0 + u * GT;
-                    pi[u] = -1;
-                    if (task < tasksA) {
-                        jc_pair(task / np, step, m, pi[u], qi[u]);
-                        jc_pair(task % np, step, m, ri[u], si[u]);
-                        const bool qv = qi[u] < b, sv = si[u] < b;
-                        b00[u] = __ldcg(&Ao[(size_t)pi[u] * ld + ri[u]]);
-                        b01[u] = sv ? __ldcg(&Ao[(size_t)pi[u] * ld + si[u]]) : 0.0;
-                        b10[u] = qv ? __ldcg(&Ao[(size_t)qi[u] * ld + ri[u]]) : 0.0;
-                        b11[u] = (qv && sv) ? __ldcg(&Ao[(size_t)qi[u] * ld + si[u]]) : 0.0;
-                    }
-                }
-                if (!synced) { __syncthreads(); synced = true; }   // rotations of this step are in shared memory
-#pragma unroll
-                for (int u = 0; u < JC_TA; u++) {
-                    if (pi[u] < 0) continue;
-                    const int task = t0 + u * GT;
-                    const int I = task / np, J = task % np;
-                    const bool qv = qi[u] < b, sv = si[u] < b;
-                    const double cI = s_c[cur][I], sI = s_s[cur][I], cJ = s_c[cur][J], sJ = s_s[cur][J];
-                    // T = B * J_J ; B' = J_I^T * T ; J = [[c, s], [-s, c]]
-                    const double t00 = cJ * b00[u] - sJ * b01[u], t01 = sJ * b00[u] + cJ * b01[u];
-                    const double t10 = cJ * b10[u] - sJ * b11[u], t11 = sJ * b10[u] + cJ * b11[u];
-                    double n00 = cI * t00 - sI * t10, n01 = cI * t01 - sI * t11;
-                    double n10 = sI * t00 + cI * t10, n11 = sI * t01 + cI * t11;
-                    if (I == J && qv && s_t[I] != 0.0) {
-                        const double tt = s_t[I];
-                        n00 = b00[u] - tt * b01[u]; n11 = b11[u] + tt * b01[u]; n01 = 0.0; n10 = 0.0;
-                    }
-                    An[(size_t)pi[u] * ld + ri[u]] = n00;
-                    if (sv) An[(size_t)pi[u] * ld + si[u]] = n01;
-                    if (qv) An[(size_t)qi[u] * ld + ri[u]] = n10;
-                    if (qv && sv) An[(size_t)qi[u] * ld + si[u]] = n11;
-                }
+            for (int u = 0; u < TA; u++) {
+                if (tI[u] >= np) continue;
+                const double cI = s_c[tI[u]], sI = s_s[tI[u]], cJ = s_c[tJ[u]], sJ = s_s[tJ[u]];
+                // T = B * J_J ; B' = J_I^T * T ; J = [[c, s], [-s, c]]
+                const double t00 = cJ * b00[u] - sJ * b01[u], t01 = sJ * b00[u] + cJ * b01[u];
+                const double t10 = cJ * b10[u] - sJ * b11[u], t11 = sJ * b10[u] + cJ * b11[u];
+                An[opr[u]] = cI * t00 - sI * t10;
+                if (ops[u] >= 0) An[ops[u]] = cI * t01 - sI * t11;
+                if (oqr[u] >= 0) An[oqr[u]] = sI * t00 + cI * t10;
+                if (oqs[u] >= 0) An[oqs[u]] = sI * t01 + cI * t11;
             }
-            cluster.sync();     // release/acquire at cluster scope; also invalidates L1
-            double *tA = Ao; Ao = An; An = tA;
-            have_prev = true;
-            cur ^= 1;
+            cluster.sync();     // release/acquire at cluster scope
+            const double *tA = Ao; Ao = An; An = (double *)tA;
+            logpos++;
         }
         sweeps++;
         // every CTA saw the same rotations, so the maximum is identical in all of them
@@ -199,15 +185,56 @@ jacobi_kernel(double *A0, double *A1, double *V0, double *V1,
         converged = s_off <= tolabs;
         __syncthreads();
     }
-    if (have_prev) {            // the last step's rotations
-        apply_v(cur ^ 1);
-        double *tV = Vo; Vo = Vn; Vn = tV;
-    }
     if (gtid == 0) {
         info[0] = sweeps;
         info[1] = (Ao == A0) ? 0 : 1;     // which buffer holds the diagonalised matrix
         info[2] = converged ? 1 : 0;
-        info[3] = (Vo == V0) ? 0 : 1;     // which buffer holds the eigenvectors
+    }
+}
+
+// V = J_1 J_2 ... J_S (all logged steps applied to the identity), two rows of V per CTA in shared
+// memory; thread J owns pair J of every step, so a step is two loads, four FMAs and a barrier.
+#define VA_ROWS 2
+__global__ void __launch_bounds__(JC_MAXPAIRS)
+vapply_kernel(const double2 *__restrict__ rotlog, const int *__restrict__ info, int b, int ld, double *__restrict__ V) {
+    extern __shared__ double s_row[];        // VA_ROWS x (b + 1)
+    const int tid = threadIdx.x;
+    const int m = (b + 1) & ~1, np = m / 2;
+    const int r0 = blockIdx.x * VA_ROWS;
+    const long nsteps = (long)info[0] * (m - 1);
+    for (int idx = tid; idx < VA_ROWS * (b + 1); idx += blockDim.x) {
+        const int rr = idx / (b + 1), c = idx % (b + 1);
+        s_row[idx] = (r0 + rr == c) ? 1.0 : 0.0;
+    }
+    int pa = 0, pb = 0;
+    if (tid < np) { if (tid == 0) { pa = m - 1; pb = 0; } else { pa = tid % (m - 1); pb = (m - 1 - tid) % (m - 1); } }
+    double2 cs = (tid < np && nsteps > 0) ? rotlog[tid] : make_double2(1.0, 0.0);
+    __syncthreads();
+    int step = 0;
+    for (long g = 0; g < nsteps; g++) {
+        double2 nxt = (tid < np && g + 1 < nsteps) ? rotlog[(g + 1) * np + tid] : make_double2(1.0, 0.0);
+        if (tid < np) {
+            const int p = min(pa, pb), q = max(pa, pb);      // q == b (bye) lands in the padding column
+#pragma unroll
+            for (int rr = 0; rr < VA_ROWS; rr++) {
+                double *row = s_row + rr * (b + 1);
+                const double v0 = row[p], v1 = row[q];
+                row[p] = cs.x * v0 - cs.y * v1;
+                row[q] = cs.y * v0 + cs.x * v1;
+            }
+            if (tid == 0) pb = pb + 1;
+            else { pa = (pa + 1 == m - 1) ? 0 : pa + 1; pb = (pb + 1 == m - 1) ? 0 : pb + 1; }
+        }
+        if (++step == m - 1) {      // new sweep: the schedule starts over
+            step = 0;
+            if (tid < np) { if (tid == 0) { pa = m - 1; pb = 0; } else { pa = tid % (m - 1); pb = (m - 1 - tid) % (m - 1); } }
+        }
+        cs = nxt;
+        __syncthreads();
+    }
+    for (int idx = tid; idx < VA_ROWS * b; idx += blockDim.x) {
+        const int rr = idx / b, c = idx % b;
+        if (r0 + rr < b) V[(size_t)(r0 + rr) * ld + c] = s_row[rr * (b + 1) + c];
     }
 }
 
@@ -241,18 +268,31 @@ int tp_jacobi(tp_ctx *ctx, double *A, int b, int ld, double *w, double *Vs, int 
               double tol) {
     TP_ARG(b >= 1 && (b + 1) / 2 <= JC_MAXPAIRS, "tp_jacobi: matrix too large for the cluster Jacobi solver");
     cudaStream_t st = ctx->stream;
+    const int max_sweeps = 40;
+    const int m = (b + 1) & ~1, np = m / 2;
     const size_t mat = (size_t)b * ld * sizeof(double);
-    TP_TRY(ctx->Jt.reserve(3 * mat + 64));
-    double *A1 = ctx->Jt.as<double>(), *V0 = A1 + (size_t)b * ld, *V1 = V0 + (size_t)b * ld;
-    int *info = (int *)(V1 + (size_t)b * ld);
+    const size_t logbytes = (size_t)max_sweeps * (m - 1) * np * sizeof(double2);
+    TP_TRY(ctx->Jt.reserve(2 * mat + logbytes + 64));
+    double *A1 = ctx->Jt.as<double>(), *V = A1 + (size_t)b * ld;
+    double2 *rotlog = (double2 *)(V + (size_t)b * ld);
+    int *info = (int *)((char *)rotlog + logbytes);
+    const int GT = JC_CLUSTER * JC_THREADS;
+    const int ta = (np * np + GT - 1) / GT;
     tp_prof_begin(ctx, PC_JACOBI);
-    jacobi_kernel<<<JC_CLUSTER, JC_THREADS, 0, st>>>(A, A1, V0, V1, b, ld, 40, tol, info);
+    if (ta <= 1) jacobi_kernel<1><<<JC_CLUSTER, JC_THREADS, 0, st>>>(A, A1, rotlog, b, ld, max_sweeps, tol, info);
+    else if (ta <= 2) jacobi_kernel<2><<<JC_CLUSTER, JC_THREADS, 0, st>>>(A, A1, rotlog, b, ld, max_sweeps, tol, info);
+    else if (ta <= 4) jacobi_kernel<4><<<JC_CLUSTER, JC_THREADS, 0, st>>>(A, A1, rotlog, b, ld, max_sweeps, tol, info);
+    else if (ta <= 8) jacobi_kernel<8><<<JC_CLUSTER, JC_THREADS, 0, st>>>(A, A1, rotlog, b, ld, max_sweeps, tol, info);
+    else if (ta <= 16) jacobi_kernel<16><<<JC_CLUSTER, JC_THREADS, 0, st>>>(A, A1, rotlog, b, ld, max_sweeps, tol, info);
+    else { tp_set_error("tp_jacobi: b = %d needs more than 16 blocks per thread", b); return TP_ERR_ARG; }
+    const size_t vsm = (size_t)VA_ROWS * (b + 1) * sizeof(double);
+    vapply_kernel<<<(b + VA_ROWS - 1) / VA_ROWS, JC_MAXPAIRS, vsm, st>>>(rotlog, info, b, ld, V);
     tp_prof_end(ctx);
-    ctx->launches += 1;
+    ctx->launches += 2;
     TP_CUDA(cudaGetLastError());
     TP_TRY(tp_pin_reserve(ctx, 64));
     int *h = (int *)ctx->pin;
-    TP_CUDA(cudaMemcpyAsync(h, info, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    TP_CUDA(cudaMemcpyAsync(h, info, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
     TP_CUDA(cudaStreamSynchronize(st));
     if (sweeps_out) *sweeps_out = h[0];
     if (getenv("TADPOLE_DEBUG")) fprintf(stderr, "[tadpole] jacobi b=%d tol=%.1e sweeps=%d converged=%d\n", b, tol, h[0], h[2]);
@@ -260,9 +300,9 @@ int tp_jacobi(tp_ctx *ctx, double *A, int b, int ld, double *w, double *Vs, int 
         tp_set_error("tp_jacobi: no convergence after %d sweeps (b = %d)", h[0], b);
         return TP_ERR_NOCONV;
     }
-    const double *Af = h[1] ? A1 : A, *Vf = h[3] ? V1 : V0;
+    const double *Af = h[1] ? A1 : A;
     int grid = b < 4 * ctx->sm_count ? b : 4 * ctx->sm_count;
-    sort_eig_kernel<<<grid, 256, (size_t)b * sizeof(int), st>>>(Af, Vf, b, ld, w, Vs, lds, ncols_out);
+    sort_eig_kernel<<<grid, 256, (size_t)b * sizeof(int), st>>>(Af, V, b, ld, w, Vs, lds, ncols_out);
     ctx->launches += 1;
     TP_CUDA(cudaGetLastError());
     return TP_OK;
@@ -275,37 +315,55 @@ int tp_jacobi(tp_ctx *ctx, double *A, int b, int ld, double *w, double *Vs, int 
 // eigen-decomposition based orthonormalisation.
 // ------------------------------------------------------------------------------------------------
 #define CH_THREADS 1024
+#define CH_PW 32                 // panel width
 __global__ void __launch_bounds__(CH_THREADS, 1)
 chol_inv_kernel(double *__restrict__ G, double *__restrict__ Linv, int b, int ld, int *__restrict__ info) {
-    extern __shared__ double s_col[];          // current column of L, b doubles
+    extern __shared__ double s_pan[];          // panel rows [j0, b) x CH_PW columns, pitch CH_PW + 1
     __shared__ double s_d;
     __shared__ int s_bad;
     const int tid = threadIdx.x;
+    constexpr int PP = CH_PW + 1;
     if (tid == 0) s_bad = 0;
     __syncthreads();
-    for (int j = 0; j < b; j++) {
-        if (tid == 0) {
-            const double d = G[(size_t)j * ld + j];
-            if (!(d > 0.0)) s_bad = 1;
-            s_d = sqrt(d > 0.0 ? d : 1.0);
-            G[(size_t)j * ld + j] = s_d;
+    // blocked right-looking Cholesky, lower triangle; the panel is factored in shared memory
+    for (int j0 = 0; j0 < b && !s_bad; j0 += CH_PW) {
+        const int w = min(CH_PW, b - j0), rows = b - j0;
+        for (int idx = tid; idx < rows * w; idx += CH_THREADS) {
+            const int r = idx / w, c = idx % w;
+            s_pan[r * PP + c] = G[(size_t)(j0 + r) * ld + j0 + c];
         }
         __syncthreads();
-        if (s_bad) break;
-        const double inv = 1.0 / s_d;
-        for (int i = j + 1 + tid; i < b; i += CH_THREADS) {
-            const double v = G[(size_t)i * ld + j] * inv;
-            G[(size_t)i * ld + j] = v;
-            s_col[i] = v;
+        for (int c = 0; c < w; c++) {
+            if (tid == 0) {
+                const double d = s_pan[c * PP + c];
+                if (!(d > 0.0)) s_bad = 1;
+                s_d = sqrt(d > 0.0 ? d : 1.0);
+            }
+            __syncthreads();
+            const double inv = 1.0 / s_d;
+            for (int r = c + tid; r < rows; r += CH_THREADS) s_pan[r * PP + c] = (r == c) ? s_d : s_pan[r * PP + c] * inv;
+            __syncthreads();
+            // remaining panel columns c2 in (c, w): P[r][c2] -= P[r][c] * P[c2][c], r >= c2
+            const int nc = w - c - 1;
+            for (int idx = tid; idx < (rows - c - 1) * nc; idx += CH_THREADS) {
+                const int r = c + 1 + idx / nc, c2 = c + 1 + idx % nc;
+                if (r >= c2) s_pan[r * PP + c2] -= s_pan[r * PP + c] * s_pan[c2 * PP + c];
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        // trailing lower triangle: G[i][k] -= L[i][j] L[k][j], j < k <= i; rows split over warps
-        const int rem = b - j - 1;
-        const int lane = tid & 31, wid = tid >> 5;
-        for (int r = wid; r < rem; r += CH_THREADS / 32) {
-            const int i = j + 1 + r;
-            const double li = s_col[i];
-            for (int k = j + 1 + lane; k <= i; k += 32) G[(size_t)i * ld + k] -= li * s_col[k];
+        for (int idx = tid; idx < rows * w; idx += CH_THREADS) {
+            const int r = idx / w, c = idx % w;
+            if (r >= c) G[(size_t)(j0 + r) * ld + j0 + c] = s_pan[r * PP + c];
+        }
+        // trailing update: G[i][k] -= sum_c P[i][c] P[k][c] for j0 + w <= k <= i < b
+        const int t0 = w, tn = rows - w;       // panel-relative rows [t0, rows)
+        for (int idx = tid; idx < tn * tn; idx += CH_THREADS) {
+            const int ri = t0 + idx / tn, rk = t0 + idx % tn;
+            if (rk > ri) continue;
+            double acc = 0.0;
+#pragma unroll 8
+            for (int c = 0; c < w; c++) acc += s_pan[ri * PP + c] * s_pan[rk * PP + c];
+            G[(size_t)(j0 + ri) * ld + j0 + rk] -= acc;
         }
         __syncthreads();
     }
@@ -339,9 +397,11 @@ int tp_chol_inv(tp_ctx *ctx, double *G, double *Linv, int b, int ld, int *bad_ou
     cudaStream_t st = ctx->stream;
     TP_TRY(ctx->Jt.reserve(64));
     int *info = ctx->Jt.as<int>();
-    TP_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(b * sizeof(double))));
+    const size_t chsm = (size_t)b * (CH_PW + 1) * sizeof(double);
+    TP_ARG(chsm <= (size_t)ctx->max_smem_optin, "tp_chol_inv: block too wide for the shared-memory panel");
+    TP_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chsm));
     tp_prof_begin(ctx, PC_JACOBI);
-    chol_inv_kernel<<<1, CH_THREADS, b * sizeof(double), st>>>(G, Linv, b, ld, info);
+    chol_inv_kernel<<<1, CH_THREADS, chsm, st>>>(G, Linv, b, ld, info);
     tp_prof_end(ctx);
     ctx->launches += 1;
     TP_CUDA(cudaGetLastError());

@@ -311,10 +311,11 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
             double *t = Y; Y = F1; F1 = t;
             return e;
         };
-        // Cholesky QR, two passes: Y <- Y L^-T.  Returns 1 in *bad when the Gram matrix is not PD.
-        auto cholqr2 = [&](int *bad) {
+        // Cholesky QR: Y <- Y L^-T.  One pass leaves ~cond^2 * eps of non-orthogonality, which is enough
+        // between two filter rounds; two passes before a Rayleigh-Ritz step.  *bad = 1 when G is not PD.
+        auto cholqr = [&](int passes, int *bad) {
             *bad = 0;
-            for (int pass = 0; pass < 2; pass++) {
+            for (int pass = 0; pass < passes; pass++) {
                 TP_TRY(gram(Y, Y, G));
                 TP_TRY(tp_chol_inv(ctx, G, S1, b, ldb, bad));
                 if (*bad) return (int)TP_OK;
@@ -377,10 +378,14 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
         auto body = [&]() -> int {
             random_block_kernel<<<(unsigned)(((size_t)n * ldb + 255) / 256), 256, 0, st>>>(Y, n, b, ldb);
             ctx->launches += 1;
-            TP_TRY(op.apply(Y, W, 1.0, nullptr, 0.0, nullptr, 0.0));
-            TP_TRY(rr_general(1e-5));
+            {   // start: orthonormalise the random block, one Rayleigh-Ritz step at low accuracy
+                int bad = 0;
+                TP_TRY(cholqr(2, &bad));
+                TP_TRY(op.apply(Y, W, 1.0, nullptr, 0.0, nullptr, 0.0));
+                if (bad) TP_TRY(rr_general(1e-5)); else TP_TRY(rr_orthonormal(1e-5));
+            }
             double *hbuf = (double *)ctx->pin;
-            const int inner = 2;             // filter + CholQR rounds between two Rayleigh-Ritz steps
+            const int inner = ctx->pca_inner;   // filter + CholQR rounds between two Rayleigh-Ritz steps
             for (it = 1; it <= ctx->pca_maxit * 2; it++) {
                 // ---- bounds from the current Ritz values -----------------------------------------
                 TP_CUDA(cudaMemcpyAsync(hbuf, theta, (size_t)b * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -417,7 +422,7 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
                     if (r > 0) TP_TRY(filter_step1());
                     TP_TRY(filter_rest());
                     int bad = 0;
-                    TP_TRY(cholqr2(&bad));
+                    TP_TRY(cholqr(r + 1 == inner ? 2 : 1, &bad));
                     if (bad) { general = true; break; }
                 }
                 TP_TRY(op.apply(Y, W, 1.0, nullptr, 0.0, nullptr, 0.0));
