@@ -317,7 +317,7 @@ int tp_jacobi(tp_ctx *ctx, double *A, int b, int ld, double *w, double *Vs, int 
 #define CH_THREADS 1024
 #define CH_PW 32                 // panel width
 __global__ void __launch_bounds__(CH_THREADS, 1)
-chol_inv_kernel(double *__restrict__ G, double *__restrict__ Linv, int b, int ld, int *__restrict__ info) {
+chol_inv_kernel(double *G, double *Linv, int b, int ld, int *info) {
     extern __shared__ double s_pan[];          // panel rows [j0, b) x CH_PW columns, pitch CH_PW + 1
     __shared__ double s_d;
     __shared__ int s_bad;
@@ -333,24 +333,36 @@ chol_inv_kernel(double *__restrict__ G, double *__restrict__ Linv, int b, int ld
             s_pan[r * PP + c] = G[(size_t)(j0 + r) * ld + j0 + c];
         }
         __syncthreads();
-        for (int c = 0; c < w; c++) {
-            if (tid == 0) {
+        // (1) warp 0 factors the w x w diagonal block (lane = row), column by column
+        if (tid < 32) {
+            for (int c = 0; c < w; c++) {
                 const double d = s_pan[c * PP + c];
-                if (!(d > 0.0)) s_bad = 1;
-                s_d = sqrt(d > 0.0 ? d : 1.0);
+                const bool ok = d > 0.0;
+                if (!ok && tid == 0) s_bad = 1;
+                const double piv = sqrt(ok ? d : 1.0);
+                __syncwarp();
+                if (tid == c) s_pan[c * PP + c] = piv;
+                if (tid > c && tid < w) s_pan[tid * PP + c] *= 1.0 / piv;
+                __syncwarp();
+                // row `tid` of the remaining block: P[tid][c2] -= P[tid][c] * P[c2][c], c < c2 <= tid
+                if (tid > c && tid < w) {
+                    const double lrc = s_pan[tid * PP + c];
+                    for (int c2 = c + 1; c2 <= tid; c2++) s_pan[tid * PP + c2] -= lrc * s_pan[c2 * PP + c];
+                }
+                __syncwarp();
             }
-            __syncthreads();
-            const double inv = 1.0 / s_d;
-            for (int r = c + tid; r < rows; r += CH_THREADS) s_pan[r * PP + c] = (r == c) ? s_d : s_pan[r * PP + c] * inv;
-            __syncthreads();
-            // remaining panel columns c2 in (c, w): P[r][c2] -= P[r][c] * P[c2][c], r >= c2
-            const int nc = w - c - 1;
-            for (int idx = tid; idx < (rows - c - 1) * nc; idx += CH_THREADS) {
-                const int r = c + 1 + idx / nc, c2 = c + 1 + idx % nc;
-                if (r >= c2) s_pan[r * PP + c2] -= s_pan[r * PP + c] * s_pan[c2 * PP + c];
-            }
-            __syncthreads();
         }
+        __syncthreads();
+        // (2) rows below the diagonal block: solve x L11^T = a, one thread per row
+        for (int r = w + tid; r < rows; r += CH_THREADS) {
+            double *row = s_pan + r * PP;
+            for (int c = 0; c < w; c++) {
+                double s = row[c];
+                for (int t = 0; t < c; t++) s -= row[t] * s_pan[c * PP + t];
+                row[c] = s / s_pan[c * PP + c];
+            }
+        }
+        __syncthreads();
         for (int idx = tid; idx < rows * w; idx += CH_THREADS) {
             const int r = idx / w, c = idx % w;
             if (r >= c) G[(size_t)(j0 + r) * ld + j0 + c] = s_pan[r * PP + c];
@@ -369,24 +381,71 @@ chol_inv_kernel(double *__restrict__ G, double *__restrict__ Linv, int b, int ld
     }
     if (s_bad) { if (tid == 0) info[0] = 1; return; }
     if (tid == 0) info[0] = 0;
-    // Linv by forward substitution, one column per group of 4 lanes; loops are uniform across the
-    // warp so that the shuffles are always executed by all lanes
-    const int grp = tid >> 2, sub = tid & 3;
-    for (int cbase = 0; cbase < b; cbase += CH_THREADS / 4) {
-        const int c = cbase + grp;
-        const bool cv = c < b;
-        for (int i = 0; i < b; i++) {
-            double s = 0.0;
-            if (cv && i > c)
-                for (int jj = c + sub; jj < i; jj += 4) s += G[(size_t)i * ld + jj] * Linv[(size_t)jj * ld + c];
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (cv && sub == 0) {
-                double x = 0.0;
-                if (i >= c) x = ((i == c ? 1.0 : 0.0) - s) / G[(size_t)i * ld + i];
-                Linv[(size_t)i * ld + c] = x;
+    __syncthreads();
+    // ---- Linv = L^-1, blocked: 32 x 32 diagonal blocks by forward substitution (one warp each, one
+    // column per lane), then every block column j independently: X_ij = -X_ii * sum_{k=j}^{i-1} L_ik X_kj
+    const int nb = (b + CH_PW - 1) / CH_PW;
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int idx = tid; idx < b * b; idx += CH_THREADS) {       // clear (upper triangle must be zero)
+        const int r = idx / b, c = idx % b;
+        if (c > r || (r / CH_PW) != (c / CH_PW)) Linv[(size_t)r * ld + c] = 0.0;
+    }
+    for (int d = wid; d < nb; d += CH_THREADS / 32) {
+        const int o = d * CH_PW, w = min(CH_PW, b - o);
+        double *Ld = s_pan + (size_t)(d % (CH_THREADS / 32)) * CH_PW * PP;     // this warp's copy of L_dd
+        for (int r = 0; r < w; r++) Ld[r * PP + lane] = (lane < w) ? G[(size_t)(o + r) * ld + o + lane] : 0.0;
+        __syncwarp();
+        // lane c: column c of the inverse
+        double x[CH_PW];
+#pragma unroll
+        for (int i = 0; i < CH_PW; i++) {
+            double s = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+            for (int jj = 0; jj < CH_PW; jj++) if (jj < i) s -= Ld[i * PP + jj] * x[jj];
+            x[i] = (i < w && lane < w && i >= lane) ? s / Ld[i * PP + i] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < CH_PW; i++) if (i < w && lane < w) Linv[(size_t)(o + i) * ld + o + lane] = x[i];
+        __syncwarp();
+    }
+    __syncthreads();
+    // block columns: group g = tid / tpg owns block column g; all groups walk i together
+    const int tpg = max(32, (CH_THREADS / max(nb, 1)) & ~31);      // threads per group (multiple of 32)
+    const int ngroups = CH_THREADS / tpg;
+    double *S = s_pan;                                            // per group 32 x PP scratch
+    for (int jb0 = 0; jb0 < nb; jb0 += ngroups) {
+        const int g = tid / tpg, gt = tid % tpg;
+        const int jb = jb0 + g;
+        double *Sg = S + (size_t)g * CH_PW * PP;
+        for (int ib = jb0 + 1; ib < nb; ib++) {
+            const bool act = g < ngroups && jb < nb && ib > jb;
+            if (act) {
+                for (int e = gt; e < CH_PW * CH_PW; e += tpg) {
+                    const int r = e / CH_PW, c = e % CH_PW;
+                    const int gr = ib * CH_PW + r, gc = jb * CH_PW + c;
+                    double acc = 0.0;
+                    if (gr < b && gc < b) {
+                        const double *Lrow = G + (size_t)gr * ld;
+                        for (int t = jb * CH_PW + c; t < ib * CH_PW; t++)     // X_kj is lower triangular: t >= gc
+                            acc += Lrow[t] * Linv[(size_t)t * ld + gc];   // same CTA wrote it: visible after the barrier
+                    }
+                    Sg[r * PP + c] = acc;
+                }
             }
-            __syncwarp();
+            __syncthreads();
+            if (act) {
+                for (int e = gt; e < CH_PW * CH_PW; e += tpg) {
+                    const int r = e / CH_PW, c = e % CH_PW;
+                    const int gr = ib * CH_PW + r, gc = jb * CH_PW + c;
+                    if (gr < b && gc < b) {
+                        double acc = 0.0;
+                        for (int t = 0; t <= r; t++)                        // X_ii lower triangular
+                            acc += Linv[(size_t)gr * ld + ib * CH_PW + t] * Sg[t * PP + c];
+                        Linv[(size_t)gr * ld + gc] = -acc;
+                    }
+                }
+            }
+            __syncthreads();
         }
     }
 }
@@ -397,7 +456,9 @@ int tp_chol_inv(tp_ctx *ctx, double *G, double *Linv, int b, int ld, int *bad_ou
     cudaStream_t st = ctx->stream;
     TP_TRY(ctx->Jt.reserve(64));
     int *info = ctx->Jt.as<int>();
-    const size_t chsm = (size_t)b * (CH_PW + 1) * sizeof(double);
+    size_t chsm = (size_t)b * (CH_PW + 1) * sizeof(double);
+    const size_t chsm2 = (size_t)32 * CH_PW * (CH_PW + 1) * sizeof(double) > (size_t)0 ? (size_t)((b + CH_PW - 1) / CH_PW < 32 ? (b + CH_PW - 1) / CH_PW : 32) * CH_PW * (CH_PW + 1) * sizeof(double) : 0;
+    if (chsm2 > chsm) chsm = chsm2;
     TP_ARG(chsm <= (size_t)ctx->max_smem_optin, "tp_chol_inv: block too wide for the shared-memory panel");
     TP_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chsm));
     tp_prof_begin(ctx, PC_JACOBI);
