@@ -71,7 +71,42 @@ __global__ void d0_kernel(const double *__restrict__ s, int n, int k, int ldk, d
 // ------------------------------------------------------------------------------------------
 // the merge loop
 // ------------------------------------------------------------------------------------------
-template <typename LinkT, bool LINKS_SMEM>
+// shared memory through explicit 32-bit shared-window addresses: the merge loop is one warp's
+// dependent chain, so every instruction of address arithmetic the compiler would add for generic
+// pointers is latency on the critical path
+__device__ __forceinline__ double lds_f64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_f64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ int lds_u16(unsigned a) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_u16(unsigned a, int v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ int lds_s32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_s32(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+template <typename LinkT, bool SMEM> struct Links {
+    unsigned sp, sn;          // shared addresses (SMEM)
+    LinkT *gp, *gn;           // global pointers (!SMEM)
+    __device__ __forceinline__ int prv(int j) const {
+        if (SMEM) return sizeof(LinkT) == 2 ? lds_u16(sp + 2 * j) : lds_s32(sp + 4 * j);
+        return (int)__ldcg(gp + j);
+    }
+    __device__ __forceinline__ int nxt(int j) const {
+        if (SMEM) return sizeof(LinkT) == 2 ? lds_u16(sn + 2 * j) : lds_s32(sn + 4 * j);
+        return (int)__ldcg(gn + j);
+    }
+    __device__ __forceinline__ void set_prv(int j, int v) const {
+        if (SMEM) { if (sizeof(LinkT) == 2) sts_u16(sp + 2 * j, v); else sts_s32(sp + 4 * j, v); }
+        else __stcg(gp + j, (LinkT)v);
+    }
+    __device__ __forceinline__ void set_nxt(int j, int v) const {
+        if (SMEM) { if (sizeof(LinkT) == 2) sts_u16(sn + 2 * j, v); else sts_s32(sn + 4 * j, v); }
+        else __stcg(gn + j, (LinkT)v);
+    }
+};
+
+#define CS_CHUNK 8     // 8 x 32 = 256 score columns loaded per batch
+
+// INV_SMEM: a table of 1/m, m = 0..n, sits in shared memory (cluster sizes are integers), replacing
+// the five FP64 divisions of a merge step by loads
+template <typename LinkT, bool LINKS_SMEM, bool INV_SMEM>
 __global__ void __launch_bounds__(32)
 coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
                     const double *__restrict__ d0, int ldd,
@@ -89,120 +124,150 @@ coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
     const int B2 = B1p >> 5;
     const int B2p = (B2 + 31) & ~31;
 
-    double *d = (double *)smem_raw;
-    double *m1 = d + n1p;
-    double *m2 = m1 + B1p;
-    LinkT *prv, *nxt;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned sd = sbase;                       // d[n1p]
+    const unsigned sm1 = sd + 8u * n1p;              // m1[B1p]
+    const unsigned sm2 = sm1 + 8u * B1p;             // m2[B2p]
+    unsigned top = sm2 + 8u * B2p;
+    Links<LinkT, LINKS_SMEM> lk;
+    lk.sp = lk.sn = 0; lk.gp = lk.gn = nullptr;
     if (LINKS_SMEM) {
-        prv = (LinkT *)(m2 + B2p);
-        nxt = prv + n1;
+        lk.sp = top; lk.sn = top + (unsigned)sizeof(LinkT) * n1;
+        top = (lk.sn + (unsigned)sizeof(LinkT) * n1 + 7u) & ~7u;
     } else {
-        prv = glinks + (size_t)blockIdx.x * 2 * n1;
-        nxt = prv + n1;
+        lk.gp = glinks + (size_t)blockIdx.x * 2 * n1;
+        lk.gn = lk.gp + n1;
     }
+    const unsigned sinv = top;                       // inv[n + 1] when INV_SMEM
     const double *d0row = d0 + (size_t)cand * ldd;
     double *seq = seqdist + (size_t)cand * ldd;
     int4 *mrg = merges + (size_t)cand * ldd;
 
-    for (int j = lane; j < n1p; j += 32) d[j] = (j < n1) ? d0row[j] : INF_D;
-    for (int j = lane; j < n1; j += 32) { st_link<LINKS_SMEM>(prv + j, j); st_link<LINKS_SMEM>(nxt + j, j + 1); }   // prv holds index+1, 0 = none
-    for (int b = lane; b < B1p; b += 32) m1[b] = INF_D;
-    for (int b = lane; b < B2p; b += 32) m2[b] = INF_D;
+    for (int j = lane; j < n1p; j += 32) sts_f64(sd + 8u * j, (j < n1) ? d0row[j] : INF_D);
+    for (int j = lane; j < n1; j += 32) { lk.set_prv(j, j); lk.set_nxt(j, j + 1); }   // prv holds index+1, 0 = none
+    for (int b = lane; b < B1p; b += 32) sts_f64(sm1 + 8u * b, INF_D);
+    for (int b = lane; b < B2p; b += 32) sts_f64(sm2 + 8u * b, INF_D);
+    if (INV_SMEM) for (int m = lane; m <= n; m += 32) sts_f64(sinv + 8u * m, m ? 1.0 / (double)m : 0.0);
     __syncwarp();
     for (int b = 0; b < B1; b++) {
-        double v = warp_min_nonneg(d[(b << 5) + lane]);
-        if (lane == 0) m1[b] = v;
+        double v = warp_min_nonneg(lds_f64(sd + 8u * ((b << 5) + lane)));
+        if (lane == 0) sts_f64(sm1 + 8u * b, v);
     }
     __syncwarp();
     for (int b = 0; b < B2; b++) {
-        double v = warp_min_nonneg(m1[(b << 5) + lane]);
-        if (lane == 0) m2[b] = v;
+        double v = warp_min_nonneg(lds_f64(sm1 + 8u * ((b << 5) + lane)));
+        if (lane == 0) sts_f64(sm2 + 8u * b, v);
     }
     __syncwarp();
 
+    auto inv_of = [&](int m) -> double { return INV_SMEM ? lds_f64(sinv + 8u * m) : 1.0 / (double)m; };
+    const double *Plane = P + lane;
     double total = 0.0;
     for (int t = 0; t < n1; t++) {
         // ---- find the lowest-index minimum ------------------------------------------------
-        double v = INF_D;
-        for (int q = lane; q < B2p; q += 32) v = fmin(v, m2[q]);
-        const double mn = warp_min_nonneg(v);
+        double mn;
         int b2 = 0;
-        for (int q0 = 0; q0 < B2p; q0 += 32) {
-            unsigned bal = __ballot_sync(0xffffffffu, m2[q0 + lane] == mn);
-            if (bal) { b2 = q0 + __ffs(bal) - 1; break; }
+        if (B2p == 32) {
+            const double v = lds_f64(sm2 + 8u * lane);
+            mn = warp_min_nonneg(v);
+            b2 = __ffs(__ballot_sync(0xffffffffu, v == mn)) - 1;
+        } else {
+            double v = INF_D;
+            for (int q = lane; q < B2p; q += 32) v = fmin(v, lds_f64(sm2 + 8u * q));
+            mn = warp_min_nonneg(v);
+            for (int q0 = 0; q0 < B2p; q0 += 32) {
+                unsigned bal = __ballot_sync(0xffffffffu, lds_f64(sm2 + 8u * (q0 + lane)) == mn);
+                if (bal) { b2 = q0 + __ffs(bal) - 1; break; }
+            }
         }
-        unsigned bal1 = __ballot_sync(0xffffffffu, m1[(b2 << 5) + lane] == mn);
+        const unsigned bal1 = __ballot_sync(0xffffffffu, lds_f64(sm1 + 8u * ((b2 << 5) + lane)) == mn);
         const int b1 = (b2 << 5) + __ffs(bal1) - 1;
-        unsigned bal0 = __ballot_sync(0xffffffffu, d[(b1 << 5) + lane] == mn);
+        const unsigned bal0 = __ballot_sync(0xffffffffu, lds_f64(sd + 8u * ((b1 << 5) + lane)) == mn);
         const int j = (b1 << 5) + __ffs(bal0) - 1;
 
         // ---- neighbours ---------------------------------------------------------------------
-        const int pj = ld_link<LINKS_SMEM>(prv + j) - 1;         // previous live boundary or -1
-        const int nj = ld_link<LINKS_SMEM>(nxt + j);            // next live boundary or n1
+        const int pj = lk.prv(j) - 1;            // previous live boundary or -1
+        const int nj = lk.nxt(j);                // next live boundary or n1
         const bool hasL = pj >= 0, hasR = nj < n1;
-        const int ppj = hasL ? ld_link<LINKS_SMEM>(prv + pj) - 1 : -1;
-        const int nnj = hasR ? ld_link<LINKS_SMEM>(nxt + nj) : n1;
+        const int ppj = hasL ? lk.prv(pj) - 1 : -1;
+        const int nnj = hasR ? lk.nxt(nj) : n1;
+        // P rows: LL = [a, b), C = [b, c), RR = [c, e)
+        const int a = ppj + 1, b = pj + 1, c = nj + 1, e = nnj + 1;
+        const double *Pa = Plane + (size_t)a * ldk, *Pb = Plane + (size_t)b * ldk;
+        const double *Pc = Plane + (size_t)c * ldk, *Pe = Plane + (size_t)e * ldk;
+        const int cC = c - b, cLL = b - a, cRR = e - c;
+        const double iC = inv_of(cC), iLL = inv_of(cLL), iRR = inv_of(cRR);
+        double accL = 0.0, accR = 0.0;
+        for (int c0 = 0; c0 < ncol; c0 += 32 * CS_CHUNK) {
+            double va[CS_CHUNK], vb[CS_CHUNK], vc[CS_CHUNK], ve[CS_CHUNK];
+            // all loads of the batch first: one L2 round trip per step instead of one per 32 columns
+#pragma unroll
+            for (int u = 0; u < CS_CHUNK; u++) {
+                const int col = c0 + 32 * u;
+                if (col >= ncol) break;
+                const bool ok = col + lane < ncol;
+                vb[u] = ok ? __ldg(Pb + col) : 0.0;
+                vc[u] = ok ? __ldg(Pc + col) : 0.0;
+                va[u] = (ok && hasL) ? __ldg(Pa + col) : 0.0;
+                ve[u] = (ok && hasR) ? __ldg(Pe + col) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < CS_CHUNK; u++) {
+                if (c0 + 32 * u >= ncol) break;
+                const double mC = (vc[u] - vb[u]) * iC;
+                const double tL = hasL ? (vb[u] - va[u]) * iLL - mC : 0.0;
+                const double tR = hasR ? mC - (ve[u] - vc[u]) * iRR : 0.0;
+                accL = fma(tL, tL, accL);
+                accR = fma(tR, tR, accR);
+            }
+        }
         total += mn;
         if (lane == 0) {
             seq[j] = total;
             mrg[t] = make_int4(j, pj, nj, 0);
-        }
-        // P rows: LL = [a, b), C = [b, c), RR = [c, e)
-        const int a = ppj + 1, b = pj + 1, c = nj + 1, e = nnj + 1;
-        const double nC = (double)(c - b), nLL = (double)(b - a), nRR = (double)(e - c);
-        const double iC = 1.0 / nC, iLL = 1.0 / nLL, iRR = 1.0 / nRR;
-        const double *Pa = P + (size_t)a * ldk, *Pb = P + (size_t)b * ldk;
-        const double *Pc = P + (size_t)c * ldk, *Pe = P + (size_t)e * ldk;
-        double accL = 0.0, accR = 0.0;
-        for (int col = lane; col < ncol; col += 32) {
-            const double pb = __ldg(Pb + col), pc = __ldg(Pc + col);
-            const double mC = (pc - pb) * iC;
-            if (hasL) { double tL = (pb - __ldg(Pa + col)) * iLL - mC; accL += tL * tL; }
-            if (hasR) { double tR = mC - (__ldg(Pe + col) - pc) * iRR; accR += tR * tR; }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             accL += __shfl_xor_sync(0xffffffffu, accL, o);
             accR += __shfl_xor_sync(0xffffffffu, accR, o);
         }
-        accL *= nLL * nC / (nLL + nC);
-        accR *= nC * nRR / (nC + nRR);
+        // n_a n_b / (n_a + n_b): integer product (exact), then the table reciprocal
+        accL *= (double)cLL * (double)cC * inv_of(cLL + cC);
+        accR *= (double)cC * (double)cRR * inv_of(cC + cRR);
 
         // ---- write back: boundary j dies, its neighbours get new increases ---------------
         if (lane == 0) {
-            d[j] = INF_D;
-            if (hasL) { d[pj] = accL; st_link<LINKS_SMEM>(nxt + pj, nj); }
-            if (hasR) { d[nj] = accR; st_link<LINKS_SMEM>(prv + nj, pj + 1); }
+            sts_f64(sd + 8u * j, INF_D);
+            if (hasL) { sts_f64(sd + 8u * pj, accL); lk.set_nxt(pj, nj); }
+            if (hasR) { sts_f64(sd + 8u * nj, accR); lk.set_prv(nj, pj + 1); }
         }
         __syncwarp();
         const int k0 = j >> 5;
         const int k1 = hasL ? (pj >> 5) : k0;
         const int k2 = hasR ? (nj >> 5) : k0;
-        {
-            double x = warp_min_nonneg(d[(k0 << 5) + lane]);
-            if (lane == 0) m1[k0] = x;
-        }
-        if (k1 != k0) {
-            double x = warp_min_nonneg(d[(k1 << 5) + lane]);
-            if (lane == 0) m1[k1] = x;
-        }
-        if (k2 != k0) {
-            double x = warp_min_nonneg(d[(k2 << 5) + lane]);
-            if (lane == 0) m1[k2] = x;
+        // independent re-reductions issued back to back (ILP), then stored
+        const double x0 = lds_f64(sd + 8u * ((k0 << 5) + lane));
+        const double x1 = lds_f64(sd + 8u * ((k1 << 5) + lane));
+        const double x2 = lds_f64(sd + 8u * ((k2 << 5) + lane));
+        const double r0 = warp_min_nonneg(x0);
+        const double r1 = (k1 != k0) ? warp_min_nonneg(x1) : r0;
+        const double r2 = (k2 != k0) ? warp_min_nonneg(x2) : r0;
+        if (lane == 0) {
+            sts_f64(sm1 + 8u * k0, r0);
+            if (k1 != k0) sts_f64(sm1 + 8u * k1, r1);
+            if (k2 != k0) sts_f64(sm1 + 8u * k2, r2);
         }
         __syncwarp();
         const int g0 = k0 >> 5, g1 = k1 >> 5, g2 = k2 >> 5;
-        {
-            double x = warp_min_nonneg(m1[(g0 << 5) + lane]);
-            if (lane == 0) m2[g0] = x;
-        }
+        const double y0 = warp_min_nonneg(lds_f64(sm1 + 8u * ((g0 << 5) + lane)));
+        if (lane == 0) sts_f64(sm2 + 8u * g0, y0);
         if (g1 != g0) {
-            double x = warp_min_nonneg(m1[(g1 << 5) + lane]);
-            if (lane == 0) m2[g1] = x;
+            const double y1 = warp_min_nonneg(lds_f64(sm1 + 8u * ((g1 << 5) + lane)));
+            if (lane == 0) sts_f64(sm2 + 8u * g1, y1);
         }
         if (g2 != g0 && g2 != g1) {
-            double x = warp_min_nonneg(m1[(g2 << 5) + lane]);
-            if (lane == 0) m2[g2] = x;
+            const double y2 = warp_min_nonneg(lds_f64(sm1 + 8u * ((g2 << 5) + lane)));
+            if (lane == 0) sts_f64(sm2 + 8u * g2, y2);
         }
         __syncwarp();
     }
@@ -349,27 +414,35 @@ int tp_sweep_device(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stri
     const int n1p = round_up(n1, 32), B1p = round_up(n1p / 32, 32), B2p = round_up(B1p / 32, 32);
     const size_t base = (size_t)(n1p + B1p + B2p) * sizeof(double);
     const bool small_links = n <= 65535;
-    const size_t link_bytes = (size_t)2 * n1 * (small_links ? 2 : 4);
+    const size_t link_bytes = round_up((int)((size_t)2 * n1 * (small_links ? 2 : 4)), 8);
+    const size_t inv_bytes = (size_t)(n + 1) * sizeof(double);
     const size_t limit = (size_t)ctx->max_smem_optin;
     TP_ARG(base <= limit, "tp_sweep: matrix too large for the shared-memory dSS array (n > ~28k bins); split by centromere");
     const bool links_smem = base + link_bytes <= limit;
-    const size_t smem = links_smem ? base + link_bytes : base;
+    size_t smem = links_smem ? base + link_bytes : base;
+    // the reciprocal table goes to shared memory while at least two candidates still fit per SM
+    const bool inv_smem = smem + inv_bytes <= limit / 2;
+    if (inv_smem) smem += inv_bytes;
     void *glinks = nullptr;
     if (!links_smem) {
         TP_TRY(ctx->links.reserve((size_t)ncand * link_bytes));
         glinks = ctx->links.p;
     }
-#define LAUNCH_SWEEP(LT, LS)                                                                              \
+#define LAUNCH_SWEEP(LT, LS, IS)                                                                          \
     do {                                                                                                  \
+        TP_CUDA(cudaFuncSetAttribute(coniss_sweep_kernel<LT, LS, IS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         tp_prof_begin(ctx, PC_SWEEP);                                                                     \
-        TP_CUDA(cudaFuncSetAttribute(coniss_sweep_kernel<LT, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        coniss_sweep_kernel<LT, LS><<<ncand, 32, smem, st>>>(ctx->P.as<double>(), ldk, n, ctx->d0.as<double>(), ldd, \
-                                                             d_cands, ctx->seqdist.as<double>(),           \
-                                                             ctx->order.as<int4>(), (LT *)glinks);         \
+        coniss_sweep_kernel<LT, LS, IS><<<ncand, 32, smem, st>>>(ctx->P.as<double>(), ldk, n, ctx->d0.as<double>(), ldd, \
+                                                                 d_cands, ctx->seqdist.as<double>(),       \
+                                                                 ctx->order.as<int4>(), (LT *)glinks);     \
         tp_prof_end(ctx);                                                                                 \
     } while (0)
-    if (small_links) { if (links_smem) LAUNCH_SWEEP(unsigned short, true); else LAUNCH_SWEEP(unsigned short, false); }
-    else             { if (links_smem) LAUNCH_SWEEP(int, true); else LAUNCH_SWEEP(int, false); }
+    if (small_links) {
+        if (links_smem) { if (inv_smem) LAUNCH_SWEEP(unsigned short, true, true); else LAUNCH_SWEEP(unsigned short, true, false); }
+        else LAUNCH_SWEEP(unsigned short, false, false);
+    } else {
+        if (links_smem) LAUNCH_SWEEP(int, true, false); else LAUNCH_SWEEP(int, false, false);
+    }
 #undef LAUNCH_SWEEP
     ctx->launches += 1;
     TP_CUDA(cudaGetLastError());
