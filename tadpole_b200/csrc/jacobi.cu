@@ -261,12 +261,17 @@ __global__ void sort_eig_kernel(const double *__restrict__ A, const double *__re
         }
 }
 
+int tp_osj(tp_ctx *ctx, double *T, int b, int ld, double *w, double *Vs, int lds, int ncols_out, int *sweeps_out,
+           double tol);
+
 // Eigen-decomposition of the symmetric b x b matrix in A (row-major, ld).  A is destroyed.
 // On return w[0..b) holds the eigenvalues in descending order and Vs (b x lds) the matching
 // eigenvectors in its first ncols_out columns.
 int tp_jacobi(tp_ctx *ctx, double *A, int b, int ld, double *w, double *Vs, int lds, int ncols_out, int *sweeps_out,
               double tol) {
     TP_ARG(b >= 1 && (b + 1) / 2 <= JC_MAXPAIRS, "tp_jacobi: matrix too large for the cluster Jacobi solver");
+    if (b >= 2 && b <= 384 && !getenv("TADPOLE_TWOSIDED"))
+        return tp_osj(ctx, A, b, ld, w, Vs, lds, ncols_out, sweeps_out, tol);
     cudaStream_t st = ctx->stream;
     const int max_sweeps = 40;
     const int m = (b + 1) & ~1, np = m / 2;
@@ -317,13 +322,19 @@ int tp_jacobi(tp_ctx *ctx, double *A, int b, int ld, double *w, double *Vs, int 
 #define CH_THREADS 1024
 #define CH_PW 32                 // panel width
 __global__ void __launch_bounds__(CH_THREADS, 1)
-chol_inv_kernel(double *G, double *Linv, int b, int ld, int *info) {
+chol_inv_kernel(double *G, double *Linv, int b, int ld, int *info, int factor_only) {
     extern __shared__ double s_pan[];          // panel rows [j0, b) x CH_PW columns, pitch CH_PW + 1
     __shared__ double s_d;
     __shared__ int s_bad;
     const int tid = threadIdx.x;
     constexpr int PP = CH_PW + 1;
-    if (tid == 0) s_bad = 0;
+    __shared__ double s_clamp;
+    if (tid == 0) {
+        s_bad = 0;
+        double mx = 0.0;
+        if (factor_only) for (int i = 0; i < b; i++) mx = fmax(mx, fabs(G[(size_t)i * ld + i]));
+        s_clamp = mx * 1e-24;      // factor_only: semi-definite input allowed, tiny pivots are clamped
+    }
     __syncthreads();
     // blocked right-looking Cholesky, lower triangle; the panel is factored in shared memory
     for (int j0 = 0; j0 < b && !s_bad; j0 += CH_PW) {
@@ -336,7 +347,8 @@ chol_inv_kernel(double *G, double *Linv, int b, int ld, int *info) {
         // (1) warp 0 factors the w x w diagonal block (lane = row), column by column
         if (tid < 32) {
             for (int c = 0; c < w; c++) {
-                const double d = s_pan[c * PP + c];
+                double d = s_pan[c * PP + c];
+                if (factor_only && !(d > s_clamp)) d = s_clamp > 0.0 ? s_clamp : 1e-300;
                 const bool ok = d > 0.0;
                 if (!ok && tid == 0) s_bad = 1;
                 const double piv = sqrt(ok ? d : 1.0);
@@ -381,6 +393,7 @@ chol_inv_kernel(double *G, double *Linv, int b, int ld, int *info) {
     }
     if (s_bad) { if (tid == 0) info[0] = 1; return; }
     if (tid == 0) info[0] = 0;
+    if (factor_only) return;
     __syncthreads();
     // ---- Linv = L^-1, blocked: 32 x 32 diagonal blocks by forward substitution (one warp each, one
     // column per lane), then every block column j independently: X_ij = -X_ii * sum_{k=j}^{i-1} L_ik X_kj
@@ -462,7 +475,7 @@ int tp_chol_inv(tp_ctx *ctx, double *G, double *Linv, int b, int ld, int *bad_ou
     TP_ARG(chsm <= (size_t)ctx->max_smem_optin, "tp_chol_inv: block too wide for the shared-memory panel");
     TP_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chsm));
     tp_prof_begin(ctx, PC_JACOBI);
-    chol_inv_kernel<<<1, CH_THREADS, chsm, st>>>(G, Linv, b, ld, info);
+    chol_inv_kernel<<<1, CH_THREADS, chsm, st>>>(G, Linv, b, ld, info, 0);
     tp_prof_end(ctx);
     ctx->launches += 1;
     TP_CUDA(cudaGetLastError());
@@ -471,5 +484,21 @@ int tp_chol_inv(tp_ctx *ctx, double *G, double *Linv, int b, int ld, int *bad_ou
     TP_CUDA(cudaMemcpyAsync(h, info, sizeof(int), cudaMemcpyDeviceToHost, st));
     TP_CUDA(cudaStreamSynchronize(st));
     *bad_out = h[0];
+    return TP_OK;
+}
+
+// G <- Cholesky factor (lower triangle), semi-definite input tolerated (pivots clamped); no read-back
+int tp_chol_factor(tp_ctx *ctx, double *G, int b, int ld) {
+    cudaStream_t st = ctx->stream;
+    TP_TRY(ctx->harm.reserve(64));
+    int *info = ctx->harm.as<int>();
+    size_t chsm = (size_t)b * (CH_PW + 1) * sizeof(double);
+    TP_ARG(chsm <= (size_t)ctx->max_smem_optin, "tp_chol_factor: block too wide for the shared-memory panel");
+    TP_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chsm));
+    tp_prof_begin(ctx, PC_JACOBI);
+    chol_inv_kernel<<<1, CH_THREADS, chsm, st>>>(G, nullptr, b, ld, info, 1);
+    tp_prof_end(ctx);
+    ctx->launches += 1;
+    TP_CUDA(cudaGetLastError());
     return TP_OK;
 }

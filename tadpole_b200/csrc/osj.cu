@@ -1,0 +1,260 @@
+// osj.cu -- one-sided (Hestenes) block Jacobi for the b x b Rayleigh-Ritz problems of stage 3, b <= 256.
+//
+// T = L L^T (Cholesky).  Right rotations W that make the columns of L orthogonal give L W = U S, and
+// then T = U S^2 U^T: the normalised columns of the rotated factor ARE the eigenvectors of T and their
+// squared norms its eigenvalues (Veselic-Hari), so no rotation product has to be accumulated.  One-sided Jacobi only ever mixes two COLUMNS, so a CTA that owns
+// a set of columns can work on them in shared memory without talking to anyone.  The 16 H columns are cut
+// into 16 half-panels of H columns; a cluster of 8 CTAs runs a block round-robin: in each of 15 block
+// steps CTA r loads two half-panels of the factor (from L2) into shared memory, orthogonalises every
+// column pair across them in H sub-steps of H disjoint pairs (one warp per pair, shuffle reductions, one
+// CTA barrier per sub-step), writes them back, and the cluster barrier ends the block step.  A sweep is
+// therefore 15 cluster barriers instead of b-1, and the rotation steps themselves run at shared-memory
+// latency.  Working on the Cholesky factor instead of T keeps the accuracy of small eigenvalues.
+#include "common.cuh"
+#include <stdlib.h>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+#define OSJ_CLUSTER 8
+#define OSJ_THREADS 512
+#define OSJ_NHP 16              // half-panels
+#define OSJ_MAXH 24             // columns per half-panel
+#define OSJ_MAX_B 384            // 2 * 24 columns x 384 rows x 8 B = 147 KB of shared memory
+
+__device__ __forceinline__ void osj_pair(int slot, int step, int m, int &p, int &q) {
+    int a, b;
+    if (slot == 0) { a = m - 1; b = step; }
+    else { a = (step + slot) % (m - 1); b = (step - slot + (m - 1)) % (m - 1); }
+    p = min(a, b); q = max(a, b);
+}
+
+__device__ __forceinline__ double osj_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    return fma(r, fma(-x, r, 1.0), r);
+}
+__device__ __forceinline__ double osj_rsqrt(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = r * fma(-0.5 * x * r, r, 1.5);
+    r = r * fma(-0.5 * x * r, r, 1.5);
+    return r * fma(-0.5 * x * r, r, 1.5);
+}
+
+// column-major copy of the Cholesky factor: Ac[c * BP + r] = L[r][c] for c <= r < b, zero elsewhere
+__global__ void osj_init_kernel(const double *__restrict__ L, int b, int ld, int BP, int NC,
+                                double *__restrict__ Ac) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)NC * BP) return;
+    const int c = (int)(idx / BP), r = (int)(idx % BP);
+    Ac[idx] = (c < b && r < b && r >= c) ? L[(size_t)r * ld + c] : 0.0;
+}
+
+// rotate columns ix and iy of the shared-memory panel; one warp, rl rows per lane (rl <= 12)
+#define OSJ_RL 12
+__device__ __forceinline__ void osj_rotate(double *sA, double *s_norm, int BP, int rl, int ix, int iy,
+                                           int lane, double skip2, double &rmax2) {
+    double *ax = sA + ix * BP, *ay = sA + iy * BP;
+    double xa[OSJ_RL], ya[OSJ_RL];
+    double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+    for (int u = 0; u < OSJ_RL; u += 2) {
+        if (u < rl) { xa[u] = ax[lane + 32 * u]; ya[u] = ay[lane + 32 * u]; g0 = fma(xa[u], ya[u], g0); }
+        if (u + 1 < rl) { xa[u + 1] = ax[lane + 32 * (u + 1)]; ya[u + 1] = ay[lane + 32 * (u + 1)]; g1 = fma(xa[u + 1], ya[u + 1], g1); }
+    }
+    double g = g0 + g1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+    const double al = s_norm[ix], be = s_norm[iy];
+    const double ab = al * be;
+    if (!(ab > 0.0)) return;
+    // squared scaled cosine g^2 / (al be): the convergence measure; a crude reciprocal is enough
+    double rab;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rab) : "d"(ab));
+    const double rel2 = g * g * rab;
+    rmax2 = fmax(rmax2, rel2);
+    if (!(rel2 > skip2)) return;
+    // t = sgn(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (be - al) / (2 g), without the division.
+    // t only steers convergence; (c, s) is renormalised to c^2 + s^2 = 1 in full precision.
+    const double dd = be - al;
+    const double hh = fma(dd, dd, 4.0 * g * g);
+    double rh;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rh) : "d"(hh));
+    rh = rh * fma(-0.5 * hh * rh, rh, 1.5);
+    const double h = hh * rh;
+    double t = 2.0 * g * osj_rcp(fabs(dd) + h);
+    if (dd < 0.0) t = -t;
+    const double c = osj_rsqrt(fma(t, t, 1.0)), sn = t * c;
+#pragma unroll
+    for (int u = 0; u < OSJ_RL; u++) {
+        if (u < rl) {
+            ax[lane + 32 * u] = c * xa[u] - sn * ya[u];
+            ay[lane + 32 * u] = sn * xa[u] + c * ya[u];
+        }
+    }
+    if (lane == 0) { s_norm[ix] = al - t * g; s_norm[iy] = be + t * g; }
+}
+
+__global__ void __cluster_dims__(OSJ_CLUSTER, 1, 1) __launch_bounds__(OSJ_THREADS, 1)
+osj_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol,
+           double *cmax, double *w_out, int *info) {
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) double s_osj[];
+    double *sA = s_osj;                       // 2H columns x BP
+    __shared__ double s_norm[2 * OSJ_MAXH];
+    const double tol2 = tol * tol;
+    __shared__ double s_red[OSJ_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int crank = cluster.block_rank();
+    const int rl = BP / 32;
+    const int Hm = (H + 1) & ~1;
+    const double skip2 = 1e-34;
+    int sweeps = 0;
+    bool converged = false;
+    while (!converged && sweeps < max_sweeps) {
+        double rmax = 0.0;
+        for (int bs = 0; bs < OSJ_NHP - 1; bs++) {
+            int hI, hJ;
+            osj_pair(crank, bs, OSJ_NHP, hI, hJ);
+            // ---- load the two half-panels (columns contiguous in global: coalesced) -----------
+            const int colsz = H * BP;
+            for (int i0 = 0; i0 < colsz; i0 += OSJ_THREADS * 8) {       // all loads of a batch in flight together
+                double ti[8], tj[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int idx = i0 + u * OSJ_THREADS + tid;
+                    if (idx < colsz) { ti[u] = __ldcg(&Ac[(size_t)hI * colsz + idx]); tj[u] = __ldcg(&Ac[(size_t)hJ * colsz + idx]); }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int idx = i0 + u * OSJ_THREADS + tid;
+                    if (idx < colsz) { sA[idx] = ti[u]; sA[colsz + idx] = tj[u]; }
+                }
+            }
+            __syncthreads();
+            // squared column norms, recomputed every block step (no drift)
+            for (int c = wid; c < 2 * H; c += OSJ_THREADS / 32) {
+                double a = 0.0;
+                for (int r = lane; r < BP; r += 32) { const double v = sA[c * BP + r]; a = fma(v, v, a); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (lane == 0) s_norm[c] = a;
+            }
+            __syncthreads();
+            // ---- pairs inside each half-panel, once per sweep ---------------------------------
+            if (bs == 0) {
+                for (int st = 0; st < Hm - 1; st++) {
+                    for (int pw = wid; pw < Hm; pw += OSJ_THREADS / 32) {      // Hm pair slots over the warps
+                        const int half = pw / (Hm / 2), slot = pw % (Hm / 2);
+                        int p, q;
+                        osj_pair(slot, st, Hm, p, q);
+                        if (q < H) osj_rotate(sA, s_norm, BP, rl, half * H + p, half * H + q, lane, skip2, rmax);
+                    }
+                    __syncthreads();
+                }
+            }
+            // ---- all pairs across the two half-panels: H sub-steps of H disjoint pairs ----------
+            for (int st = 0; st < H; st++) {
+                for (int pw = wid; pw < H; pw += OSJ_THREADS / 32) {
+                    int jj = pw + st; if (jj >= H) jj -= H;
+                    osj_rotate(sA, s_norm, BP, rl, pw, H + jj, lane, skip2, rmax);
+                }
+                __syncthreads();
+            }
+            // ---- write back ---------------------------------------------------------------------------
+            for (int idx = tid; idx < colsz; idx += OSJ_THREADS) {
+                Ac[(size_t)hI * colsz + idx] = sA[idx];
+                Ac[(size_t)hJ * colsz + idx] = sA[colsz + idx];
+            }
+            if (bs == OSJ_NHP - 2 && w_out) {           // eigenvalue estimates of this sweep
+                for (int c = tid; c < 2 * H; c += OSJ_THREADS) {
+                    const int gcol = (c < H ? hI : hJ) * H + (c < H ? c : c - H);
+                    w_out[gcol] = s_norm[c];
+                }
+            }
+            cluster.sync();
+        }
+        sweeps++;
+        // largest scaled cosine seen by this CTA -> cluster-wide maximum through global memory
+        rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, 16));   // only lane values of the warp matter
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+        if (lane == 0) s_red[wid] = rmax;
+        __syncthreads();
+        if (tid == 0) {
+            double v = 0.0;
+            for (int w = 0; w < OSJ_THREADS / 32; w++) v = fmax(v, s_red[w]);
+            cmax[(sweeps & 1) * OSJ_CLUSTER + crank] = v;
+        }
+        cluster.sync();
+        double v = 0.0;
+        for (int r = 0; r < OSJ_CLUSTER; r++) v = fmax(v, __ldcg(&cmax[(sweeps & 1) * OSJ_CLUSTER + r]));
+        converged = v <= tol2;          // squared scaled cosines
+    }
+    if (crank == 0 && tid == 0) { info[0] = sweeps; info[1] = converged ? 1 : 0; }
+}
+
+// eigenvalues w (unsorted, one per column) -> descending order; eigenvector = normalised column of the
+// rotated factor: Vs[r][rank(c)] = Ac[c * BP + r] / sqrt(w_c)
+__global__ void osj_sort_kernel(const double *__restrict__ w_in, const double *__restrict__ Vc, int b, int BP,
+                                double *__restrict__ w, double *__restrict__ Vs, int lds, int ncols_out) {
+    extern __shared__ int s_rank[];
+    for (int i = threadIdx.x; i < b; i += blockDim.x) {
+        const double wi = w_in[i];
+        int rank = 0;
+        for (int j = 0; j < b; j++) {
+            const double wj = w_in[j];
+            rank += (wj > wi) || (wj == wi && j < i);
+        }
+        s_rank[i] = rank;
+        if (blockIdx.x == 0) w[rank] = wi;
+    }
+    __syncthreads();
+    for (int c = blockIdx.x; c < b; c += gridDim.x) {
+        const int dst = s_rank[c];
+        if (dst >= ncols_out) continue;
+        const double wc = w_in[c];
+        const double sc = wc > 0.0 ? 1.0 / sqrt(wc) : 0.0;
+        for (int r = threadIdx.x; r < b; r += blockDim.x) Vs[(size_t)r * lds + dst] = Vc[(size_t)c * BP + r] * sc;
+    }
+}
+
+int tp_chol_factor(tp_ctx *ctx, double *G, int b, int ld);
+
+// Eigen-decomposition of the symmetric positive semi-definite b x b matrix T (row-major, ld), b <= 384.
+// T is destroyed.  w[0..b) descending, Vs (b x lds) eigenvectors in its first ncols_out columns.
+int tp_osj(tp_ctx *ctx, double *T, int b, int ld, double *w, double *Vs, int lds, int ncols_out, int *sweeps_out,
+           double tol) {
+    TP_ARG(b >= 2 && b <= OSJ_MAX_B, "tp_osj: b out of range");
+    cudaStream_t st = ctx->stream;
+    const int H = (b + OSJ_NHP - 1) / OSJ_NHP, NC = H * OSJ_NHP, BP = round_up(b, 32);
+    const size_t panel = (size_t)NC * BP * sizeof(double);
+    TP_TRY(ctx->Jt.reserve(panel + (size_t)(NC + 64) * sizeof(double) + 64));
+    double *Ac = ctx->Jt.as<double>();
+    double *wtmp = Ac + (size_t)NC * BP, *cmax = wtmp + NC;
+    int *info = (int *)(cmax + 32);
+    TP_TRY(tp_chol_factor(ctx, T, b, ld));
+    tp_prof_begin(ctx, PC_JACOBI);
+    osj_init_kernel<<<(unsigned)(((size_t)NC * BP + 255) / 256), 256, 0, st>>>(T, b, ld, BP, NC, Ac);
+    const size_t smem = (size_t)2 * H * BP * sizeof(double);
+    TP_CUDA(cudaFuncSetAttribute(osj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const double otol = tol > 2e-15 ? tol : 2e-15;
+    osj_kernel<<<OSJ_CLUSTER, OSJ_THREADS, smem, st>>>(Ac, b, BP, H, 30, otol, cmax, wtmp, info);
+    const int grid = b < 2 * ctx->sm_count ? b : 2 * ctx->sm_count;
+    osj_sort_kernel<<<grid, 256, (size_t)b * sizeof(int), st>>>(wtmp, Ac, b, BP, w, Vs, lds, ncols_out);
+    tp_prof_end(ctx);
+    ctx->launches += 3;
+    TP_CUDA(cudaGetLastError());
+    TP_TRY(tp_pin_reserve(ctx, 64));
+    int *h = (int *)ctx->pin;
+    TP_CUDA(cudaMemcpyAsync(h, info, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    TP_CUDA(cudaStreamSynchronize(st));
+    if (sweeps_out) *sweeps_out = h[0];
+    if (getenv("TADPOLE_DEBUG")) fprintf(stderr, "[tadpole] osj b=%d tol=%.1e sweeps=%d converged=%d\n", b, otol, h[0], h[1]);
+    if (!h[1]) {
+        tp_set_error("tp_osj: no convergence after %d sweeps (b = %d)", h[0], b);
+        return TP_ERR_NOCONV;
+    }
+    return TP_OK;
+}
