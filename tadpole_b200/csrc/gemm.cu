@@ -66,8 +66,8 @@ dgemm_kernel(GemmArgs g, double *__restrict__ partial, int kt_per_split) {
     extern __shared__ __align__(16) double gsm[];
 
     const int tm = blockIdx.y, tn = blockIdx.x;
-    if (g.sym && tn < tm) return;
     const int m0 = tm * BM, n0 = tn * BN;
+    if (g.sym && n0 + BN <= m0) return;          // tile entirely below the diagonal: its mirror image is computed
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm0 = (warp / WN) * WTM, wn0 = (warp % WN) * WTN;
 
@@ -184,17 +184,27 @@ static int launch_cfg(tp_ctx *ctx, const GemmArgs &g, double *partial, int split
 }
 
 template <bool A_KC, bool B_KC>
-static int launch_layout(tp_ctx *ctx, const GemmArgs &g, bool big, double *partial, int splits, int ktp) {
-    if (big) return launch_cfg<A_KC, B_KC, 128, 128, 2, 4>(ctx, g, partial, splits, ktp);
-    return launch_cfg<A_KC, B_KC, 64, 64, 2, 2>(ctx, g, partial, splits, ktp);
+static int launch_layout(tp_ctx *ctx, const GemmArgs &g, int cfg, double *partial, int splits, int ktp) {
+    if (cfg == 2) return launch_cfg<A_KC, B_KC, 128, 128, 2, 4>(ctx, g, partial, splits, ktp);
+    if (cfg == 1) return launch_cfg<A_KC, B_KC, 64, 64, 2, 2>(ctx, g, partial, splits, ktp);
+    return launch_cfg<A_KC, B_KC, 32, 64, 1, 4>(ctx, g, partial, splits, ktp);
 }
 
 int tp_gemm(tp_ctx *ctx, const GemmArgs &g) {
     TP_ARG(g.A && g.B && g.D && g.M > 0 && g.N > 0 && g.K > 0, "tp_gemm: bad arguments");
     TP_ARG((g.lda % 2) == 0 && (g.ldb % 2) == 0, "tp_gemm: leading dimensions must be even");
-    // 128x128 tiles once they fill the machine, 64x64 otherwise
+    // 128x128 tiles once they fill the machine; otherwise 64x64 or 32x64, whichever leaves the 148 SMs
+    // better balanced (time ~ ceil(tiles / SMs) * tile area when every SM holds its tiles at once)
     const long tiles128 = (long)((g.M + 127) / 128) * ((g.N + 127) / 128) / (g.sym ? 2 : 1);
-    const bool big = tiles128 >= ctx->sm_count;
+    int cfg = 2;
+    if (tiles128 < ctx->sm_count) {
+        const long z = g.splitk > 1 ? g.splitk : 1;
+        const long t64 = (long)((g.M + 63) / 64) * ((g.N + 63) / 64) * z / (g.sym ? 2 : 1);
+        const long t32 = (long)((g.M + 31) / 32) * ((g.N + 63) / 64) * z / (g.sym ? 2 : 1);
+        const long c64 = ((t64 + ctx->sm_count - 1) / ctx->sm_count) * 2;
+        const long c32 = ((t32 + ctx->sm_count - 1) / ctx->sm_count) * 1;
+        cfg = (c32 < c64) ? 0 : 1;
+    }
     const int KT = (g.K + GEMM_BK - 1) / GEMM_BK;
     int splits = g.splitk;
     if (splits > KT) splits = KT;
@@ -209,10 +219,10 @@ int tp_gemm(tp_ctx *ctx, const GemmArgs &g) {
         partial = ctx->part.as<double>();
     }
     int rc;
-    if (g.a_kc) rc = g.b_kc ? launch_layout<true, true>(ctx, g, big, partial, splits, ktp)
-                            : launch_layout<true, false>(ctx, g, big, partial, splits, ktp);
-    else        rc = g.b_kc ? launch_layout<false, true>(ctx, g, big, partial, splits, ktp)
-                            : launch_layout<false, false>(ctx, g, big, partial, splits, ktp);
+    if (g.a_kc) rc = g.b_kc ? launch_layout<true, true>(ctx, g, cfg, partial, splits, ktp)
+                            : launch_layout<true, false>(ctx, g, cfg, partial, splits, ktp);
+    else        rc = g.b_kc ? launch_layout<false, true>(ctx, g, cfg, partial, splits, ktp)
+                            : launch_layout<false, false>(ctx, g, cfg, partial, splits, ktp);
     TP_TRY(rc);
     if (splits > 1) {
         const size_t total = (size_t)g.M * g.N;

@@ -51,22 +51,28 @@ __global__ void osj_init_kernel(const double *__restrict__ L, int b, int ld, int
     Ac[idx] = (c < b && r < b && r >= c) ? L[(size_t)r * ld + c] : 0.0;
 }
 
-// rotate columns ix and iy of the shared-memory panel; one warp, rl rows per lane (rl <= 12)
-#define OSJ_RL 12
-__device__ __forceinline__ void osj_rotate(double *sA, double *s_norm, int BP, int rl, int ix, int iy,
+// shared memory through 32-bit shared-window addresses (no generic-address arithmetic in the chain)
+__device__ __forceinline__ double osj_lds(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void osj_sts(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+
+// rotate columns ix and iy of the shared-memory panel; one warp, RL rows per lane
+template <int RL>
+__device__ __forceinline__ void osj_rotate(unsigned sA, unsigned sN, int BP, int ix, int iy,
                                            int lane, double skip2, double &rmax2) {
-    double *ax = sA + ix * BP, *ay = sA + iy * BP;
-    double xa[OSJ_RL], ya[OSJ_RL];
+    const unsigned ax = sA + 8u * (ix * BP + lane), ay = sA + 8u * (iy * BP + lane);
+    double xa[RL], ya[RL];
     double g0 = 0.0, g1 = 0.0;
 #pragma unroll
-    for (int u = 0; u < OSJ_RL; u += 2) {
-        if (u < rl) { xa[u] = ax[lane + 32 * u]; ya[u] = ay[lane + 32 * u]; g0 = fma(xa[u], ya[u], g0); }
-        if (u + 1 < rl) { xa[u + 1] = ax[lane + 32 * (u + 1)]; ya[u + 1] = ay[lane + 32 * (u + 1)]; g1 = fma(xa[u + 1], ya[u + 1], g1); }
+    for (int u = 0; u < RL; u++) { xa[u] = osj_lds(ax + 256u * u); ya[u] = osj_lds(ay + 256u * u); }
+    const double al = osj_lds(sN + 8u * ix), be = osj_lds(sN + 8u * iy);
+#pragma unroll
+    for (int u = 0; u < RL; u += 2) {
+        g0 = fma(xa[u], ya[u], g0);
+        if (u + 1 < RL) g1 = fma(xa[u + 1], ya[u + 1], g1);
     }
     double g = g0 + g1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
-    const double al = s_norm[ix], be = s_norm[iy];
     const double ab = al * be;
     if (!(ab > 0.0)) return;
     // squared scaled cosine g^2 / (al be): the convergence measure; a crude reciprocal is enough
@@ -87,15 +93,14 @@ __device__ __forceinline__ void osj_rotate(double *sA, double *s_norm, int BP, i
     if (dd < 0.0) t = -t;
     const double c = osj_rsqrt(fma(t, t, 1.0)), sn = t * c;
 #pragma unroll
-    for (int u = 0; u < OSJ_RL; u++) {
-        if (u < rl) {
-            ax[lane + 32 * u] = c * xa[u] - sn * ya[u];
-            ay[lane + 32 * u] = sn * xa[u] + c * ya[u];
-        }
+    for (int u = 0; u < RL; u++) {
+        osj_sts(ax + 256u * u, c * xa[u] - sn * ya[u]);
+        osj_sts(ay + 256u * u, sn * xa[u] + c * ya[u]);
     }
-    if (lane == 0) { s_norm[ix] = al - t * g; s_norm[iy] = be + t * g; }
+    if (lane == 0) { osj_sts(sN + 8u * ix, al - t * g); osj_sts(sN + 8u * iy, be + t * g); }
 }
 
+template <int RL>
 __global__ void __cluster_dims__(OSJ_CLUSTER, 1, 1) __launch_bounds__(OSJ_THREADS, 1)
 osj_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol,
            double *cmax, double *w_out, int *info) {
@@ -107,7 +112,7 @@ osj_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol,
     __shared__ double s_red[OSJ_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int crank = cluster.block_rank();
-    const int rl = BP / 32;
+    const unsigned uA = (unsigned)__cvta_generic_to_shared(sA), uN = (unsigned)__cvta_generic_to_shared(s_norm);
     const int Hm = (H + 1) & ~1;
     const double skip2 = 1e-34;
     int sweeps = 0;
@@ -149,7 +154,7 @@ osj_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol,
                         const int half = pw / (Hm / 2), slot = pw % (Hm / 2);
                         int p, q;
                         osj_pair(slot, st, Hm, p, q);
-                        if (q < H) osj_rotate(sA, s_norm, BP, rl, half * H + p, half * H + q, lane, skip2, rmax);
+                        if (q < H) osj_rotate<RL>(uA, uN, BP, half * H + p, half * H + q, lane, skip2, rmax);
                     }
                     __syncthreads();
                 }
@@ -158,7 +163,7 @@ osj_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol,
             for (int st = 0; st < H; st++) {
                 for (int pw = wid; pw < H; pw += OSJ_THREADS / 32) {
                     int jj = pw + st; if (jj >= H) jj -= H;
-                    osj_rotate(sA, s_norm, BP, rl, pw, H + jj, lane, skip2, rmax);
+                    osj_rotate<RL>(uA, uN, BP, pw, H + jj, lane, skip2, rmax);
                 }
                 __syncthreads();
             }
@@ -238,9 +243,18 @@ int tp_osj(tp_ctx *ctx, double *T, int b, int ld, double *w, double *Vs, int lds
     tp_prof_begin(ctx, PC_JACOBI);
     osj_init_kernel<<<(unsigned)(((size_t)NC * BP + 255) / 256), 256, 0, st>>>(T, b, ld, BP, NC, Ac);
     const size_t smem = (size_t)2 * H * BP * sizeof(double);
-    TP_CUDA(cudaFuncSetAttribute(osj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const double otol = tol > 2e-15 ? tol : 2e-15;
-    osj_kernel<<<OSJ_CLUSTER, OSJ_THREADS, smem, st>>>(Ac, b, BP, H, 30, otol, cmax, wtmp, info);
+#define OSJ_LAUNCH(R)                                                                                         \
+    case R:                                                                                                   \
+        TP_CUDA(cudaFuncSetAttribute(osj_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        osj_kernel<R><<<OSJ_CLUSTER, OSJ_THREADS, smem, st>>>(Ac, b, BP, H, 30, otol, cmax, wtmp, info);      \
+        break;
+    switch (BP / 32) {
+        OSJ_LAUNCH(1) OSJ_LAUNCH(2) OSJ_LAUNCH(3) OSJ_LAUNCH(4) OSJ_LAUNCH(5) OSJ_LAUNCH(6)
+        OSJ_LAUNCH(7) OSJ_LAUNCH(8) OSJ_LAUNCH(9) OSJ_LAUNCH(10) OSJ_LAUNCH(11) OSJ_LAUNCH(12)
+        default: tp_set_error("tp_osj: unsupported panel height"); return TP_ERR_ARG;
+    }
+#undef OSJ_LAUNCH
     const int grid = b < 2 * ctx->sm_count ? b : 2 * ctx->sm_count;
     osj_sort_kernel<<<grid, 256, (size_t)b * sizeof(int), st>>>(wtmp, Ac, b, BP, w, Vs, lds, ncols_out);
     tp_prof_end(ctx);

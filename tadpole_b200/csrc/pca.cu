@@ -382,7 +382,7 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
                 int bad = 0;
                 TP_TRY(cholqr(2, &bad));
                 TP_TRY(op.apply(Y, W, 1.0, nullptr, 0.0, nullptr, 0.0));
-                if (bad) TP_TRY(rr_general(1e-5)); else TP_TRY(rr_orthonormal(1e-5));
+                if (bad) TP_TRY(rr_general(1e-3)); else TP_TRY(rr_orthonormal(1e-3));
             }
             double *hbuf = (double *)ctx->pin;
             const int inner = ctx->pca_inner;   // filter + CholQR rounds between two Rayleigh-Ritz steps
