@@ -264,34 +264,52 @@ def run_b200(args, rank, world, local_rank):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
         nf, k = res["nf"], res["k"]
         fp64_peak = measure_fp64_peak(torch)
-        top = max(("jacobi", "dgemm", "coniss_sweep", "ch", "rowmean"), key=lambda c: prof[c][0])
-        t_ms, cnt = prof[top]
-        per_launch_ms = t_ms / max(cnt, 1)
-        if top == "coniss_sweep":
-            # 8*Nf*k(k+1)/2 read + 8*k*(Nf-1) written per sweep launch
-            alg = 8.0 * nf * k * (k + 1) / 2 + 8.0 * k * (nf - 1)
-            roof = {"kernel": "coniss_sweep_kernel", "bound": "hbm", "achieved": alg / (per_launch_ms * 1e-3) / 1e9,
-                    "peak": hbm_peak, "unit": "GB/s", "traffic": None,
-                    "merges_per_s": k * (nf - 1) / (per_launch_ms * 1e-3)}
-        elif top == "dgemm":
-            # algorithmic flops summed by the library per launch (2MNK; one triangle for SYRK shapes);
-            # denominator: cuBLAS DGEMM measured in this same run (no FP64 peak in MEASURED_PEAKS.json)
-            gflop = prof["gemm_gflop"][0]
-            roof = {"kernel": "dgemm_kernel (FP64 DMMA mma.sync m8n8k4)", "bound": "tensor",
-                    "achieved": gflop / t_ms, "peak": fp64_peak, "unit": "TFLOP/s", "traffic": None}
-            peak_src = "cuBLAS DGEMM 4096^3 via torch.matmul, best of 5, measured in this run"
-        else:
-            # Jacobi eigensolver on a b x b L2-resident matrix: algorithmic bytes = read A, write V (2 b^2 doubles)
-            b = -(-(k + max(32, k // 4)) // 32) * 32 if nf > 512 else nf
-            alg = 2.0 * 8.0 * b * b
-            roof = {"kernel": f"{top}_kernel", "bound": "hbm", "achieved": alg / (per_launch_ms * 1e-3) / 1e9,
-                    "peak": hbm_peak, "unit": "GB/s", "traffic": None,
-                    "note": "latency-bound: serial rotation steps on an L2-resident matrix"}
-        if roof.get("achieved") is not None and roof.get("peak"):
-            roof["frac"] = roof["achieved"] / roof["peak"]
-        roof["peak_source"] = peak_src
-        roof["share_of_step"] = t_ms / ms
-        roof["avg_launch_ms"] = per_launch_ms
+        b_blk = -(-(k + max(32, k // 4)) // 32) * 32 if nf > 512 else nf      # width of the Rayleigh-Ritz problems
+        nlev = float(np.count_nonzero(~np.isnan(res["scores"]))) if res.get("scores") is not None else 0.0
+
+        def roof_of(cls):
+            t_ms, cnt = prof[cls]
+            if not cnt:
+                return None
+            per = t_ms / cnt                                   # ms per launch (CUDA events around each launch)
+            src = peak_src
+            if cls == "dgemm":
+                # algorithmic flops summed by the library per launch (2MNK; M N (K+1) for SYRK shapes);
+                # denominator: cuBLAS DGEMM measured in this same run (no FP64 peak in MEASURED_PEAKS.json)
+                r = {"kernel": "dgemm_kernel (FP64 DMMA mma.sync m8n8k4)", "bound": "tensor",
+                     "achieved": prof["gemm_gflop"][0] / t_ms, "peak": fp64_peak, "unit": "TFLOP/s", "traffic": None}
+                src = "cuBLAS DGEMM 4096^3 via torch.matmul, best of 6, measured in this run"
+            else:
+                if cls == "coniss_sweep":      # 8 Nf k(k+1)/2 read + 8 k (Nf-1) written per sweep
+                    alg, name = 8.0 * nf * k * (k + 1) / 2 + 8.0 * k * (nf - 1), "coniss_sweep_kernel"
+                elif cls == "ch":              # S5: 8 (Nf-1) per candidate + 24 k per scored level
+                    alg, name = 8.0 * (nf - 1) * k + 24.0 * k * nlev, "ch_kernel"
+                elif cls == "rowmean":         # S1: one pass over the N x N input
+                    alg, name = 8.0 * n * n, "rowmean_kernel"
+                elif cls == "compact":         # S1: Nf x Nf gather written once
+                    alg, name = 8.0 * nf * nf, "compact_kernel"
+                elif cls == "chol":            # read G, write L and L^-1 (lower triangles): 3 * 8 * b(b+1)/2
+                    alg, name = 12.0 * b_blk * (b_blk + 1), "cholinv8_kernel"
+                else:                          # eigensolver: read T, write V: 2 * 8 * b^2
+                    alg, name = 16.0 * b_blk * b_blk, "osj_kernel"
+                r = {"kernel": name, "bound": "hbm", "achieved": alg / (per * 1e-3) / 1e9, "peak": hbm_peak,
+                     "unit": "GB/s", "traffic": None}
+                if cls == "coniss_sweep":
+                    r["merges_per_s"] = k * (nf - 1) / (per * 1e-3)
+                if cls in ("jacobi", "chol", "coniss_sweep"):
+                    r["note"] = "latency-bound: serial dependent steps on L2 / shared-memory resident data"
+            r["frac"] = r["achieved"] / r["peak"]
+            r["peak_source"] = src
+            r["share_of_step"] = t_ms / ms
+            r["avg_launch_ms"] = per
+            r["launches_per_step"] = cnt / args.steps
+            return r
+
+        classes = ("dgemm", "jacobi", "chol", "coniss_sweep", "ch", "rowmean", "compact")
+        roofs = {c: roof_of(c) for c in classes}
+        roofs = {c: r for c, r in roofs.items() if r}
+        top = max(roofs, key=lambda c: roofs[c]["share_of_step"])
+        roof = roofs[top]
 
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -309,6 +327,7 @@ def run_b200(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": roof,
+            "roofline_all_kernels": roofs,
             "fp64_dgemm_peak_tflops_measured": fp64_peak,
             "stage_ms_last_step": {k_: round(v, 4) for k_, v in stage.items()},
             "kernel_ms_per_step": {c: round(v[0] / args.steps, 4) for c, v in prof.items() if v[1]},

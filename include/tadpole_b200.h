@@ -60,9 +60,11 @@ int tp_ctx_timings(tp_ctx *ctx, double *out10);
 
 /* per-kernel-class device time: when enabled, every launch of the classes below is bracketed by
  * CUDA events on the context stream; reading sums them since the last enable/reset.
- * classes: [0] rowmean (filter) [1] compact [2] dgemm [3] jacobi [4] coniss_sweep [5] ch [6] difft
- * [7] in ms_out8: GFLOP (algorithmic) of the profiled dgemm launches.  enable: 1 = start/reset, 0 = stop, -1 = just read. */
-int tp_ctx_profile(tp_ctx *ctx, int enable, double *ms_out8, long long *count_out8);
+ * classes: [0] rowmean (filter) [1] compact [2] dgemm [3] jacobi (b x b eigensolver) [4] coniss_sweep [5] ch
+ * [6] difft [8] chol (b x b Cholesky + triangular inverse) [9] igemm (tcgen05 integer GEMM) [10..11] spare;
+ * [7] in ms_out12: GFLOP (algorithmic) of the profiled dgemm launches.
+ * enable: 1 = start/reset, 0 = stop, -1 = just read. */
+int tp_ctx_profile(tp_ctx *ctx, int enable, double *ms_out12, long long *count_out12);
 
 /* ---- stage 1: load_mat numeric core (R/TADpole.R:19-22,35-37) ----------------------------- */
 /* Uploads (or adopts, when on_device) the N x N matrix, computes rowMeans of the symmetrised
@@ -90,6 +92,12 @@ int tp_set_correlation(tp_ctx *ctx, const double *cor, int nf);
 int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out);
 int tp_get_scores(tp_ctx *ctx, double *scores_out);         /* nf x k row-major, host */
 int tp_set_scores(tp_ctx *ctx, const double *scores, int nf, int k);
+
+/* test hooks for the b x b kernels inside tp_pca (host in / out, row-major b x b): Cholesky factor (lower triangle of
+ * l_out) and, unless factor_only, L^-1 of a symmetric positive definite g, *bad_out = 1 when it is not; eigenvalues
+ * (descending) and eigenvectors (columns of v_out) of a symmetric positive semi-definite t */
+int tp_test_cholinv(tp_ctx *ctx, const double *g, int b, int factor_only, double *l_out, double *linv_out, int *bad_out);
+int tp_test_eig(tp_ctx *ctx, const double *t, int b, double tol, double *w_out, double *v_out, int *sweeps_out);
 
 /* ---- stages 4+5: the find_params sweep (R/TADpole.R:104-123) --------------------------------------
  * For candidates i = cand_begin + t*cand_stride < k (0-based: candidate i clusters on the first

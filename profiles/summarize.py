@@ -1,0 +1,91 @@
+"""Turn ncu output brought back in gpurun_out/ into the small text summaries committed under profiles/.
+
+  python profiles/summarize.py launches gpurun_out/launches.csv  > profiles/rNN_launches.md
+  python profiles/summarize.py full gpurun_out/prof_x.ncu-rep ... > profiles/rNN_full.md
+
+`launches` aggregates the `--metrics gpu__time_duration.sum` launch list per kernel (count, total,
+share: cold-cache serialised times, so only the SHARES are comparable with bench.py).
+`full` extracts the counters the roofline discussion uses from `--set full` reports."""
+import csv
+import subprocess
+import sys
+from collections import OrderedDict
+
+WANT = [
+    ("gpu__time_duration.sum", "duration"),
+    ("launch__grid_size", "grid"),
+    ("launch__block_size", "block"),
+    ("launch__registers_per_thread", "regs/thread"),
+    ("launch__shared_mem_per_block_dynamic", "dyn smem/block"),
+    ("dram__bytes_read.sum", "dram read"),
+    ("dram__bytes_write.sum", "dram write"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram % of peak"),
+    ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe active %"),
+    ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64 pipe active %"),
+    ("sm__inst_executed_pipe_tensor_op_dmma.sum", "DMMA instructions"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
+    ("smsp__cycles_active.avg", "SMSP active cycles"),
+    ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
+]
+
+
+def simplify(name):
+    name = name.replace("void ", "")
+    p = name.find("(")
+    return name[:p] if p > 0 else name
+
+
+def launches(path):
+    rows = []
+    with open(path) as fh:
+        lines = [l for l in fh if l.startswith('"')]
+    rd = csv.DictReader(lines)
+    for r in rd:
+        if r.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        v = float(r["Metric Value"].replace(",", ""))
+        unit = r["Metric Unit"]
+        v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit, 1.0)
+        rows.append((simplify(r["Kernel Name"]), r["Grid Size"], r["Block Size"], v))
+    agg = OrderedDict()
+    for k, g, b, v in rows:
+        a = agg.setdefault(k, [0, 0.0, g, b])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    print(f"launches: {len(rows)}   total device time (serialised, cold): {tot / 1e3:.3f} ms\n")
+    print("| kernel | launches | total us | share | avg us | grid (first) | block |")
+    print("|---|---:|---:|---:|---:|---|---|")
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"| `{k}` | {a[0]} | {a[1]:.1f} | {100 * a[1] / tot:.1f}% | {a[1] / a[0]:.1f} | {a[2]} | {a[3]} |")
+
+
+def full(paths):
+    for p in paths:
+        out = subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader([l for l in out.splitlines() if l.startswith('"')]))
+        if len(rows) < 3:
+            print(f"## {p}: no data\n")
+            continue
+        hdr, units = rows[0], rows[1]
+        print(f"## {p}\n")
+        for r in rows[2:]:
+            name = r[hdr.index("Kernel Name")]
+            print(f"### `{simplify(name)}`  grid {r[hdr.index('Grid Size')]} block {r[hdr.index('Block Size')]}\n")
+            print("| counter | value |")
+            print("|---|---|")
+            for key, label in WANT:
+                if key in hdr:
+                    i = hdr.index(key)
+                    print(f"| {label} (`{key}`) | {r[i]} {units[i]} |")
+            print()
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2])
+    else:
+        full(sys.argv[2:])

@@ -22,7 +22,7 @@ EXPORTED = [
     "tp_ctx_launches", "tp_ctx_set", "tp_ctx_timings", "tp_ctx_profile", "tp_filter", "tp_compact", "tp_set_filtered",
     "tp_get_filtered", "tp_correlation", "tp_get_correlation", "tp_set_correlation", "tp_pca",
     "tp_get_scores", "tp_set_scores", "tp_sweep", "tp_get_dendro", "tp_select", "tp_call", "tp_call_arm",
-    "tp_difft_batch", "tp_assemble",
+    "tp_difft_batch", "tp_assemble", "tp_test_cholinv", "tp_test_eig",
 ]
 
 
@@ -65,6 +65,8 @@ def load():
         "tp_get_correlation": (c_int, [vp, dp]),
         "tp_set_correlation": (c_int, [vp, dp, c_int]),
         "tp_pca": (c_int, [vp, c_int, ip]),
+        "tp_test_cholinv": (c_int, [vp, dp, c_int, c_int, dp, dp, ip]),
+        "tp_test_eig": (c_int, [vp, dp, c_int, c_double, dp, dp, ip]),
         "tp_get_scores": (c_int, [vp, dp]),
         "tp_set_scores": (c_int, [vp, dp, c_int, c_int]),
         "tp_sweep": (c_int, [vp, c_int, c_int, c_int, ip, dp, c_int, ip]),
@@ -138,12 +140,13 @@ class Context:
                 "pca_iterations", "pca_applications", "jacobi_sweeps"]
         return dict(zip(keys, out.tolist()))
 
-    PROFILE_CLASSES = ["rowmean", "compact", "dgemm", "jacobi", "coniss_sweep", "ch", "difft", "gemm_gflop"]
+    PROFILE_CLASSES = ["rowmean", "compact", "dgemm", "jacobi", "coniss_sweep", "ch", "difft", "gemm_gflop", "chol", "igemm",
+                       "spare2", "spare3"]
 
     def profile(self, enable=-1):
         """enable: 1 start/reset, 0 stop, -1 read.  Returns {class: (ms, launches)} accumulated so far."""
-        ms = np.zeros(8)
-        cnt = np.zeros(8, dtype=np.int64)
+        ms = np.zeros(12)
+        cnt = np.zeros(12, dtype=np.int64)
         check(self.lib.tp_ctx_profile(self._h, int(enable), _dp(ms), cnt.ctypes.data_as(POINTER(c_longlong))))
         return {k: (float(m), int(c)) for k, m, c in zip(self.PROFILE_CLASSES, ms, cnt)}
 
@@ -199,6 +202,22 @@ class Context:
         k = c_int(0)
         check(self.lib.tp_pca(self._h, int(max_pcs), ctypes.byref(k)))
         return k.value
+
+    def test_cholinv(self, g, factor_only=False):
+        """(L, Linv or None, bad) of a symmetric positive definite b x b matrix (test hook)."""
+        g = np.ascontiguousarray(g, dtype=np.float64)
+        b = g.shape[0]
+        l = np.zeros((b, b)); li = np.zeros((b, b)); bad = np.zeros(1, dtype=np.int32)
+        check(self.lib.tp_test_cholinv(self._h, _dp(g), b, int(factor_only), _dp(l), _dp(li), _ip(bad)))
+        return np.tril(l), (None if factor_only else li), int(bad[0])
+
+    def test_eig(self, t, tol=1e-14):
+        """(w descending, V, sweeps) of a symmetric positive semi-definite b x b matrix (test hook)."""
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        b = t.shape[0]
+        w = np.zeros(b); v = np.zeros((b, b)); sw = np.zeros(1, dtype=np.int32)
+        check(self.lib.tp_test_eig(self._h, _dp(t), b, float(tol), _dp(w), _dp(v), _ip(sw)))
+        return w, v, int(sw[0])
 
     def get_scores(self, nf, k):
         out = np.zeros((nf, k))

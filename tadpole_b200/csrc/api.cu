@@ -133,10 +133,10 @@ void tp_prof_end(tp_ctx *ctx) {
     ctx->prof_used += 2;
 }
 
-extern "C" int tp_ctx_profile(tp_ctx *ctx, int enable, double *ms_out8, long long *count_out8) {
+extern "C" int tp_ctx_profile(tp_ctx *ctx, int enable, double *ms_out12, long long *count_out12) {
     TP_ARG(ctx, "tp_ctx_profile: null context");
     TP_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (ms_out8 || count_out8) {
+    if (ms_out12 || count_out12) {
         double ms[PC_COUNT] = {};
         long long cnt[PC_COUNT] = {};
         for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
@@ -147,10 +147,61 @@ extern "C" int tp_ctx_profile(tp_ctx *ctx, int enable, double *ms_out8, long lon
             } else (void)cudaGetLastError();
         }
         ms[PC_SPARE] = ctx->prof_gemm_flop * 1e-9;   // slot 7: GFLOP of the profiled GEMM launches
-        for (int c = 0; c < PC_COUNT; c++) { if (ms_out8) ms_out8[c] = ms[c]; if (count_out8) count_out8[c] = cnt[c]; }
+        for (int c = 0; c < PC_COUNT; c++) { if (ms_out12) ms_out12[c] = ms[c]; if (count_out12) count_out12[c] = cnt[c]; }
     }
     if (enable == 1) { ctx->prof = true; ctx->prof_used = 0; ctx->prof_gemm_flop = 0.0; }
     else if (enable == 0) ctx->prof = false;
+    return TP_OK;
+}
+
+// ---- test hooks for the b x b kernels of stage 3 ---------------------------------------------------
+int tp_chol_inv(tp_ctx *ctx, double *G, double *Linv, int b, int ld, int *bad_out);
+int tp_chol_factor(tp_ctx *ctx, double *G, int b, int ld);
+int tp_jacobi(tp_ctx *ctx, double *A, int b, int ld, double *w, double *Vs, int lds, int ncols_out, int *sweeps_out,
+              double tol);
+
+extern "C" int tp_test_cholinv(tp_ctx *ctx, const double *g, int b, int factor_only, double *l_out, double *linv_out,
+                               int *bad_out) {
+    TP_ARG(ctx && g && b >= 1 && l_out, "tp_test_cholinv: bad arguments");
+    TP_CUDA(cudaSetDevice(ctx->device));
+    const int ld = round_up(b, 8);
+    const size_t bytes = (size_t)b * ld * sizeof(double);
+    TP_TRY(ctx->G.reserve(bytes)); TP_TRY(ctx->small1.reserve(bytes));
+    TP_CUDA(cudaMemsetAsync(ctx->G.p, 0, bytes, ctx->stream));
+    TP_CUDA(cudaMemsetAsync(ctx->small1.p, 0, bytes, ctx->stream));
+    TP_CUDA(cudaMemcpy2DAsync(ctx->G.p, (size_t)ld * sizeof(double), g, (size_t)b * sizeof(double),
+                              (size_t)b * sizeof(double), b, cudaMemcpyHostToDevice, ctx->stream));
+    int bad = 0;
+    if (factor_only) TP_TRY(tp_chol_factor(ctx, ctx->G.as<double>(), b, ld));
+    else TP_TRY(tp_chol_inv(ctx, ctx->G.as<double>(), ctx->small1.as<double>(), b, ld, &bad));
+    if (bad_out) *bad_out = bad;
+    TP_CUDA(cudaMemcpy2DAsync(l_out, (size_t)b * sizeof(double), ctx->G.p, (size_t)ld * sizeof(double),
+                              (size_t)b * sizeof(double), b, cudaMemcpyDeviceToHost, ctx->stream));
+    if (linv_out && !factor_only)
+        TP_CUDA(cudaMemcpy2DAsync(linv_out, (size_t)b * sizeof(double), ctx->small1.p, (size_t)ld * sizeof(double),
+                                  (size_t)b * sizeof(double), b, cudaMemcpyDeviceToHost, ctx->stream));
+    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return TP_OK;
+}
+
+extern "C" int tp_test_eig(tp_ctx *ctx, const double *t, int b, double tol, double *w_out, double *v_out,
+                           int *sweeps_out) {
+    TP_ARG(ctx && t && b >= 1 && w_out && v_out, "tp_test_eig: bad arguments");
+    TP_CUDA(cudaSetDevice(ctx->device));
+    const int ld = round_up(b, 8);
+    const size_t bytes = (size_t)b * ld * sizeof(double);
+    TP_TRY(ctx->T.reserve(bytes)); TP_TRY(ctx->Jv.reserve(bytes)); TP_TRY(ctx->Jw.reserve((size_t)4 * b * sizeof(double)));
+    TP_CUDA(cudaMemsetAsync(ctx->T.p, 0, bytes, ctx->stream));
+    TP_CUDA(cudaMemsetAsync(ctx->Jv.p, 0, bytes, ctx->stream));
+    TP_CUDA(cudaMemcpy2DAsync(ctx->T.p, (size_t)ld * sizeof(double), t, (size_t)b * sizeof(double),
+                              (size_t)b * sizeof(double), b, cudaMemcpyHostToDevice, ctx->stream));
+    int sweeps = 0;
+    TP_TRY(tp_jacobi(ctx, ctx->T.as<double>(), b, ld, ctx->Jw.as<double>(), ctx->Jv.as<double>(), ld, b, &sweeps, tol));
+    if (sweeps_out) *sweeps_out = sweeps;
+    TP_CUDA(cudaMemcpyAsync(w_out, ctx->Jw.p, (size_t)b * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    TP_CUDA(cudaMemcpy2DAsync(v_out, (size_t)b * sizeof(double), ctx->Jv.p, (size_t)ld * sizeof(double),
+                              (size_t)b * sizeof(double), b, cudaMemcpyDeviceToHost, ctx->stream));
+    TP_CUDA(cudaStreamSynchronize(ctx->stream));
     return TP_OK;
 }
 

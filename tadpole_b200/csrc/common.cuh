@@ -116,7 +116,7 @@ struct tp_ctx {
     double prof_gemm_flop = 0.0;           // algorithmic flops of the GEMM launches profiled
 };
 
-enum { PC_ROWMEAN = 0, PC_COMPACT, PC_GEMM, PC_JACOBI, PC_SWEEP, PC_CH, PC_DIFFT, PC_SPARE, PC_COUNT };
+enum { PC_ROWMEAN = 0, PC_COMPACT, PC_GEMM, PC_JACOBI, PC_SWEEP, PC_CH, PC_DIFFT, PC_SPARE, PC_CHOL, PC_IGEMM, PC_SPARE2, PC_SPARE3, PC_COUNT };
 void tp_prof_begin(tp_ctx *ctx, int cls);
 void tp_prof_end(tp_ctx *ctx);
 

@@ -329,6 +329,7 @@ chol_inv_kernel(double *G, double *Linv, int b, int ld, int *info, int factor_on
     const int tid = threadIdx.x;
     constexpr int PP = CH_PW + 1;
     __shared__ double s_clamp;
+    __shared__ double s_rd[CH_PW];             // reciprocal pivots of the current panel (0: column dropped)
     if (tid == 0) {
         s_bad = 0;
         double mx = 0.0;
@@ -348,13 +349,15 @@ chol_inv_kernel(double *G, double *Linv, int b, int ld, int *info, int factor_on
         if (tid < 32) {
             for (int c = 0; c < w; c++) {
                 double d = s_pan[c * PP + c];
-                if (factor_only && !(d > s_clamp)) d = s_clamp > 0.0 ? s_clamp : 1e-300;
+                // semi-definite input: a round-off level pivot keeps a tiny diagonal and a zero column
+                const bool tiny = factor_only && !(d > s_clamp);
+                if (tiny) d = s_clamp > 0.0 ? s_clamp : 1e-300;
                 const bool ok = d > 0.0;
                 if (!ok && tid == 0) s_bad = 1;
                 const double piv = sqrt(ok ? d : 1.0);
                 __syncwarp();
-                if (tid == c) s_pan[c * PP + c] = piv;
-                if (tid > c && tid < w) s_pan[tid * PP + c] *= 1.0 / piv;
+                if (tid == c) { s_pan[c * PP + c] = piv; s_rd[c] = tiny ? 0.0 : 1.0 / piv; }
+                if (tid > c && tid < w) s_pan[tid * PP + c] *= tiny ? 0.0 : 1.0 / piv;
                 __syncwarp();
                 // row `tid` of the remaining block: P[tid][c2] -= P[tid][c] * P[c2][c], c < c2 <= tid
                 if (tid > c && tid < w) {
@@ -371,7 +374,7 @@ chol_inv_kernel(double *G, double *Linv, int b, int ld, int *info, int factor_on
             for (int c = 0; c < w; c++) {
                 double s = row[c];
                 for (int t = 0; t < c; t++) s -= row[t] * s_pan[c * PP + t];
-                row[c] = s / s_pan[c * PP + c];
+                row[c] = s * s_rd[c];
             }
         }
         __syncthreads();
@@ -463,40 +466,17 @@ chol_inv_kernel(double *G, double *Linv, int b, int ld, int *info, int factor_on
     }
 }
 
-// G (b x b, ld) is overwritten by its Cholesky factor; Linv receives L^-1.  *bad_out = 1 when G is
-// not numerically positive definite.
-int tp_chol_inv(tp_ctx *ctx, double *G, double *Linv, int b, int ld, int *bad_out) {
+// single-CTA launcher (b > 256; the cluster kernel in cholinv.cu handles the common sizes)
+int tp_chol_inv_1cta(tp_ctx *ctx, double *G, double *Linv, int b, int ld, int *info, int factor_only) {
     cudaStream_t st = ctx->stream;
-    TP_TRY(ctx->Jt.reserve(64));
-    int *info = ctx->Jt.as<int>();
     size_t chsm = (size_t)b * (CH_PW + 1) * sizeof(double);
-    const size_t chsm2 = (size_t)32 * CH_PW * (CH_PW + 1) * sizeof(double) > (size_t)0 ? (size_t)((b + CH_PW - 1) / CH_PW < 32 ? (b + CH_PW - 1) / CH_PW : 32) * CH_PW * (CH_PW + 1) * sizeof(double) : 0;
-    if (chsm2 > chsm) chsm = chsm2;
+    const int nbw = (b + CH_PW - 1) / CH_PW;
+    const size_t chsm2 = (size_t)(nbw < 32 ? nbw : 32) * CH_PW * (CH_PW + 1) * sizeof(double);
+    if (!factor_only && chsm2 > chsm) chsm = chsm2;
     TP_ARG(chsm <= (size_t)ctx->max_smem_optin, "tp_chol_inv: block too wide for the shared-memory panel");
     TP_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chsm));
-    tp_prof_begin(ctx, PC_JACOBI);
-    chol_inv_kernel<<<1, CH_THREADS, chsm, st>>>(G, Linv, b, ld, info, 0);
-    tp_prof_end(ctx);
-    ctx->launches += 1;
-    TP_CUDA(cudaGetLastError());
-    TP_TRY(tp_pin_reserve(ctx, 64));
-    int *h = (int *)ctx->pin;
-    TP_CUDA(cudaMemcpyAsync(h, info, sizeof(int), cudaMemcpyDeviceToHost, st));
-    TP_CUDA(cudaStreamSynchronize(st));
-    *bad_out = h[0];
-    return TP_OK;
-}
-
-// G <- Cholesky factor (lower triangle), semi-definite input tolerated (pivots clamped); no read-back
-int tp_chol_factor(tp_ctx *ctx, double *G, int b, int ld) {
-    cudaStream_t st = ctx->stream;
-    TP_TRY(ctx->harm.reserve(64));
-    int *info = ctx->harm.as<int>();
-    size_t chsm = (size_t)b * (CH_PW + 1) * sizeof(double);
-    TP_ARG(chsm <= (size_t)ctx->max_smem_optin, "tp_chol_factor: block too wide for the shared-memory panel");
-    TP_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chsm));
-    tp_prof_begin(ctx, PC_JACOBI);
-    chol_inv_kernel<<<1, CH_THREADS, chsm, st>>>(G, nullptr, b, ld, info, 1);
+    tp_prof_begin(ctx, PC_CHOL);
+    chol_inv_kernel<<<1, CH_THREADS, chsm, st>>>(G, Linv, b, ld, info, factor_only);
     tp_prof_end(ctx);
     ctx->launches += 1;
     TP_CUDA(cudaGetLastError());
