@@ -28,6 +28,24 @@ int tp_pin_reserve(tp_ctx *ctx, size_t bytes) {
     return TP_OK;
 }
 
+int tp_flags_reset(tp_ctx *ctx) {
+    TP_TRY(ctx->status.reserve(64));
+    TP_CUDA(cudaMemsetAsync(ctx->status.p, 0, 64, ctx->stream));
+    return TP_OK;
+}
+int tp_flags_enqueue(tp_ctx *ctx) {
+    TP_TRY(ctx->status.reserve(64));
+    if (!ctx->pin_flags) TP_CUDA(cudaMallocHost((void **)&ctx->pin_flags, 64));
+    TP_CUDA(cudaMemcpyAsync(ctx->pin_flags, ctx->status.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    return TP_OK;
+}
+int tp_flags_read(tp_ctx *ctx, int out[4]) {
+    TP_TRY(tp_flags_enqueue(ctx));
+    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 4; i++) out[i] = ctx->pin_flags[i];
+    return TP_OK;
+}
+
 extern "C" int tp_ctx_create(int device, tp_ctx **out) {
     TP_ARG(out, "tp_ctx_create: null output pointer");
     int ndev = 0;
@@ -53,6 +71,7 @@ extern "C" int tp_ctx_create(int device, tp_ctx **out) {
     TP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (int i = 0; i < EV_COUNT; i++) TP_CUDA(cudaEventCreate(&ctx->ev[i]));
     TP_TRY(tp_pin_reserve(ctx, 1 << 16));
+    TP_TRY(tp_flags_reset(ctx));
     *out = ctx;
     return TP_OK;
 }
@@ -65,11 +84,12 @@ extern "C" int tp_ctx_destroy(tp_ctx *ctx) {
                       &ctx->colstat, &ctx->scores, &ctx->M, &ctx->Y0, &ctx->Y1, &ctx->Y2, &ctx->W, &ctx->G, &ctx->T,
                       &ctx->Q, &ctx->Jw, &ctx->Jv, &ctx->Jt, &ctx->small1, &ctx->small2, &ctx->part, &ctx->resid,
                       &ctx->P, &ctx->Qp, &ctx->d0, &ctx->seqdist, &ctx->order, &ctx->ncl, &ctx->chs, &ctx->bsbuf,
-                      &ctx->links, &ctx->harm, &ctx->lx, &ctx->ly, &ctx->dout, &ctx->dhash, &ctx->lhash};
+                      &ctx->links, &ctx->harm, &ctx->status, &ctx->lx, &ctx->ly, &ctx->dout, &ctx->dhash, &ctx->lhash};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->pin_flags) cudaFreeHost(ctx->pin_flags);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return TP_OK;

@@ -95,6 +95,9 @@ struct tp_ctx {
     // PCA
     int k = 0, ldk = 0;          // scores: nf x ldk row-major
     DevBuf scores, M, Y0, Y1, Y2, W, G, T, Q, Jw, Jv, Jt, small1, small2, part, resid;
+    // sticky status words of the small dense kernels, read back at the solver's own sync points:
+    // [0] Cholesky met a non-positive pivot  [1] eigensolver did not converge  [2] eigensolver sweeps (sum)
+    DevBuf status;
     bool have_scores = false;
     // sweep
     DevBuf P, Qp, d0, seqdist, order, ncl, chs, bsbuf, links, harm;
@@ -105,6 +108,7 @@ struct tp_ctx {
     // pinned staging for small read-backs
     void *pin = nullptr;
     size_t pin_cap = 0;
+    int *pin_flags = nullptr;    // 64 pinned bytes for the status words
 
     double timing[10] = {};
 
@@ -121,6 +125,9 @@ void tp_prof_begin(tp_ctx *ctx, int cls);
 void tp_prof_end(tp_ctx *ctx);
 
 int tp_pin_reserve(tp_ctx *ctx, size_t bytes);
+int tp_flags_reset(tp_ctx *ctx);                 // zero the status words (stream ordered)
+int tp_flags_read(tp_ctx *ctx, int out[4]);      // copy them to the host (synchronises the stream)
+int tp_flags_enqueue(tp_ctx *ctx);               // async copy into ctx->pin_flags; valid after the next stream sync
 // record a timing event on the context stream
 #define TP_MARK(ctx, id)                                              \
     do {                                                              \

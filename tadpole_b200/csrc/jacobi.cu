@@ -394,8 +394,7 @@ chol_inv_kernel(double *G, double *Linv, int b, int ld, int *info, int factor_on
         }
         __syncthreads();
     }
-    if (s_bad) { if (tid == 0) info[0] = 1; return; }
-    if (tid == 0) info[0] = 0;
+    if (s_bad) { if (tid == 0) info[0] = 1; return; }       // sticky status word: never cleared here
     if (factor_only) return;
     __syncthreads();
     // ---- Linv = L^-1, blocked: 32 x 32 diagonal blocks by forward substitution (one warp each, one

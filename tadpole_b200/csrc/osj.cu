@@ -197,7 +197,7 @@ osj_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol,
         for (int r = 0; r < OSJ_CLUSTER; r++) v = fmax(v, __ldcg(&cmax[(sweeps & 1) * OSJ_CLUSTER + r]));
         converged = v <= tol2;          // squared scaled cosines
     }
-    if (crank == 0 && tid == 0) { info[0] = sweeps; info[1] = converged ? 1 : 0; }
+    if (crank == 0 && tid == 0) { if (!converged) info[1] = 1; info[2] += sweeps; }     // sticky status words
 }
 
 // eigenvalues w (unsorted, one per column) -> descending order; eigenvector = normalised column of the
@@ -238,7 +238,9 @@ int tp_osj(tp_ctx *ctx, double *T, int b, int ld, double *w, double *Vs, int lds
     TP_TRY(ctx->Jt.reserve(panel + (size_t)(NC + 64) * sizeof(double) + 64));
     double *Ac = ctx->Jt.as<double>();
     double *wtmp = Ac + (size_t)NC * BP, *cmax = wtmp + NC;
-    int *info = (int *)(cmax + 32);
+    TP_TRY(ctx->status.reserve(64));
+    int *info = ctx->status.as<int>();
+    if (sweeps_out) TP_TRY(tp_flags_reset(ctx));
     TP_TRY(tp_chol_factor(ctx, T, b, ld));
     tp_prof_begin(ctx, PC_JACOBI);
     osj_init_kernel<<<(unsigned)(((size_t)NC * BP + 255) / 256), 256, 0, st>>>(T, b, ld, BP, NC, Ac);
@@ -260,15 +262,15 @@ int tp_osj(tp_ctx *ctx, double *T, int b, int ld, double *w, double *Vs, int lds
     tp_prof_end(ctx);
     ctx->launches += 3;
     TP_CUDA(cudaGetLastError());
-    TP_TRY(tp_pin_reserve(ctx, 64));
-    int *h = (int *)ctx->pin;
-    TP_CUDA(cudaMemcpyAsync(h, info, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    TP_CUDA(cudaStreamSynchronize(st));
-    if (sweeps_out) *sweeps_out = h[0];
-    if (getenv("TADPOLE_DEBUG")) fprintf(stderr, "[tadpole] osj b=%d tol=%.1e sweeps=%d converged=%d\n", b, otol, h[0], h[1]);
-    if (!h[1]) {
-        tp_set_error("tp_osj: no convergence after %d sweeps (b = %d)", h[0], b);
-        return TP_ERR_NOCONV;
+    if (sweeps_out) {        // synchronous use: status read back now; otherwise the caller polls tp_flags_read
+        int f[4];
+        TP_TRY(tp_flags_read(ctx, f));
+        *sweeps_out = f[2];
+        if (getenv("TADPOLE_DEBUG")) fprintf(stderr, "[tadpole] osj b=%d tol=%.1e sweeps=%d converged=%d\n", b, otol, f[2], !f[1]);
+        if (f[1]) {
+            tp_set_error("tp_osj: no convergence after %d sweeps (b = %d)", f[2], b);
+            return TP_ERR_NOCONV;
+        }
     }
     return TP_OK;
 }

@@ -313,24 +313,43 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
         };
         // Cholesky QR: Y <- Y L^-T.  One pass leaves ~cond^2 * eps of non-orthogonality, which is enough
         // between two filter rounds; two passes before a Rayleigh-Ritz step.  *bad = 1 when G is not PD.
+        // Fast mode (safe == false): nothing is read back here; a non-positive pivot sets a sticky status word that
+        // body() polls at its own synchronisation points and answers by running the whole solve again in safe mode.
+        bool safe = false;
         auto cholqr = [&](int passes, int *bad) {
             *bad = 0;
             for (int pass = 0; pass < passes; pass++) {
                 TP_TRY(gram(Y, Y, G));
-                TP_TRY(tp_chol_inv(ctx, G, S1, b, ldb, bad));
+                TP_TRY(tp_chol_inv(ctx, G, S1, b, ldb, safe ? bad : nullptr));
                 if (*bad) return (int)TP_OK;
                 TP_TRY(rotate(S1, 1));          // B = Linv^T: (k, n) at Linv[n*ldb + k]
             }
             return (int)TP_OK;
+        };
+        // eigensolver call: synchronous status in safe mode only
+        auto eig = [&](double *A, double *w, double jtol) {
+            int sw = 0;
+            TP_TRY(tp_jacobi(ctx, A, b, ldb, w, JV, ldb, b, safe ? &sw : nullptr, jtol));
+            sweeps_total += sw;
+            return (int)TP_OK;
+        };
+        // status words of the fast mode, polled where the host waits anyway: 0 fine, 1 rerun in safe mode
+        const int RERUN = -1000;
+        // (the copy is enqueued before the stream synchronisation the caller does anyway)
+        auto poll = [&]() -> int {
+            if (safe) return TP_OK;
+            const int *f = ctx->pin_flags;
+            if (f[0]) return RERUN;
+            if (f[1]) { tp_set_error("tp_pca: b x b eigensolver did not converge (b = %d)", b); return TP_ERR_NOCONV; }
+            sweeps_total = f[2];
+            return TP_OK;
         };
         // Rayleigh-Ritz on an orthonormal block: T = Y^T W, T = Z diag(theta) Z^T, Y <- Y Z
         auto rr_orthonormal = [&](double jtol) {
             TP_TRY(gram(Y, W, T));
             symmetrize_kernel<<<gb, 256, 0, st>>>(T, b, ldb);
             ctx->launches += 1;
-            int sw = 0;
-            TP_TRY(tp_jacobi(ctx, T, b, ldb, theta, JV, ldb, b, &sw, jtol));
-            sweeps_total += sw;
+            TP_TRY(eig(T, theta, jtol));
             return rotate(JV, 0);
         };
         // orthonormalisation and Rayleigh-Ritz together as the generalised problem (G = Y^T Y,
@@ -340,17 +359,14 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
             TP_TRY(gram(Y, W, T));
             scale_gram_kernel<<<gb, 256, 0, st>>>(G, T, b, ldb, S1, S2, dvec);       // S1 = Gs, S2 = Ts
             ctx->launches += 1;
-            int sw = 0;
-            TP_TRY(tp_jacobi(ctx, S1, b, ldb, gval, JV, ldb, b, &sw, jtol));          // Gs = JV diag(gval) JV^T
-            sweeps_total += sw;
+            TP_TRY(eig(S1, gval, jtol));                                             // Gs = JV diag(gval) JV^T
             whiten_kernel<<<gb, 256, 0, st>>>(JV, gval, b, ldb, S1);                 // S1 = X
             ctx->launches += 1;
             TP_TRY(small_gemm(ctx, S2, 1, S1, 0, G, b, ldb));                        // G  = Ts X
             TP_TRY(small_gemm(ctx, S1, 0, G, 0, T, b, ldb));                         // T  = X^T Ts X
             symmetrize_kernel<<<gb, 256, 0, st>>>(T, b, ldb);
             ctx->launches += 1;
-            TP_TRY(tp_jacobi(ctx, T, b, ldb, theta, JV, ldb, b, &sw, jtol));          // T = JV diag(theta) JV^T
-            sweeps_total += sw;
+            TP_TRY(eig(T, theta, jtol));                                             // T = JV diag(theta) JV^T
             TP_TRY(small_gemm(ctx, S1, 1, JV, 0, Q, b, ldb));                        // Q = X Z
             scale_rows_kernel<<<gb, 256, 0, st>>>(Q, b, ldb, dvec);                  // Q = D X Z
             ctx->launches += 1;
@@ -376,6 +392,9 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
         };
 
         auto body = [&]() -> int {
+            TP_TRY(tp_flags_reset(ctx));
+            sweeps_total = 0; it = 0; converged = false; op.applications = 0;
+            Y = ctx->Y0.as<double>(); F1 = ctx->Y1.as<double>(); F2 = ctx->Y2.as<double>();
             random_block_kernel<<<(unsigned)(((size_t)n * ldb + 255) / 256), 256, 0, st>>>(Y, n, b, ldb);
             ctx->launches += 1;
             {   // start: orthonormalise the random block, one Rayleigh-Ritz step at low accuracy
@@ -389,7 +408,9 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
             for (it = 1; it <= ctx->pca_maxit * 2; it++) {
                 // ---- bounds from the current Ritz values -----------------------------------------
                 TP_CUDA(cudaMemcpyAsync(hbuf, theta, (size_t)b * sizeof(double), cudaMemcpyDeviceToHost, st));
+                TP_TRY(tp_flags_enqueue(ctx));
                 TP_CUDA(cudaStreamSynchronize(st));
+                TP_TRY(poll());
                 hbuf = (double *)ctx->pin;
                 bd.top = hbuf[0]; bd.thk = hbuf[k - 1];
                 double cut = hbuf[b - 1];
@@ -408,7 +429,9 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
                 residual_kernel<<<(k + 31) / 32, 256, 0, st>>>(Y, F1, n, ldb, k, theta, bd.e / bd.sig1, bd.c, res);
                 ctx->launches += 1;
                 TP_CUDA(cudaMemcpyAsync(hbuf, res, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, st));
+                TP_TRY(tp_flags_enqueue(ctx));
                 TP_CUDA(cudaStreamSynchronize(st));
+                TP_TRY(poll());
                 double rmax = 0.0;
                 for (int j = 0; j < k; j++) rmax = (hbuf[j] > rmax || hbuf[j] != hbuf[j]) ? hbuf[j] : rmax;
                 last_res = rmax / bd.top;
@@ -432,6 +455,10 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
             return TP_OK;
         };
         rc = body();
+        if (rc == RERUN) {           // rank-deficient block met by the fast path: slow and careful this time
+            safe = true;
+            rc = body();
+        }
         zbuf.release();
         TP_TRY(rc);
         ctx->timing[7] = it;
