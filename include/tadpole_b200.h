@@ -51,7 +51,7 @@ void *tp_ctx_stream(tp_ctx *ctx);
 /* number of kernels this context has launched so far */
 long long tp_ctx_launches(tp_ctx *ctx);
 /* tunables: "pca_block" (subspace width, 0 = auto), "pca_tol" (x1e-16), "pca_maxit",
- * "jacobi_direct_max", "level_cap" */
+ * "jacobi_direct_max", "level_cap", "dist_min_n" */
 int tp_ctx_set(tp_ctx *ctx, const char *key, double value);
 /* per-stage device milliseconds of the last tp_call / stage call, measured with CUDA events on
  * the context stream: [0] filter [1] compact [2] correlation [3] pca [4] sweep (CONISS) [5] CH
@@ -61,10 +61,26 @@ int tp_ctx_timings(tp_ctx *ctx, double *out10);
 /* per-kernel-class device time: when enabled, every launch of the classes below is bracketed by
  * CUDA events on the context stream; reading sums them since the last enable/reset.
  * classes: [0] rowmean (filter) [1] compact [2] dgemm [3] jacobi (b x b eigensolver) [4] coniss_sweep [5] ch
- * [6] difft [8] chol (b x b Cholesky + triangular inverse) [9] igemm (tcgen05 integer GEMM) [10..11] spare;
+ * [6] difft [8] chol (b x b Cholesky + triangular inverse) [9] igemm (tcgen05 integer GEMM) [10] NCCL collectives
+ * [11] spare;
  * [7] in ms_out12: GFLOP (algorithmic) of the profiled dgemm launches.
  * enable: 1 = start/reset, 0 = stop, -1 = just read. */
 int tp_ctx_profile(tp_ctx *ctx, int enable, double *ms_out12, long long *count_out12);
+
+/* ---- multi-GPU: one process per GPU, NCCL bound at run time (single-GPU use never touches it) ------------------
+ * The reference shards the n_pcs sweep over forked workers (foreach %dopar%, R/TADpole.R:103-104); here one call can
+ * also spread its O(N^3) stages over the GPUs of a node.  tp_comm_unique_id (one rank) -> the 128 bytes travel to the
+ * other ranks by any host channel (the Python host uses torch.distributed) -> tp_ctx_comm_init on every rank of the
+ * group.  Slots hold several communicators at once (slot 0: the whole job; another slot: the ranks working on one
+ * chromosome arm); tp_ctx_comm_select picks the one the following calls are collective over, -1 = none.
+ * While a communicator is selected, tp_correlation / tp_pca / tp_call / tp_call_arm must be entered by every rank of
+ * it with the same arguments and the same matrix; every rank returns the same results.  Row blocks of the
+ * correlation matrix (and of every operator application of the PCA) are computed by their owner and all-gathered
+ * when nf >= "dist_min_n" (tp_ctx_set, default 4096); the candidates of the sweep are dealt out rank-interleaved. */
+int tp_comm_unique_id(void *id128);
+int tp_ctx_comm_init(tp_ctx *ctx, const void *id128, int rank, int nranks, int slot);
+int tp_ctx_comm_select(tp_ctx *ctx, int slot);
+int tp_ctx_comm_info(tp_ctx *ctx, int *rank_out, int *nranks_out);
 
 /* ---- stage 1: load_mat numeric core (R/TADpole.R:19-22,35-37) ----------------------------- */
 /* Uploads (or adopts, when on_device) the N x N matrix, computes rowMeans of the symmetrised

@@ -23,6 +23,7 @@ EXPORTED = [
     "tp_get_filtered", "tp_correlation", "tp_get_correlation", "tp_set_correlation", "tp_pca",
     "tp_get_scores", "tp_set_scores", "tp_sweep", "tp_get_dendro", "tp_select", "tp_call", "tp_call_arm",
     "tp_difft_batch", "tp_assemble", "tp_test_cholinv", "tp_test_eig",
+    "tp_comm_unique_id", "tp_ctx_comm_init", "tp_ctx_comm_select", "tp_ctx_comm_info",
 ]
 
 
@@ -65,6 +66,10 @@ def load():
         "tp_get_correlation": (c_int, [vp, dp]),
         "tp_set_correlation": (c_int, [vp, dp, c_int]),
         "tp_pca": (c_int, [vp, c_int, ip]),
+        "tp_comm_unique_id": (c_int, [vp]),
+        "tp_ctx_comm_init": (c_int, [vp, vp, c_int, c_int, c_int]),
+        "tp_ctx_comm_select": (c_int, [vp, c_int]),
+        "tp_ctx_comm_info": (c_int, [vp, ip, ip]),
         "tp_test_cholinv": (c_int, [vp, dp, c_int, c_int, dp, dp, ip]),
         "tp_test_eig": (c_int, [vp, dp, c_int, c_double, dp, dp, ip]),
         "tp_get_scores": (c_int, [vp, dp]),
@@ -141,7 +146,7 @@ class Context:
         return dict(zip(keys, out.tolist()))
 
     PROFILE_CLASSES = ["rowmean", "compact", "dgemm", "jacobi", "coniss_sweep", "ch", "difft", "gemm_gflop", "chol", "igemm",
-                       "spare2", "spare3"]
+                       "comm", "spare3"]
 
     def profile(self, enable=-1):
         """enable: 1 start/reset, 0 stop, -1 read.  Returns {class: (ms, launches)} accumulated so far."""
@@ -202,6 +207,25 @@ class Context:
         k = c_int(0)
         check(self.lib.tp_pca(self._h, int(max_pcs), ctypes.byref(k)))
         return k.value
+
+    # ---- multi-GPU ----
+    def comm_unique_id(self):
+        """128-byte NCCL unique id (call on one rank, ship the bytes to the others)."""
+        buf = ctypes.create_string_buffer(128)
+        check(self.lib.tp_comm_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
+        return buf.raw
+
+    def comm_init(self, unique_id, rank, nranks, slot=0):
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        check(self.lib.tp_ctx_comm_init(self._h, ctypes.cast(buf, ctypes.c_void_p), int(rank), int(nranks), int(slot)))
+
+    def comm_select(self, slot):
+        check(self.lib.tp_ctx_comm_select(self._h, int(slot)))
+
+    def comm_info(self):
+        r, n = c_int(0), c_int(1)
+        check(self.lib.tp_ctx_comm_info(self._h, ctypes.byref(r), ctypes.byref(n)))
+        return r.value, n.value
 
     def test_cholinv(self, g, factor_only=False):
         """(L, Linv or None, bad) of a symmetric positive definite b x b matrix (test hook)."""

@@ -161,8 +161,12 @@ def _messages_optimal(res):
 
 
 def TADpole(mat_file, max_pcs=200, min_clusters=2, bad_frac=0.01, chr=None, start=None, end=None, resol=None,
-            centromere_search=False, ctx=None):
-    """Call hierarchical TADs (R/TADpole.R:344-501)."""
+            centromere_search=False, ctx=None, dist=None):
+    """Call hierarchical TADs (R/TADpole.R:344-501).
+
+    dist: a sharding.DistEnv when the call is spread over several GPUs (one process per GPU, every rank calls with
+    the same matrix and gets the same object back).  Without centromere_search the whole job works on the one
+    matrix; with it the ranks split between the two arms, as the arms are independent (R/TADpole.R:357)."""
     ctx = ctx or get_context()
     mat = read_matrix(mat_file)
     if not centromere_search:
@@ -190,10 +194,20 @@ def TADpole(mat_file, max_pcs=200, min_clusters=2, bad_frac=0.01, chr=None, star
     tp = Tadpole()
     fixed_arms = []
     ncen = len(lm.centromere)
+    arm_res = {}
+    if dist is not None and dist.world > 1:
+        # every rank runs its own arm (collectively with the other ranks of that arm); the small result summaries
+        # are then exchanged so that every rank assembles the same object
+        dist.select_arm()
+        mine = ctx.call_arm(getattr(lm, dist.my_arm).keep, max_pcs=max_pcs, min_clusters=min_clusters)
+        dist.select_world()
+        every = dist.exchange((dist.my_arm, mine))
+        for arm in ("p", "q"):
+            arm_res[arm] = every[dist.arms[arm][0]][1]
     for arm in ("p", "q"):
         message(f"Processing arm {arm}")
         la = getattr(lm, arm)
-        res = ctx.call_arm(la.keep, max_pcs=max_pcs, min_clusters=min_clusters)
+        res = arm_res[arm] if arm in arm_res else ctx.call_arm(la.keep, max_pcs=max_pcs, min_clusters=min_clusters)
         _messages_optimal(res)
         a = _Obj()
         a.n_pcs = res["n_pcs"]

@@ -86,6 +86,7 @@ extern "C" int tp_ctx_destroy(tp_ctx *ctx) {
                       &ctx->P, &ctx->Qp, &ctx->d0, &ctx->seqdist, &ctx->order, &ctx->ncl, &ctx->chs, &ctx->bsbuf,
                       &ctx->links, &ctx->harm, &ctx->status, &ctx->lx, &ctx->ly, &ctx->dout, &ctx->dhash, &ctx->lhash};
     for (DevBuf *b : bufs) b->release();
+    tp_comm_destroy_all(ctx);
     for (int i = 0; i < EV_COUNT; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->pin) cudaFreeHost(ctx->pin);
@@ -113,6 +114,7 @@ extern "C" int tp_ctx_set(tp_ctx *ctx, const char *key, double value) {
     else if (k == "pca_inner") ctx->pca_inner = (int)value < 1 ? 1 : (int)value;
     else if (k == "jacobi_direct_max") ctx->jacobi_direct_max = (int)value;
     else if (k == "level_cap") ctx->level_cap = (int)value;
+    else if (k == "dist_min_n") ctx->dist_min_n = (int)value;
     else { tp_set_error("tp_ctx_set: unknown key '%s'", key); return TP_ERR_ARG; }
     return TP_OK;
 }
@@ -283,13 +285,31 @@ extern "C" int tp_get_scores(tp_ctx *ctx, double *scores_out) {
 }
 
 // ---- stages 4 + 5 ---------------------------------------------------------------------------------
+// rows of candidates this rank did not run become 0 so that the sum over ranks is the union (NaN + 0 = NaN)
+__global__ void zero_foreign_rows_kernel(double *chs, int *ncl, int k, int ld, int begin, int stride) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)k * ld) return;
+    const int c = (int)(idx / ld);
+    if (c < begin || (c - begin) % stride != 0) {
+        chs[idx] = 0.0;
+        if (idx % ld == 0) ncl[c] = 0;       // (a second, wider pass finds the sums of the first one here)
+    }
+}
+
+// collective == true: the candidates are dealt out rank-interleaved over the current communicator (cost grows with
+// the number of PCs) and the level counts / CH rows are combined on every rank; cand_begin / cand_stride are ignored
 static int sweep_impl(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stride,
-                      int *n_cluster_out, double *scores_out, int ld_scores, int *maxlev_out) {
+                      int *n_cluster_out, double *scores_out, int ld_scores, int *maxlev_out, bool collective = false) {
     int ncand = 0;
+    collective = collective && tp_nranks(ctx) > 1;
+    if (collective) {
+        TP_ARG(ctx->k >= tp_nranks(ctx), "tp_sweep: fewer candidates than ranks");
+        cand_begin = tp_rank(ctx); cand_stride = tp_nranks(ctx);
+    }
     TP_TRY(tp_sweep_device(ctx, min_clusters, cand_begin, cand_stride, &ncand));
     const int k = ctx->k;
     if (maxlev_out) *maxlev_out = 0;
-    if (ncand == 0) {
+    if (ncand == 0 && !collective) {
         if (n_cluster_out) std::fill(n_cluster_out, n_cluster_out + k, 0);
         return TP_OK;
     }
@@ -299,6 +319,13 @@ static int sweep_impl(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_st
     int maxlev = 0;
     for (int pass = 0; pass < 2; pass++) {
         TP_TRY(tp_ch_device(ctx, min_clusters, ncand, ld));
+        if (collective) {
+            zero_foreign_rows_kernel<<<(unsigned)(((size_t)k * ld + 255) / 256), 256, 0, ctx->stream>>>(
+                ctx->chs.as<double>(), ctx->ncl.as<int>(), k, ld, cand_begin, cand_stride);
+            ctx->launches += 1;
+            TP_TRY(tp_comm_allreduce_sum(ctx, ctx->ncl.p, (size_t)k, 0));
+            TP_TRY(tp_comm_allreduce_sum(ctx, ctx->chs.p, (size_t)k * ld, 1));
+        }
         TP_CUDA(cudaMemcpyAsync(h_ncl, ctx->ncl.p, (size_t)k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         TP_CUDA(cudaStreamSynchronize(ctx->stream));
         maxlev = 0;
@@ -401,14 +428,14 @@ static int call_from_compacted(tp_ctx *ctx, int max_pcs, int min_clusters, int *
     // first try with the caller's width; when scores_out is NULL use a local buffer
     int rc;
     if (sc) {
-        rc = sweep_impl(ctx, min_clusters, 0, 1, nullptr, sc, ld, &maxlev);
+        rc = sweep_impl(ctx, min_clusters, 0, 1, nullptr, sc, ld, &maxlev, true);
     } else {
         local.assign((size_t)k * ld, NAN);
-        rc = sweep_impl(ctx, min_clusters, 0, 1, nullptr, local.data(), ld, &maxlev);
+        rc = sweep_impl(ctx, min_clusters, 0, 1, nullptr, local.data(), ld, &maxlev, true);
         if (rc == TP_ERR_ARG && maxlev > ld) {
             ld = maxlev;
             local.assign((size_t)k * ld, NAN);
-            rc = sweep_impl(ctx, min_clusters, 0, 1, nullptr, local.data(), ld, &maxlev);
+            rc = sweep_impl(ctx, min_clusters, 0, 1, nullptr, local.data(), ld, &maxlev, true);
         }
         sc = local.data();
     }
@@ -418,6 +445,10 @@ static int call_from_compacted(tp_ctx *ctx, int max_pcs, int min_clusters, int *
     TP_TRY(tp_select(sc, k, ld, maxlev, &oc, &ol));
     if (n_pcs_out) *n_pcs_out = oc + 1;
     if (n_clusters_out) *n_clusters_out = ol + 1;
+    if (tp_nranks(ctx) > 1) {       // the optimal candidate's dendrogram lives on the rank that ran it
+        const int n1 = ctx->nf - 1, ldd = round_up(n1, 8);
+        TP_TRY(tp_comm_bcast(ctx, ctx->seqdist.as<double>() + (size_t)oc * ldd, (size_t)n1, oc % tp_nranks(ctx)));
+    }
     if (seqdist_out) TP_TRY(tp_get_dendro(ctx, oc, seqdist_out, nullptr));
     TP_MARK(ctx, EV_TOTAL1);
     return TP_OK;

@@ -65,6 +65,9 @@ enum { EV_FILTER0 = 0, EV_FILTER1, EV_COMPACT0, EV_COMPACT1, EV_CORR0, EV_CORR1,
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+#define TP_COMM_SLOTS 4
+struct TpCommSlot { void *handle = nullptr; int rank = 0, nranks = 1; };
+
 struct tp_ctx {
     int device = 0;
     int sm_count = 148;
@@ -73,6 +76,12 @@ struct tp_ctx {
     cudaEvent_t ev[EV_COUNT] = {};
     bool ev_set[EV_COUNT] = {};
     long long launches = 0;
+
+    // communicators (comm.cu): slot 0 is conventionally the whole job, others sub-groups (chromosome arms);
+    // comm_cur = -1: no collective (single GPU, or replicated / independent work)
+    TpCommSlot comm[TP_COMM_SLOTS];
+    int comm_cur = -1;
+    int dist_min_n = 4096;       // matrices smaller than this are not row-sharded (only the candidate sweep is)
 
     // tunables
     int pca_block = 0;
@@ -120,11 +129,33 @@ struct tp_ctx {
     double prof_gemm_flop = 0.0;           // algorithmic flops of the GEMM launches profiled
 };
 
-enum { PC_ROWMEAN = 0, PC_COMPACT, PC_GEMM, PC_JACOBI, PC_SWEEP, PC_CH, PC_DIFFT, PC_SPARE, PC_CHOL, PC_IGEMM, PC_SPARE2, PC_SPARE3, PC_COUNT };
+enum { PC_ROWMEAN = 0, PC_COMPACT, PC_GEMM, PC_JACOBI, PC_SWEEP, PC_CH, PC_DIFFT, PC_SPARE, PC_CHOL, PC_IGEMM, PC_COMM, PC_SPARE3, PC_COUNT };
 void tp_prof_begin(tp_ctx *ctx, int cls);
 void tp_prof_end(tp_ctx *ctx);
 
 int tp_pin_reserve(tp_ctx *ctx, size_t bytes);
+
+// ---- multi-GPU (comm.cu) ----
+static inline int tp_nranks(const tp_ctx *ctx) { return ctx->comm_cur < 0 ? 1 : ctx->comm[ctx->comm_cur].nranks; }
+static inline int tp_rank(const tp_ctx *ctx) { return ctx->comm_cur < 0 ? 0 : ctx->comm[ctx->comm_cur].rank; }
+// rows of an n-row matrix owned by this rank when the matrix is row-sharded: equal chunks of `rpr` rows
+// (a multiple of 64), the last ones possibly short or empty.  Buffers that are all-gathered in place are
+// allocated with nranks * rpr rows.
+struct TpRows { int rpr, r0, r1, padded; };
+static inline TpRows tp_rows(const tp_ctx *ctx, int n) {
+    const int R = tp_nranks(ctx), rank = tp_rank(ctx);
+    TpRows t;
+    t.rpr = round_up((n + R - 1) / R, 64);
+    t.r0 = rank * t.rpr < n ? rank * t.rpr : n;
+    t.r1 = t.r0 + t.rpr < n ? t.r0 + t.rpr : n;
+    t.padded = R * t.rpr;
+    return t;
+}
+static inline bool tp_row_sharded(const tp_ctx *ctx, int n) { return tp_nranks(ctx) > 1 && n >= ctx->dist_min_n; }
+int tp_comm_allgather(tp_ctx *ctx, double *buf, size_t chunk);          // in place, chunk doubles per rank
+int tp_comm_allreduce_sum(tp_ctx *ctx, void *buf, size_t count, int is_double);
+int tp_comm_bcast(tp_ctx *ctx, double *buf, size_t count, int root);
+int tp_comm_destroy_all(tp_ctx *ctx);
 int tp_flags_reset(tp_ctx *ctx);                 // zero the status words (stream ordered)
 int tp_flags_read(tp_ctx *ctx, int out[4]);      // copy them to the host (synchronises the stream)
 int tp_flags_enqueue(tp_ctx *ctx);               // async copy into ctx->pin_flags; valid after the next stream sync

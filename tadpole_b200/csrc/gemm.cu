@@ -1,5 +1,6 @@
 // gemm.cu -- FP64 DMMA GEMM (see gemm.cuh).
 #include "gemm.cuh"
+#include <stdlib.h>
 
 #define GEMM_BK 16
 #define GEMM_STAGES 3
@@ -137,8 +138,8 @@ dgemm_kernel(GemmArgs g, double *__restrict__ partial, int kt_per_split) {
                 }
                 if (g.epi == EPI_CORR) {
                     // (crossprod - nrow * tcrossprod(colMeans)) / (nrow - 1), then / tcrossprod(sd); NaN -> 0
-                    v = (v - g.nrows * (g.mean[m] * g.mean[nn])) / (g.nrows - 1.0);
-                    v = v / (g.sd[m] * g.sd[nn]);
+                    v = (v - g.nrows * (g.mean[m + g.epi_row0] * g.mean[nn])) / (g.nrows - 1.0);
+                    v = v / (g.sd[m + g.epi_row0] * g.sd[nn]);
                     v = nan_to_zero(v);
                 } else {
                     v *= g.alpha;
@@ -203,8 +204,9 @@ int tp_gemm(tp_ctx *ctx, const GemmArgs &g) {
         const long t32 = (long)((g.M + 31) / 32) * ((g.N + 63) / 64) * z / (g.sym ? 2 : 1);
         const long c64 = ((t64 + ctx->sm_count - 1) / ctx->sm_count) * 2;
         const long c32 = ((t32 + ctx->sm_count - 1) / ctx->sm_count) * 1;
-        cfg = (c32 < c64) ? 0 : 1;
+        cfg = (c32 <= c64) ? 0 : 1;      // tie: the smaller tile puts two CTAs (8 warps) on an SM
     }
+    if (const char *e = getenv("TADPOLE_GEMM_CFG")) { if (cfg != 2 || atoi(e) >= 10) cfg = atoi(e) % 10; }   // tuning aid
     const int KT = (g.K + GEMM_BK - 1) / GEMM_BK;
     int splits = g.splitk;
     if (splits > KT) splits = KT;

@@ -21,6 +21,7 @@ struct GemmArgs {
     int sym = 0;          // D symmetric (A*B with B = A^T): compute tiles n >= m only, mirror on store
     int epi = EPI_LINEAR;
     const double *mean = nullptr, *sd = nullptr; double nrows = 0.0;  // EPI_CORR
+    int epi_row0 = 0;     // EPI_CORR: global index of row 0 of this launch (row-sharded correlation)
     int splitk = 1;       // > 1: deterministic split-K through a workspace and a second kernel
 };
 

@@ -169,7 +169,9 @@ int tp_correlation(tp_ctx *ctx) {
     TP_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int n = ctx->nf, ld = ctx->ldx;
-    TP_TRY(ctx->C.reserve((size_t)n * ld * sizeof(double)));
+    const bool shard = tp_row_sharded(ctx, n);
+    const TpRows rw = tp_rows(ctx, n);
+    TP_TRY(ctx->C.reserve((size_t)(shard ? rw.padded : n) * ld * sizeof(double)));
     TP_TRY(ctx->colstat.reserve((size_t)3 * n * sizeof(double)));
     double *mean = ctx->colstat.as<double>(), *sd = mean + n;
     TP_MARK(ctx, EV_CORR0);
@@ -181,7 +183,15 @@ int tp_correlation(tp_ctx *ctx) {
     g.D = ctx->C.as<double>(); g.ldd = ld;
     g.M = n; g.N = n; g.K = n;
     g.sym = 1; g.epi = EPI_CORR; g.mean = mean; g.sd = sd; g.nrows = (double)n;
-    TP_TRY(tp_gemm(ctx, g));
+    if (shard) {
+        // row block [r0, r1) of the correlation matrix on this rank, then NCCL all-gather of the row blocks.  Every
+        // element is the same k-ordered sum as in the symmetric single-GPU launch, so the result is bit-identical.
+        g.A += (size_t)rw.r0 * ld; g.D += (size_t)rw.r0 * ld; g.M = rw.r1 - rw.r0; g.sym = 0; g.epi_row0 = rw.r0;
+        if (g.M > 0) TP_TRY(tp_gemm(ctx, g));
+        TP_TRY(tp_comm_allgather(ctx, ctx->C.as<double>(), (size_t)rw.rpr * ld));
+    } else {
+        TP_TRY(tp_gemm(ctx, g));
+    }
     TP_MARK(ctx, EV_CORR1);
     ctx->have_C = true;
     ctx->have_scores = ctx->have_sweep = false;
@@ -196,24 +206,39 @@ struct PcaOp {
     const double *M;      // explicit M (n x ld) or nullptr
     double *Z;            // scratch n x ldb for the two-GEMM form
     int b, ldb;
+    bool shard = false;   // row blocks computed by their owner rank and all-gathered (buffers hold rw.padded rows)
+    TpRows rw{};
     long applications = 0;
+    // D[rows] = alpha * A[rows, :] * B + beta * E1[rows] + gamma * E2[rows]; rows = all, or this rank's block
+    int rows_gemm(GemmArgs g, double *D, const double *E1, const double *E2) {
+        g.D = D; g.E1 = E1; g.E2 = E2;
+        if (!shard) return tp_gemm(ctx, g);
+        const size_t r0 = (size_t)rw.r0;
+        g.A += g.a_kc ? r0 * g.lda : r0;
+        g.D += r0 * g.ldd;
+        if (g.E1) g.E1 += r0 * g.lde1;
+        if (g.E2) g.E2 += r0 * g.lde2;
+        g.M = rw.r1 - rw.r0;
+        if (g.M > 0) TP_TRY(tp_gemm(ctx, g));
+        return tp_comm_allgather(ctx, D, (size_t)rw.rpr * g.ldd);
+    }
     // Yout = alpha * M * Yin + beta * E1 + gamma * E2
     int apply(const double *Yin, double *Yout, double alpha, const double *E1, double beta, const double *E2,
               double gamma) {
         GemmArgs g;
-        g.M = n; g.N = b; g.D = Yout; g.ldd = ldb; g.alpha = alpha;
-        g.E1 = E1; g.lde1 = ldb; g.beta = beta; g.E2 = E2; g.lde2 = ldb; g.gamma = gamma;
+        g.M = n; g.N = b; g.ldd = ldb; g.alpha = alpha;
+        g.lde1 = ldb; g.beta = beta; g.lde2 = ldb; g.gamma = gamma;
         applications++;
         if (M) {
             g.A = M; g.lda = ld; g.a_kc = 1; g.B = Yin; g.ldb = ldb; g.b_kc = 0; g.K = n;
-            return tp_gemm(ctx, g);
+            return rows_gemm(g, Yout, E1, E2);
         }
         GemmArgs z;   // Z = Xc^T Yin
         z.A = Xc; z.lda = ld; z.a_kc = 0; z.B = Yin; z.ldb = ldb; z.b_kc = 0;
-        z.D = Z; z.ldd = ldb; z.M = n; z.N = b; z.K = n;
-        TP_TRY(tp_gemm(ctx, z));
+        z.ldd = ldb; z.M = n; z.N = b; z.K = n;
+        TP_TRY(rows_gemm(z, Z, nullptr, nullptr));
         g.A = Xc; g.lda = ld; g.a_kc = 1; g.B = Z; g.ldb = ldb; g.b_kc = 0; g.K = n;
-        return tp_gemm(ctx, g);
+        return rows_gemm(g, Yout, E1, E2);
     }
 };
 
@@ -248,13 +273,22 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
     const bool direct = n <= ctx->jacobi_direct_max || b >= n;
     const bool explicitM = direct || n <= 12288;
     double *M = nullptr;
+    const bool shard = !direct && tp_row_sharded(ctx, n);
+    const TpRows rw = tp_rows(ctx, n);
+    const size_t nrows_alloc = shard ? (size_t)rw.padded : (size_t)n;
     if (explicitM) {
-        TP_TRY(ctx->M.reserve((size_t)n * ld * sizeof(double)));
+        TP_TRY(ctx->M.reserve(nrows_alloc * ld * sizeof(double)));
         M = ctx->M.as<double>();
         GemmArgs g;
         g.A = C; g.lda = ld; g.a_kc = 1; g.B = C; g.ldb = ld; g.b_kc = 1;
         g.D = M; g.ldd = ld; g.M = n; g.N = n; g.K = n; g.sym = 1;
-        TP_TRY(tp_gemm(ctx, g));
+        if (shard) {      // row blocks of M = Xc Xc^T by their owner, all-gathered
+            g.A += (size_t)rw.r0 * ld; g.D += (size_t)rw.r0 * ld; g.M = rw.r1 - rw.r0; g.sym = 0;
+            if (g.M > 0) TP_TRY(tp_gemm(ctx, g));
+            TP_TRY(tp_comm_allgather(ctx, M, (size_t)rw.rpr * ld));
+        } else {
+            TP_TRY(tp_gemm(ctx, g));
+        }
     }
     if (direct) {
         TP_ARG(n <= 1024, "tp_pca: direct eigensolver limited to 1024 bins; lower pca_block");
@@ -269,7 +303,7 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
         ctx->launches += 1;
     } else {
         const int ldb = round_up(b, 8);
-        const size_t blk = (size_t)n * ldb * sizeof(double);
+        const size_t blk = nrows_alloc * ldb * sizeof(double);
         const size_t sm = (size_t)b * ldb * sizeof(double);
         TP_TRY(ctx->Y0.reserve(blk)); TP_TRY(ctx->Y1.reserve(blk)); TP_TRY(ctx->Y2.reserve(blk));
         TP_TRY(ctx->W.reserve(blk));
@@ -284,6 +318,7 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
         double *gval = ctx->Jw.as<double>(), *theta = gval + b, *dvec = theta + b;
         double *res = ctx->resid.as<double>();
         PcaOp op{ctx, n, ld, C, M, nullptr, b, ldb};
+        op.shard = shard; op.rw = rw;
         DevBuf zbuf;   // scratch for the two-GEMM operator
         if (!M) { TP_TRY(zbuf.reserve(blk)); op.Z = zbuf.as<double>(); }
 

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["candidate_range", "sharded_sweep", "select"]
+__all__ = ["candidate_range", "sharded_sweep", "select", "DistEnv", "arm_plan"]
 
 
 def candidate_range(rank, world, k):
@@ -55,3 +55,66 @@ def select(scores):
     _lib.check(lib.tp_select(sc.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), sc.shape[0], sc.shape[1], sc.shape[1],
                              ctypes.byref(oc), ctypes.byref(ol)))
     return oc.value + 1, ol.value + 1
+
+
+def arm_plan(world):
+    """Which ranks work on which chromosome arm (R/TADpole.R:357: the arms are independent from load_mat on):
+    the first half of the ranks takes p, the second half q.  Returns {arm: [ranks]}; world == 1 -> both on rank 0."""
+    if world == 1:
+        return {"p": [0], "q": [0]}
+    half = world // 2
+    return {"p": list(range(half)), "q": list(range(half, world))}
+
+
+class DistEnv:
+    """torch.distributed bootstrap for the library's own NCCL communicators (one process per GPU).
+
+    slot 0: all ranks (one call spread over the whole job); slot 1: the ranks sharing this rank's chromosome arm.
+    The 128-byte NCCL ids travel through torch.distributed object broadcasts; the data path never goes through
+    torch.  With a CPU (gloo) process group only the host-side plan and the object exchange are available, which is
+    what the CPU tests cover."""
+
+    def __init__(self, ctx=None, init_nccl=True):
+        import torch.distributed as dist
+        self.dist = dist
+        self.ctx = ctx
+        self.rank = dist.get_rank()
+        self.world = dist.get_world_size()
+        self.arms = arm_plan(self.world)
+        self.my_arm = "p" if self.rank in self.arms["p"] else "q"
+        self.arm_ranks = self.arms[self.my_arm]
+        self.arm_slot = -1
+        self.world_slot = -1
+        # sub-groups must be created by every rank, in the same order
+        self._groups = {}
+        if self.world > 1:
+            for arm in ("p", "q"):
+                self._groups[arm] = dist.new_group(self.arms[arm]) if len(self.arms[arm]) > 1 else None
+        if ctx is not None and init_nccl and self.world > 1:
+            self._init_slot(0, list(range(self.world)), None)
+            self.world_slot = 0
+            if len(self.arm_ranks) > 1:
+                self._init_slot(1, self.arm_ranks, self._groups[self.my_arm])
+                self.arm_slot = 1
+            ctx.comm_select(self.world_slot)
+
+    def _init_slot(self, slot, ranks, group):
+        ids = [self.ctx.comm_unique_id() if self.rank == ranks[0] else None]
+        self.dist.broadcast_object_list(ids, src=ranks[0], group=group)
+        self.ctx.comm_init(ids[0], ranks.index(self.rank), len(ranks), slot)
+
+    def select_world(self):
+        if self.ctx is not None:
+            self.ctx.comm_select(self.world_slot)
+
+    def select_arm(self):
+        if self.ctx is not None:
+            self.ctx.comm_select(self.arm_slot)
+
+    def exchange(self, obj):
+        """all-gather of small host objects (result summaries); returns the list indexed by rank."""
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out

@@ -66,3 +66,33 @@ def test_candidate_partition_is_balanced():
         for r in range(world):
             seen += list(range(*sharding.candidate_range(r, world, 200)))
         assert sorted(seen) == list(range(200))
+
+
+def _env_worker(rank, world, port, outdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import json
+    import torch.distributed as dist
+    from tadpole_b200 import sharding
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    env = sharding.DistEnv(ctx=None, init_nccl=False)          # host-side plan only: no GPU here
+    got = env.exchange((env.my_arm, {"rank": rank, "n_pcs": 10 + rank}))
+    with open(os.path.join(outdir, f"r{rank}.json"), "w") as fh:
+        json.dump({"arm": env.my_arm, "arm_ranks": env.arm_ranks, "got": got}, fh)
+    dist.destroy_process_group()
+
+
+def test_arm_plan_and_exchange_world2(tmp_path):
+    """Arms are dealt out to halves of the job and the per-arm result summaries reach every rank."""
+    import json
+    import torch.multiprocessing as mp
+    from tadpole_b200 import sharding
+    assert sharding.arm_plan(1) == {"p": [0], "q": [0]}
+    assert sharding.arm_plan(2) == {"p": [0], "q": [1]}
+    assert sharding.arm_plan(8) == {"p": [0, 1, 2, 3], "q": [4, 5, 6, 7]}
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_env_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = json.load(open(tmp_path / "r0.json"))
+    r1 = json.load(open(tmp_path / "r1.json"))
+    assert (r0["arm"], r1["arm"]) == ("p", "q") and r0["arm_ranks"] == [0] and r1["arm_ranks"] == [1]
+    assert r0["got"] == r1["got"] == [["p", {"rank": 0, "n_pcs": 10}], ["q", {"rank": 1, "n_pcs": 11}]]
