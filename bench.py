@@ -308,6 +308,16 @@ def run_b200(args, rank, world, local_rank):
         classes = ("dgemm", "jacobi", "chol", "coniss_sweep", "ch", "rowmean", "compact")
         roofs = {c: roof_of(c) for c in classes}
         roofs = {c: r for c, r in roofs.items() if r}
+        try:        # DRAM traffic per launch measured by ncu --set full (profiles/), N = 2000 workload only
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+                traffic = json.load(fh)
+            if n == 2000:
+                for r in roofs.values():
+                    if r["kernel"] in traffic:
+                        r["traffic"] = traffic[r["kernel"]]
+                        r["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
+        except OSError:
+            pass
         top = max(roofs, key=lambda c: roofs[c]["share_of_step"])
         roof = roofs[top]
 
