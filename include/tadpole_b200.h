@@ -165,6 +165,12 @@ int tp_difft_batch(tp_ctx *ctx, const int32_t *labels_x, const int32_t *labels_y
 int tp_assemble(const double *seqdist, int nf, int n_clusters, const int *names, const int *bad,
                 int nbad, int *start_out, int *end_out, int *nrows_out, int *labels_out);
 
+/* every requested level of one dendrogram in one call (same tables as nlev calls of tp_assemble): levels[nlev] =
+ * numbers of clusters; offsets_out[nlev + 1] delimits each level's rows in start_out / end_out, which need room for
+ * sum(levels[i] + max(nbad, 0) + 1) rows */
+int tp_assemble_levels(const double *seqdist, int nf, const int *levels, int nlev, const int *names,
+                       const int *bad, int nbad, int *start_out, int *end_out, int *offsets_out);
+
 #ifdef __cplusplus
 }
 #endif

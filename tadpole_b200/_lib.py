@@ -22,7 +22,7 @@ EXPORTED = [
     "tp_ctx_launches", "tp_ctx_set", "tp_ctx_timings", "tp_ctx_profile", "tp_filter", "tp_compact", "tp_set_filtered",
     "tp_get_filtered", "tp_correlation", "tp_get_correlation", "tp_set_correlation", "tp_pca",
     "tp_get_scores", "tp_set_scores", "tp_sweep", "tp_get_dendro", "tp_select", "tp_call", "tp_call_arm",
-    "tp_difft_batch", "tp_assemble", "tp_test_cholinv", "tp_test_eig",
+    "tp_difft_batch", "tp_assemble", "tp_assemble_levels", "tp_test_cholinv", "tp_test_eig",
     "tp_comm_unique_id", "tp_ctx_comm_init", "tp_ctx_comm_select", "tp_ctx_comm_info",
 ]
 
@@ -81,6 +81,7 @@ def load():
         "tp_call_arm": (c_int, [vp, ip, c_int, c_int, c_int, ip, ip, ip, dp, c_int, ip, dp]),
         "tp_difft_batch": (c_int, [vp, vp, vp, c_int, c_int, c_int, vp]),
         "tp_assemble": (c_int, [dp, c_int, c_int, ip, ip, c_int, ip, ip, ip, ip]),
+        "tp_assemble_levels": (c_int, [dp, c_int, ip, c_int, ip, ip, c_int, ip, ip, ip]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -359,3 +360,22 @@ def assemble(seqdist, n_clusters, names, bad):
     check(lib.tp_assemble(_dp(seqdist), nf, int(n_clusters), _ip(names), _ip(badarr), nbad, _ip(start), _ip(end),
                           ctypes.byref(nrows), _ip(labels)))
     return np.stack([start[:nrows.value], end[:nrows.value]], axis=1).astype(np.int64), labels
+
+
+def assemble_levels(seqdist, levels, names, bad):
+    """tp_assemble_levels: {level: [rows, 2] start/end table (1-based)} for many hierarchical levels at once."""
+    lib = load()
+    seqdist = np.ascontiguousarray(seqdist, dtype=np.float64)
+    names = np.ascontiguousarray(names, dtype=np.int32)
+    levels = np.ascontiguousarray(levels, dtype=np.int32)
+    nf = names.size
+    nbad = -1 if bad is None else len(bad)
+    badarr = np.ascontiguousarray(bad if bad is not None else [], dtype=np.int32)
+    cap = int(levels.sum()) + levels.size * (max(nbad, 0) + 2)
+    start = np.zeros(max(cap, 1), dtype=np.int32)
+    end = np.zeros(max(cap, 1), dtype=np.int32)
+    off = np.zeros(levels.size + 1, dtype=np.int32)
+    check(lib.tp_assemble_levels(_dp(seqdist), nf, _ip(levels), int(levels.size), _ip(names), _ip(badarr), nbad,
+                                 _ip(start), _ip(end), _ip(off)))
+    tab = np.stack([start[: off[-1]], end[: off[-1]]], axis=1).astype(np.int64)
+    return {int(k): tab[off[i]: off[i + 1]] for i, k in enumerate(levels)}

@@ -147,12 +147,10 @@ class Tadpole(_Obj):
 
 def _levels_table(res, names, bad_cols):
     """for (k in which(!is.na(scores[n_PCs, ]))) ... (R/TADpole.R:381-408,470-497)."""
-    out = {}
     row = res["scores"][res["n_pcs"] - 1]
-    for k in np.flatnonzero(~np.isnan(row)) + 1:
-        tab, _ = _lib.assemble(res["seqdist"], int(k), names, bad_cols)
-        out[str(int(k))] = tab
-    return out
+    levels = np.flatnonzero(~np.isnan(row)) + 1
+    tabs = _lib.assemble_levels(res["seqdist"], levels, names, bad_cols)
+    return {str(int(k)): tabs[int(k)] for k in levels}
 
 
 def _messages_optimal(res):

@@ -546,3 +546,68 @@ extern "C" int tp_assemble(const double *seqdist, int nf, int n_clusters, const 
     *nrows_out = rows;
     return TP_OK;
 }
+
+// All requested levels of one dendrogram at once: the boundaries are ranked once (rioja's .find.groups order), and
+// every level re-uses the ranking; same tables as nlev calls of tp_assemble.  levels[nlev] = numbers of clusters;
+// offsets_out[nlev + 1] delimits each level's rows in start_out / end_out, which need room for
+// sum(levels[i] + max(nbad, 0) + 1) rows.
+extern "C" int tp_assemble_levels(const double *seqdist, int nf, const int *levels, int nlev, const int *names,
+                                  const int *bad, int nbad, int *start_out, int *end_out, int *offsets_out) {
+    TP_ARG(seqdist && levels && names && start_out && end_out && offsets_out && nlev >= 0, "tp_assemble_levels: null argument");
+    TP_ARG(nf >= 2, "tp_assemble_levels: bad sizes");
+    TP_ARG(nbad <= 0 || bad, "tp_assemble_levels: null bad list");
+    const int n1 = nf - 1;
+    // rank[b] = position of boundary b when sorted by (seqdist descending, index descending): level k cuts rank < k - 1
+    std::vector<int> idx(n1), rank(n1);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::sort(idx.begin(), idx.end(), [&](int a, int b) {
+        return seqdist[a] > seqdist[b] || (seqdist[a] == seqdist[b] && a > b);
+    });
+    for (int i = 0; i < n1; i++) rank[idx[i]] = i;
+    // positions of the good bins and of the bad bins in the merged order (good first on equal names), once
+    const int nb = nbad > 0 ? nbad : 0;
+    const int total = nbad >= 0 ? nf + nb : nf;
+    std::vector<int> src(total);          // >= 0: index of the good bin, -1: bad bin
+    if (nbad >= 0) {
+        int i = 0, j = 0, p = 0;
+        while (i < nf || j < nb) {
+            if (j >= nb || (i < nf && names[i] <= bad[j])) src[p++] = i++;
+            else { src[p++] = -1; j++; }
+        }
+    } else {
+        std::iota(src.begin(), src.end(), 0);
+    }
+    std::vector<int> good(nf), fixed(total), vals, lens;
+    int rows = 0;
+    offsets_out[0] = 0;
+    for (int l = 0; l < nlev; l++) {
+        const int kc = levels[l];
+        TP_ARG(kc >= 1 && kc <= nf, "tp_assemble_levels: level out of range");
+        int lab = 1;
+        for (int i = 0; i < nf; i++) {
+            good[i] = lab;
+            if (i < n1 && rank[i] < kc - 1) lab++;
+        }
+        for (int p = 0; p < total; p++) fixed[p] = src[p] >= 0 ? good[src[p]] : 0;
+        if (nbad >= 0) {      // fix_values on the run values, left to right (R/TADpole.R:503-510)
+            vals.clear(); lens.clear();
+            for (int p = 0; p < total; p++) {
+                if (p == 0 || fixed[p] != fixed[p - 1]) { vals.push_back(fixed[p]); lens.push_back(1); }
+                else lens.back()++;
+            }
+            for (size_t r = 1; r + 1 < vals.size(); r++)
+                if (vals[r] == 0 && vals[r - 1] == vals[r + 1]) vals[r] = vals[r - 1];
+            int p = 0;
+            for (size_t r = 0; r < vals.size(); r++) for (int t = 0; t < lens[r]; t++) fixed[p++] = vals[r];
+        }
+        int p = 0;
+        while (p < total) {
+            int q = p;
+            while (q + 1 < total && fixed[q + 1] == fixed[p]) q++;
+            if (fixed[p] != 0 || nbad < 0) { start_out[rows] = p + 1; end_out[rows] = q + 1; rows++; }
+            p = q + 1;
+        }
+        offsets_out[l + 1] = rows;
+    }
+    return TP_OK;
+}

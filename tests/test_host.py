@@ -142,3 +142,22 @@ def test_centromere_split_host_logic_matches_oracle():
     assert (kp + 1).tolist() == lm.p.names.tolist() and (kq + 1).tolist() == lm.q.names.tolist()
     assert cen.tolist() == lm.centromere.tolist()
     assert (bq is None) == (lm.q.bad_columns is None)
+
+
+def test_assemble_levels_matches_per_level_calls():
+    """tp_assemble_levels (one ranking for all levels) gives the tables of tp_assemble level by level,
+    with bad bins re-inserted, without, and with bad_columns = NULL."""
+    from tadpole_b200 import _lib
+    rng = np.random.default_rng(11)
+    nf = 300
+    seq = rng.random(nf - 1)
+    seq[40] = seq[41] = seq[42]                       # ties: first index merges first
+    allbins = np.arange(1, nf + 40 + 1)
+    bad = np.sort(rng.choice(allbins, 40, replace=False)).astype(np.int32)
+    names = np.setdiff1d(allbins, bad).astype(np.int32)
+    levels = np.array([1, 2, 3, 17, 120, nf], dtype=np.int32)
+    for b in (bad, np.zeros(0, np.int32), None):
+        got = _lib.assemble_levels(seq, levels, names, b)
+        for k in levels:
+            ref, _ = _lib.assemble(seq, int(k), names, b)
+            assert np.array_equal(got[int(k)], ref), (k, None if b is None else len(b))
