@@ -51,7 +51,8 @@ void *tp_ctx_stream(tp_ctx *ctx);
 /* number of kernels this context has launched so far */
 long long tp_ctx_launches(tp_ctx *ctx);
 /* tunables: "pca_block" (subspace width, 0 = auto), "pca_tol" (x1e-16), "pca_maxit",
- * "jacobi_direct_max", "level_cap", "dist_min_n" */
+ * "jacobi_direct_max", "level_cap", "dist_min_n", "igemm_min_n" (smallest nf that takes the tcgen05 int8 Gram path
+ * when the counts are integers; 0 = never) */
 int tp_ctx_set(tp_ctx *ctx, const char *key, double value);
 /* per-stage device milliseconds of the last tp_call / stage call, measured with CUDA events on
  * the context stream: [0] filter [1] compact [2] correlation [3] pca [4] sweep (CONISS) [5] CH
@@ -114,6 +115,9 @@ int tp_set_scores(tp_ctx *ctx, const double *scores, int nf, int k);
  * (descending) and eigenvectors (columns of v_out) of a symmetric positive semi-definite t */
 int tp_test_cholinv(tp_ctx *ctx, const double *g, int b, int factor_only, double *l_out, double *linv_out, int *bad_out);
 int tp_test_eig(tp_ctx *ctx, const double *t, int b, double tol, double *w_out, double *v_out, int *sweeps_out);
+/* test hook of the tcgen05 int8 Gram kernel behind tp_correlation: X X^T of a symmetric n x n matrix of integer counts,
+ * exact; *used_out = 0 when x is not integer-valued below 2^20 (gram_out untouched) */
+int tp_test_igram(tp_ctx *ctx, const double *x, int n, double *gram_out, int *used_out);
 
 /* ---- stages 4+5: the find_params sweep (R/TADpole.R:104-123) --------------------------------------
  * For candidates i = cand_begin + t*cand_stride < k (0-based: candidate i clusters on the first
@@ -125,6 +129,8 @@ int tp_test_eig(tp_ctx *ctx, const double *t, int b, double tol, double *w_out, 
  * TP_ERR_ARG is returned. */
 int tp_sweep(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stride,
              int *n_cluster_out, double *scores_out, int ld_scores, int *maxlev_out);
+/* score matrix of the last sweep (tp_sweep, tp_call, tp_call_arm): k x maxlev, NaN padded, row pitch ld_scores */
+int tp_get_sweep_scores(tp_ctx *ctx, double *scores_out, int ld_scores);
 /* seqdist (nf-1 doubles) and merge order (nf-1 ints: boundary removed at each step) of one
  * candidate of the last sweep; either pointer may be NULL */
 int tp_get_dendro(tp_ctx *ctx, int cand, double *seqdist_out, int *order_out);
@@ -136,7 +142,8 @@ int tp_select(const double *scores, int k, int ld, int maxlev, int *opt_cand, in
 /* ---- one-shot: filter -> compact -> correlation -> PCA -> sweep -> selection -------------------
  * The non-centromere path of TADpole() (R/TADpole.R:444-468) from an in-memory matrix.
  * bad_out[n]; scores_out[k * ld_scores] (k = min(max_pcs, nf)); seqdist_out[nf-1] of the optimal
- * candidate.  nf_out/k_out/maxlev_out report the sizes actually used. */
+ * candidate.  nf_out/k_out/maxlev_out report the sizes actually used.  When ld_scores < *maxlev_out the call returns
+ * TP_ERR_ARG with every other output filled: fetch the scores with tp_get_sweep_scores, nothing has to be recomputed. */
 int tp_call(tp_ctx *ctx, const double *mat, int n, int colmajor, int on_device,
             int max_pcs, int min_clusters, double bad_frac,
             uint8_t *bad_out, int *nf_out, int *k_out,

@@ -21,8 +21,8 @@ EXPORTED = [
     "tp_last_error", "tp_version", "tp_ctx_create", "tp_ctx_destroy", "tp_ctx_sync", "tp_ctx_stream",
     "tp_ctx_launches", "tp_ctx_set", "tp_ctx_timings", "tp_ctx_profile", "tp_filter", "tp_compact", "tp_set_filtered",
     "tp_get_filtered", "tp_correlation", "tp_get_correlation", "tp_set_correlation", "tp_pca",
-    "tp_get_scores", "tp_set_scores", "tp_sweep", "tp_get_dendro", "tp_select", "tp_call", "tp_call_arm",
-    "tp_difft_batch", "tp_assemble", "tp_assemble_levels", "tp_test_cholinv", "tp_test_eig",
+    "tp_get_scores", "tp_set_scores", "tp_sweep", "tp_get_sweep_scores", "tp_get_dendro", "tp_select", "tp_call", "tp_call_arm",
+    "tp_difft_batch", "tp_assemble", "tp_assemble_levels", "tp_test_cholinv", "tp_test_eig", "tp_test_igram",
     "tp_comm_unique_id", "tp_ctx_comm_init", "tp_ctx_comm_select", "tp_ctx_comm_info",
 ]
 
@@ -72,10 +72,12 @@ def load():
         "tp_ctx_comm_info": (c_int, [vp, ip, ip]),
         "tp_test_cholinv": (c_int, [vp, dp, c_int, c_int, dp, dp, ip]),
         "tp_test_eig": (c_int, [vp, dp, c_int, c_double, dp, dp, ip]),
+        "tp_test_igram": (c_int, [vp, dp, c_int, dp, ip]),
         "tp_get_scores": (c_int, [vp, dp]),
         "tp_set_scores": (c_int, [vp, dp, c_int, c_int]),
         "tp_sweep": (c_int, [vp, c_int, c_int, c_int, ip, dp, c_int, ip]),
         "tp_get_dendro": (c_int, [vp, c_int, dp, ip]),
+        "tp_get_sweep_scores": (c_int, [vp, dp, c_int]),
         "tp_select": (c_int, [dp, c_int, c_int, c_int, ip, ip]),
         "tp_call": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, c_double, u8p, ip, ip, ip, ip, dp, c_int, ip, dp]),
         "tp_call_arm": (c_int, [vp, ip, c_int, c_int, c_int, ip, ip, ip, dp, c_int, ip, dp]),
@@ -244,6 +246,15 @@ class Context:
         check(self.lib.tp_test_eig(self._h, _dp(t), b, float(tol), _dp(w), _dp(v), _ip(sw)))
         return w, v, int(sw[0])
 
+    def test_igram(self, x):
+        """Exact Gram matrix x @ x.T of a symmetric integer-count matrix (tcgen05 int8 path), or None when the
+        input is not integer-valued (test hook)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n = x.shape[0]
+        g = np.zeros((n, n)); used = np.zeros(1, dtype=np.int32)
+        check(self.lib.tp_test_igram(self._h, _dp(x), n, _dp(g), _ip(used)))
+        return g if used[0] else None
+
     def get_scores(self, nf, k):
         out = np.zeros((nf, k))
         check(self.lib.tp_get_scores(self._h, _dp(out)))
@@ -303,9 +314,12 @@ class Context:
                                   bad.ctypes.data_as(POINTER(c_uint8)), ctypes.byref(nf), ctypes.byref(k),
                                   ctypes.byref(npcs), ctypes.byref(ncl),
                                   _dp(sc) if want_scores else None, ld, ctypes.byref(maxlev), _dp(seq))
-            if rc == TP_ERR_ARG and maxlev.value > ld:
+            if rc == TP_ERR_ARG and maxlev.value > ld:       # everything else is filled in: fetch the wider score matrix
                 ld = maxlev.value
-                continue
+                if want_scores:
+                    sc = np.empty((kmax, ld))
+                    check(self.lib.tp_get_sweep_scores(self._h, _dp(sc), ld))
+                break
             check(rc)
             break
         return dict(bad=bad.astype(bool), nf=nf.value, k=k.value, n_pcs=npcs.value, n_clusters=ncl.value,
@@ -324,7 +338,9 @@ class Context:
                                       ctypes.byref(npcs), ctypes.byref(ncl), _dp(sc), ld, ctypes.byref(maxlev), _dp(seq))
             if rc == TP_ERR_ARG and maxlev.value > ld:
                 ld = maxlev.value
-                continue
+                sc = np.empty((kmax, ld))
+                check(self.lib.tp_get_sweep_scores(self._h, _dp(sc), ld))
+                break
             check(rc)
             break
         return dict(nf=nf, k=k.value, n_pcs=npcs.value, n_clusters=ncl.value,

@@ -6,6 +6,7 @@
 
 int tp_sweep_device(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stride, int *ncand_out);
 int tp_ch_device(tp_ctx *ctx, int min_clusters, int ncand, int ld_chs);
+extern "C" int tp_get_sweep_scores(tp_ctx *ctx, double *scores_out, int ld_scores);
 
 static thread_local char g_err[1024] = "";
 
@@ -84,7 +85,7 @@ extern "C" int tp_ctx_destroy(tp_ctx *ctx) {
                       &ctx->colstat, &ctx->scores, &ctx->M, &ctx->Y0, &ctx->Y1, &ctx->Y2, &ctx->W, &ctx->G, &ctx->T,
                       &ctx->Q, &ctx->Jw, &ctx->Jv, &ctx->Jt, &ctx->small1, &ctx->small2, &ctx->part, &ctx->resid,
                       &ctx->P, &ctx->Qp, &ctx->d0, &ctx->seqdist, &ctx->order, &ctx->ncl, &ctx->chs, &ctx->bsbuf,
-                      &ctx->links, &ctx->harm, &ctx->status, &ctx->lx, &ctx->ly, &ctx->dout, &ctx->dhash, &ctx->lhash};
+                      &ctx->links, &ctx->harm, &ctx->status, &ctx->islices, &ctx->lx, &ctx->ly, &ctx->dout, &ctx->dhash, &ctx->lhash};
     for (DevBuf *b : bufs) b->release();
     tp_comm_destroy_all(ctx);
     for (int i = 0; i < EV_COUNT; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -115,6 +116,7 @@ extern "C" int tp_ctx_set(tp_ctx *ctx, const char *key, double value) {
     else if (k == "jacobi_direct_max") ctx->jacobi_direct_max = (int)value;
     else if (k == "level_cap") ctx->level_cap = (int)value;
     else if (k == "dist_min_n") ctx->dist_min_n = (int)value;
+    else if (k == "igemm_min_n") ctx->igemm_min_n = (int)value;
     else { tp_set_error("tp_ctx_set: unknown key '%s'", key); return TP_ERR_ARG; }
     return TP_OK;
 }
@@ -223,6 +225,29 @@ extern "C" int tp_test_eig(tp_ctx *ctx, const double *t, int b, double tol, doub
     TP_CUDA(cudaMemcpyAsync(w_out, ctx->Jw.p, (size_t)b * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     TP_CUDA(cudaMemcpy2DAsync(v_out, (size_t)b * sizeof(double), ctx->Jv.p, (size_t)ld * sizeof(double),
                               (size_t)b * sizeof(double), b, cudaMemcpyDeviceToHost, ctx->stream));
+    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return TP_OK;
+}
+
+int tp_igram(tp_ctx *ctx, const double *X, int n, int ld, double *C, int ldc, const double *mean, const double *sd,
+             int raw, int *used_out);
+
+// Gram matrix X X^T of a symmetric n x n matrix of integer counts through the tcgen05 int8 path (host in / out,
+// row-major); *used_out = 0 when the input is not integer-valued (gram_out untouched)
+extern "C" int tp_test_igram(tp_ctx *ctx, const double *x, int n, double *gram_out, int *used_out) {
+    TP_ARG(ctx && x && n >= 1 && gram_out && used_out, "tp_test_igram: bad arguments");
+    TP_CUDA(cudaSetDevice(ctx->device));
+    const int ld = round_up(n, 8);
+    const size_t bytes = (size_t)n * ld * sizeof(double);
+    TP_TRY(ctx->X.reserve(bytes)); TP_TRY(ctx->C.reserve(bytes));
+    TP_CUDA(cudaMemsetAsync(ctx->X.p, 0, bytes, ctx->stream));
+    TP_CUDA(cudaMemcpy2DAsync(ctx->X.p, (size_t)ld * sizeof(double), x, (size_t)n * sizeof(double),
+                              (size_t)n * sizeof(double), n, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->have_X = ctx->have_C = false;
+    TP_TRY(tp_igram(ctx, ctx->X.as<double>(), n, ld, ctx->C.as<double>(), ld, nullptr, nullptr, 1, used_out));
+    if (*used_out)
+        TP_CUDA(cudaMemcpy2DAsync(gram_out, (size_t)n * sizeof(double), ctx->C.p, (size_t)ld * sizeof(double),
+                                  (size_t)n * sizeof(double), n, cudaMemcpyDeviceToHost, ctx->stream));
     TP_CUDA(cudaStreamSynchronize(ctx->stream));
     return TP_OK;
 }
@@ -341,6 +366,7 @@ static int sweep_impl(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_st
         ld = round_up(maxlev, 8);          // rare: more levels than the cap; redo the cheap CH pass wider
     }
     if (maxlev_out) *maxlev_out = maxlev;
+    ctx->last_maxlev = maxlev;
     if (n_cluster_out) memcpy(n_cluster_out, h_ncl, (size_t)k * sizeof(int));
     if (scores_out) {
         if (ld_scores < maxlev) {
@@ -355,6 +381,20 @@ static int sweep_impl(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_st
                                       cudaMemcpyDeviceToHost, ctx->stream));
         TP_CUDA(cudaStreamSynchronize(ctx->stream));
     }
+    return TP_OK;
+}
+
+// score matrix of the last sweep: k rows (candidates) x maxlev columns, NaN padded, row pitch ld_scores >= maxlev
+extern "C" int tp_get_sweep_scores(tp_ctx *ctx, double *scores_out, int ld_scores) {
+    TP_ARG(ctx && scores_out && ctx->have_sweep, "tp_get_sweep_scores: run tp_sweep / tp_call first");
+    const int k = ctx->k, maxlev = ctx->last_maxlev;
+    TP_ARG(ld_scores >= maxlev, "tp_get_sweep_scores: ld_scores smaller than the number of levels");
+    for (size_t i = 0; i < (size_t)k * ld_scores; i++) scores_out[i] = NAN;
+    if (maxlev > 0)
+        TP_CUDA(cudaMemcpy2DAsync(scores_out, (size_t)ld_scores * sizeof(double), ctx->chs.p,
+                                  (size_t)ctx->ld_chs * sizeof(double), (size_t)maxlev * sizeof(double), k,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    TP_CUDA(cudaStreamSynchronize(ctx->stream));
     return TP_OK;
 }
 
@@ -421,26 +461,16 @@ static int call_from_compacted(tp_ctx *ctx, int max_pcs, int min_clusters, int *
     TP_TRY(tp_correlation(ctx));
     TP_TRY(tp_pca(ctx, max_pcs, &k));
     if (k_out) *k_out = k;
-    std::vector<double> local;
-    double *sc = scores_out;
-    int ld = ld_scores;
-    if (!sc) { ld = std::max(ctx->level_cap, 8); }
-    // first try with the caller's width; when scores_out is NULL use a local buffer
-    int rc;
-    if (sc) {
-        rc = sweep_impl(ctx, min_clusters, 0, 1, nullptr, sc, ld, &maxlev, true);
-    } else {
-        local.assign((size_t)k * ld, NAN);
-        rc = sweep_impl(ctx, min_clusters, 0, 1, nullptr, local.data(), ld, &maxlev, true);
-        if (rc == TP_ERR_ARG && maxlev > ld) {
-            ld = maxlev;
-            local.assign((size_t)k * ld, NAN);
-            rc = sweep_impl(ctx, min_clusters, 0, 1, nullptr, local.data(), ld, &maxlev, true);
-        }
-        sc = local.data();
-    }
+    // the sweep runs once; the score matrix stays on the device (tp_get_sweep_scores) and is copied to the caller's
+    // buffer when that is wide enough.  A narrow buffer makes the call return TP_ERR_ARG with *maxlev_out set and every
+    // other output filled, so the caller only has to fetch the scores again, not to repeat the pipeline.
+    int rc = sweep_impl(ctx, min_clusters, 0, 1, nullptr, nullptr, 0, &maxlev, true);
     if (maxlev_out) *maxlev_out = maxlev;
     TP_TRY(rc);
+    const int ld = std::max(maxlev, 1);
+    std::vector<double> local((size_t)k * ld);
+    TP_TRY(tp_get_sweep_scores(ctx, local.data(), ld));
+    const double *sc = local.data();
     int oc = 0, ol = 0;
     TP_TRY(tp_select(sc, k, ld, maxlev, &oc, &ol));
     if (n_pcs_out) *n_pcs_out = oc + 1;
@@ -451,6 +481,17 @@ static int call_from_compacted(tp_ctx *ctx, int max_pcs, int min_clusters, int *
     }
     if (seqdist_out) TP_TRY(tp_get_dendro(ctx, oc, seqdist_out, nullptr));
     TP_MARK(ctx, EV_TOTAL1);
+    if (scores_out) {
+        if (ld_scores < maxlev) {
+            tp_set_error("tp_call: ld_scores = %d is smaller than the %d levels found (fetch them with tp_get_sweep_scores)",
+                         ld_scores, maxlev);
+            return TP_ERR_ARG;
+        }
+        for (int r = 0; r < k; r++) {
+            memcpy(scores_out + (size_t)r * ld_scores, local.data() + (size_t)r * ld, (size_t)maxlev * sizeof(double));
+            for (int c = maxlev; c < ld_scores; c++) scores_out[(size_t)r * ld_scores + c] = NAN;
+        }
+    }
     return TP_OK;
 }
 

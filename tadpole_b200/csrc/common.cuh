@@ -81,7 +81,8 @@ struct tp_ctx {
     // comm_cur = -1: no collective (single GPU, or replicated / independent work)
     TpCommSlot comm[TP_COMM_SLOTS];
     int comm_cur = -1;
-    int dist_min_n = 4096;       // matrices smaller than this are not row-sharded (only the candidate sweep is)
+    int dist_min_n = 4096;
+    int igemm_min_n = 1024;      // integer-count matrices at least this large take the tcgen05 int8 Gram path (0 = never)       // matrices smaller than this are not row-sharded (only the candidate sweep is)
 
     // tunables
     int pca_block = 0;
@@ -99,7 +100,7 @@ struct tp_ctx {
     DevBuf rowmean, ranks, flags, qtmp, keep;
     // filtered matrix / correlation (nf x ldx row-major, ldx multiple of 8)
     int nf = 0, ldx = 0;
-    DevBuf X, C, colstat;
+    DevBuf X, C, colstat, islices;      // islices: int8 digit planes of X for the tcgen05 integer Gram (igemm.cu)
     bool have_X = false, have_C = false;
     // PCA
     int k = 0, ldk = 0;          // scores: nf x ldk row-major
@@ -111,6 +112,7 @@ struct tp_ctx {
     // sweep
     DevBuf P, Qp, d0, seqdist, order, ncl, chs, bsbuf, links, harm;
     int ld_chs = 0;
+    int last_maxlev = 0;         // levels (columns) of the score matrix of the last sweep
     bool have_sweep = false;
     // diffT
     DevBuf lx, ly, dout, dhash, lhash;

@@ -1,0 +1,292 @@
+// igemm.cu -- stage 2 (sparse_cor, R/TADpole.R:94-100) for integer contact counts: the Gram matrix X^T X = X X^T on
+// the 5th-generation tensor cores, exactly.
+//
+// tcgen05.mma has no FP64 kind, but Hi-C contact matrices are integer counts.  Every count v (|v| < 2^20) is cut into
+// three balanced base-128 digits v = d0 + 128 d1 + 128^2 d2, d in [-64, 63], stored as three int8 matrices.  The
+// nine digit products are accumulated in INT32 by tcgen05.mma.kind::i8, grouped by scale: D_s = sum_{a+b=s} X_a X_b^T,
+// s = 0..4, five accumulators in tensor memory (5 x 64 columns).  |digit product| <= 4096 and at most 3 n products
+// meet in one accumulator, so nothing overflows below n = 174 000; the epilogue recombines
+// G = sum_s 128^s D_s in FP64 (exact while G < 2^53) and applies the reference's covariance -> correlation -> NaN->0
+// arithmetic in the reference's order, so the only rounding left in stage 2 is the reference's own epilogue.
+//
+// One CTA per 128 x 64 tile of the upper triangle (tiles below the diagonal are mirrored on store).  Warp 0: TMA
+// producer (cp.async.bulk.tensor, SWIZZLE_128B, 3-stage mbarrier ring, 72 KB per stage: three digit tiles of A and
+// of B).  Warp 1: allocates tensor memory and issues the MMAs (one elected thread, 36 per k-block of 128).
+// Warps 2-5: epilogue (tcgen05.ld 32x32b, one output row per thread).  Non-integer input (or counts >= 2^20) is
+// detected by the slicing pass and sent to the FP64 DMMA path instead.
+#include "common.cuh"
+#include "gemm.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+
+#define IG_BM 128
+#define IG_BN 64
+#define IG_BK 128                 // int8 elements = bytes: one 128-byte swizzle row
+#define IG_STAGES 3
+#define IG_THREADS 192
+#define IG_A_BYTES (IG_BM * IG_BK)            // one digit tile of A: 16 KB
+#define IG_B_BYTES (IG_BN * IG_BK)            // one digit tile of B: 8 KB
+#define IG_STAGE_BYTES (3 * IG_A_BYTES + 3 * IG_B_BYTES)
+#define IG_TMEM_COLS 512
+
+// ---- digit slicing -------------------------------------------------------------------------------------------------
+// S[s][row][k], row pitch Kp bytes, rows / columns beyond n zero; flag |= 1 when a value is not an integer below 2^20
+__global__ void __launch_bounds__(256)
+ig_slice_kernel(const double *__restrict__ X, int n, int ld, int8_t *__restrict__ S, int rows_pad, int Kp, int *flag) {
+    const size_t chunk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // 16 consecutive k of one row
+    const int cpr = Kp / 16;
+    if (chunk >= (size_t)rows_pad * cpr) return;
+    const int row = (int)(chunk / cpr), k0 = (int)(chunk % cpr) * 16;
+    alignas(16) int8_t d[3][16];
+    int bad = 0;
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        const int k = k0 + t;
+        double x = (row < n && k < n) ? X[(size_t)row * ld + k] : 0.0;
+        const double r = rint(x);
+        if (!(r == x) || !(fabs(x) < 1048576.0)) { bad = 1; x = 0.0; }
+        int v = (int)r;
+        const int d0 = ((v + 64) & 127) - 64; v = (v - d0) >> 7;
+        const int d1 = ((v + 64) & 127) - 64; v = (v - d1) >> 7;
+        d[0][t] = (int8_t)d0; d[1][t] = (int8_t)d1; d[2][t] = (int8_t)v;
+    }
+    const size_t plane = (size_t)rows_pad * Kp;
+#pragma unroll
+    for (int s = 0; s < 3; s++)
+        *reinterpret_cast<int4 *>(S + s * plane + (size_t)row * Kp + k0) = *reinterpret_cast<const int4 *>(d[s]);
+    if (bad) atomicOr(flag, 1);
+}
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ig_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ig_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void ig_mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ig_mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void ig_tma_load_3d(unsigned dst, const CUtensorMap *tmap, unsigned bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void ig_mma_i8(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned idesc,
+                                          unsigned accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void ig_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void ig_tmem_ld16(unsigned taddr, unsigned (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 bytes apart (SBO), LBO unused
+__device__ __forceinline__ unsigned long long ig_desc(unsigned smem_addr) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((smem_addr >> 4) & 0x3fff);            // start address, 16-byte units
+    d |= (unsigned long long)1 << 16;                                // leading byte offset (ignored for swizzled K-major)
+    d |= (unsigned long long)(1024 >> 4) << 32;                      // stride byte offset
+    d |= (unsigned long long)1 << 46;                                // descriptor version (sm_100)
+    d |= (unsigned long long)2 << 61;                                // SWIZZLE_128B
+    return d;
+}
+
+struct IgParams {
+    int n;                 // valid rows / columns
+    int kblocks;           // Kp / 128
+    double *C; long ldc;   // output, row-major
+    const double *mean, *sd; double nrows;
+    int raw;               // 1: store the Gram matrix itself (test hook)
+};
+
+__global__ void __launch_bounds__(IG_THREADS, 1)
+ig_gram_kernel(const __grid_constant__ CUtensorMap tmap, IgParams p) {
+    const int m0 = blockIdx.y * IG_BM, n0 = blockIdx.x * IG_BN;
+    if (n0 + IG_BN <= m0 || m0 >= p.n || n0 >= p.n) return;          // below the diagonal (mirrored) or padding
+    extern __shared__ unsigned char ig_raw[];
+    unsigned char *tiles = (unsigned char *)(((uintptr_t)ig_raw + 1023) & ~(uintptr_t)1023);    // 1024-byte aligned
+    __shared__ __align__(8) unsigned long long s_full[IG_STAGES], s_empty[IG_STAGES], s_done;
+    __shared__ unsigned s_tmem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < IG_STAGES; s++) { ig_mbar_init(ig_smem(&s_full[s]), 1); ig_mbar_init(ig_smem(&s_empty[s]), 1); }
+        ig_mbar_init(ig_smem(&s_done), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ig_smem(&s_tmem)), "n"(IG_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = s_tmem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < p.kblocks; kb++) {
+                const int st = kb % IG_STAGES;
+                ig_mbar_wait(ig_smem(&s_empty[st]), ((kb / IG_STAGES) & 1) ^ 1);
+                const unsigned bar = ig_smem(&s_full[st]);
+                ig_mbar_expect_tx(bar, IG_STAGE_BYTES);
+                const unsigned base = ig_smem(tiles + (size_t)st * IG_STAGE_BYTES);
+                for (int d = 0; d < 3; d++) {
+                    ig_tma_load_3d(base + d * IG_A_BYTES, &tmap, bar, kb * IG_BK, m0, d);
+                    ig_tma_load_3d(base + d * IG_A_BYTES + IG_A_BYTES / 2, &tmap, bar, kb * IG_BK, m0 + 64, d);
+                    ig_tma_load_3d(base + 3 * IG_A_BYTES + d * IG_B_BYTES, &tmap, bar, kb * IG_BK, n0, d);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: D_{a+b} += A_a B_b^T =====
+        // instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, N = 64, M = 128
+        const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((IG_BN >> 3) << 17) | ((IG_BM >> 4) << 24);
+        if (lane == 0) {
+            for (int kb = 0; kb < p.kblocks; kb++) {
+                const int st = kb % IG_STAGES;
+                ig_mbar_wait(ig_smem(&s_full[st]), (kb / IG_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned base = ig_smem(tiles + (size_t)st * IG_STAGE_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < IG_BK / 32; kk++) {
+#pragma unroll
+                    for (int a = 0; a < 3; a++) {
+                        const unsigned long long ad = ig_desc(base + a * IG_A_BYTES) + (unsigned long long)(kk * 32 >> 4);
+#pragma unroll
+                        for (int b = 0; b < 3; b++) {
+                            const unsigned long long bd = ig_desc(base + 3 * IG_A_BYTES + b * IG_B_BYTES) + (unsigned long long)(kk * 32 >> 4);
+                            const bool first = kb == 0 && kk == 0 && (a == 0 || b == 2);     // first product of scale a + b
+                            ig_mma_i8(tmem + (unsigned)(a + b) * IG_BN, ad, bd, idesc, first ? 0u : 1u);
+                        }
+                    }
+                }
+                ig_commit(ig_smem(&s_empty[st]));          // frees the stage once these MMAs have read it
+            }
+            ig_commit(ig_smem(&s_done));                   // accumulators complete
+        }
+    } else {
+        // ===== epilogue: one output row per thread =====
+        ig_mbar_wait(ig_smem(&s_done), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int lg = warp & 3;                           // tensor-memory lane group this warp may read
+        const int row = m0 + lg * 32 + lane;
+        const double mi = (row < p.n && !p.raw) ? p.mean[row] : 0.0, si = (row < p.n && !p.raw) ? p.sd[row] : 1.0;
+        for (int c0 = 0; c0 < IG_BN; c0 += 16) {
+            unsigned r[5][16];
+#pragma unroll
+            for (int s = 0; s < 5; s++) ig_tmem_ld16(tmem + ((unsigned)(lg * 32) << 16) + (unsigned)(s * IG_BN + c0), r[s]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < p.n) {
+#pragma unroll
+                for (int c = 0; c < 16; c++) {
+                    const int col = n0 + c0 + c;
+                    if (col >= p.n) continue;
+                    double g = (double)(int)r[4][c];
+                    g = fma(g, 128.0, (double)(int)r[3][c]);
+                    g = fma(g, 128.0, (double)(int)r[2][c]);
+                    g = fma(g, 128.0, (double)(int)r[1][c]);
+                    g = fma(g, 128.0, (double)(int)r[0][c]);
+                    double v = g;
+                    if (!p.raw) {
+                        // (crossprod - nrow * tcrossprod(colMeans)) / (nrow - 1), then / tcrossprod(sd); NaN -> 0
+                        v = (g - p.nrows * (mi * p.mean[col])) / (p.nrows - 1.0);
+                        v = v / (si * p.sd[col]);
+                        v = nan_to_zero(v);
+                    }
+                    p.C[(size_t)row * p.ldc + col] = v;
+                    if (col != row) p.C[(size_t)col * p.ldc + row] = v;      // mirror (the tile below the diagonal is skipped)
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(IG_TMEM_COLS));
+    }
+}
+
+// ---- host ----------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int ig_encode(CUtensorMap *map, void *base, int rows_pad, int Kp) {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        TP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres));
+        if (!sym || qres != cudaDriverEntryPointSuccess) { tp_set_error("cuTensorMapEncodeTiled not available"); return TP_ERR_CUDA; }
+        fn = (PFN_encodeTiled)sym;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows_pad, 3};
+    const cuuint64_t strides[2] = {(cuuint64_t)Kp, (cuuint64_t)Kp * rows_pad};          // bytes, dims 1 and 2
+    const cuuint32_t box[3] = {IG_BK, 64, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { tp_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return TP_ERR_CUDA; }
+    return TP_OK;
+}
+
+// C = correlation (or raw Gram when raw != 0) of the n x n symmetric matrix X of integer counts.  *used_out = 0 when
+// the input is not integer (nothing written to C): the caller takes the FP64 DMMA path.
+int tp_igram(tp_ctx *ctx, const double *X, int n, int ld, double *C, int ldc, const double *mean, const double *sd,
+             int raw, int *used_out) {
+    cudaStream_t st = ctx->stream;
+    const int rows_pad = round_up(n, IG_BM), Kp = round_up(n, IG_BK);
+    const size_t plane = (size_t)rows_pad * Kp;
+    TP_TRY(ctx->islices.reserve(3 * plane + 64));
+    int8_t *S = ctx->islices.as<int8_t>();
+    int *flag = (int *)(S + 3 * plane);                       // (3 * plane is a multiple of 128)
+    TP_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    const size_t chunks = (size_t)rows_pad * (Kp / 16);
+    tp_prof_begin(ctx, PC_IGEMM);
+    ig_slice_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(X, n, ld, S, rows_pad, Kp, flag);
+    tp_prof_end(ctx);
+    ctx->launches += 1;
+    TP_TRY(tp_pin_reserve(ctx, 64));
+    int *h = (int *)ctx->pin;
+    TP_CUDA(cudaMemcpyAsync(h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TP_CUDA(cudaStreamSynchronize(st));
+    if (h[0]) { *used_out = 0; return TP_OK; }
+    CUtensorMap map;
+    TP_TRY(ig_encode(&map, S, rows_pad, Kp));
+    IgParams p;
+    p.n = n; p.kblocks = Kp / IG_BK; p.C = C; p.ldc = ldc; p.mean = mean; p.sd = sd; p.nrows = (double)n; p.raw = raw;
+    const size_t smem = (size_t)IG_STAGES * IG_STAGE_BYTES + 1024;
+    TP_CUDA(cudaFuncSetAttribute(ig_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(rows_pad / IG_BN, rows_pad / IG_BM);
+    tp_prof_begin(ctx, PC_IGEMM);
+    ig_gram_kernel<<<grid, IG_THREADS, smem, st>>>(map, p);
+    tp_prof_end(ctx);
+    ctx->launches += 1;
+    TP_CUDA(cudaGetLastError());
+    *used_out = 1;
+    return TP_OK;
+}

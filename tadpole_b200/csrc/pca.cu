@@ -20,6 +20,8 @@
 
 int tp_jacobi(tp_ctx *ctx, double *A, int b, int ld, double *w, double *Vs, int lds, int ncols_out, int *sweeps_out,
               double tol);
+int tp_igram(tp_ctx *ctx, const double *X, int n, int ld, double *C, int ldc, const double *mean, const double *sd,
+             int raw, int *used_out);
 int tp_chol_inv(tp_ctx *ctx, double *G, double *Linv, int b, int ld, int *bad_out);
 
 // ---- small kernels -------------------------------------------------------------------------------
@@ -183,7 +185,13 @@ int tp_correlation(tp_ctx *ctx) {
     g.D = ctx->C.as<double>(); g.ldd = ld;
     g.M = n; g.N = n; g.K = n;
     g.sym = 1; g.epi = EPI_CORR; g.mean = mean; g.sd = sd; g.nrows = (double)n;
-    if (shard) {
+    int igemm_used = 0;
+    if (ctx->igemm_min_n > 0 && n >= ctx->igemm_min_n)
+        // integer counts: exact Gram on the tcgen05 int8 path with the same epilogue (igemm.cu).  Several times
+        // faster than a row block of the FP64 path, so with more than one rank it simply runs replicated.
+        TP_TRY(tp_igram(ctx, ctx->X.as<double>(), n, ld, ctx->C.as<double>(), ld, mean, sd, 0, &igemm_used));
+    if (igemm_used) {
+    } else if (shard) {
         // row block [r0, r1) of the correlation matrix on this rank, then NCCL all-gather of the row blocks.  Every
         // element is the same k-ordered sum as in the symmetric single-GPU launch, so the result is bit-identical.
         g.A += (size_t)rw.r0 * ld; g.D += (size_t)rw.r0 * ld; g.M = rw.r1 - rw.r0; g.sym = 0; g.epi_row0 = rw.r0;
