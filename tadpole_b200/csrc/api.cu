@@ -85,7 +85,7 @@ extern "C" int tp_ctx_destroy(tp_ctx *ctx) {
                       &ctx->colstat, &ctx->scores, &ctx->M, &ctx->Y0, &ctx->Y1, &ctx->Y2, &ctx->W, &ctx->G, &ctx->T,
                       &ctx->Q, &ctx->Jw, &ctx->Jv, &ctx->Jt, &ctx->small1, &ctx->small2, &ctx->part, &ctx->resid,
                       &ctx->P, &ctx->Qp, &ctx->d0, &ctx->seqdist, &ctx->order, &ctx->ncl, &ctx->chs, &ctx->bsbuf,
-                      &ctx->links, &ctx->harm, &ctx->status, &ctx->islices, &ctx->lx, &ctx->ly, &ctx->dout, &ctx->dhash, &ctx->lhash};
+                      &ctx->links, &ctx->harm, &ctx->status, &ctx->islices, &ctx->ioA, &ctx->ioB, &ctx->ioscale, &ctx->lx, &ctx->ly, &ctx->dout, &ctx->dhash, &ctx->lhash};
     for (DevBuf *b : bufs) b->release();
     tp_comm_destroy_all(ctx);
     for (int i = 0; i < EV_COUNT; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -117,6 +117,9 @@ extern "C" int tp_ctx_set(tp_ctx *ctx, const char *key, double value) {
     else if (k == "level_cap") ctx->level_cap = (int)value;
     else if (k == "dist_min_n") ctx->dist_min_n = (int)value;
     else if (k == "igemm_min_n") ctx->igemm_min_n = (int)value;
+    else if (k == "iop_min_n") ctx->iop_min_n = (int)value;
+    else if (k == "iop_switch") ctx->iop_switch = value;
+    else if (k == "iop_final") ctx->iop_final = ((int)value == 8) ? 8 : 0;
     else { tp_set_error("tp_ctx_set: unknown key '%s'", key); return TP_ERR_ARG; }
     return TP_OK;
 }

@@ -82,7 +82,10 @@ struct tp_ctx {
     TpCommSlot comm[TP_COMM_SLOTS];
     int comm_cur = -1;
     int dist_min_n = 4096;
-    int igemm_min_n = 1024;      // integer-count matrices at least this large take the tcgen05 int8 Gram path (0 = never)       // matrices smaller than this are not row-sharded (only the candidate sweep is)
+    int igemm_min_n = 1024;
+    int iop_min_n = 1024;        // smallest nf whose early subspace-iteration rounds use the sliced int8 operator (0 = never)
+    int iop_final = 8;           // operator of the later rounds where the sliced one is in use: 8 digit planes, or 0 = FP64 DMMA
+    double iop_switch = 1e-3;    // relative residual below which the FP64 DMMA operator takes over (the first iteration always starts sliced)      // integer-count matrices at least this large take the tcgen05 int8 Gram path (0 = never)       // matrices smaller than this are not row-sharded (only the candidate sweep is)
 
     // tunables
     int pca_block = 0;
@@ -100,6 +103,8 @@ struct tp_ctx {
     DevBuf rowmean, ranks, flags, qtmp, keep;
     // filtered matrix / correlation (nf x ldx row-major, ldx multiple of 8)
     int nf = 0, ldx = 0;
+    DevBuf ioA, ioB, ioscale;            // digit planes / scales of the sliced int8 operator of stage 3 (igemm.cu)
+    int io_n = 0;
     DevBuf X, C, colstat, islices;      // islices: int8 digit planes of X for the tcgen05 integer Gram (igemm.cu)
     bool have_X = false, have_C = false;
     // PCA
@@ -122,6 +127,7 @@ struct tp_ctx {
     int *pin_flags = nullptr;    // 64 pinned bytes for the status words
 
     double timing[10] = {};
+    long lowprec_applications = 0;     // operator applications of the last tp_pca done by the sliced int8 operator
 
     // per-kernel-class profiling (tp_ctx_profile)
     bool prof = false;

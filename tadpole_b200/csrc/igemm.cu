@@ -290,3 +290,336 @@ int tp_igram(tp_ctx *ctx, const double *X, int n, int ld, double *C, int ldc, co
     *used_out = 1;
     return TP_OK;
 }
+
+// =====================================================================================================================
+// Sliced FP64 x FP64 product for the operator applications of stage 3 (Ozaki-style error-free digit products):
+//   Yout = alpha * S * Yin + beta * E1 + gamma * E2,   S symmetric n x n (M = Xc Xc^T), Yin n x b.
+// Row i of S is scaled by 2^-e_i (e_i = exponent of its largest entry) and cut into NP digits of 7 bits,
+// a = 2^e sum_s d_s 2^(-6-7s), |d_s| <= 64; column j of Yin likewise with exponent f_j (planes stored transposed,
+// K-major).  The digit products with s + t <= NP - 1 are accumulated exactly in INT32 by tcgen05.mma.kind::i8, one
+// accumulator per scale g = s + t, and recombined in FP64 in the epilogue.  The digit pairs left out are below
+// 2^(-7 NP) of the row scale x column scale (NP = 5: 3e-11), so this operator carries the early filter rounds of the
+// subspace iteration while the residual is far above that; the last rounds and every residual check use the FP64 DMMA
+// operator (pca.cu).
+// Tiles 128 x 64 x 64 (SWIZZLE_64B rows of 64 bytes), stage = NP x (8 KB + 4 KB), 3 stages.
+// =====================================================================================================================
+#define IO_BM 128
+#define IO_BN 64
+#define IO_BK 64
+#define IO_MAXNP 8                // digit planes kept of the operator; a product uses the first NP of them (5 or 8)
+#define IO_A_BYTES (IO_BM * IO_BK)
+#define IO_B_BYTES (IO_BN * IO_BK)
+template <int NP> struct IoCfg {
+    static constexpr int STAGES = NP <= 5 ? 3 : 2;
+    static constexpr int STAGE_BYTES = NP * (IO_A_BYTES + IO_B_BYTES);
+};
+
+// exponent e with max < 2^e (max > 0), else 0; scale arrays hold 2^(e-6)
+__device__ __forceinline__ int io_exponent(double mx) {
+    if (!(mx > 0.0) || !isfinite(mx)) return 0;
+    int e;
+    frexp(mx, &e);                 // mx = f 2^e, f in [0.5, 1)
+    return e;
+}
+
+// one warp per row: largest |entry| of row r of A (n x n, ld) -> exponent and scale
+__global__ void io_rowmax_kernel(const double *__restrict__ A, int n, int ld, int *__restrict__ expo,
+                                 double *__restrict__ scale) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const double *row = A + (size_t)w * ld;
+    double mx = 0.0;
+    for (int c = lane; c < n; c += 32) mx = fmax(mx, fabs(row[c]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) { const int e = io_exponent(mx); expo[w] = e; scale[w] = ldexp(1.0, e - 6); }
+}
+
+// largest |entry| of every column of Y (n x b, ld): 64-row slabs, one atomicMax per column and slab on the IEEE bit
+// pattern (non-negative doubles order like unsigned integers; max is exact and order independent)
+__global__ void __launch_bounds__(256)
+io_colmax_kernel(const double *__restrict__ Y, int n, int b, int ld, unsigned long long *__restrict__ colmax_bits) {
+    const int r0 = blockIdx.x * 64, r1 = min(n, r0 + 64);
+    for (int c = threadIdx.x; c < b; c += 256) {
+        double mx = 0.0;
+        for (int r = r0; r < r1; r++) mx = fmax(mx, fabs(Y[(size_t)r * ld + c]));
+        if (mx > 0.0 && isfinite(mx)) atomicMax(colmax_bits + c, (unsigned long long)__double_as_longlong(mx));
+    }
+}
+__global__ void io_colscale_kernel(const unsigned long long *__restrict__ colmax_bits, int b, int *__restrict__ expo,
+                                   double *__restrict__ scale) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= b) return;
+    const int e = io_exponent(__longlong_as_double((long long)colmax_bits[c]));
+    expo[c] = e; scale[c] = ldexp(1.0, e - 6);
+}
+
+template <int NP>
+__device__ __forceinline__ void io_digits(double a, int e, int8_t (&d)[NP]) {
+    double x = ldexp(a, 6 - e);                 // |x| <= 64
+    if (!isfinite(x)) x = 0.0;
+#pragma unroll
+    for (int s = 0; s < NP; s++) {
+        const double r = rint(x);
+        d[s] = (int8_t)(int)r;
+        x = (x - r) * 128.0;                    // |x - r| <= 0.5 -> next digit in [-64, 64]
+    }
+}
+
+// planes P[s][row][k] (row pitch Kp bytes) of the rows of A: 16 consecutive k per thread
+template <int NP>
+__global__ void __launch_bounds__(256)
+io_slice_rows_kernel(const double *__restrict__ A, int n, int ld, const int *__restrict__ expo, int8_t *__restrict__ P,
+                     int rows_pad, int Kp) {
+    const size_t chunk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cpr = Kp / 16;
+    if (chunk >= (size_t)rows_pad * cpr) return;
+    const int row = (int)(chunk / cpr), k0 = (int)(chunk % cpr) * 16;
+    alignas(16) int8_t d[NP][16];
+    const int e = row < n ? expo[row] : 0;
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        const int k = k0 + t;
+        int8_t dd[NP];
+        io_digits<NP>((row < n && k < n) ? A[(size_t)row * ld + k] : 0.0, e, dd);
+#pragma unroll
+        for (int s = 0; s < NP; s++) d[s][t] = dd[s];
+    }
+    const size_t plane = (size_t)rows_pad * Kp;
+#pragma unroll
+    for (int s = 0; s < NP; s++)
+        *reinterpret_cast<int4 *>(P + s * plane + (size_t)row * Kp + k0) = *reinterpret_cast<const int4 *>(d[s]);
+}
+
+// planes P[s][j][k] of the COLUMNS of Y (n x b, ld): 32 x 32 tiles transposed through shared memory
+template <int NP>
+__global__ void __launch_bounds__(256)
+io_slice_cols_kernel(const double *__restrict__ Y, int n, int b, int ld, const int *__restrict__ expo,
+                     int8_t *__restrict__ P, int rows_pad, int Kp) {
+    __shared__ int8_t s[NP][32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int k0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    for (int kk = ty; kk < 32; kk += 8) {
+        const int k = k0 + kk, j = j0 + tx;
+        int8_t dd[NP];
+        io_digits<NP>((k < n && j < b) ? Y[(size_t)k * ld + j] : 0.0, j < b ? expo[j] : 0, dd);
+#pragma unroll
+        for (int p = 0; p < NP; p++) s[p][kk][tx] = dd[p];
+    }
+    __syncthreads();
+    const size_t plane = (size_t)rows_pad * Kp;
+    for (int jj = ty; jj < 32; jj += 8) {
+        const int j = j0 + jj, k = k0 + tx;
+        if (j < rows_pad && k < Kp)
+#pragma unroll
+            for (int p = 0; p < NP; p++) P[p * plane + (size_t)j * Kp + k] = s[p][tx][jj];
+    }
+}
+
+__device__ __forceinline__ unsigned long long io_desc(unsigned smem_addr) {      // K-major, 64-byte rows, SWIZZLE_64B
+    unsigned long long d = 0;
+    d |= (unsigned long long)((smem_addr >> 4) & 0x3fff);
+    d |= (unsigned long long)1 << 16;
+    d |= (unsigned long long)(512 >> 4) << 32;                       // 8 rows x 64 bytes
+    d |= (unsigned long long)1 << 46;
+    d |= (unsigned long long)4 << 61;                                // SWIZZLE_64B
+    return d;
+}
+
+struct IoParams {
+    int n, b;              // rows of S / of the output, columns of Y
+    int row_begin, row_end;
+    int kblocks;
+    double *D; long ldd;
+    const double *E1; long lde1; const double *E2; long lde2;
+    double alpha, beta, gamma;
+    const double *rowscale, *colscale;       // 2^(e_i - 6), 2^(f_j - 6)
+};
+
+template <int NP>
+__global__ void __launch_bounds__(IG_THREADS, 1)
+io_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, IoParams p) {
+    constexpr int IO_STAGES = IoCfg<NP>::STAGES, IO_STAGE_BYTES = IoCfg<NP>::STAGE_BYTES, IO_NP = NP;
+    const int m0 = p.row_begin + blockIdx.y * IO_BM, n0 = blockIdx.x * IO_BN;
+    extern __shared__ unsigned char ig_raw[];
+    unsigned char *tiles = (unsigned char *)(((uintptr_t)ig_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) unsigned long long s_full[IO_STAGES], s_empty[IO_STAGES], s_done;
+    __shared__ unsigned s_tmem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < IO_STAGES; s++) { ig_mbar_init(ig_smem(&s_full[s]), 1); ig_mbar_init(ig_smem(&s_empty[s]), 1); }
+        ig_mbar_init(ig_smem(&s_done), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ig_smem(&s_tmem)), "n"(IG_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < p.kblocks; kb++) {
+                const int st = kb % IO_STAGES;
+                ig_mbar_wait(ig_smem(&s_empty[st]), ((kb / IO_STAGES) & 1) ^ 1);
+                const unsigned bar = ig_smem(&s_full[st]);
+                ig_mbar_expect_tx(bar, IO_STAGE_BYTES);
+                const unsigned base = ig_smem(tiles + (size_t)st * IO_STAGE_BYTES);
+                for (int d = 0; d < IO_NP; d++) {
+                    ig_tma_load_3d(base + d * IO_A_BYTES, &tmapA, bar, kb * IO_BK, m0, d);
+                    ig_tma_load_3d(base + d * IO_A_BYTES + IO_A_BYTES / 2, &tmapA, bar, kb * IO_BK, m0 + 64, d);
+                    ig_tma_load_3d(base + IO_NP * IO_A_BYTES + d * IO_B_BYTES, &tmapB, bar, kb * IO_BK, n0, d);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((IO_BN >> 3) << 17) | ((IO_BM >> 4) << 24);
+        if (lane == 0) {
+            for (int kb = 0; kb < p.kblocks; kb++) {
+                const int st = kb % IO_STAGES;
+                ig_mbar_wait(ig_smem(&s_full[st]), (kb / IO_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned base = ig_smem(tiles + (size_t)st * IO_STAGE_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < IO_BK / 32; kk++) {
+#pragma unroll
+                    for (int a = 0; a < IO_NP; a++) {
+                        const unsigned long long ad = io_desc(base + a * IO_A_BYTES) + (unsigned long long)(kk * 32 >> 4);
+#pragma unroll
+                        for (int b = 0; b < IO_NP - a; b++) {          // digit pairs with a + b <= NP - 1
+                            const unsigned long long bd = io_desc(base + IO_NP * IO_A_BYTES + b * IO_B_BYTES) + (unsigned long long)(kk * 32 >> 4);
+                            const bool first = kb == 0 && kk == 0 && a == 0;
+                            ig_mma_i8(tmem + (unsigned)(a + b) * IO_BN, ad, bd, idesc, first ? 0u : 1u);
+                        }
+                    }
+                }
+                ig_commit(ig_smem(&s_empty[st]));
+            }
+            ig_commit(ig_smem(&s_done));
+        }
+    } else {
+        ig_mbar_wait(ig_smem(&s_done), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int lg = warp & 3;
+        const int row = m0 + lg * 32 + lane;
+        const bool rok = row < p.row_end && row < p.n;
+        const double rs = rok ? p.alpha * p.rowscale[row] : 0.0;
+        for (int c0 = 0; c0 < IO_BN; c0 += 16) {
+            unsigned r[IO_NP][16];
+#pragma unroll
+            for (int s = 0; s < IO_NP; s++) ig_tmem_ld16(tmem + ((unsigned)(lg * 32) << 16) + (unsigned)(s * IO_BN + c0), r[s]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (rok) {
+#pragma unroll
+                for (int c = 0; c < 16; c++) {
+                    const int col = n0 + c0 + c;
+                    if (col >= p.b) continue;
+                    double g = (double)(int)r[IO_NP - 1][c];
+#pragma unroll
+                    for (int s = IO_NP - 2; s >= 0; s--) g = fma(g, 0.0078125, (double)(int)r[s][c]);
+                    double v = rs * p.colscale[col] * g;
+                    if (p.E1) v += p.beta * p.E1[(size_t)row * p.lde1 + col];
+                    if (p.E2) v += p.gamma * p.E2[(size_t)row * p.lde2 + col];
+                    p.D[(size_t)row * p.ldd + col] = v;
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(IG_TMEM_COLS));
+    }
+}
+
+static int io_encode(CUtensorMap *map, void *base, int rows_pad, int Kp, int planes) {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        TP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres));
+        if (!sym || qres != cudaDriverEntryPointSuccess) { tp_set_error("cuTensorMapEncodeTiled not available"); return TP_ERR_CUDA; }
+        fn = (PFN_encodeTiled)sym;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows_pad, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)Kp, (cuuint64_t)Kp * rows_pad};
+    const cuuint32_t box[3] = {IO_BK, 64, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { tp_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return TP_ERR_CUDA; }
+    return TP_OK;
+}
+
+// digit planes of the symmetric operator S (n x n, ld); kept in the context until the next call
+int tp_iop_prepare(tp_ctx *ctx, const double *S, int n, int ld) {
+    cudaStream_t st = ctx->stream;
+    const int rows_pad = round_up(n, IO_BM), Kp = round_up(n, 128);
+    const size_t plane = (size_t)rows_pad * Kp;
+    TP_TRY(ctx->ioA.reserve(IO_MAXNP * plane));
+    TP_TRY(ctx->ioscale.reserve((size_t)(n + 1024) * (sizeof(double) + sizeof(int)) * 2 + 1024 * sizeof(unsigned long long)));
+    double *rowscale = ctx->ioscale.as<double>();
+    int *rowexp = (int *)(rowscale + 2 * (n + 1024));
+    tp_prof_begin(ctx, PC_IGEMM);
+    io_rowmax_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(S, n, ld, rowexp, rowscale);
+    const size_t chunks = (size_t)rows_pad * (Kp / 16);
+    io_slice_rows_kernel<IO_MAXNP><<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(S, n, ld, rowexp, ctx->ioA.as<int8_t>(), rows_pad, Kp);
+    tp_prof_end(ctx);
+    ctx->launches += 2;
+    TP_CUDA(cudaGetLastError());
+    ctx->io_n = n;
+    return TP_OK;
+}
+
+// D[rows] = alpha S[rows, :] Yin + beta E1[rows] + gamma E2[rows], rows = [row_begin, row_end); NP = 5 (digit pairs
+// left out below 2^-35 of row scale x column scale) or 8 (2^-56: FP64 level)
+template <int NP>
+static int iop_apply_np(tp_ctx *ctx, const double *Yin, int b, int ldy, double *D, int ldd, double alpha, const double *E1,
+                        int lde1, double beta, const double *E2, int lde2, double gamma, int row_begin, int row_end) {
+    cudaStream_t st = ctx->stream;
+    const int n = ctx->io_n;
+    const int rows_padA = round_up(n, IO_BM), Kp = round_up(n, 128);
+    const int rows_padB = round_up(b, IO_BN);
+    const size_t planeB = (size_t)rows_padB * Kp;
+    TP_TRY(ctx->ioB.reserve(IO_MAXNP * planeB));
+    double *rowscale = ctx->ioscale.as<double>();
+    double *colscale = rowscale + (n + 1024);
+    int *rowexp = (int *)(rowscale + 2 * (n + 1024));
+    int *colexp = rowexp + (n + 1024);
+    tp_prof_begin(ctx, PC_IGEMM);
+    unsigned long long *cmax = (unsigned long long *)(colexp + (n + 1024));
+    TP_CUDA(cudaMemsetAsync(cmax, 0, (size_t)b * sizeof(unsigned long long), st));
+    io_colmax_kernel<<<(n + 63) / 64, 256, 0, st>>>(Yin, n, b, ldy, cmax);
+    io_colscale_kernel<<<(b + 255) / 256, 256, 0, st>>>(cmax, b, colexp, colscale);
+    dim3 sg(Kp / 32, rows_padB / 32);
+    io_slice_cols_kernel<NP><<<sg, 256, 0, st>>>(Yin, n, b, ldy, colexp, ctx->ioB.as<int8_t>(), rows_padB, Kp);
+    CUtensorMap mapA, mapB;
+    TP_TRY(io_encode(&mapA, ctx->ioA.p, rows_padA, Kp, NP));        // the first NP of the IO_MAXNP planes
+    TP_TRY(io_encode(&mapB, ctx->ioB.p, rows_padB, Kp, NP));
+    IoParams p;
+    p.n = n; p.b = b; p.row_begin = row_begin; p.row_end = row_end; p.kblocks = Kp / IO_BK;
+    p.D = D; p.ldd = ldd; p.E1 = E1; p.lde1 = lde1; p.E2 = E2; p.lde2 = lde2;
+    p.alpha = alpha; p.beta = beta; p.gamma = gamma; p.rowscale = rowscale; p.colscale = colscale;
+    const size_t smem = (size_t)IoCfg<NP>::STAGES * IoCfg<NP>::STAGE_BYTES + 1024;
+    TP_CUDA(cudaFuncSetAttribute(io_gemm_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(rows_padB / IO_BN, (row_end - row_begin + IO_BM - 1) / IO_BM);
+    io_gemm_kernel<NP><<<grid, IG_THREADS, smem, st>>>(mapA, mapB, p);
+    tp_prof_end(ctx);
+    ctx->launches += 4;
+    TP_CUDA(cudaGetLastError());
+    return TP_OK;
+}
+
+int tp_iop_apply(tp_ctx *ctx, const double *Yin, int b, int ldy, double *D, int ldd, double alpha, const double *E1,
+                 int lde1, double beta, const double *E2, int lde2, double gamma, int row_begin, int row_end, int np) {
+    TP_ARG(ctx->io_n > 0, "tp_iop_apply: tp_iop_prepare first");
+    TP_ARG(b <= 1024, "tp_iop_apply: block wider than 1024 columns");
+    TP_ARG(np == 5 || np == 8, "tp_iop_apply: 5 or 8 digit planes");
+    if (np == 5) return iop_apply_np<5>(ctx, Yin, b, ldy, D, ldd, alpha, E1, lde1, beta, E2, lde2, gamma, row_begin, row_end);
+    return iop_apply_np<8>(ctx, Yin, b, ldy, D, ldd, alpha, E1, lde1, beta, E2, lde2, gamma, row_begin, row_end);
+}

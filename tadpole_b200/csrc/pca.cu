@@ -23,6 +23,9 @@ int tp_jacobi(tp_ctx *ctx, double *A, int b, int ld, double *w, double *Vs, int 
 int tp_igram(tp_ctx *ctx, const double *X, int n, int ld, double *C, int ldc, const double *mean, const double *sd,
              int raw, int *used_out);
 int tp_chol_inv(tp_ctx *ctx, double *G, double *Linv, int b, int ld, int *bad_out);
+int tp_iop_prepare(tp_ctx *ctx, const double *S, int n, int ld);
+int tp_iop_apply(tp_ctx *ctx, const double *Yin, int b, int ldy, double *D, int ldd, double alpha, const double *E1,
+                 int lde1, double beta, const double *E2, int lde2, double gamma, int row_begin, int row_end, int np);
 
 // ---- small kernels -------------------------------------------------------------------------------
 // per row: mean and sd of the one-pass formula (columns == rows: the matrix is symmetric)
@@ -216,7 +219,9 @@ struct PcaOp {
     int b, ldb;
     bool shard = false;   // row blocks computed by their owner rank and all-gathered (buffers hold rw.padded rows)
     TpRows rw{};
-    long applications = 0;
+    int np = 0;           // 0: FP64 DMMA operator; 5 / 8: sliced int8 operator on the tcgen05 tensor cores with that many
+                          // digit planes (igemm.cu; needs explicit M): 5 for the early rounds, 8 is FP64-level
+    long applications = 0, lowprec_applications = 0;
     // D[rows] = alpha * A[rows, :] * B + beta * E1[rows] + gamma * E2[rows]; rows = all, or this rank's block
     int rows_gemm(GemmArgs g, double *D, const double *E1, const double *E2) {
         g.D = D; g.E1 = E1; g.E2 = E2;
@@ -237,6 +242,13 @@ struct PcaOp {
         g.M = n; g.N = b; g.ldd = ldb; g.alpha = alpha;
         g.lde1 = ldb; g.beta = beta; g.lde2 = ldb; g.gamma = gamma;
         applications++;
+        if (M && np) {
+            lowprec_applications++;
+            const int r0 = shard ? rw.r0 : 0, r1 = shard ? rw.r1 : n;
+            if (r1 > r0)
+                TP_TRY(tp_iop_apply(ctx, Yin, b, ldb, Yout, ldb, alpha, E1, ldb, beta, E2, ldb, gamma, r0, r1, np));
+            return shard ? tp_comm_allgather(ctx, Yout, (size_t)rw.rpr * ldb) : (int)TP_OK;
+        }
         if (M) {
             g.A = M; g.lda = ld; g.a_kc = 1; g.B = Yin; g.ldb = ldb; g.b_kc = 0; g.K = n;
             return rows_gemm(g, Yout, E1, E2);
@@ -279,7 +291,8 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
 
     int b = ctx->pca_block > 0 ? ctx->pca_block : round_up(k + (k / 4 > 32 ? k / 4 : 32), 32);
     const bool direct = n <= ctx->jacobi_direct_max || b >= n;
-    const bool explicitM = direct || n <= 12288;
+    const bool use_iop = !direct && ctx->iop_min_n > 0 && n >= ctx->iop_min_n;
+    const bool explicitM = direct || n <= 12288 || use_iop;
     double *M = nullptr;
     const bool shard = !direct && tp_row_sharded(ctx, n);
     const TpRows rw = tp_rows(ctx, n);
@@ -327,6 +340,7 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
         double *res = ctx->resid.as<double>();
         PcaOp op{ctx, n, ld, C, M, nullptr, b, ldb};
         op.shard = shard; op.rw = rw;
+        if (use_iop) TP_TRY(tp_iop_prepare(ctx, M, n, ld));
         DevBuf zbuf;   // scratch for the two-GEMM operator
         if (!M) { TP_TRY(zbuf.reserve(blk)); op.Z = zbuf.as<double>(); }
 
@@ -436,7 +450,9 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
 
         auto body = [&]() -> int {
             TP_TRY(tp_flags_reset(ctx));
-            sweeps_total = 0; it = 0; converged = false; op.applications = 0;
+            sweeps_total = 0; it = 0; converged = false; op.applications = 0; op.lowprec_applications = 0;
+            op.np = use_iop ? 5 : 0;
+            double prev_res = 1e300;
             Y = ctx->Y0.as<double>(); F1 = ctx->Y1.as<double>(); F2 = ctx->Y2.as<double>();
             random_block_kernel<<<(unsigned)(((size_t)n * ldb + 255) / 256), 256, 0, st>>>(Y, n, b, ldb);
             ctx->launches += 1;
@@ -468,19 +484,27 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
                     if (ratio <= 1e5) bd.deg = mdeg; else break;
                 }
                 // ---- first filter step doubles as the residual check ---------------------------------
-                TP_TRY(filter_step1());
-                residual_kernel<<<(k + 31) / 32, 256, 0, st>>>(Y, F1, n, ldb, k, theta, bd.e / bd.sig1, bd.c, res);
-                ctx->launches += 1;
-                TP_CUDA(cudaMemcpyAsync(hbuf, res, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, st));
-                TP_TRY(tp_flags_enqueue(ctx));
-                TP_CUDA(cudaStreamSynchronize(st));
-                TP_TRY(poll());
                 double rmax = 0.0;
-                for (int j = 0; j < k; j++) rmax = (hbuf[j] > rmax || hbuf[j] != hbuf[j]) ? hbuf[j] : rmax;
-                last_res = rmax / bd.top;
-                if (getenv("TADPOLE_DEBUG"))
-                    fprintf(stderr, "[tadpole] pca it=%d res=%.3e top=%.4e thk=%.4e cut=%.4e deg=%d\n", it, last_res,
-                            bd.top, bd.thk, bd.cut, bd.deg);
+                for (int attempt = 0; attempt < 2; attempt++) {
+                    TP_TRY(filter_step1());
+                    residual_kernel<<<(k + 31) / 32, 256, 0, st>>>(Y, F1, n, ldb, k, theta, bd.e / bd.sig1, bd.c, res);
+                    ctx->launches += 1;
+                    TP_CUDA(cudaMemcpyAsync(hbuf, res, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, st));
+                    TP_TRY(tp_flags_enqueue(ctx));
+                    TP_CUDA(cudaStreamSynchronize(st));
+                    TP_TRY(poll());
+                    rmax = 0.0;
+                    for (int j = 0; j < k; j++) rmax = (hbuf[j] > rmax || hbuf[j] != hbuf[j]) ? hbuf[j] : rmax;
+                    last_res = rmax / bd.top;
+                    if (getenv("TADPOLE_DEBUG"))
+                        fprintf(stderr, "[tadpole] pca it=%d res=%.3e top=%.4e thk=%.4e cut=%.4e deg=%d %s\n", it, last_res,
+                                bd.top, bd.thk, bd.cut, bd.deg, op.np == 5 ? "int8x5" : (op.np == 8 ? "int8x8" : "fp64"));
+                    // the sliced operator carries the iteration down to iop_switch (or until it stops helping); from
+                    // there on, and for every decision about convergence, the FP64 operator is used
+                    if (op.np != 5 || !(last_res <= ctx->iop_switch || last_res > 0.1 * prev_res)) break;
+                    op.np = n >= 4096 ? ctx->iop_final : 0;      // small problems: the FP64 operator is as fast
+                }
+                prev_res = last_res;
                 if (rmax <= ctx->pca_tol * bd.top) { converged = true; return TP_OK; }
                 // ---- filter / orthonormalise rounds, then one Rayleigh-Ritz ------------------------
                 bool general = false;
@@ -506,6 +530,7 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
         TP_TRY(rc);
         ctx->timing[7] = it;
         ctx->timing[8] = (double)op.applications;
+        ctx->lowprec_applications = op.lowprec_applications;
         ctx->timing[9] = sweeps_total;
         if (!converged) {
             tp_set_error("tp_pca: subspace iteration stopped at relative residual %.3e after %d iterations", last_res, it);
