@@ -164,6 +164,13 @@ class ClockSampler:
         return out
 
 
+def h2d_bytes(n):
+    """bytes tp_filter copies to the device for a row-major n x n host matrix: band copies of the upper triangle
+    (csrc/filter.cu): rows [r, r + band) x columns [r, n)"""
+    band = max(n // 32, 64)
+    return sum((n - r) * 8 * min(band, n - r) for r in range(0, n, band))
+
+
 def measure_fp64_peak(torch):
     """cuBLAS DGEMM TFLOP/s on this box (library GEMM used only as the roofline denominator)."""
     a = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
@@ -279,6 +286,13 @@ def run_b200(args, rank, world, local_rank):
                 r = {"kernel": "dgemm_kernel (FP64 DMMA mma.sync m8n8k4)", "bound": "tensor",
                      "achieved": prof["gemm_gflop"][0] / t_ms, "peak": fp64_peak, "unit": "TFLOP/s", "traffic": None}
                 src = "cuBLAS DGEMM 4096^3 via torch.matmul, best of 6, measured in this run"
+            elif cls == "igemm":
+                # tcgen05 int8 launches (exact Gram of the correlation, sliced operator of the PCA; the class also
+                # holds their digit-slicing kernels): executed int8 operations / class time against the NOMINAL dense
+                # int8 rate (no measured int8 peak in MEASURED_PEAKS.json)
+                r = {"kernel": "ig_gram_kernel + io_gemm_kernel (tcgen05.mma kind::i8)", "bound": "tensor",
+                     "achieved": prof["igemm_gop"][0] / t_ms, "peak": 4500.0, "unit": "TOP/s", "traffic": None}
+                src = "nominal B200 dense int8 (4.5 POP/s); executed digit-product operations, not FP64 flops"
             else:
                 if cls == "coniss_sweep":      # 8 Nf k(k+1)/2 read + 8 k (Nf-1) written per sweep
                     alg, name = 8.0 * nf * k * (k + 1) / 2 + 8.0 * k * (nf - 1), "coniss_sweep_kernel"
@@ -305,7 +319,7 @@ def run_b200(args, rank, world, local_rank):
             r["launches_per_step"] = cnt / args.steps
             return r
 
-        classes = ("dgemm", "jacobi", "chol", "coniss_sweep", "ch", "rowmean", "compact")
+        classes = ("dgemm", "igemm", "jacobi", "chol", "coniss_sweep", "ch", "rowmean", "compact")
         roofs = {c: roof_of(c) for c in classes}
         roofs = {c: r for c, r in roofs.items() if r}
         try:        # DRAM traffic per launch measured by ncu --set full (profiles/), N = 2000 workload only
@@ -332,7 +346,7 @@ def run_b200(args, rank, world, local_rank):
                        "l2": f"pool of {POOL} different {n}x{n} f64 matrices per rank ({POOL * n * n * 8 >> 20} MiB > L2) "
                              "cycled, no step re-reads a warm input",
                        "parallelism": f"{world} independent calls (one per GPU), no collective on the data path"},
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * n * 8, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(n), "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms_all / args.steps},
             "gpu_launches": int(launches),
             "clocks": clk,
@@ -341,6 +355,7 @@ def run_b200(args, rank, world, local_rank):
             "fp64_dgemm_peak_tflops_measured": fp64_peak,
             "stage_ms_last_step": {k_: round(v, 4) for k_, v in stage.items()},
             "kernel_ms_per_step": {c: round(v[0] / args.steps, 4) for c, v in prof.items() if v[1]},
+            "h2d_note": "only the upper triangle of the matrix is uploaded (band copies)",
             "kernel_launches_per_step": {c: v[1] / args.steps for c, v in prof.items() if v[1]},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -63,7 +63,7 @@ int tp_ctx_timings(tp_ctx *ctx, double *out10);
  * CUDA events on the context stream; reading sums them since the last enable/reset.
  * classes: [0] rowmean (filter) [1] compact [2] dgemm [3] jacobi (b x b eigensolver) [4] coniss_sweep [5] ch
  * [6] difft [8] chol (b x b Cholesky + triangular inverse) [9] igemm (tcgen05 integer GEMM) [10] NCCL collectives
- * [11] spare;
+ * [11] in ms_out12: executed int8 GOP (2 per multiply-add) of the profiled tcgen05 launches;
  * [7] in ms_out12: GFLOP (algorithmic) of the profiled dgemm launches.
  * enable: 1 = start/reset, 0 = stop, -1 = just read. */
 int tp_ctx_profile(tp_ctx *ctx, int enable, double *ms_out12, long long *count_out12);

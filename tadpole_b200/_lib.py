@@ -149,7 +149,7 @@ class Context:
         return dict(zip(keys, out.tolist()))
 
     PROFILE_CLASSES = ["rowmean", "compact", "dgemm", "jacobi", "coniss_sweep", "ch", "difft", "gemm_gflop", "chol", "igemm",
-                       "comm", "spare3"]
+                       "comm", "igemm_gop"]
 
     def profile(self, enable=-1):
         """enable: 1 start/reset, 0 stop, -1 read.  Returns {class: (ms, launches)} accumulated so far."""

@@ -174,9 +174,10 @@ extern "C" int tp_ctx_profile(tp_ctx *ctx, int enable, double *ms_out12, long lo
             } else (void)cudaGetLastError();
         }
         ms[PC_SPARE] = ctx->prof_gemm_flop * 1e-9;   // slot 7: GFLOP of the profiled GEMM launches
+        ms[PC_SPARE3] = ctx->prof_imma_ops * 1e-9;   // slot 11: executed int8 GOP of the profiled tcgen05 launches
         for (int c = 0; c < PC_COUNT; c++) { if (ms_out12) ms_out12[c] = ms[c]; if (count_out12) count_out12[c] = cnt[c]; }
     }
-    if (enable == 1) { ctx->prof = true; ctx->prof_used = 0; ctx->prof_gemm_flop = 0.0; }
+    if (enable == 1) { ctx->prof = true; ctx->prof_used = 0; ctx->prof_gemm_flop = 0.0; ctx->prof_imma_ops = 0.0; }
     else if (enable == 0) ctx->prof = false;
     return TP_OK;
 }

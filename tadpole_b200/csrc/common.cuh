@@ -135,6 +135,7 @@ struct tp_ctx {
     std::vector<int> prof_cls;             // class of pair i
     size_t prof_used = 0;                  // events used
     double prof_gemm_flop = 0.0;           // algorithmic flops of the GEMM launches profiled
+    double prof_imma_ops = 0.0;            // executed int8 multiply-add operations (2 per MAC) of the tcgen05 launches profiled
 };
 
 enum { PC_ROWMEAN = 0, PC_COMPACT, PC_GEMM, PC_JACOBI, PC_SWEEP, PC_CH, PC_DIFFT, PC_SPARE, PC_CHOL, PC_IGEMM, PC_COMM, PC_SPARE3, PC_COUNT };

@@ -283,6 +283,10 @@ int tp_igram(tp_ctx *ctx, const double *X, int n, int ld, double *C, int ldc, co
     TP_CUDA(cudaFuncSetAttribute(ig_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(rows_pad / IG_BN, rows_pad / IG_BM);
     tp_prof_begin(ctx, PC_IGEMM);
+    if (ctx->prof) {       // executed: 9 digit products on the tiles of the upper triangle
+        const double tiles = 0.5 * ((double)rows_pad / IG_BM) * ((double)rows_pad / IG_BN);
+        ctx->prof_imma_ops += 2.0 * 9.0 * tiles * IG_BM * IG_BN * (double)Kp;
+    }
     ig_gram_kernel<<<grid, IG_THREADS, smem, st>>>(map, p);
     tp_prof_end(ctx);
     ctx->launches += 1;
@@ -608,6 +612,7 @@ static int iop_apply_np(tp_ctx *ctx, const double *Yin, int b, int ldy, double *
     const size_t smem = (size_t)IoCfg<NP>::STAGES * IoCfg<NP>::STAGE_BYTES + 1024;
     TP_CUDA(cudaFuncSetAttribute(io_gemm_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(rows_padB / IO_BN, (row_end - row_begin + IO_BM - 1) / IO_BM);
+    if (ctx->prof) ctx->prof_imma_ops += 2.0 * (NP * (NP + 1) / 2) * (double)grid.x * grid.y * IO_BM * IO_BN * (double)Kp;
     io_gemm_kernel<NP><<<grid, IG_THREADS, smem, st>>>(mapA, mapB, p);
     tp_prof_end(ctx);
     ctx->launches += 4;
