@@ -2,7 +2,9 @@
 #include "gemm.cuh"
 #include <stdlib.h>
 
+#ifndef GEMM_BK
 #define GEMM_BK 16
+#endif
 #define GEMM_STAGES 3
 #define PITCH_K (GEMM_BK + 4)   // operand stored [row][k]: pitch 20 doubles -> conflict-free fragment reads
 

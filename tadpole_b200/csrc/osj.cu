@@ -83,15 +83,25 @@ __device__ __forceinline__ void osj_rotate(unsigned sA, unsigned sN, int BP, int
     if (!(rel2 > skip2)) return;
     // t = sgn(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (be - al) / (2 g), without the division.
     // t only steers convergence; (c, s) is renormalised to c^2 + s^2 = 1 in full precision.
+    // The tangent only steers convergence (an error of 2^-22 in t leaves 2^-22 of the pair's cosine behind, far below
+    // what the other rotations of the sweep put back), so h and the quotient come from the bare MUFU approximations;
+    // (c, s) is then normalised to c^2 + s^2 = 1 in full precision: two Newton steps take 2^-22.9 to 2^-89.
     const double dd = be - al;
     const double hh = fma(dd, dd, 4.0 * g * g);
     double rh;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rh) : "d"(hh));
-    rh = rh * fma(-0.5 * hh * rh, rh, 1.5);
-    const double h = hh * rh;
-    double t = 2.0 * g * osj_rcp(fabs(dd) + h);
+    double rden;
+    const double den = fma(hh, rh, fabs(dd));
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rden) : "d"(den));
+    double t = 2.0 * g * rden;
     if (dd < 0.0) t = -t;
-    const double c = osj_rsqrt(fma(t, t, 1.0)), sn = t * c;
+    const double tt = fma(t, t, 1.0);
+    double c;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(c) : "d"(tt));
+    const double htt = 0.5 * tt;
+    c = c * fma(-htt * c, c, 1.5);
+    c = c * fma(-htt * c, c, 1.5);
+    const double sn = t * c;
 #pragma unroll
     for (int u = 0; u < RL; u++) {
         osj_sts(ax + 256u * u, c * xa[u] - sn * ya[u]);
