@@ -11,7 +11,12 @@ matrix with nested block TADs and power-law decay.  With N > 1 every rank calls 
 matrices (multi-chromosome batch, no data-path collective): weak scaling.
 
 value  : calls/s with the input matrices already resident in HBM (device pointers through the
-         C ABI), timed with CUDA events on the library's stream, max over ranks.
+         C ABI), timed with CUDA events on the library's streams, max over ranks.  A single 2000-bin call
+         leaves most of the GPU idle (its b x b eigen / Cholesky kernels run on one 8-CTA cluster), so, as a
+         genome-wide run over many chromosomes would, --streams S independent calls are in flight per GPU
+         (tadpole_b200.batch: one context, stream and host thread each); the K steps are dealt out to them.
+         `single_call` in the JSON line is the same measured with one call at a time (latency), and the
+         per-kernel rooflines are taken from that pass.
 e2e    : the same through the public API TADpole(matrix) with the matrix in pinned HOST memory;
          H2D copy of the matrix and D2H of the results are inside the timed region.
 A pool of different matrices larger than L2 (5 x 32 MB) is cycled, so no step re-reads a warm input.
@@ -47,7 +52,9 @@ UNIT = "calls/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--streams", type=int, default=4,
+                    help="independent calls in flight per GPU (own context / stream / host thread each)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bins", type=int, default=N_BINS)
@@ -186,14 +193,16 @@ def measure_fp64_peak(torch):
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from tadpole_b200 import Context, TADpole, api
+    from tadpole_b200 import ContextPool, TADpole, api
     from tadpole_b200.synth import synth_hic
 
     api.QUIET = True
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    ctx = Context(local_rank)
+    S = max(1, args.streams)
+    pool = ContextPool(local_rank, S)
+    ctx = pool.contexts[0]
     n = args.bins
 
     # synthetic inputs: POOL different matrices per rank; pinned host copies for e2e, device copies for value
@@ -205,7 +214,7 @@ def run_b200(args, rank, world, local_rank):
         host.append(t)
     dev = [t.cuda(non_blocking=False) for t in host]
     torch.cuda.synchronize()
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    streams = [torch.cuda.ExternalStream(c.stream, device=torch.device("cuda", local_rank)) for c in pool.contexts]
 
     def barrier():
         torch.cuda.synchronize()
@@ -213,48 +222,60 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_dev(i):
+    def step_dev(c, i):
         d = dev[i % POOL]
-        return ctx.call(device_ptr=d.data_ptr(), n=n, colmajor=0, max_pcs=MAX_PCS)
+        return c.call(device_ptr=d.data_ptr(), n=n, colmajor=0, max_pcs=MAX_PCS)
 
-    def step_e2e(i):
-        return TADpole(host[i % POOL].numpy(), max_pcs=MAX_PCS, ctx=ctx)
+    def step_e2e(c, i):
+        return TADpole(host[i % POOL].numpy(), max_pcs=MAX_PCS, ctx=c)
 
-    # ---- value: inputs resident in HBM, CUDA events on the library's stream --------------------
-    for i in range(args.warmup):
-        step_dev(i)
-    barrier()
+    def timed_pass(fn, steps, contexts, event_streams):
+        """`steps` calls dealt out to the contexts; device time from a CUDA event recorded before the first call to the
+        last end event over the contexts' streams; also wall seconds."""
+        sub = ContextPool.__new__(ContextPool)
+        sub.device, sub.contexts = local_rank, contexts
+        e0 = torch.cuda.Event(enable_timing=True)
+        ends = [torch.cuda.Event(enable_timing=True) for _ in contexts]
+        barrier()
+        e0.record(event_streams[0])
+        t0 = time.perf_counter()
+        out = sub.map(fn, range(steps))
+        for c, ev, st in zip(contexts, ends, event_streams):
+            ev.record(st)
+        for c in contexts:
+            c.sync()
+        wall = time.perf_counter() - t0
+        barrier()
+        return max(e0.elapsed_time(ev) for ev in ends), wall, out
+
+    # ---- warm-up: every context allocates its buffers --------------------------------------------
+    for w in range(max(args.warmup, 3)):
+        pool.map(lambda c, i: step_dev(c, i), range(S))
+    # ---- single call at a time: latency, per-kernel device times (CUDA events around each launch) ----
+    lat_steps = max(5, min(args.steps, 20))
     clocks = ClockSampler(local_rank) if rank == 0 else None
     ctx.profile(1)
-    l0 = ctx.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(args.steps):
-        res = step_dev(args.warmup + i)
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = ctx.launches - l0
+    l0 = sum(c.launches for c in pool.contexts)
+    ms, _, outs = timed_pass(lambda c, i: step_dev(c, args.warmup + i), lat_steps, [ctx], streams[:1])
+    res = outs[-1]
     prof = ctx.profile(0)
     stage = ctx.timings()
+    # ---- value: S calls in flight ------------------------------------------------------------------
+    ms_thr, _, _ = timed_pass(lambda c, i: step_dev(c, args.warmup + i), args.steps, pool.contexts, streams)
+    launches = sum(c.launches for c in pool.contexts) - l0
     clk = clocks.stop() if clocks else None
-
-    # ---- e2e: public API, pinned host input, copies inside the timed region --------------------
-    for i in range(min(args.warmup, 3)):
-        step_e2e(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        tp = step_e2e(args.warmup + i)
-    ctx.sync()
-    t_e2e = time.perf_counter() - t0
-    barrier()
+    # ---- e2e: public API, pinned host input, copies inside the timed region -----------------------
+    pool.map(lambda c, i: step_e2e(c, i), range(S))
+    _, t_e2e, tps = timed_pass(lambda c, i: step_e2e(c, args.warmup + i), args.steps, pool.contexts, streams)
+    _, t_e2e_single, _ = timed_pass(lambda c, i: step_e2e(c, args.warmup + i), lat_steps, [ctx], streams[:1])
+    tp = tps[-1]
     d2h = int(n + tp.scores.size * 8 + (res["nf"] - 1) * 8)
 
-    tmax = torch.tensor([ms, t_e2e * 1e3], dtype=torch.float64, device="cuda")
+    tmax = torch.tensor([ms_thr, t_e2e * 1e3, ms, t_e2e_single * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_all, e2e_ms_all = float(tmax[0]), float(tmax[1])
+    ms_all, e2e_ms_all, ms_single_all, e2e_single_all = (float(v) for v in tmax)
+    args_steps_single = lat_steps
 
     if rank == 0:
         value = world * args.steps / (ms_all * 1e-3)
@@ -314,9 +335,9 @@ def run_b200(args, rank, world, local_rank):
                     r["note"] = "latency-bound: serial dependent steps on L2 / shared-memory resident data"
             r["frac"] = r["achieved"] / r["peak"]
             r["peak_source"] = src
-            r["share_of_step"] = t_ms / ms
+            r["share_of_step"] = t_ms / ms          # of the one-call-at-a-time pass the classes were timed in
             r["avg_launch_ms"] = per
-            r["launches_per_step"] = cnt / args.steps
+            r["launches_per_step"] = cnt / args_steps_single
             return r
 
         classes = ("dgemm", "igemm", "jacobi", "chol", "coniss_sweep", "ch", "rowmean", "compact")
@@ -345,18 +366,23 @@ def run_b200(args, rank, world, local_rank):
                        "optimal_n_clusters": res["n_clusters"],
                        "l2": f"pool of {POOL} different {n}x{n} f64 matrices per rank ({POOL * n * n * 8 >> 20} MiB > L2) "
                              "cycled, no step re-reads a warm input",
-                       "parallelism": f"{world} independent calls (one per GPU), no collective on the data path"},
+                       "calls_in_flight_per_gpu": S,
+                       "parallelism": f"{world} GPU(s) x {S} independent calls in flight (own context, stream and host thread "
+                                      "each), no collective on the data path"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(n), "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms_all / args.steps},
+            "single_call": {"ms_per_call": ms_single_all / args_steps_single, "calls_per_s": world * args_steps_single / (ms_single_all * 1e-3),
+                            "e2e_ms_per_call": e2e_single_all / args_steps_single,
+                            "note": "one call at a time per GPU (latency); rooflines and kernel_ms_per_step are from this pass"},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": roof,
             "roofline_all_kernels": roofs,
             "fp64_dgemm_peak_tflops_measured": fp64_peak,
             "stage_ms_last_step": {k_: round(v, 4) for k_, v in stage.items()},
-            "kernel_ms_per_step": {c: round(v[0] / args.steps, 4) for c, v in prof.items() if v[1]},
+            "kernel_ms_per_step": {c: round(v[0] / args_steps_single, 4) for c, v in prof.items() if v[1]},
             "h2d_note": "only the upper triangle of the matrix is uploaded (band copies)",
-            "kernel_launches_per_step": {c: v[1] / args.steps for c, v in prof.items() if v[1]},
+            "kernel_launches_per_step": {c: v[1] / args_steps_single for c, v in prof.items() if v[1]},
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -367,7 +393,7 @@ def run_b200(args, rank, world, local_rank):
                            f"({detail['front_s']} s), {detail['candidates']} of {detail['k']} candidates on {threads} "
                            f"threads ({detail['sweep_sample_s']} s) scaled by k/candidates")}
         print(json.dumps(line), flush=True)
-    ctx.close()
+    pool.close()
     if world > 1:
         dist.destroy_process_group()
 

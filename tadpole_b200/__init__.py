@@ -7,7 +7,8 @@ libtadpole_b200.so (hand-written CUDA for sm_100a behind a C ABI, include/tadpol
 from .api import TADpole, load_mat, diffT, diffT_batch, random_bed, bin_index, Tadpole, LoadedMatrix, get_context
 from ._lib import Context, TadpoleError, assemble
 from .hclust import Dendro, find_groups, cutree
+from .batch import ContextPool, TADpole_batch
 
 __all__ = ["TADpole", "load_mat", "diffT", "diffT_batch", "random_bed", "bin_index", "Tadpole", "LoadedMatrix",
-           "get_context", "Context", "TadpoleError", "assemble", "Dendro", "find_groups", "cutree"]
+           "get_context", "ContextPool", "TADpole_batch", "Context", "TadpoleError", "assemble", "Dendro", "find_groups", "cutree"]
 __version__ = "0.1.0"

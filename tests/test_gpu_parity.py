@@ -252,3 +252,26 @@ def test_difft_full_size_properties(ctx):
     assert (sym == out).all()                                  # symmetric in its arguments
     for p in (0, 63):
         assert (out[p] == O.difft_from_labels_c(lx[p], ly[p])).all()
+
+
+# ---- several calls in flight on one GPU ------------------------------------------------------------------
+def test_batch_of_calls_equals_sequential_calls():
+    """TADpole_batch runs independent calls concurrently on one GPU (one context / stream / host thread each);
+    every result must be bit-identical to the call done alone."""
+    from tadpole_b200 import Context, ContextPool, TADpole, TADpole_batch, api
+    from tadpole_b200.synth import synth_hic
+    api.QUIET = True
+    mats = [synth_hic(n, seed=40 + i) for i, n in enumerate((300, 1200, 600, 1200, 300, 900))]
+    pool = ContextPool(0, streams=3)
+    got = TADpole_batch(mats, pool=pool)
+    pool.close()
+    solo = Context(0)
+    for m, g in zip(mats, got):
+        r = TADpole(m, ctx=solo)
+        assert (r.n_pcs, r.optimal_n_clusters) == (g.n_pcs, g.optimal_n_clusters)
+        assert np.array_equal(r.dendro.seqdist, g.dendro.seqdist)
+        assert np.array_equal(r.scores, g.scores, equal_nan=True)
+        assert r.clusters.keys() == g.clusters.keys()
+        for key in r.clusters:
+            assert np.array_equal(r.clusters[key], g.clusters[key])
+    solo.close()
