@@ -21,6 +21,7 @@
 #ifndef TADPOLE_B200_H
 #define TADPOLE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -82,6 +83,24 @@ int tp_comm_unique_id(void *id128);
 int tp_ctx_comm_init(tp_ctx *ctx, const void *id128, int rank, int nranks, int slot);
 int tp_ctx_comm_select(tp_ctx *ctx, int slot);
 int tp_ctx_comm_info(tp_ctx *ctx, int *rank_out, int *nranks_out);
+
+/* ---- input side: read.big.matrix(mat_file, type = 'double', sep = '\t') (R/TADpole.R:17) ----------------------
+ * A header-less, separator-delimited N x N text matrix (host memory or a file) is uploaded as text and parsed on the
+ * device into the context's N x N row-major FP64 matrix; every field is converted exactly (round to nearest even of
+ * the decimal value, like strtod).  NA / NaN / empty fields become NaN (zeroed by stage 1, R/TADpole.R:19).  A row
+ * whose field count differs from the number of rows is an error.  `sep` is the separator byte ('\t' in the reference).
+ * tp_ingested returns the device pointer and N to hand to tp_filter / tp_call with on_device = 1, colmajor = 0; the
+ * matrix stays valid until the next tp_ingest_* or the next tp_filter / tp_call from a HOST matrix on this context.
+ * tp_get_ingested copies it to the host (n x n doubles, row-major).  tp_ingest_stats: [0] wall ms of the last ingest
+ * (read + upload + parse), [1] device ms of the parse kernels, [2] text bytes, [3] fields converted on the host. */
+int tp_ingest_tsv(tp_ctx *ctx, const char *text, size_t nbytes, int sep, int *n_out);
+int tp_ingest_tsv_file(tp_ctx *ctx, const char *path, int sep, int *n_out);
+int tp_ingested(tp_ctx *ctx, const double **dev_out, int *n_out);
+int tp_get_ingested(tp_ctx *ctx, double *out);
+int tp_ingest_stats(tp_ctx *ctx, double *out4);
+/* host-only test hook: the field conversion the parse kernel runs; returns 0 (value in *out) or 1 (field is left to
+ * the host's strtod); needs no GPU */
+int tp_test_parse_field(const char *s, int len, double *out);
 
 /* ---- stage 1: load_mat numeric core (R/TADpole.R:19-22,35-37) ----------------------------- */
 /* Uploads (or adopts, when on_device) the N x N matrix, computes rowMeans of the symmetrised
@@ -161,6 +180,22 @@ int tp_call_arm(tp_ctx *ctx, const int *keep, int nf, int max_pcs, int min_clust
  * cumulative score, normalised by its last value unless every per-bin score is 0. */
 int tp_difft_batch(tp_ctx *ctx, const int32_t *labels_x, const int32_t *labels_y, int L, int npairs,
                    int on_device, double *out);
+
+/* diffT null distribution: random_bed (R/DiffT.R:61-73) drawn nperm times ON THE DEVICE, each random partition scored
+ * against the one observed call with diffT (R/DiffT.R:41-49).
+ *   labels_x[L]   padded labels of the observed call over the common extent (host), as tp_difft_batch takes them;
+ *   the random partitions have `ntads` TADs over the size = L - pad_left - pad_right bins that follow pad_left, and are
+ *   padded with label 1 on the left and their largest label on the right (R/DiffT.R:31-36);
+ *   bad_positions[nbad]  1-based positions within start:end that cannot carry a border ((start:end)[-bad_columns]);
+ *   seed          selects the Philox4x32-10 stream; R's own sample() stream cannot be reproduced, the distribution
+ *                 (uniform (ntads-1)-subsets of bins[-1]) is the same.
+ * Outputs (host, each may be NULL): borders_out[nperm x (ntads-1)] sorted border bins as offsets from `start`
+ * (the BED rows are start = c(start, borders - 1), end = c(borders - 2, end)); labels_out[nperm x L];
+ * curves_out[nperm x L] diffT curves; totals_out[nperm] un-normalised totals (last value of cumsum(scores)).
+ * Errors as sample() does when ntads - 1 exceeds the number of candidate bins. */
+int tp_difft_null(tp_ctx *ctx, const int32_t *labels_x, int L, int pad_left, int pad_right, int ntads,
+                  const int32_t *bad_positions, int nbad, unsigned long long seed, int nperm,
+                  int32_t *borders_out, int32_t *labels_out, double *curves_out, double *totals_out);
 
 /* ---- result assembly (host integer logic, R/TADpole.R:470-497 and fix_values :503-510) ----------
  * Cuts the dendrogram `seqdist` (nf-1) into n_clusters contiguous clusters, re-inserts the bad bins

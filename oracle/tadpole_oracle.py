@@ -504,9 +504,11 @@ def bin_index(bed, size):
     bed = np.asarray(bed, dtype=np.int64)
     tad = np.zeros(size, dtype=np.int64)
     for t in range(bed.shape[0]):
-        for b in range(bed[t, 0], bed[t, 1] + 1):
-            pos = b - bed[0, 0] + 1
-            tad[pos - 1] = t + 1
+        a, b = int(bed[t, 0]), int(bed[t, 1])
+        for v in (range(a, b + 1) if a <= b else range(a, b - 1, -1)):      # seq(a, b) counts down when a > b
+            pos = v - bed[0, 0] + 1
+            if pos >= 1:                                                   # tad_index[0] <- tad is a no-op in R
+                tad[pos - 1] = t + 1
     return tad
 
 
@@ -569,3 +571,88 @@ def read_bed(path):
             if len(f) >= 3:
                 rows.append((int(f[1]), int(f[2])))
     return np.array(rows, dtype=np.int64)
+
+
+# ----------------------------------------------------------------------------------------
+# input side: the matrix file
+# ----------------------------------------------------------------------------------------
+
+
+def read_matrix_text(text, sep="\t"):
+    """bigmemory::read.big.matrix(mat_file, type='double', sep='\\t')[, ] (R/TADpole.R:17) on the file's text:
+    header-less, one row per line, every field through a correctly rounded decimal -> double conversion
+    (Python's float() is one, like C's strtod); NA / NaN / empty fields -> NaN (zeroed later, :19)."""
+    if isinstance(text, (bytes, bytearray)):
+        text = text.decode()
+    lines = text.replace("\r\n", "\n").rstrip("\n\r ").split("\n")
+
+    def conv(f):
+        f = f.strip()
+        return float("nan") if f in ("", "NA") else float(f)
+
+    rows = [[conv(f) for f in ln.split(sep)] for ln in lines]
+    n = len(rows)
+    for i, r in enumerate(rows):
+        if len(r) != n:
+            raise ValueError(f"row {i + 1} has {len(r)} fields but the file has {n} rows")
+    return np.array(rows, dtype=np.float64)
+
+
+def matrix_to_text(mat, fmt=None, sep="\t"):
+    """Text of a matrix file as the reference expects it (test helper): integers print without a decimal point,
+    other values with repr() (shortest round-trip form) unless fmt is given."""
+    def one(v):
+        if v != v:
+            return "NA"
+        if fmt is not None:
+            return fmt % v
+        return str(int(v)) if float(v).is_integer() and abs(v) < 2 ** 53 else repr(float(v))
+    return "\n".join(sep.join(one(v) for v in row) for row in np.asarray(mat).tolist()) + "\n"
+
+
+# ----------------------------------------------------------------------------------------
+# diffT null distribution: random_bed
+# ----------------------------------------------------------------------------------------
+
+
+def philox4x32(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw 2011; pinned by the Random123 known-answer vectors in
+    tests/test_oracle.py).  Vectorised over c0; returns the four 32-bit output words as uint64 arrays."""
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), 0x9E3779B9, 0xBB67AE85
+    mask, s32 = np.uint64(0xFFFFFFFF), np.uint64(32)
+    x0 = np.atleast_1d(np.asarray(c0, dtype=np.uint64)) & mask
+    x1, x2, x3 = (np.full_like(x0, np.uint64(c & 0xFFFFFFFF)) for c in (c1, c2, c3))
+    for _ in range(10):
+        p0, p1 = M0 * x0, M1 * x2
+        x0, x1, x2, x3 = (p1 >> s32) ^ x1 ^ np.uint64(k0), p1 & mask, (p0 >> s32) ^ x3 ^ np.uint64(k1), p0 & mask
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return x0, x1, x2, x3
+
+
+def philox_key64(c0, c1, seed):
+    """Per-position random key of the device generator (csrc/difft.cu): the first 64 bits of Philox4x32-10 on
+    counter (position, permutation, 0, 0x7ad) with key = seed."""
+    x0, x1, _, _ = philox4x32(c0, c1, 0, 0x7AD, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    return (x0 << np.uint64(32)) | x1
+
+
+def random_bed(bed, bad_columns=None, seed=0, perm=0):
+    """random_bed (R/DiffT.R:61-73) with the device generator's draw in place of R's sample():
+        bins <- (start:end)[-bad_columns]; borders <- sort(sample(bins[-1], nrow(bed) - 1))
+        start = c(start, borders - 1); end = c(borders - 2, start + size - 1)
+    sample(): the nrow(bed) - 1 candidates with the smallest (philox_key64(position, perm, seed), position)."""
+    bed = np.asarray(bed, dtype=np.int64)
+    start, end = int(bed[0, 0]), int(bed[-1, 1])
+    size = end - start + 1
+    pos = np.arange(size)
+    if bad_columns is not None:
+        bc = np.asarray(bad_columns, dtype=np.int64)
+        pos = np.delete(pos, bc[(bc >= 1) & (bc <= size)] - 1)
+    cand = pos[1:]
+    m = bed.shape[0] - 1
+    if m > cand.size:
+        raise ValueError("cannot take a sample larger than the population when 'replace = FALSE'")
+    keys = philox_key64(cand, perm, seed)
+    take = np.lexsort((cand, keys))[:m]
+    borders = np.sort(cand[take]) + start
+    return np.stack([np.concatenate(([start], borders - 1)), np.concatenate((borders - 2, [start + size - 1]))], axis=1)

@@ -24,6 +24,8 @@ EXPORTED = [
     "tp_get_scores", "tp_set_scores", "tp_sweep", "tp_get_sweep_scores", "tp_get_dendro", "tp_select", "tp_call", "tp_call_arm",
     "tp_difft_batch", "tp_assemble", "tp_assemble_levels", "tp_test_cholinv", "tp_test_eig", "tp_test_igram",
     "tp_comm_unique_id", "tp_ctx_comm_init", "tp_ctx_comm_select", "tp_ctx_comm_info",
+    "tp_ingest_tsv", "tp_ingest_tsv_file", "tp_ingested", "tp_get_ingested", "tp_ingest_stats", "tp_test_parse_field",
+    "tp_difft_null",
 ]
 
 
@@ -58,6 +60,12 @@ def load():
         "tp_ctx_set": (c_int, [vp, c_char_p, c_double]),
         "tp_ctx_timings": (c_int, [vp, dp]),
         "tp_ctx_profile": (c_int, [vp, c_int, dp, POINTER(c_longlong)]),
+        "tp_ingest_tsv": (c_int, [vp, c_char_p, ctypes.c_size_t, c_int, ip]),
+        "tp_ingest_tsv_file": (c_int, [vp, c_char_p, c_int, ip]),
+        "tp_ingested": (c_int, [vp, POINTER(vp), ip]),
+        "tp_get_ingested": (c_int, [vp, dp]),
+        "tp_ingest_stats": (c_int, [vp, dp]),
+        "tp_test_parse_field": (c_int, [c_char_p, c_int, dp]),
         "tp_filter": (c_int, [vp, vp, c_int, c_int, c_int, c_double, u8p, dp, dp]),
         "tp_compact": (c_int, [vp, ip, c_int]),
         "tp_set_filtered": (c_int, [vp, dp, c_int]),
@@ -82,6 +90,7 @@ def load():
         "tp_call": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, c_double, u8p, ip, ip, ip, ip, dp, c_int, ip, dp]),
         "tp_call_arm": (c_int, [vp, ip, c_int, c_int, c_int, ip, ip, ip, dp, c_int, ip, dp]),
         "tp_difft_batch": (c_int, [vp, vp, vp, c_int, c_int, c_int, vp]),
+        "tp_difft_null": (c_int, [vp, vp, c_int, c_int, c_int, c_int, vp, c_int, ctypes.c_ulonglong, c_int, vp, vp, vp, vp]),
         "tp_assemble": (c_int, [dp, c_int, c_int, ip, ip, c_int, ip, ip, ip, ip]),
         "tp_assemble_levels": (c_int, [dp, c_int, ip, c_int, ip, ip, c_int, ip, ip, ip]),
     }
@@ -158,8 +167,32 @@ class Context:
         check(self.lib.tp_ctx_profile(self._h, int(enable), _dp(ms), cnt.ctypes.data_as(POINTER(c_longlong))))
         return {k: (float(m), int(c)) for k, m, c in zip(self.PROFILE_CLASSES, ms, cnt)}
 
+    # ---- input side ----
+    def ingest_tsv(self, src, sep="\t"):
+        """Parse a header-less separator-delimited square matrix on the device (R/TADpole.R:17).  src: a path (str /
+        os.PathLike) or the text itself (bytes).  Returns (device_ptr, n) for filter()/call() with device_ptr=."""
+        n = c_int(0)
+        if isinstance(src, (bytes, bytearray, memoryview)):
+            buf = bytes(src)
+            check(self.lib.tp_ingest_tsv(self._h, buf, len(buf), ord(sep), ctypes.byref(n)))
+        else:
+            check(self.lib.tp_ingest_tsv_file(self._h, os.fsencode(src), ord(sep), ctypes.byref(n)))
+        ptr = c_void_p()
+        check(self.lib.tp_ingested(self._h, ctypes.byref(ptr), ctypes.byref(n)))
+        return ptr.value, n.value
+
+    def get_ingested(self, n):
+        out = np.empty((n, n))
+        check(self.lib.tp_get_ingested(self._h, _dp(out)))
+        return out
+
+    def ingest_stats(self):
+        out = np.zeros(4)
+        check(self.lib.tp_ingest_stats(self._h, _dp(out)))
+        return dict(wall_ms=out[0], parse_ms=out[1], text_bytes=int(out[2]), host_fields=int(out[3]))
+
     # ---- stage 1 ----
-    def filter(self, mat, bad_frac=0.01, colmajor=None, device_ptr=None, n=None):
+    def filter(self, mat=None, bad_frac=0.01, colmajor=None, device_ptr=None, n=None):
         """mat: numpy n x n float64 (C or F order), or device_ptr + n (+ colmajor)."""
         if device_ptr is None:
             mat = np.asarray(mat)
@@ -356,8 +389,35 @@ class Context:
                                       out.ctypes.data))
         return out
 
+    def difft_null(self, labels_x, ntads, nperm, pad_left=0, pad_right=0, bad_positions=None, seed=0,
+                   want_curves=True, want_labels=False):
+        """tp_difft_null: nperm random partitions drawn on the device, each scored against labels_x.
+        Returns dict(borders [nperm, ntads-1], totals [nperm], curves [nperm, L] or None, labels or None)."""
+        lx = np.ascontiguousarray(labels_x, dtype=np.int32)
+        L = lx.size
+        bad = np.ascontiguousarray(bad_positions if bad_positions is not None else [], dtype=np.int32)
+        borders = np.empty((nperm, max(ntads - 1, 0)), dtype=np.int32)
+        totals = np.empty(nperm)
+        curves = np.empty((nperm, L)) if want_curves else None
+        labels = np.empty((nperm, L), dtype=np.int32) if want_labels else None
+        check(self.lib.tp_difft_null(self._h, lx.ctypes.data, L, int(pad_left), int(pad_right), int(ntads),
+                                     bad.ctypes.data if bad.size else None, int(bad.size), int(seed) & (2 ** 64 - 1), int(nperm),
+                                     borders.ctypes.data if borders.size else None,
+                                     labels.ctypes.data if want_labels else None,
+                                     curves.ctypes.data if want_curves else None, totals.ctypes.data))
+        return dict(borders=borders, totals=totals, curves=curves, labels=labels)
+
     def difft_batch_dev(self, lx_ptr, ly_ptr, L, npairs, out_ptr):
         check(self.lib.tp_difft_batch(self._h, int(lx_ptr), int(ly_ptr), int(L), int(npairs), 1, int(out_ptr)))
+
+
+def parse_field(text):
+    """tp_test_parse_field (host-only hook): (status, value) of one field as the device parser converts it."""
+    lib = load()
+    b = text.encode() if isinstance(text, str) else bytes(text)
+    out = c_double(0.0)
+    st = lib.tp_test_parse_field(b, len(b), ctypes.byref(out))
+    return st, out.value
 
 
 def assemble(seqdist, n_clusters, names, bad):

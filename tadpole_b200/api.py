@@ -22,7 +22,7 @@ import numpy as np
 from . import _lib
 from .hclust import Dendro
 
-__all__ = ["TADpole", "load_mat", "diffT", "random_bed", "bin_index", "Tadpole", "LoadedMatrix", "get_context"]
+__all__ = ["TADpole", "load_mat", "diffT", "diffT_null", "random_bed", "random_bed_batch", "bin_index", "Tadpole", "LoadedMatrix", "get_context"]
 
 _CTX = {}
 QUIET = False
@@ -41,13 +41,24 @@ def get_context(device=0):
     return ctx
 
 
-def read_matrix(mat_file):
+def read_matrix(mat_file, ctx=None):
     """bigmemory::read.big.matrix(mat_file, type='double', sep='\\t') (R/TADpole.R:17): header-less
-    tab-separated numeric matrix.  An in-memory square array is accepted as well."""
+    tab-separated numeric matrix, as a numpy array.  The text is uploaded and parsed on the GPU
+    (csrc/ingest.cu); an in-memory square array is passed through."""
     if isinstance(mat_file, np.ndarray):
         return mat_file
-    import pandas as pd
-    return pd.read_csv(mat_file, sep="\t", header=None, dtype=np.float64, na_values=["NA", "NaN"]).to_numpy()
+    ctx = ctx or get_context()
+    _, n = ctx.ingest_tsv(mat_file)
+    return ctx.get_ingested(n)
+
+
+def _matrix_args(mat_file, ctx):
+    """Keyword arguments that hand the input matrix to Context.filter / Context.call: an in-memory array as it is,
+    a file through the device-side parser -- the FP64 matrix of a file never exists on the host."""
+    if isinstance(mat_file, np.ndarray):
+        return dict(mat=mat_file)
+    ptr, n = ctx.ingest_tsv(mat_file)
+    return dict(mat=None, device_ptr=ptr, n=n, colmajor=0)
 
 
 class LoadedMatrix:
@@ -110,8 +121,7 @@ def load_mat(mat_file, chr=None, start=None, end=None, resol=None, bad_frac=0.01
     """Load a Hi-C matrix, flag bad columns, optionally split at the centromere (R/TADpole.R:15-92).
     Plots (R/TADpole.R:24-53) are out of scope."""
     ctx = ctx or get_context()
-    mat = read_matrix(mat_file)
-    bad, _, _ = ctx.filter(mat, bad_frac=bad_frac)
+    bad, _, _ = ctx.filter(bad_frac=bad_frac, **_matrix_args(mat_file, ctx))
     return _loaded_from_flags(ctx, bad, centromere_search)
 
 
@@ -166,9 +176,9 @@ def TADpole(mat_file, max_pcs=200, min_clusters=2, bad_frac=0.01, chr=None, star
     the same matrix and gets the same object back).  Without centromere_search the whole job works on the one
     matrix; with it the ranks split between the two arms, as the arms are independent (R/TADpole.R:357)."""
     ctx = ctx or get_context()
-    mat = read_matrix(mat_file)
+    mat = _matrix_args(mat_file, ctx)
     if not centromere_search:
-        res = ctx.call(mat, max_pcs=max_pcs, min_clusters=min_clusters, bad_frac=bad_frac)
+        res = ctx.call(max_pcs=max_pcs, min_clusters=min_clusters, bad_frac=bad_frac, **mat)
         bad = res["bad"]
         message(f"{int(bad.sum())} bad columns found at position(s):")
         message(" ".join(str(i) for i in np.flatnonzero(bad) + 1))
@@ -183,7 +193,7 @@ def TADpole(mat_file, max_pcs=200, min_clusters=2, bad_frac=0.01, chr=None, star
         tp.scores = res["scores"]
         return tp
 
-    bad, _, _ = ctx.filter(mat, bad_frac=bad_frac)
+    bad, _, _ = ctx.filter(bad_frac=bad_frac, **mat)
     lm = _loaded_from_flags(ctx, bad, True)
     if not lm.is_split:
         # R/TADpole.R:356-359 then does mat$centromer / mat[['p']] on a plain matrix and errors (quirk Q4)
@@ -255,7 +265,8 @@ def bin_index(bed, size):
     tad = np.zeros(int(size), dtype=np.int32)
     off = bed[0, 0]
     for t in range(bed.shape[0]):
-        tad[bed[t, 0] - off: bed[t, 1] - off + 1] = t + 1
+        lo, hi = sorted((int(bed[t, 0] - off), int(bed[t, 1] - off)))      # seq(a, b) runs downwards when a > b
+        tad[max(lo, 0): hi + 1] = t + 1                                     # tad_index[0] <- x is a no-op in R
     return tad
 
 
@@ -298,3 +309,46 @@ def random_bed(bed, bad_columns=None, rng=None):
         bins = np.delete(bins, np.asarray(bad_columns, dtype=np.int64) - 1)
     borders = np.sort(rng.choice(bins[1:], size=rows.shape[0] - 1, replace=False))
     return np.stack([np.concatenate(([start], borders - 1)), np.concatenate((borders - 2, [start + size - 1]))], axis=1)
+
+
+def _bad_positions(bad_columns):
+    return None if bad_columns is None else np.asarray(bad_columns, dtype=np.int64).astype(np.int32)
+
+
+def _beds_from_borders(rows, borders):
+    """data.frame(start = c(start, borders - 1), end = c(borders - 2, start + size - 1)) (R/DiffT.R:70-72)."""
+    start, end = int(rows[0, 0]), int(rows[-1, 1])
+    b = borders.astype(np.int64) + start
+    n = b.shape[0]
+    return np.stack([np.concatenate((np.full((n, 1), start), b - 1), axis=1),
+                     np.concatenate((b - 2, np.full((n, 1), end)), axis=1)], axis=2)
+
+
+def random_bed_batch(bed, n, bad_columns=None, seed=0, ctx=None):
+    """n draws of random_bed(bed, bad_columns) (R/DiffT.R:61-73) generated on the GPU: [n, T, 2] (start, end)."""
+    ctx = ctx or get_context()
+    rows = _bed_rows(bed)
+    size = int(rows[-1, 1] - rows[0, 0] + 1)
+    res = ctx.difft_null(np.ones(size, np.int32), rows.shape[0], n, bad_positions=_bad_positions(bad_columns), seed=seed,
+                         want_curves=False)
+    return _beds_from_borders(rows, res["borders"])
+
+
+def diffT_null(bed_x, bed_y=None, nperm=1000, bad_columns=None, seed=0, ctx=None):
+    """The diffT null distribution: diffT(bed_x, random_bed(bed_y, bad_columns)) for nperm random partitions
+    (R/DiffT.R:19-50 and :61-73), partitions drawn and scored on the GPU.  bed_y defaults to bed_x (random
+    partitions with the observed call's own extent and TAD count).  Returns an object with `curves` [nperm, L],
+    `totals` [nperm] (un-normalised total score) and `beds` [nperm, T, 2]."""
+    ctx = ctx or get_context()
+    bx = _bed_rows(bed_x)
+    by = bx if bed_y is None else _bed_rows(bed_y)
+    if bx.shape[0] != by.shape[0]:
+        raise ValueError("Both calls must have the same number of TADs.")       # R/DiffT.R:20
+    sx, sy, ex, ey = int(bx[0, 0]), int(by[0, 0]), int(bx[-1, 1]), int(by[-1, 1])
+    tx = bin_index(bx, ex - sx + 1)
+    tx = np.concatenate((np.ones(max(0, sx - sy), np.int32), tx, np.full(max(0, ey - ex), tx.max(), np.int32)))
+    res = ctx.difft_null(tx, by.shape[0], nperm, pad_left=max(0, sy - sx), pad_right=max(0, ex - ey),
+                         bad_positions=_bad_positions(bad_columns), seed=seed)
+    out = _Obj()
+    out.curves, out.totals, out.beds = res["curves"], res["totals"], _beds_from_borders(by, res["borders"])
+    return out

@@ -85,11 +85,16 @@ extern "C" int tp_ctx_destroy(tp_ctx *ctx) {
                       &ctx->colstat, &ctx->scores, &ctx->M, &ctx->Y0, &ctx->Y1, &ctx->Y2, &ctx->W, &ctx->G, &ctx->T,
                       &ctx->Q, &ctx->Jw, &ctx->Jv, &ctx->Jt, &ctx->small1, &ctx->small2, &ctx->part, &ctx->resid,
                       &ctx->P, &ctx->Qp, &ctx->d0, &ctx->seqdist, &ctx->order, &ctx->ncl, &ctx->chs, &ctx->bsbuf,
-                      &ctx->links, &ctx->harm, &ctx->status, &ctx->islices, &ctx->ioA, &ctx->ioB, &ctx->ioscale, &ctx->lx, &ctx->ly, &ctx->dout, &ctx->dhash, &ctx->lhash};
+                      &ctx->links, &ctx->harm, &ctx->status, &ctx->islices, &ctx->ioA, &ctx->ioB, &ctx->ioscale, &ctx->lx, &ctx->ly, &ctx->dout, &ctx->dhash, &ctx->lhash,
+                      &ctx->itext, &ctx->icounts, &ctx->irows, &ctx->islow};
     for (DevBuf *b : bufs) b->release();
     tp_comm_destroy_all(ctx);
     for (int i = 0; i < EV_COUNT; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+    for (int b = 0; b < 2; b++) {
+        if (ctx->ipin[b]) cudaFreeHost(ctx->ipin[b]);
+        if (ctx->ipin_ev[b]) cudaEventDestroy(ctx->ipin_ev[b]);
+    }
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->pin_flags) cudaFreeHost(ctx->pin_flags);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -61,7 +61,7 @@ struct DevBuf {
 };
 
 enum { EV_FILTER0 = 0, EV_FILTER1, EV_COMPACT0, EV_COMPACT1, EV_CORR0, EV_CORR1, EV_PCA0, EV_PCA1,
-       EV_SWEEP0, EV_SWEEP1, EV_CH1, EV_TOTAL0, EV_TOTAL1, EV_DIFFT0, EV_DIFFT1, EV_COUNT };
+       EV_SWEEP0, EV_SWEEP1, EV_CH1, EV_TOTAL0, EV_TOTAL1, EV_DIFFT0, EV_DIFFT1, EV_INGEST0, EV_INGEST1, EV_COUNT };
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -94,6 +94,13 @@ struct tp_ctx {
     int pca_inner = 4;
     int jacobi_direct_max = 512;
     int level_cap = 256;
+
+    // input side (ingest.cu): text of the matrix file, row-end offsets, fields left to the host, pinned staging
+    DevBuf itext, icounts, irows, islow;
+    void *ipin[2] = {nullptr, nullptr};
+    cudaEvent_t ipin_ev[2] = {nullptr, nullptr};
+    int ingested_n = 0;                  // > 0: raw_own holds a matrix parsed on the device (row-major n x n)
+    double ingest_stats[4] = {};         // wall ms (read + upload + parse), parse kernels ms, text bytes, host-converted fields
 
     // stage 1 state
     DevBuf raw_own;              // uploaded copy of the caller's matrix (when it came from the host)

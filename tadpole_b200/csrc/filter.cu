@@ -183,6 +183,7 @@ int tp_filter(tp_ctx *ctx, const double *mat, int n, int colmajor, int on_device
         // Only the upper triangle is ever read (forceSymmetric(uplo = 'U')), so only it crosses PCIe: ~32 band copies
         // (row bands from the diagonal to the right edge; column bands from the top to the diagonal for R's layout),
         // 52 % of the bytes of the full matrix.
+        ctx->ingested_n = 0;                       // raw_own is about to be overwritten
         TP_TRY(ctx->raw_own.reserve(bytes));
         double *dst = ctx->raw_own.as<double>();
         const int band = n / 32 > 64 ? n / 32 : 64;

@@ -190,3 +190,38 @@ def test_synth_generators():
     assert (m == m.T).all() and m.dtype == np.float64 and (m >= 0).all()
     lx, ly = synth_partition_pairs(3, 500, 20, seed=1)
     assert lx.shape == (3, 500) and lx.max() == 20 and ly.max() == 20 and (lx == 0).any()
+
+
+# ---- diffT null distribution: the generator the device uses, restated ------------------------------
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32 10 rounds
+    z = O.philox4x32(0, 0, 0, 0, 0, 0)
+    assert [int(v[0]) for v in z] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = O.philox4x32(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff)
+    assert [int(v[0]) for v in f] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    p = O.philox4x32(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0)
+    assert [int(v[0]) for v in p] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_random_bed_structure():
+    bed = np.array([[11, 40], [41, 90], [91, 95], [96, 300], [301, 410]])
+    seen = set()
+    for perm in range(200):
+        rb = O.random_bed(bed, bad_columns=[1, 5, 6], seed=4, perm=perm)
+        borders = rb[1:, 0] + 1
+        assert rb[0, 0] == 11 and rb[-1, 1] == 410 and (np.diff(borders) > 0).all()
+        assert (rb[1:, 0] == rb[:-1, 1] + 1).all()
+        assert borders.min() > 12 and not np.isin(borders - 11 + 1, [1, 5, 6]).any()
+        seen.add(tuple(borders))
+        # bin_index of a random bed: every bin labelled, labels 1..T in order (later rows overwrite, R/DiffT.R:1-9)
+        lab = O.bin_index(rb, 400)
+        assert lab.min() >= 1 and lab.max() == 5 and (np.diff(lab) >= 0).all()
+    assert len(seen) > 190
+    with pytest.raises(ValueError):
+        O.random_bed(np.array([[1, 1], [2, 2], [3, 3], [3, 3]]))
+
+
+def test_bin_index_descending_range_quirk():
+    # seq(a, b) with a > b counts down in R: the row [5, 4] labels bins 5 and 4; position 0 is a no-op
+    assert O.bin_index(np.array([[3, 4], [7, 6], [8, 9]]), 7).tolist() == [1, 1, 0, 2, 2, 3, 3]
+    assert O.bin_index(np.array([[1, 0], [1, 3]]), 3).tolist() == [2, 2, 2]
