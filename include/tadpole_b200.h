@@ -175,6 +175,15 @@ int tp_call_arm(tp_ctx *ctx, const int *keep, int nf, int max_pcs, int min_clust
                 int *k_out, int *n_pcs_out, int *n_clusters_out,
                 double *scores_out, int ld_scores, int *maxlev_out, double *seqdist_out);
 
+/* The context is a device-resident pipeline handle: after tp_call / tp_call_arm / tp_pca the PC scores stay in HBM, and
+ * after a sweep so do all k dendrograms (tp_get_dendro) and the score matrix (tp_get_sweep_scores).  tp_recall repeats
+ * only the n_pcs sweep and the selection for another max_pcs (<= the number of PCs computed) and / or min_clusters:
+ * prcomp(rank. = k') is the first k' columns of the same decomposition (R/TADpole.R:366-367), so the result equals a
+ * fresh tp_call with those arguments; the reference has to repeat load_mat, cor and prcomp for this.
+ * Outputs as tp_call_arm. */
+int tp_recall(tp_ctx *ctx, int max_pcs, int min_clusters, int *k_out, int *n_pcs_out, int *n_clusters_out,
+              double *scores_out, int ld_scores, int *maxlev_out, double *seqdist_out);
+
 /* ---- stage 6: diffT (R/DiffT.R:41-49) on padded label vectors -------------------------------------
  * labels_x / labels_y: npairs x L int32 row-major (0 = uncovered bin); out: npairs x L doubles =
  * cumulative score, normalised by its last value unless every per-bin score is 0. */

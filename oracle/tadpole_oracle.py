@@ -93,8 +93,10 @@ class LoadedMat:
     n_bins: int = 0
 
 
-def load_mat_numeric(mat, bad_frac=0.01, centromere_search=False):
-    """Numeric part of load_mat (R/TADpole.R:17-22,35-37,55-91); plots are out of scope."""
+def load_mat_numeric(mat, bad_frac=0.01, centromere_search=False, fix_q_arm=False):
+    """Numeric part of load_mat (R/TADpole.R:17-22,35-37,55-91); plots are out of scope.
+    fix_q_arm=True is NOT the reference: it removes the q-arm bad columns by their position within the arm
+    (quirk Q3 repaired), the checker of the product's opt-in centromere_fix mode."""
     sym = symmetrise_upper(mat)
     n = sym.shape[0]
     bad, _, _ = bad_columns(sym, bad_frac)
@@ -124,7 +126,7 @@ def load_mat_numeric(mat, bad_frac=0.01, centromere_search=False):
             # Quirk Q3 (R/TADpole.R:80): original-coordinate indices used as negative
             # positional indices into the re-based q arm; out-of-range ones are ignored.
             keep = np.ones(mat_q.shape[0], bool)
-            inr = bad_q[bad_q <= mat_q.shape[0]]
+            inr = bad_q - ce if fix_q_arm else bad_q[bad_q <= mat_q.shape[0]]
             keep[inr - 1] = False
             mat_q, names_q = mat_q[np.ix_(keep, keep)], names_q[keep]
         return LoadedMat(p=LoadedMat(mat=mat_p, names=names_p, bad_columns=bad_p if bad_p.size else None),
@@ -465,9 +467,9 @@ def _call_one(lm, max_pcs, min_clusters, coniss):
 
 
 def tadpole(mat, max_pcs=200, min_clusters=2, bad_frac=0.01, centromere_search=False,
-            coniss=coniss_lw):
+            coniss=coniss_lw, fix_q_arm=False):
     """TADpole() (R/TADpole.R:344-501) from an in-memory matrix."""
-    lm = load_mat_numeric(mat, bad_frac, centromere_search)
+    lm = load_mat_numeric(mat, bad_frac, centromere_search, fix_q_arm)
     if centromere_search:
         if lm.p is None:
             raise ValueError("centromere_search=TRUE but the matrix was not split (reference errors, quirk Q4)")

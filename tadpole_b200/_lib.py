@@ -25,7 +25,7 @@ EXPORTED = [
     "tp_difft_batch", "tp_assemble", "tp_assemble_levels", "tp_test_cholinv", "tp_test_eig", "tp_test_igram",
     "tp_comm_unique_id", "tp_ctx_comm_init", "tp_ctx_comm_select", "tp_ctx_comm_info",
     "tp_ingest_tsv", "tp_ingest_tsv_file", "tp_ingested", "tp_get_ingested", "tp_ingest_stats", "tp_test_parse_field",
-    "tp_difft_null",
+    "tp_difft_null", "tp_recall",
 ]
 
 
@@ -89,6 +89,7 @@ def load():
         "tp_select": (c_int, [dp, c_int, c_int, c_int, ip, ip]),
         "tp_call": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, c_double, u8p, ip, ip, ip, ip, dp, c_int, ip, dp]),
         "tp_call_arm": (c_int, [vp, ip, c_int, c_int, c_int, ip, ip, ip, dp, c_int, ip, dp]),
+        "tp_recall": (c_int, [vp, c_int, c_int, ip, ip, ip, dp, c_int, ip, dp]),
         "tp_difft_batch": (c_int, [vp, vp, vp, c_int, c_int, c_int, vp]),
         "tp_difft_null": (c_int, [vp, vp, c_int, c_int, c_int, c_int, vp, c_int, ctypes.c_ulonglong, c_int, vp, vp, vp, vp]),
         "tp_assemble": (c_int, [dp, c_int, c_int, ip, ip, c_int, ip, ip, ip, ip]),
@@ -123,6 +124,7 @@ class Context:
         self._h = c_void_p()
         check(self.lib.tp_ctx_create(int(device), ctypes.byref(self._h)))
         self.device = int(device)
+        self.generation = 0          # bumped whenever the resident matrix / scores are replaced (stale-handle check)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -171,6 +173,7 @@ class Context:
     def ingest_tsv(self, src, sep="\t"):
         """Parse a header-less separator-delimited square matrix on the device (R/TADpole.R:17).  src: a path (str /
         os.PathLike) or the text itself (bytes).  Returns (device_ptr, n) for filter()/call() with device_ptr=."""
+        self.generation += 1
         n = c_int(0)
         if isinstance(src, (bytes, bytearray, memoryview)):
             buf = bytes(src)
@@ -204,6 +207,7 @@ class Context:
             ptr, ondev = mat.ctypes.data, 0
         else:
             ptr, ondev, colmajor = int(device_ptr), 1, int(bool(colmajor))
+        self.generation += 1
         bad = np.zeros(n, dtype=np.uint8)
         rm = np.zeros(n)
         thr = np.zeros(1)
@@ -212,11 +216,13 @@ class Context:
         return bad.astype(bool), rm, float(thr[0])
 
     def compact(self, keep):
+        self.generation += 1
         keep = np.ascontiguousarray(keep, dtype=np.int32)
         check(self.lib.tp_compact(self._h, _ip(keep), keep.size))
         return keep.size
 
     def set_filtered(self, x):
+        self.generation += 1
         x = np.ascontiguousarray(x, dtype=np.float64)
         check(self.lib.tp_set_filtered(self._h, _dp(x), x.shape[0]))
 
@@ -240,6 +246,7 @@ class Context:
 
     # ---- stage 3 ----
     def pca(self, max_pcs=200):
+        self.generation += 1
         k = c_int(0)
         check(self.lib.tp_pca(self._h, int(max_pcs), ctypes.byref(k)))
         return k.value
@@ -294,6 +301,7 @@ class Context:
         return out
 
     def set_scores(self, scores):
+        self.generation += 1
         scores = np.ascontiguousarray(scores, dtype=np.float64)
         check(self.lib.tp_set_scores(self._h, _dp(scores), scores.shape[0], scores.shape[1]))
 
@@ -337,6 +345,7 @@ class Context:
             ptr, ondev = mat.ctypes.data, 0
         else:
             ptr, ondev, colmajor = int(device_ptr), 1, int(bool(colmajor))
+        self.generation += 1
         bad = np.zeros(n, dtype=np.uint8)
         nf, k, npcs, ncl, maxlev = c_int(0), c_int(0), c_int(0), c_int(0), c_int(0)
         kmax = min(int(max_pcs), n)
@@ -360,6 +369,7 @@ class Context:
                     seqdist=seq[:nf.value - 1].copy())
 
     def call_arm(self, keep, max_pcs=200, min_clusters=2, ld=256):
+        self.generation += 1
         keep = np.ascontiguousarray(keep, dtype=np.int32)
         nf = keep.size
         k, npcs, ncl, maxlev = c_int(0), c_int(0), c_int(0), c_int(0)
@@ -376,6 +386,24 @@ class Context:
                 break
             check(rc)
             break
+        return dict(nf=nf, k=k.value, n_pcs=npcs.value, n_clusters=ncl.value,
+                    scores=sc[:k.value, :maxlev.value].copy(), seqdist=seq)
+
+    def recall(self, nf, max_pcs=200, min_clusters=2, ld=256):
+        """tp_recall: the n_pcs sweep and the selection again on the PC scores resident in the context."""
+        self.generation += 1
+        k, npcs, ncl, maxlev = c_int(0), c_int(0), c_int(0), c_int(0)
+        kmax = min(int(max_pcs), nf)
+        seq = np.zeros(nf - 1)
+        sc = np.empty((kmax, ld))
+        rc = self.lib.tp_recall(self._h, int(max_pcs), int(min_clusters), ctypes.byref(k), ctypes.byref(npcs),
+                                ctypes.byref(ncl), _dp(sc), ld, ctypes.byref(maxlev), _dp(seq))
+        if rc == TP_ERR_ARG and maxlev.value > ld:
+            ld = maxlev.value
+            sc = np.empty((kmax, ld))
+            check(self.lib.tp_get_sweep_scores(self._h, _dp(sc), ld))
+        else:
+            check(rc)
         return dict(nf=nf, k=k.value, n_pcs=npcs.value, n_clusters=ncl.value,
                     scores=sc[:k.value, :maxlev.value].copy(), seqdist=seq)
 

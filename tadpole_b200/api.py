@@ -89,8 +89,9 @@ class LoadedMatrix:
         return (self.keep.size, self.keep.size)
 
 
-def _split_centromere(bad):
-    """R/TADpole.R:58-86 on the bad flags.  Returns None when the matrix is not split."""
+def _split_centromere(bad, fix=False):
+    """R/TADpole.R:58-86 on the bad flags.  Returns None when the matrix is not split.
+    fix=True removes the q-arm bad columns by their position within the arm (quirk Q3 repaired)."""
     n = bad.size
     idx = np.flatnonzero(bad) + 1
     brk = np.flatnonzero(np.diff(idx) > 1) + 1
@@ -110,28 +111,31 @@ def _split_centromere(bad):
     keep_q = np.ones(idx_q.size, bool)
     # R/TADpole.R:80 applies the ORIGINAL indices of the q-arm bad columns as negative positional
     # indices to the re-based q matrix; out-of-range ones are silently ignored.
-    inr = bad_q[bad_q <= idx_q.size]
-    keep_q[inr - 1] = False
+    if fix:
+        keep_q[bad_q - ce - 1] = False
+    else:
+        inr = bad_q[bad_q <= idx_q.size]
+        keep_q[inr - 1] = False
     return (idx_p[keep_p] - 1, bad_p if bad_p.size else None), (idx_q[keep_q] - 1, bad_q if bad_q.size else None), \
         np.arange(cs, ce + 1)
 
 
 def load_mat(mat_file, chr=None, start=None, end=None, resol=None, bad_frac=0.01, centromere_search=False,
-             ctx=None):
+             ctx=None, centromere_fix=False):
     """Load a Hi-C matrix, flag bad columns, optionally split at the centromere (R/TADpole.R:15-92).
-    Plots (R/TADpole.R:24-53) are out of scope."""
+    Plots (R/TADpole.R:24-53) are out of scope.  centromere_fix: see TADpole()."""
     ctx = ctx or get_context()
     bad, _, _ = ctx.filter(bad_frac=bad_frac, **_matrix_args(mat_file, ctx))
-    return _loaded_from_flags(ctx, bad, centromere_search)
+    return _loaded_from_flags(ctx, bad, centromere_search, centromere_fix)
 
 
-def _loaded_from_flags(ctx, bad, centromere_search):
+def _loaded_from_flags(ctx, bad, centromere_search, fix=False):
     n = bad.size
     bad_names = [str(i) for i in np.flatnonzero(bad) + 1]
     message(f"{int(bad.sum())} bad columns found at position(s):")
     message(" ".join(bad_names))
     if bad.any() and centromere_search:
-        split = _split_centromere(bad)
+        split = _split_centromere(bad, fix)
         if split is not None:
             (kp, bp), (kq, bq), cen = split
             return LoadedMatrix(ctx, n, None, None, split=(LoadedMatrix(ctx, n, kp.astype(np.int32), bp),
@@ -152,7 +156,34 @@ class Tadpole(_Obj):
     """The returned 'tadpole' object (R/TADpole.R:463-468; arms :354,376-378,407,442):
     n_pcs, optimal_n_clusters, dendro, clusters (dict keyed by str(k) -> [rows, 2] start/end),
     scores; with centromere_search: p, q (each n_pcs, optimal_n_clusters, dendro, cluster) and
-    merging_arms."""
+    merging_arms.
+
+    Beyond the reference: a whole-chromosome object is also a handle on the pipeline state that stays in HBM
+    (PC scores, all k dendrograms): recall() repeats only the n_pcs sweep for another max_pcs / min_clusters, and
+    dendro_for() returns the dendrogram of any candidate number of PCs (what CH_map / plot_hierarchy browse),
+    as long as the context has not been used for another matrix since."""
+
+    def _resident(self):
+        h = object.__getattribute__(self, "__dict__").get("_handle")
+        if h is None:
+            raise RuntimeError("this tadpole object carries no device handle (centromere_search results do not)")
+        if h["ctx"].generation != h["generation"]:
+            raise RuntimeError("the GPU context has been used for another matrix since this call; its resident state is gone")
+        return h
+
+    def recall(self, max_pcs=200, min_clusters=2):
+        """TADpole() again on the same matrix with another max_pcs (<= the one computed) / min_clusters, from the
+        resident PC scores: same result as a fresh call, without load_mat, cor and prcomp."""
+        h = self._resident()
+        res = h["ctx"].recall(h["nf"], max_pcs=max_pcs, min_clusters=min_clusters)
+        res["bad"] = h["bad"]
+        return _tadpole_from_result(res, h["ctx"])       # the sweep state was replaced: this object is now stale
+
+    def dendro_for(self, n_pcs):
+        """chclust dendrogram of the candidate that clusters on the first n_pcs PCs (R/TADpole.R:108)."""
+        h = self._resident()
+        seq, _ = h["ctx"].dendro(int(n_pcs) - 1, h["nf"])
+        return Dendro(seq, labels=h["names"])
 
 
 def _levels_table(res, names, bad_cols):
@@ -168,9 +199,32 @@ def _messages_optimal(res):
     message(f"Optimal number of clusters: {res['n_clusters']}")
 
 
+def _tadpole_from_result(res, ctx):
+    """Packs the whole-chromosome result (R/TADpole.R:463-497) and attaches the device handle."""
+    bad = res["bad"]
+    _messages_optimal(res)
+    names = (np.flatnonzero(~bad) + 1).astype(np.int32)
+    bad_cols = (np.flatnonzero(bad) + 1).astype(np.int32)
+    tp = Tadpole()
+    tp.n_pcs = res["n_pcs"]
+    tp.optimal_n_clusters = res["n_clusters"]
+    tp.dendro = Dendro(res["seqdist"], labels=names)
+    tp.clusters = _levels_table(res, names, bad_cols)
+    tp.scores = res["scores"]
+    object.__getattribute__(tp, "__dict__")["_handle"] = dict(ctx=ctx, generation=ctx.generation, nf=int(names.size),
+                                                             names=names, bad=bad)
+    return tp
+
+
 def TADpole(mat_file, max_pcs=200, min_clusters=2, bad_frac=0.01, chr=None, start=None, end=None, resol=None,
-            centromere_search=False, ctx=None, dist=None):
+            centromere_search=False, ctx=None, dist=None, centromere_fix=False):
     """Call hierarchical TADs (R/TADpole.R:344-501).
+
+    centromere_fix (default False = the reference's behaviour, quirks included): opt-in repairs of the
+    centromere_search path (SURVEY.md quirks Q3, Q4 and the TODO at R/TADpole.R:304): the q-arm's bad columns are
+    removed by their position within the arm; a chromosome that load_mat does not split (no bad columns, or the
+    longest bad stretch touches an end) is processed whole instead of raising; and every arm also carries its
+    `scores` matrix and the `clusters` spelling, so that CH_map-style consumers work on arms.
 
     dist: a sharding.DistEnv when the call is spread over several GPUs (one process per GPU, every rank calls with
     the same matrix and gets the same object back).  Without centromere_search the whole job works on the one
@@ -182,19 +236,14 @@ def TADpole(mat_file, max_pcs=200, min_clusters=2, bad_frac=0.01, chr=None, star
         bad = res["bad"]
         message(f"{int(bad.sum())} bad columns found at position(s):")
         message(" ".join(str(i) for i in np.flatnonzero(bad) + 1))
-        _messages_optimal(res)
-        names = (np.flatnonzero(~bad) + 1).astype(np.int32)
-        bad_cols = (np.flatnonzero(bad) + 1).astype(np.int32)
-        tp = Tadpole()
-        tp.n_pcs = res["n_pcs"]
-        tp.optimal_n_clusters = res["n_clusters"]
-        tp.dendro = Dendro(res["seqdist"], labels=names)
-        tp.clusters = _levels_table(res, names, bad_cols)
-        tp.scores = res["scores"]
-        return tp
+        return _tadpole_from_result(res, ctx)
 
     bad, _, _ = ctx.filter(bad_frac=bad_frac, **mat)
-    lm = _loaded_from_flags(ctx, bad, True)
+    lm = _loaded_from_flags(ctx, bad, True, centromere_fix)
+    if not lm.is_split and centromere_fix:
+        res = ctx.call_arm(lm.keep, max_pcs=max_pcs, min_clusters=min_clusters)
+        res["bad"] = bad
+        return _tadpole_from_result(res, ctx)
     if not lm.is_split:
         # R/TADpole.R:356-359 then does mat$centromer / mat[['p']] on a plain matrix and errors (quirk Q4)
         raise ValueError("centromere_search=TRUE but load_mat did not split the matrix "
@@ -222,6 +271,8 @@ def TADpole(mat_file, max_pcs=200, min_clusters=2, bad_frac=0.01, chr=None, star
         a.optimal_n_clusters = res["n_clusters"]
         a.dendro = Dendro(res["seqdist"], labels=la.names)
         a.cluster = _levels_table(res, la.names.astype(np.int32), la.bad_columns)
+        if centromere_fix:
+            a.clusters, a.scores = a.cluster, res["scores"]
         tp[arm] = a
         # optimal level of this arm, bad columns re-inserted, fix_values applied (R/TADpole.R:411-431)
         bad_for_merge = la.bad_columns if la.bad_columns is not None else np.zeros(0, np.int32)

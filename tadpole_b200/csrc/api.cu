@@ -304,7 +304,7 @@ extern "C" int tp_get_correlation(tp_ctx *ctx, double *cor_out) {
 extern "C" int tp_set_scores(tp_ctx *ctx, const double *scores, int nf, int k) {
     TP_ARG(ctx && scores && nf >= 3 && k >= 1 && k <= nf, "tp_set_scores: bad arguments");
     TP_CUDA(cudaSetDevice(ctx->device));
-    ctx->nf = nf; ctx->k = k; ctx->ldk = round_up(k, 8);
+    ctx->nf = nf; ctx->k = ctx->k_full = k; ctx->ldk = round_up(k, 8);
     TP_TRY(ctx->scores.reserve((size_t)nf * ctx->ldk * sizeof(double)));
     TP_CUDA(cudaMemsetAsync(ctx->scores.p, 0, (size_t)nf * ctx->ldk * sizeof(double), ctx->stream));
     TP_CUDA(cudaMemcpy2DAsync(ctx->scores.p, (size_t)ctx->ldk * sizeof(double), scores, (size_t)k * sizeof(double),
@@ -463,13 +463,11 @@ extern "C" int tp_select(const double *scores, int k, int ld, int maxlev, int *o
 }
 
 // ---- one-shot -----------------------------------------------------------------------------------------
-static int call_from_compacted(tp_ctx *ctx, int max_pcs, int min_clusters, int *k_out, int *n_pcs_out,
-                               int *n_clusters_out, double *scores_out, int ld_scores, int *maxlev_out,
-                               double *seqdist_out) {
-    int k = 0, maxlev = 0;
-    TP_TRY(tp_correlation(ctx));
-    TP_TRY(tp_pca(ctx, max_pcs, &k));
-    if (k_out) *k_out = k;
+// stages 4 + 5 and the selection on the context's PC scores (first ctx->k columns)
+static int sweep_and_select(tp_ctx *ctx, int min_clusters, int *n_pcs_out, int *n_clusters_out, double *scores_out,
+                            int ld_scores, int *maxlev_out, double *seqdist_out) {
+    const int k = ctx->k;
+    int maxlev = 0;
     // the sweep runs once; the score matrix stays on the device (tp_get_sweep_scores) and is copied to the caller's
     // buffer when that is wide enough.  A narrow buffer makes the call return TP_ERR_ARG with *maxlev_out set and every
     // other output filled, so the caller only has to fetch the scores again, not to repeat the pipeline.
@@ -502,6 +500,38 @@ static int call_from_compacted(tp_ctx *ctx, int max_pcs, int min_clusters, int *
         }
     }
     return TP_OK;
+}
+
+static int call_from_compacted(tp_ctx *ctx, int max_pcs, int min_clusters, int *k_out, int *n_pcs_out,
+                               int *n_clusters_out, double *scores_out, int ld_scores, int *maxlev_out,
+                               double *seqdist_out) {
+    int k = 0;
+    TP_TRY(tp_correlation(ctx));
+    TP_TRY(tp_pca(ctx, max_pcs, &k));
+    if (k_out) *k_out = k;
+    return sweep_and_select(ctx, min_clusters, n_pcs_out, n_clusters_out, scores_out, ld_scores, maxlev_out, seqdist_out);
+}
+
+// The PC scores of the last call stay in the context: another (max_pcs, min_clusters) only repeats the n_pcs sweep.
+// prcomp(rank. = k') returns the first k' columns of the same decomposition, so restricting the resident scores to
+// their first k' columns is what a fresh call with max_pcs = k' computes (R/TADpole.R:366-367; CH on those k'
+// columns, quirk Q2).
+extern "C" int tp_recall(tp_ctx *ctx, int max_pcs, int min_clusters, int *k_out, int *n_pcs_out, int *n_clusters_out,
+                         double *scores_out, int ld_scores, int *maxlev_out, double *seqdist_out) {
+    TP_ARG(ctx, "tp_recall: null context");
+    TP_ARG(ctx->have_scores && ctx->k_full >= 1, "tp_recall: no PC scores in the context (run tp_call / tp_call_arm / tp_pca first)");
+    TP_ARG(max_pcs >= 1, "tp_recall: max_pcs must be positive");
+    const int want = max_pcs < ctx->nf ? max_pcs : ctx->nf;
+    if (want > ctx->k_full) {
+        tp_set_error("tp_recall: max_pcs = %d needs %d PCs but the context holds %d; run the call again", max_pcs, want, ctx->k_full);
+        return TP_ERR_ARG;
+    }
+    TP_CUDA(cudaSetDevice(ctx->device));
+    TP_MARK(ctx, EV_TOTAL0);
+    ctx->k = want;
+    ctx->have_sweep = false;
+    if (k_out) *k_out = want;
+    return sweep_and_select(ctx, min_clusters, n_pcs_out, n_clusters_out, scores_out, ld_scores, maxlev_out, seqdist_out);
 }
 
 extern "C" int tp_call(tp_ctx *ctx, const double *mat, int n, int colmajor, int on_device,

@@ -115,7 +115,8 @@ struct tp_ctx {
     DevBuf X, C, colstat, islices;      // islices: int8 digit planes of X for the tcgen05 integer Gram (igemm.cu)
     bool have_X = false, have_C = false;
     // PCA
-    int k = 0, ldk = 0;          // scores: nf x ldk row-major
+    int k = 0, ldk = 0;          // scores: nf x ldk row-major; the sweep uses the first k columns
+    int k_full = 0;              // PCs computed by the last tp_pca (tp_recall may lower k below it)
     DevBuf scores, M, Y0, Y1, Y2, W, G, T, Q, Jw, Jv, Jt, small1, small2, part, resid;
     // sticky status words of the small dense kernels, read back at the solver's own sync points:
     // [0] Cholesky met a non-positive pivot  [1] eigensolver did not converge  [2] eigensolver sweeps (sum)

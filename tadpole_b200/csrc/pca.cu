@@ -542,7 +542,7 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
     }
     TP_CUDA(cudaGetLastError());
     TP_MARK(ctx, EV_PCA1);
-    ctx->k = k; ctx->ldk = ldk;
+    ctx->k = ctx->k_full = k; ctx->ldk = ldk;
     ctx->have_scores = true;
     ctx->have_sweep = false;
     return TP_OK;
