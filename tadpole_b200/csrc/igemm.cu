@@ -339,14 +339,20 @@ __global__ void io_rowmax_kernel(const double *__restrict__ A, int n, int ld, in
     if (lane == 0) { const int e = io_exponent(mx); expo[w] = e; scale[w] = ldexp(1.0, e - 6); }
 }
 
-// largest |entry| of every column of Y (n x b, ld): 64-row slabs, one atomicMax per column and slab on the IEEE bit
-// pattern (non-negative doubles order like unsigned integers; max is exact and order independent)
+// largest |entry| of every column of Y (n x b, ld): 16-row slabs (n / 16 CTAs: several waves of the 148 SMs, 16
+// independent coalesced loads in flight per thread), one atomicMax per column and slab on the IEEE bit pattern
+// (non-negative doubles order like unsigned integers; max is exact and order independent)
+#define IO_CM_ROWS 16
 __global__ void __launch_bounds__(256)
 io_colmax_kernel(const double *__restrict__ Y, int n, int b, int ld, unsigned long long *__restrict__ colmax_bits) {
-    const int r0 = blockIdx.x * 64, r1 = min(n, r0 + 64);
+    const int r0 = blockIdx.x * IO_CM_ROWS;
     for (int c = threadIdx.x; c < b; c += 256) {
+        double v[IO_CM_ROWS];
+#pragma unroll
+        for (int t = 0; t < IO_CM_ROWS; t++) v[t] = (r0 + t < n) ? Y[(size_t)(r0 + t) * ld + c] : 0.0;
         double mx = 0.0;
-        for (int r = r0; r < r1; r++) mx = fmax(mx, fabs(Y[(size_t)r * ld + c]));
+#pragma unroll
+        for (int t = 0; t < IO_CM_ROWS; t++) mx = fmax(mx, fabs(v[t]));
         if (mx > 0.0 && isfinite(mx)) atomicMax(colmax_bits + c, (unsigned long long)__double_as_longlong(mx));
     }
 }
@@ -598,7 +604,7 @@ static int iop_apply_np(tp_ctx *ctx, const double *Yin, int b, int ldy, double *
     tp_prof_begin(ctx, PC_IGEMM);
     unsigned long long *cmax = (unsigned long long *)(colexp + (n + 1024));
     TP_CUDA(cudaMemsetAsync(cmax, 0, (size_t)b * sizeof(unsigned long long), st));
-    io_colmax_kernel<<<(n + 63) / 64, 256, 0, st>>>(Yin, n, b, ldy, cmax);
+    io_colmax_kernel<<<(n + IO_CM_ROWS - 1) / IO_CM_ROWS, 256, 0, st>>>(Yin, n, b, ldy, cmax);
     io_colscale_kernel<<<(b + 255) / 256, 256, 0, st>>>(cmax, b, colexp, colscale);
     dim3 sg(Kp / 32, rows_padB / 32);
     io_slice_cols_kernel<NP><<<sg, 256, 0, st>>>(Yin, n, b, ldy, colexp, ctx->ioB.as<int8_t>(), rows_padB, Kp);

@@ -497,8 +497,8 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
                     for (int j = 0; j < k; j++) rmax = (hbuf[j] > rmax || hbuf[j] != hbuf[j]) ? hbuf[j] : rmax;
                     last_res = rmax / bd.top;
                     if (getenv("TADPOLE_DEBUG"))
-                        fprintf(stderr, "[tadpole] pca it=%d res=%.3e top=%.4e thk=%.4e cut=%.4e deg=%d %s\n", it, last_res,
-                                bd.top, bd.thk, bd.cut, bd.deg, op.np == 5 ? "int8x5" : (op.np == 8 ? "int8x8" : "fp64"));
+                        fprintf(stderr, "[tadpole] pca it=%d res=%.3e top=%.4e thk=%.4e cut=%.4e deg=%d %s eig_sweeps_so_far=%d apps=%d\n", it, last_res,
+                                bd.top, bd.thk, bd.cut, bd.deg, op.np == 5 ? "int8x5" : (op.np == 8 ? "int8x8" : "fp64"), sweeps_total, op.applications);
                     // the sliced operator carries the iteration down to iop_switch (or until it stops helping); from
                     // there on, and for every decision about convergence, the FP64 operator is used
                     if (op.np != 5 || !(last_res <= ctx->iop_switch || last_res > 0.1 * prev_res)) break;
