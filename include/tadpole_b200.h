@@ -53,7 +53,8 @@ void *tp_ctx_stream(tp_ctx *ctx);
 long long tp_ctx_launches(tp_ctx *ctx);
 /* tunables: "pca_block" (subspace width, 0 = auto), "pca_tol" (x1e-16), "pca_maxit",
  * "jacobi_direct_max", "level_cap", "dist_min_n", "igemm_min_n" (smallest nf that takes the tcgen05 int8 Gram path
- * when the counts are integers; 0 = never) */
+ * when the counts are integers; 0 = never), "iop_min_n" / "iop_switch" / "iop_final" (sliced int8 operator of the
+ * subspace iteration), "mgram_min_n" (smallest nf whose M = Xc Xc^T is formed by the sliced int8 Gram; 0 = FP64 DMMA) */
 int tp_ctx_set(tp_ctx *ctx, const char *key, double value);
 /* per-stage device milliseconds of the last tp_call / stage call, measured with CUDA events on
  * the context stream: [0] filter [1] compact [2] correlation [3] pca [4] sweep (CONISS) [5] CH
@@ -137,6 +138,10 @@ int tp_test_eig(tp_ctx *ctx, const double *t, int b, double tol, double *w_out, 
 /* test hook of the tcgen05 int8 Gram kernel behind tp_correlation: X X^T of a symmetric n x n matrix of integer counts,
  * exact; *used_out = 0 when x is not integer-valued below 2^20 (gram_out untouched) */
 int tp_test_igram(tp_ctx *ctx, const double *x, int n, double *gram_out, int *used_out);
+/* test hook of the sliced int8 Gram that forms M = Xc Xc^T in tp_pca (8 digit planes per row, FP64 level): rows
+ * [row_begin, row_end) of a a^T for a general n x n FP64 matrix a; all rows = the symmetric launch (upper tiles mirrored),
+ * a proper row block = what one rank of a sharded call computes.  Rows outside the block keep gram_out's values. */
+int tp_test_mgram(tp_ctx *ctx, const double *a, int n, int row_begin, int row_end, double *gram_out);
 
 /* ---- stages 4+5: the find_params sweep (R/TADpole.R:104-123) --------------------------------------
  * For candidates i = cand_begin + t*cand_stride < k (0-based: candidate i clusters on the first

@@ -123,6 +123,7 @@ extern "C" int tp_ctx_set(tp_ctx *ctx, const char *key, double value) {
     else if (k == "dist_min_n") ctx->dist_min_n = (int)value;
     else if (k == "igemm_min_n") ctx->igemm_min_n = (int)value;
     else if (k == "iop_min_n") ctx->iop_min_n = (int)value;
+    else if (k == "mgram_min_n") ctx->mgram_min_n = (int)value;
     else if (k == "iop_switch") ctx->iop_switch = value;
     else if (k == "iop_final") ctx->iop_final = ((int)value == 8) ? 8 : 0;
     else { tp_set_error("tp_ctx_set: unknown key '%s'", key); return TP_ERR_ARG; }
@@ -257,6 +258,29 @@ extern "C" int tp_test_igram(tp_ctx *ctx, const double *x, int n, double *gram_o
     if (*used_out)
         TP_CUDA(cudaMemcpy2DAsync(gram_out, (size_t)n * sizeof(double), ctx->C.p, (size_t)ld * sizeof(double),
                                   (size_t)n * sizeof(double), n, cudaMemcpyDeviceToHost, ctx->stream));
+    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return TP_OK;
+}
+
+int tp_igram_sliced(tp_ctx *ctx, const double *A, int n, int ld, double *M, int ldm, int row_begin, int row_end);
+
+// A A^T of a general n x n FP64 matrix through the sliced int8 Gram that forms M = Xc Xc^T in tp_pca (host in / out,
+// row-major); rows [row_begin, row_end) of the result are written, the others left as they are in gram_out
+extern "C" int tp_test_mgram(tp_ctx *ctx, const double *a, int n, int row_begin, int row_end, double *gram_out) {
+    TP_ARG(ctx && a && n >= 1 && gram_out && 0 <= row_begin && row_begin <= row_end && row_end <= n, "tp_test_mgram: bad arguments");
+    TP_CUDA(cudaSetDevice(ctx->device));
+    const int ld = round_up(n, 8);
+    const size_t bytes = (size_t)n * ld * sizeof(double);
+    TP_TRY(ctx->C.reserve(bytes)); TP_TRY(ctx->M.reserve(bytes));
+    TP_CUDA(cudaMemsetAsync(ctx->C.p, 0, bytes, ctx->stream));
+    TP_CUDA(cudaMemcpy2DAsync(ctx->C.p, (size_t)ld * sizeof(double), a, (size_t)n * sizeof(double),
+                              (size_t)n * sizeof(double), n, cudaMemcpyHostToDevice, ctx->stream));
+    TP_CUDA(cudaMemcpy2DAsync(ctx->M.p, (size_t)ld * sizeof(double), gram_out, (size_t)n * sizeof(double),
+                              (size_t)n * sizeof(double), n, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->have_C = ctx->have_scores = ctx->have_sweep = false;
+    TP_TRY(tp_igram_sliced(ctx, ctx->C.as<double>(), n, ld, ctx->M.as<double>(), ld, row_begin, row_end));
+    TP_CUDA(cudaMemcpy2DAsync(gram_out, (size_t)n * sizeof(double), ctx->M.p, (size_t)ld * sizeof(double),
+                              (size_t)n * sizeof(double), n, cudaMemcpyDeviceToHost, ctx->stream));
     TP_CUDA(cudaStreamSynchronize(ctx->stream));
     return TP_OK;
 }

@@ -444,13 +444,26 @@ struct IoParams {
     const double *E1; long lde1; const double *E2; long lde2;
     double alpha, beta, gamma;
     const double *rowscale, *colscale;       // 2^(e_i - 6), 2^(f_j - 6)
+    int banded;            // 1: tile order in bands of 8 tile rows (see the kernel)
+    int sym;               // 1: symmetric product (B = A, square output): tiles below the diagonal are skipped and every
+                           // element is stored twice, as in ig_gram_kernel
 };
 
 template <int NP>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 io_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, IoParams p) {
     constexpr int IO_STAGES = IoCfg<NP>::STAGES, IO_STAGE_BYTES = IoCfg<NP>::STAGE_BYTES, IO_NP = NP;
-    const int m0 = p.row_begin + blockIdx.y * IO_BM, n0 = blockIdx.x * IO_BN;
+    unsigned bx = blockIdx.x, by = blockIdx.y;
+    if (p.banded) {
+        // wide outputs (Gram): bands of 8 tile rows walked column by column, so that the CTAs resident together share
+        // 8 A row blocks and ~18 B row blocks through L2 instead of one A and 148 B
+        const unsigned id = blockIdx.y * gridDim.x + blockIdx.x, per = 8u * gridDim.x;
+        const unsigned band = id / per, in = id % per;
+        const unsigned h = gridDim.y - band * 8u < 8u ? gridDim.y - band * 8u : 8u;
+        by = band * 8u + in % h; bx = in / h;
+    }
+    const int m0 = p.row_begin + (int)by * IO_BM, n0 = (int)bx * IO_BN;
+    if (n0 >= p.b || (p.sym && n0 + IO_BN <= m0)) return;           // padding, or mirrored from the tile above the diagonal
     extern __shared__ unsigned char ig_raw[];
     unsigned char *tiles = (unsigned char *)(((uintptr_t)ig_raw + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) unsigned long long s_full[IO_STAGES], s_empty[IO_STAGES], s_done;
@@ -535,6 +548,9 @@ io_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                     if (p.E1) v += p.beta * p.E1[(size_t)row * p.lde1 + col];
                     if (p.E2) v += p.gamma * p.E2[(size_t)row * p.lde2 + col];
                     p.D[(size_t)row * p.ldd + col] = v;
+                    // the digit sums are symmetric in (row, col) and the scales are powers of two: the mirrored
+                    // element is the same bits
+                    if (p.sym && col != row) p.D[(size_t)col * p.ldd + row] = v;
                 }
             }
         }
@@ -614,7 +630,7 @@ static int iop_apply_np(tp_ctx *ctx, const double *Yin, int b, int ldy, double *
     IoParams p;
     p.n = n; p.b = b; p.row_begin = row_begin; p.row_end = row_end; p.kblocks = Kp / IO_BK;
     p.D = D; p.ldd = ldd; p.E1 = E1; p.lde1 = lde1; p.E2 = E2; p.lde2 = lde2;
-    p.alpha = alpha; p.beta = beta; p.gamma = gamma; p.rowscale = rowscale; p.colscale = colscale;
+    p.alpha = alpha; p.beta = beta; p.gamma = gamma; p.rowscale = rowscale; p.colscale = colscale; p.sym = 0; p.banded = 0;
     const size_t smem = (size_t)IoCfg<NP>::STAGES * IoCfg<NP>::STAGE_BYTES + 1024;
     TP_CUDA(cudaFuncSetAttribute(io_gemm_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(rows_padB / IO_BN, (row_end - row_begin + IO_BM - 1) / IO_BM);
@@ -633,4 +649,48 @@ int tp_iop_apply(tp_ctx *ctx, const double *Yin, int b, int ldy, double *D, int 
     TP_ARG(np == 5 || np == 8, "tp_iop_apply: 5 or 8 digit planes");
     if (np == 5) return iop_apply_np<5>(ctx, Yin, b, ldy, D, ldd, alpha, E1, lde1, beta, E2, lde2, gamma, row_begin, row_end);
     return iop_apply_np<8>(ctx, Yin, b, ldy, D, ldd, alpha, E1, lde1, beta, E2, lde2, gamma, row_begin, row_end);
+}
+
+// M[rows] = A[rows, :] A^T for an FP64 matrix A (n x n, ld), rows = [row_begin, row_end): the sliced product above with
+// both operands cut from the rows of A (one set of 8 digit planes, per-row exponents), FP64 level (digit pairs left out
+// below 2^-56 of row scale x row scale; every product kept is exact, so the sum carries no accumulation rounding at all
+// -- the FP64 DMMA Gram carries ~sqrt(n) ulp).  Used for M = Xc Xc^T of stage 3 (pca.cu).  With all rows requested only
+// the tiles on and above the diagonal are computed (36 digit products x n^3 / 2 MACs) and mirrored; a row block (rank
+// of a sharded call) computes its full width.  The planes share ctx->ioA with tp_iop_prepare, which runs after this.
+int tp_igram_sliced(tp_ctx *ctx, const double *A, int n, int ld, double *M, int ldm, int row_begin, int row_end) {
+    constexpr int NP = IO_MAXNP;
+    cudaStream_t st = ctx->stream;
+    const int rows_pad = round_up(n, IO_BM), Kp = round_up(n, 128);
+    const size_t plane = (size_t)rows_pad * Kp;
+    TP_TRY(ctx->ioA.reserve(IO_MAXNP * plane));
+    TP_TRY(ctx->ioscale.reserve((size_t)(n + 1024) * (sizeof(double) + sizeof(int)) * 2 + 1024 * sizeof(unsigned long long)));
+    double *rowscale = ctx->ioscale.as<double>();
+    int *rowexp = (int *)(rowscale + 2 * (n + 1024));
+    tp_prof_begin(ctx, PC_IGEMM);
+    io_rowmax_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(A, n, ld, rowexp, rowscale);
+    const size_t chunks = (size_t)rows_pad * (Kp / 16);
+    io_slice_rows_kernel<NP><<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(A, n, ld, rowexp, ctx->ioA.as<int8_t>(), rows_pad, Kp);
+    ctx->launches += 2;
+    if (row_end > row_begin) {
+        CUtensorMap map;
+        TP_TRY(io_encode(&map, ctx->ioA.p, rows_pad, Kp, NP));
+        IoParams p;
+        p.n = n; p.b = n; p.row_begin = row_begin; p.row_end = row_end; p.kblocks = Kp / IO_BK;
+        p.D = M; p.ldd = ldm; p.E1 = nullptr; p.lde1 = 0; p.E2 = nullptr; p.lde2 = 0;
+        p.alpha = 1.0; p.beta = 0.0; p.gamma = 0.0; p.rowscale = rowscale; p.colscale = rowscale;
+        p.sym = (row_begin == 0 && row_end == n) ? 1 : 0; p.banded = 1;
+        const size_t smem = (size_t)IoCfg<NP>::STAGES * IoCfg<NP>::STAGE_BYTES + 1024;
+        TP_CUDA(cudaFuncSetAttribute(io_gemm_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(rows_pad / IO_BN, (row_end - row_begin + IO_BM - 1) / IO_BM);
+        if (ctx->prof) {
+            double tiles = (double)grid.x * grid.y;
+            if (p.sym) tiles = 0.5 * tiles + 0.5 * grid.x;          // on and above the diagonal (128 x 64 tiles)
+            ctx->prof_imma_ops += 2.0 * (NP * (NP + 1) / 2) * tiles * IO_BM * IO_BN * (double)Kp;
+        }
+        io_gemm_kernel<NP><<<grid, IG_THREADS, smem, st>>>(map, map, p);
+        ctx->launches += 1;
+    }
+    tp_prof_end(ctx);
+    TP_CUDA(cudaGetLastError());
+    return TP_OK;
 }

@@ -24,6 +24,7 @@ int tp_igram(tp_ctx *ctx, const double *X, int n, int ld, double *C, int ldc, co
              int raw, int *used_out);
 int tp_chol_inv(tp_ctx *ctx, double *G, double *Linv, int b, int ld, int *bad_out);
 int tp_iop_prepare(tp_ctx *ctx, const double *S, int n, int ld);
+int tp_igram_sliced(tp_ctx *ctx, const double *A, int n, int ld, double *M, int ldm, int row_begin, int row_end);
 int tp_iop_apply(tp_ctx *ctx, const double *Yin, int b, int ldy, double *D, int ldd, double alpha, const double *E1,
                  int lde1, double beta, const double *E2, int lde2, double gamma, int row_begin, int row_end, int np);
 
@@ -303,7 +304,12 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
         GemmArgs g;
         g.A = C; g.lda = ld; g.a_kc = 1; g.B = C; g.ldb = ld; g.b_kc = 1;
         g.D = M; g.ldd = ld; g.M = n; g.N = n; g.K = n; g.sym = 1;
-        if (shard) {      // row blocks of M = Xc Xc^T by their owner, all-gathered
+        if (use_iop && ctx->mgram_min_n > 0 && n >= ctx->mgram_min_n) {
+            // sliced int8 Gram on the tcgen05 tensor cores (8 digit planes of Xc, FP64 level); row blocks when sharded
+            const int r0 = shard ? rw.r0 : 0, r1 = shard ? rw.r1 : n;
+            TP_TRY(tp_igram_sliced(ctx, C, n, ld, M, ld, r0, r1));
+            if (shard) TP_TRY(tp_comm_allgather(ctx, M, (size_t)rw.rpr * ld));
+        } else if (shard) {      // row blocks of M = Xc Xc^T by their owner, all-gathered
             g.A += (size_t)rw.r0 * ld; g.D += (size_t)rw.r0 * ld; g.M = rw.r1 - rw.r0; g.sym = 0;
             if (g.M > 0) TP_TRY(tp_gemm(ctx, g));
             TP_TRY(tp_comm_allgather(ctx, M, (size_t)rw.rpr * ld));
