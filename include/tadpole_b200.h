@@ -54,8 +54,10 @@ long long tp_ctx_launches(tp_ctx *ctx);
 /* tunables: "pca_block" (subspace width, 0 = auto), "pca_tol" (x1e-16), "pca_maxit",
  * "jacobi_direct_max", "level_cap", "dist_min_n", "igemm_min_n" (smallest nf that takes the tcgen05 int8 Gram path
  * when the counts are integers; 0 = never), "iop_min_n" / "iop_switch" / "iop_final" (sliced int8 operator of the
- * subspace iteration), "mgram_min_n" (smallest nf whose M = Xc Xc^T is formed by the sliced int8 Gram; 0 = FP64 DMMA) */
+ * subspace iteration; "iop_final_min_n" = smallest nf whose later rounds stay on the 8-plane sliced operator),
+ * "mgram_min_n" (smallest nf whose M = Xc Xc^T is formed by the sliced int8 Gram; 0 = FP64 DMMA) */
 int tp_ctx_set(tp_ctx *ctx, const char *key, double value);
+/* The environment variable TADPOLE_TUNE="key=value,key=value" applies tp_ctx_set to every context at creation. */
 /* per-stage device milliseconds of the last tp_call / stage call, measured with CUDA events on
  * the context stream: [0] filter [1] compact [2] correlation [3] pca [4] sweep (CONISS) [5] CH
  * [6] total; and counters [7] pca iterations [8] pca operator applications [9] jacobi sweeps */

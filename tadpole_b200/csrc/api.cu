@@ -47,6 +47,9 @@ int tp_flags_read(tp_ctx *ctx, int out[4]) {
     return TP_OK;
 }
 
+extern "C" int tp_ctx_set(tp_ctx *ctx, const char *key, double value);
+extern "C" int tp_ctx_destroy(tp_ctx *ctx);
+
 extern "C" int tp_ctx_create(int device, tp_ctx **out) {
     TP_ARG(out, "tp_ctx_create: null output pointer");
     int ndev = 0;
@@ -73,6 +76,28 @@ extern "C" int tp_ctx_create(int device, tp_ctx **out) {
     for (int i = 0; i < EV_COUNT; i++) TP_CUDA(cudaEventCreate(&ctx->ev[i]));
     TP_TRY(tp_pin_reserve(ctx, 1 << 16));
     TP_TRY(tp_flags_reset(ctx));
+    // TADPOLE_TUNE="key=value,key=value": tp_ctx_set applied to every new context (for hosts that do not expose the
+    // tunables, e.g. the R functions, and for experiments); an unknown key is an error, not ignored
+    if (const char *tune = getenv("TADPOLE_TUNE")) {
+        std::string t(tune);
+        size_t pos = 0;
+        while (pos < t.size()) {
+            size_t end = t.find(',', pos);
+            if (end == std::string::npos) end = t.size();
+            const std::string item = t.substr(pos, end - pos);
+            pos = end + 1;
+            if (item.empty()) continue;
+            const size_t eq = item.find('=');
+            char *endp = nullptr;
+            const double v = eq == std::string::npos ? 0.0 : strtod(item.c_str() + eq + 1, &endp);
+            if (eq == std::string::npos || eq == 0 || endp == item.c_str() + eq + 1 || *endp) {
+                tp_set_error("tp_ctx_create: TADPOLE_TUNE item '%s' is not key=number", item.c_str());
+                tp_ctx_destroy(ctx);
+                return TP_ERR_ARG;
+            }
+            if (tp_ctx_set(ctx, item.substr(0, eq).c_str(), v) != TP_OK) { tp_ctx_destroy(ctx); return TP_ERR_ARG; }
+        }
+    }
     *out = ctx;
     return TP_OK;
 }
@@ -126,6 +151,7 @@ extern "C" int tp_ctx_set(tp_ctx *ctx, const char *key, double value) {
     else if (k == "mgram_min_n") ctx->mgram_min_n = (int)value;
     else if (k == "iop_switch") ctx->iop_switch = value;
     else if (k == "iop_final") ctx->iop_final = ((int)value == 8) ? 8 : 0;
+    else if (k == "iop_final_min_n") ctx->iop_final_min_n = (int)value;
     else { tp_set_error("tp_ctx_set: unknown key '%s'", key); return TP_ERR_ARG; }
     return TP_OK;
 }

@@ -85,6 +85,7 @@ struct tp_ctx {
     int igemm_min_n = 1024;
     int iop_min_n = 1024;        // smallest nf whose early subspace-iteration rounds use the sliced int8 operator (0 = never)
     int mgram_min_n = 1024;      // smallest nf whose M = Xc Xc^T is formed by the sliced int8 Gram (needs the sliced operator; 0 = FP64 DMMA)
+    int iop_final_min_n = 4096;  // below this nf the later rounds use the FP64 DMMA operator whatever iop_final says
     int iop_final = 8;           // operator of the later rounds where the sliced one is in use: 8 digit planes, or 0 = FP64 DMMA
     double iop_switch = 1e-3;    // relative residual below which the FP64 DMMA operator takes over (the first iteration always starts sliced)      // integer-count matrices at least this large take the tcgen05 int8 Gram path (0 = never)       // matrices smaller than this are not row-sharded (only the candidate sweep is)
 

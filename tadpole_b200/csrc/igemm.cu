@@ -164,6 +164,7 @@ ig_gram_kernel(const __grid_constant__ CUtensorMap tmap, IgParams p) {
         // ===== MMA issuer: D_{a+b} += A_a B_b^T =====
         // instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, N = 64, M = 128
         const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((IG_BN >> 3) << 17) | ((IG_BM >> 4) << 24);
+        const unsigned idesc3 = (2u << 4) | (1u << 7) | (1u << 10) | (((3 * IG_BN) >> 3) << 17) | ((IG_BM >> 4) << 24);    // N = 192
         if (lane == 0) {
             for (int kb = 0; kb < p.kblocks; kb++) {
                 const int st = kb % IG_STAGES;
@@ -172,14 +173,24 @@ ig_gram_kernel(const __grid_constant__ CUtensorMap tmap, IgParams p) {
                 const unsigned base = ig_smem(tiles + (size_t)st * IG_STAGE_BYTES);
 #pragma unroll
                 for (int kk = 0; kk < IG_BK / 32; kk++) {
+                    // The three B digit tiles of a stage are contiguous (64 rows x 128 B each) and so are the accumulators
+                    // of scales a, a+1, a+2: one N = 192 MMA per A digit multiplies it with all three B digits, reading the
+                    // A tile from shared memory once instead of three times (the N = 64 form is bound by that traffic:
+                    // 6 KB per 32 tensor cycles against 128 B / cycle).  The very first k-step has to start accumulators
+                    // 3 and 4 at zero while 1 and 2 already accumulate, so it keeps the per-pair form.
+                    const unsigned long long bd0 = ig_desc(base + 3 * IG_A_BYTES) + (unsigned long long)(kk * 32 >> 4);
 #pragma unroll
                     for (int a = 0; a < 3; a++) {
                         const unsigned long long ad = ig_desc(base + a * IG_A_BYTES) + (unsigned long long)(kk * 32 >> 4);
+                        if (kb == 0 && kk == 0) {
 #pragma unroll
-                        for (int b = 0; b < 3; b++) {
-                            const unsigned long long bd = ig_desc(base + 3 * IG_A_BYTES + b * IG_B_BYTES) + (unsigned long long)(kk * 32 >> 4);
-                            const bool first = kb == 0 && kk == 0 && (a == 0 || b == 2);     // first product of scale a + b
-                            ig_mma_i8(tmem + (unsigned)(a + b) * IG_BN, ad, bd, idesc, first ? 0u : 1u);
+                            for (int b = 0; b < 3; b++) {
+                                const unsigned long long bd = ig_desc(base + 3 * IG_A_BYTES + b * IG_B_BYTES) + (unsigned long long)(kk * 32 >> 4);
+                                const bool first = a == 0 || b == 2;                         // first product of scale a + b
+                                ig_mma_i8(tmem + (unsigned)(a + b) * IG_BN, ad, bd, idesc, first ? 0u : 1u);
+                            }
+                        } else {
+                            ig_mma_i8(tmem + (unsigned)a * IG_BN, ad, bd0, idesc3, 1u);
                         }
                     }
                 }
@@ -310,6 +321,7 @@ int tp_igram(tp_ctx *ctx, const double *X, int n, int ld, double *C, int ldc, co
 #define IO_BM 128
 #define IO_BN 64
 #define IO_BK 64
+#define IO_NGROUP 4               // adjacent B digit planes multiplied by one MMA (N = 64 x group, at most 256)
 #define IO_MAXNP 8                // digit planes kept of the operator; a product uses the first NP of them (5 or 8)
 #define IO_A_BYTES (IO_BM * IO_BK)
 #define IO_B_BYTES (IO_BN * IO_BK)
@@ -500,7 +512,6 @@ io_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((IO_BN >> 3) << 17) | ((IO_BM >> 4) << 24);
         if (lane == 0) {
             for (int kb = 0; kb < p.kblocks; kb++) {
                 const int st = kb % IO_STAGES;
@@ -512,11 +523,18 @@ io_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 #pragma unroll
                     for (int a = 0; a < IO_NP; a++) {
                         const unsigned long long ad = io_desc(base + a * IO_A_BYTES) + (unsigned long long)(kk * 32 >> 4);
+                        // digit pairs with a + b <= NP - 1.  The B digit tiles of a stage are contiguous (64 rows x 64 B each)
+                        // and so are the accumulators of adjacent scales: one MMA of N = 64 m multiplies A digit a with
+                        // m <= IO_NGROUP adjacent B digits, so the A tile is read from shared memory once per group
+                        // instead of once per pair (NP = 8: 123 KB instead of 221 KB per 32-deep k-step, below the
+                        // 1152 tensor cycles x 128 B / cycle of shared-memory bandwidth)
 #pragma unroll
-                        for (int b = 0; b < IO_NP - a; b++) {          // digit pairs with a + b <= NP - 1
-                            const unsigned long long bd = io_desc(base + IO_NP * IO_A_BYTES + b * IO_B_BYTES) + (unsigned long long)(kk * 32 >> 4);
-                            const bool first = kb == 0 && kk == 0 && a == 0;
-                            ig_mma_i8(tmem + (unsigned)(a + b) * IO_BN, ad, bd, idesc, first ? 0u : 1u);
+                        for (int b0 = 0; b0 < IO_NP - a; b0 += IO_NGROUP) {
+                            const int m = IO_NP - a - b0 < IO_NGROUP ? IO_NP - a - b0 : IO_NGROUP;
+                            const unsigned idm = (2u << 4) | (1u << 7) | (1u << 10) | (((unsigned)(m * IO_BN) >> 3) << 17) | ((IO_BM >> 4) << 24);
+                            const unsigned long long bd = io_desc(base + IO_NP * IO_A_BYTES + b0 * IO_B_BYTES) + (unsigned long long)(kk * 32 >> 4);
+                            const bool first = kb == 0 && kk == 0 && a == 0;      // a = 0 touches every accumulator
+                            ig_mma_i8(tmem + (unsigned)(a + b0) * IO_BN, ad, bd, idm, first ? 0u : 1u);
                         }
                     }
                 }

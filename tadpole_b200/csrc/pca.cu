@@ -508,7 +508,7 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
                     // the sliced operator carries the iteration down to iop_switch (or until it stops helping); from
                     // there on, and for every decision about convergence, the FP64 operator is used
                     if (op.np != 5 || !(last_res <= ctx->iop_switch || last_res > 0.1 * prev_res)) break;
-                    op.np = n >= 4096 ? ctx->iop_final : 0;      // small problems: the FP64 operator is as fast
+                    op.np = n >= ctx->iop_final_min_n ? ctx->iop_final : 0;
                 }
                 prev_res = last_res;
                 if (rmax <= ctx->pca_tol * bd.top) { converged = true; return TP_OK; }
