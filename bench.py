@@ -59,6 +59,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bins", type=int, default=N_BINS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--large-n", type=int, default=8000,
+                    help="bins of one extra profiled call whose tensor-kernel rooflines are reported beside the workload's "
+                         "(N = 1 only; 0 = skip)")
     ap.add_argument("--cpu-sample", type=int, default=8, help="candidates timed per CPU sample")
     return ap.parse_args()
 
@@ -311,7 +314,7 @@ def run_b200(args, rank, world, local_rank):
                 # tcgen05 int8 launches (exact Gram of the correlation, sliced operator of the PCA; the class also
                 # holds their digit-slicing kernels): executed int8 operations / class time against the NOMINAL dense
                 # int8 rate (no measured int8 peak in MEASURED_PEAKS.json)
-                r = {"kernel": "ig_gram_kernel + io_gemm_kernel (tcgen05.mma kind::i8)", "bound": "tensor",
+                r = {"kernel": "ig_gram_kernel + io_gemm_kernel (tcgen05.mma kind::i8; digit slicing timed apart as islice)", "bound": "tensor",
                      "achieved": prof["igemm_gop"][0] / t_ms, "peak": 4500.0, "unit": "TOP/s", "traffic": None}
                 src = "nominal B200 dense int8 (4.5 POP/s); executed digit-product operations, not FP64 flops"
             else:
@@ -392,6 +395,34 @@ def run_b200(args, rank, world, local_rank):
                 "sample": (f"oracle/ (numpy + C restatement; R unavailable): filter+correlation+full SVD timed in full "
                            f"({detail['front_s']} s), {detail['candidates']} of {detail['k']} candidates on {threads} "
                            f"threads ({detail['sweep_sample_s']} s) scaled by k/candidates")}
+            # the tensor-core kernels at a size where they are the step (the 2000-bin workload leaves them 64-CTA grids)
+            if args.large_n > 0:
+                nl = args.large_n
+                ml = synth_hic(nl, seed=77)
+                c0 = pool.contexts[0]
+                for _ in range(2):
+                    rl = c0.call(ml, max_pcs=MAX_PCS)
+                c0.profile(1)
+                rl = c0.call(ml, max_pcs=MAX_PCS)
+                pl = c0.profile(0)
+                stl = c0.timings()
+                big = {"bins": nl, "good_bins": rl["nf"], "n_pcs_found": rl["n_pcs"],
+                       "stage_ms": {k_: round(v, 3) for k_, v in stl.items()},
+                       "kernel_ms": {c: round(v[0], 3) for c, v in pl.items() if v[1]},
+                       "kernel_launches": {c: v[1] for c, v in pl.items() if v[1]}}
+                if pl["igemm"][1]:
+                    a = pl["igemm_gop"][0] / pl["igemm"][0]
+                    big["igemm_roofline"] = {"kernel": "ig_gram_kernel + io_gemm_kernel<5|8> (tcgen05.mma kind::i8)", "bound": "tensor",
+                                             "achieved": a, "peak": 4500.0, "unit": "TOP/s", "frac": a / 4500.0,
+                                             "peak_source": "nominal B200 dense int8; executed digit-product operations over the "
+                                                            "CUDA-event time of the tcgen05 launches of one call"}
+                if pl["dgemm"][1]:
+                    a = pl["gemm_gflop"][0] / pl["dgemm"][0]
+                    big["dgemm_roofline"] = {"kernel": "dgemm_kernel (FP64 DMMA)", "bound": "tensor", "achieved": a, "peak": fp64_peak,
+                                             "unit": "TFLOP/s", "frac": a / fp64_peak,
+                                             "peak_source": "cuBLAS DGEMM 4096^3 measured in this run"}
+                line["large_n_call"] = big
+                del ml
             # input side: the same call starting from the matrix FILE, text parsed on the GPU
             try:
                 import tempfile

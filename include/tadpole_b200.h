@@ -66,11 +66,12 @@ int tp_ctx_timings(tp_ctx *ctx, double *out10);
 /* per-kernel-class device time: when enabled, every launch of the classes below is bracketed by
  * CUDA events on the context stream; reading sums them since the last enable/reset.
  * classes: [0] rowmean (filter) [1] compact [2] dgemm [3] jacobi (b x b eigensolver) [4] coniss_sweep [5] ch
- * [6] difft [8] chol (b x b Cholesky + triangular inverse) [9] igemm (tcgen05 integer GEMM) [10] NCCL collectives
- * [11] in ms_out12: executed int8 GOP (2 per multiply-add) of the profiled tcgen05 launches;
- * [7] in ms_out12: GFLOP (algorithmic) of the profiled dgemm launches.
+ * [6] difft [8] chol (b x b Cholesky + triangular inverse) [9] igemm (the tcgen05 int8 kernels only) [10] NCCL collectives
+ * [12] islice (digit slicing and exponent kernels feeding the tcgen05 kernels; HBM-bound); [13..15] unused;
+ * [11] in ms_out16: executed int8 GOP (2 per multiply-add) of the profiled tcgen05 launches;
+ * [7] in ms_out16: GFLOP (algorithmic) of the profiled dgemm launches.
  * enable: 1 = start/reset, 0 = stop, -1 = just read. */
-int tp_ctx_profile(tp_ctx *ctx, int enable, double *ms_out12, long long *count_out12);
+int tp_ctx_profile(tp_ctx *ctx, int enable, double *ms_out16, long long *count_out16);
 
 /* ---- multi-GPU: one process per GPU, NCCL bound at run time (single-GPU use never touches it) ------------------
  * The reference shards the n_pcs sweep over forked workers (foreach %dopar%, R/TADpole.R:103-104); here one call can

@@ -161,12 +161,12 @@ class Context:
         return dict(zip(keys, out.tolist()))
 
     PROFILE_CLASSES = ["rowmean", "compact", "dgemm", "jacobi", "coniss_sweep", "ch", "difft", "gemm_gflop", "chol", "igemm",
-                       "comm", "igemm_gop"]
+                       "comm", "igemm_gop", "islice", "spare13", "spare14", "spare15"]
 
     def profile(self, enable=-1):
         """enable: 1 start/reset, 0 stop, -1 read.  Returns {class: (ms, launches)} accumulated so far."""
-        ms = np.zeros(12)
-        cnt = np.zeros(12, dtype=np.int64)
+        ms = np.zeros(16)
+        cnt = np.zeros(16, dtype=np.int64)
         check(self.lib.tp_ctx_profile(self._h, int(enable), _dp(ms), cnt.ctypes.data_as(POINTER(c_longlong))))
         return {k: (float(m), int(c)) for k, m, c in zip(self.PROFILE_CLASSES, ms, cnt)}
 

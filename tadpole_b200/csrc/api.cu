@@ -192,10 +192,10 @@ void tp_prof_end(tp_ctx *ctx) {
     ctx->prof_used += 2;
 }
 
-extern "C" int tp_ctx_profile(tp_ctx *ctx, int enable, double *ms_out12, long long *count_out12) {
+extern "C" int tp_ctx_profile(tp_ctx *ctx, int enable, double *ms_out16, long long *count_out16) {
     TP_ARG(ctx, "tp_ctx_profile: null context");
     TP_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (ms_out12 || count_out12) {
+    if (ms_out16 || count_out16) {
         double ms[PC_COUNT] = {};
         long long cnt[PC_COUNT] = {};
         for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
@@ -207,7 +207,7 @@ extern "C" int tp_ctx_profile(tp_ctx *ctx, int enable, double *ms_out12, long lo
         }
         ms[PC_SPARE] = ctx->prof_gemm_flop * 1e-9;   // slot 7: GFLOP of the profiled GEMM launches
         ms[PC_SPARE3] = ctx->prof_imma_ops * 1e-9;   // slot 11: executed int8 GOP of the profiled tcgen05 launches
-        for (int c = 0; c < PC_COUNT; c++) { if (ms_out12) ms_out12[c] = ms[c]; if (count_out12) count_out12[c] = cnt[c]; }
+        for (int c = 0; c < PC_COUNT; c++) { if (ms_out16) ms_out16[c] = ms[c]; if (count_out16) count_out16[c] = cnt[c]; }
     }
     if (enable == 1) { ctx->prof = true; ctx->prof_used = 0; ctx->prof_gemm_flop = 0.0; ctx->prof_imma_ops = 0.0; }
     else if (enable == 0) ctx->prof = false;

@@ -85,7 +85,7 @@ struct tp_ctx {
     int igemm_min_n = 1024;
     int iop_min_n = 1024;        // smallest nf whose early subspace-iteration rounds use the sliced int8 operator (0 = never)
     int mgram_min_n = 1024;      // smallest nf whose M = Xc Xc^T is formed by the sliced int8 Gram (needs the sliced operator; 0 = FP64 DMMA)
-    int iop_final_min_n = 4096;  // below this nf the later rounds use the FP64 DMMA operator whatever iop_final says
+    int iop_final_min_n = 1024;  // below this nf the later rounds use the FP64 DMMA operator whatever iop_final says (measured at N = 2000, 8 calls in flight: 224 -> 264 calls/s with the sliced operator)
     int iop_final = 8;           // operator of the later rounds where the sliced one is in use: 8 digit planes, or 0 = FP64 DMMA
     double iop_switch = 1e-3;    // relative residual below which the FP64 DMMA operator takes over (the first iteration always starts sliced)      // integer-count matrices at least this large take the tcgen05 int8 Gram path (0 = never)       // matrices smaller than this are not row-sharded (only the candidate sweep is)
 
@@ -148,7 +148,7 @@ struct tp_ctx {
     double prof_imma_ops = 0.0;            // executed int8 multiply-add operations (2 per MAC) of the tcgen05 launches profiled
 };
 
-enum { PC_ROWMEAN = 0, PC_COMPACT, PC_GEMM, PC_JACOBI, PC_SWEEP, PC_CH, PC_DIFFT, PC_SPARE, PC_CHOL, PC_IGEMM, PC_COMM, PC_SPARE3, PC_COUNT };
+enum { PC_ROWMEAN = 0, PC_COMPACT, PC_GEMM, PC_JACOBI, PC_SWEEP, PC_CH, PC_DIFFT, PC_SPARE, PC_CHOL, PC_IGEMM, PC_COMM, PC_SPARE3, PC_ISLICE, PC_SPARE4, PC_SPARE5, PC_SPARE6, PC_COUNT };   // 16 slots
 void tp_prof_begin(tp_ctx *ctx, int cls);
 void tp_prof_end(tp_ctx *ctx);
 

@@ -106,17 +106,20 @@ template <typename LinkT, bool SMEM> struct Links {
 
 // INV_SMEM: a table of 1/m, m = 0..n, sits in shared memory (cluster sizes are integers), replacing
 // the five FP64 divisions of a merge step by loads
+// One warp per candidate, WPC = blockDim.x / 32 candidates per CTA (per-candidate shared memory `cand_smem` bytes each, the
+// reciprocal table shared by the CTA after them).  Packing several candidates into one CTA keeps the sweep on few SMs:
+// 200 one-warp CTAs would be spread over all 148 SMs, and their 25-40 KB of shared memory each would keep the
+// ~200 KB CTAs of the tcgen05 kernels of OTHER calls in flight on the same GPU off every SM for the whole sweep.
 template <typename LinkT, bool LINKS_SMEM, bool INV_SMEM>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(256)
 coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
                     const double *__restrict__ d0, int ldd,
-                    const int *__restrict__ cand_list,
+                    const int *__restrict__ cand_list, int ncand, unsigned cand_smem,
                     double *__restrict__ seqdist, int4 *__restrict__ merges,
                     LinkT *__restrict__ glinks) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x;
-    const int cand = cand_list[blockIdx.x];
-    const int ncol = cand + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const int slot = blockIdx.x * wpc + warp;
     const int n1 = n - 1;
     const int n1p = (n1 + 31) & ~31;
     const int B1 = n1p >> 5;
@@ -124,21 +127,27 @@ coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
     const int B2 = B1p >> 5;
     const int B2p = (B2 + 31) & ~31;
 
-    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned sbase0 = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned sinv = sbase0 + (unsigned)wpc * cand_smem;      // inv[n + 1] when INV_SMEM, shared by the CTA
+    if (INV_SMEM) {
+        for (int m = threadIdx.x; m <= n; m += blockDim.x) sts_f64(sinv + 8u * m, m ? 1.0 / (double)m : 0.0);
+        __syncthreads();
+    }
+    if (slot >= ncand) return;
+    const int cand = cand_list[slot];
+    const int ncol = cand + 1;
+    const unsigned sbase = sbase0 + (unsigned)warp * cand_smem;
     const unsigned sd = sbase;                       // d[n1p]
     const unsigned sm1 = sd + 8u * n1p;              // m1[B1p]
     const unsigned sm2 = sm1 + 8u * B1p;             // m2[B2p]
-    unsigned top = sm2 + 8u * B2p;
     Links<LinkT, LINKS_SMEM> lk;
     lk.sp = lk.sn = 0; lk.gp = lk.gn = nullptr;
     if (LINKS_SMEM) {
-        lk.sp = top; lk.sn = top + (unsigned)sizeof(LinkT) * n1;
-        top = (lk.sn + (unsigned)sizeof(LinkT) * n1 + 7u) & ~7u;
+        lk.sp = sm2 + 8u * B2p; lk.sn = lk.sp + (unsigned)sizeof(LinkT) * n1;
     } else {
-        lk.gp = glinks + (size_t)blockIdx.x * 2 * n1;
+        lk.gp = glinks + (size_t)slot * 2 * n1;
         lk.gn = lk.gp + n1;
     }
-    const unsigned sinv = top;                       // inv[n + 1] when INV_SMEM
     const double *d0row = d0 + (size_t)cand * ldd;
     double *seq = seqdist + (size_t)cand * ldd;
     int4 *mrg = merges + (size_t)cand * ldd;
@@ -147,7 +156,6 @@ coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
     for (int j = lane; j < n1; j += 32) { lk.set_prv(j, j); lk.set_nxt(j, j + 1); }   // prv holds index+1, 0 = none
     for (int b = lane; b < B1p; b += 32) sts_f64(sm1 + 8u * b, INF_D);
     for (int b = lane; b < B2p; b += 32) sts_f64(sm2 + 8u * b, INF_D);
-    if (INV_SMEM) for (int m = lane; m <= n; m += 32) sts_f64(sinv + 8u * m, m ? 1.0 / (double)m : 0.0);
     __syncwarp();
     for (int b = 0; b < B1; b++) {
         double v = warp_min_nonneg(lds_f64(sd + 8u * ((b << 5) + lane)));
@@ -410,7 +418,8 @@ int tp_sweep_device(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stri
     d0_kernel<<<(n1 + 127) / 128, 128, 0, st>>>(ctx->scores.as<double>(), n, k, ldk, ctx->d0.as<double>(), ldd);
     ctx->launches += 3;
 
-    // shared memory plan
+    // shared memory plan: per candidate the dSS array with its min tree (+ the boundary links when they fit); several
+    // candidates per CTA (one warp each) sharing one reciprocal table while that fits
     const int n1p = round_up(n1, 32), B1p = round_up(n1p / 32, 32), B2p = round_up(B1p / 32, 32);
     const size_t base = (size_t)(n1p + B1p + B2p) * sizeof(double);
     const bool small_links = n <= 65535;
@@ -419,10 +428,15 @@ int tp_sweep_device(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stri
     const size_t limit = (size_t)ctx->max_smem_optin;
     TP_ARG(base <= limit, "tp_sweep: matrix too large for the shared-memory dSS array (n > ~28k bins); split by centromere");
     const bool links_smem = base + link_bytes <= limit;
-    size_t smem = links_smem ? base + link_bytes : base;
-    // the reciprocal table goes to shared memory while at least two candidates still fit per SM
-    const bool inv_smem = smem + inv_bytes <= limit / 2;
-    if (inv_smem) smem += inv_bytes;
+    const size_t cand_smem = round_up((int)(links_smem ? base + link_bytes : base), 16);
+    // the reciprocal table goes to shared memory while at least two candidates still fit beside it
+    const bool inv_smem = 2 * cand_smem + inv_bytes <= limit;
+    int wpc = (int)((limit - (inv_smem ? inv_bytes : 0)) / cand_smem);
+    wpc = wpc < 1 ? 1 : (wpc > 4 ? 4 : wpc);      // one warp per SM sub-partition: 8 slowed each merge chain by 19 %
+    // (not more warps than needed to give every SM-sized group of candidates a CTA: a lone call still wants them spread)
+    while (wpc > 1 && (ncand + wpc - 1) / wpc < 16) wpc--;
+    const size_t smem = (size_t)wpc * cand_smem + (inv_smem ? inv_bytes : 0);
+    const int nblocks = (ncand + wpc - 1) / wpc;
     void *glinks = nullptr;
     if (!links_smem) {
         TP_TRY(ctx->links.reserve((size_t)ncand * link_bytes));
@@ -432,8 +446,8 @@ int tp_sweep_device(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stri
     do {                                                                                                  \
         TP_CUDA(cudaFuncSetAttribute(coniss_sweep_kernel<LT, LS, IS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         tp_prof_begin(ctx, PC_SWEEP);                                                                     \
-        coniss_sweep_kernel<LT, LS, IS><<<ncand, 32, smem, st>>>(ctx->P.as<double>(), ldk, n, ctx->d0.as<double>(), ldd, \
-                                                                 d_cands, ctx->seqdist.as<double>(),       \
+        coniss_sweep_kernel<LT, LS, IS><<<nblocks, 32 * wpc, smem, st>>>(ctx->P.as<double>(), ldk, n, ctx->d0.as<double>(), ldd, \
+                                                                 d_cands, ncand, (unsigned)cand_smem, ctx->seqdist.as<double>(), \
                                                                  ctx->order.as<int4>(), (LT *)glinks);     \
         tp_prof_end(ctx);                                                                                 \
     } while (0)

@@ -277,7 +277,7 @@ int tp_igram(tp_ctx *ctx, const double *X, int n, int ld, double *C, int ldc, co
     int *flag = (int *)(S + 3 * plane);                       // (3 * plane is a multiple of 128)
     TP_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
     const size_t chunks = (size_t)rows_pad * (Kp / 16);
-    tp_prof_begin(ctx, PC_IGEMM);
+    tp_prof_begin(ctx, PC_ISLICE);
     ig_slice_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(X, n, ld, S, rows_pad, Kp, flag);
     tp_prof_end(ctx);
     ctx->launches += 1;
@@ -609,7 +609,7 @@ int tp_iop_prepare(tp_ctx *ctx, const double *S, int n, int ld) {
     TP_TRY(ctx->ioscale.reserve((size_t)(n + 1024) * (sizeof(double) + sizeof(int)) * 2 + 1024 * sizeof(unsigned long long)));
     double *rowscale = ctx->ioscale.as<double>();
     int *rowexp = (int *)(rowscale + 2 * (n + 1024));
-    tp_prof_begin(ctx, PC_IGEMM);
+    tp_prof_begin(ctx, PC_ISLICE);
     io_rowmax_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(S, n, ld, rowexp, rowscale);
     const size_t chunks = (size_t)rows_pad * (Kp / 16);
     io_slice_rows_kernel<IO_MAXNP><<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(S, n, ld, rowexp, ctx->ioA.as<int8_t>(), rows_pad, Kp);
@@ -635,13 +635,14 @@ static int iop_apply_np(tp_ctx *ctx, const double *Yin, int b, int ldy, double *
     double *colscale = rowscale + (n + 1024);
     int *rowexp = (int *)(rowscale + 2 * (n + 1024));
     int *colexp = rowexp + (n + 1024);
-    tp_prof_begin(ctx, PC_IGEMM);
+    tp_prof_begin(ctx, PC_ISLICE);
     unsigned long long *cmax = (unsigned long long *)(colexp + (n + 1024));
     TP_CUDA(cudaMemsetAsync(cmax, 0, (size_t)b * sizeof(unsigned long long), st));
     io_colmax_kernel<<<(n + IO_CM_ROWS - 1) / IO_CM_ROWS, 256, 0, st>>>(Yin, n, b, ldy, cmax);
     io_colscale_kernel<<<(b + 255) / 256, 256, 0, st>>>(cmax, b, colexp, colscale);
     dim3 sg(Kp / 32, rows_padB / 32);
     io_slice_cols_kernel<NP><<<sg, 256, 0, st>>>(Yin, n, b, ldy, colexp, ctx->ioB.as<int8_t>(), rows_padB, Kp);
+    tp_prof_end(ctx);
     CUtensorMap mapA, mapB;
     TP_TRY(io_encode(&mapA, ctx->ioA.p, rows_padA, Kp, NP));        // the first NP of the IO_MAXNP planes
     TP_TRY(io_encode(&mapB, ctx->ioB.p, rows_padB, Kp, NP));
@@ -653,6 +654,7 @@ static int iop_apply_np(tp_ctx *ctx, const double *Yin, int b, int ldy, double *
     TP_CUDA(cudaFuncSetAttribute(io_gemm_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(rows_padB / IO_BN, (row_end - row_begin + IO_BM - 1) / IO_BM);
     if (ctx->prof) ctx->prof_imma_ops += 2.0 * (NP * (NP + 1) / 2) * (double)grid.x * grid.y * IO_BM * IO_BN * (double)Kp;
+    tp_prof_begin(ctx, PC_IGEMM);
     io_gemm_kernel<NP><<<grid, IG_THREADS, smem, st>>>(mapA, mapB, p);
     tp_prof_end(ctx);
     ctx->launches += 4;
@@ -684,10 +686,11 @@ int tp_igram_sliced(tp_ctx *ctx, const double *A, int n, int ld, double *M, int 
     TP_TRY(ctx->ioscale.reserve((size_t)(n + 1024) * (sizeof(double) + sizeof(int)) * 2 + 1024 * sizeof(unsigned long long)));
     double *rowscale = ctx->ioscale.as<double>();
     int *rowexp = (int *)(rowscale + 2 * (n + 1024));
-    tp_prof_begin(ctx, PC_IGEMM);
+    tp_prof_begin(ctx, PC_ISLICE);
     io_rowmax_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(A, n, ld, rowexp, rowscale);
     const size_t chunks = (size_t)rows_pad * (Kp / 16);
     io_slice_rows_kernel<NP><<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(A, n, ld, rowexp, ctx->ioA.as<int8_t>(), rows_pad, Kp);
+    tp_prof_end(ctx);
     ctx->launches += 2;
     if (row_end > row_begin) {
         CUtensorMap map;
@@ -705,10 +708,11 @@ int tp_igram_sliced(tp_ctx *ctx, const double *A, int n, int ld, double *M, int 
             if (p.sym) tiles = 0.5 * tiles + 0.5 * grid.x;          // on and above the diagonal (128 x 64 tiles)
             ctx->prof_imma_ops += 2.0 * (NP * (NP + 1) / 2) * tiles * IO_BM * IO_BN * (double)Kp;
         }
+        tp_prof_begin(ctx, PC_IGEMM);
         io_gemm_kernel<NP><<<grid, IG_THREADS, smem, st>>>(map, map, p);
+        tp_prof_end(ctx);
         ctx->launches += 1;
     }
-    tp_prof_end(ctx);
     TP_CUDA(cudaGetLastError());
     return TP_OK;
 }
