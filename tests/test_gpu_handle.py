@@ -94,3 +94,15 @@ def test_centromere_fix_mode(ctx):
     with pytest.raises(ValueError):
         TADpole(m3, centromere_search=True, bad_frac=0.0, ctx=ctx)
     same_result(TADpole(m3, centromere_search=True, bad_frac=0.0, centromere_fix=True, ctx=ctx), O.tadpole(m3, bad_frac=0.0))
+
+
+def test_tadpole_tune_environment(monkeypatch):
+    """TADPOLE_TUNE applies tp_ctx_set at context creation; unknown keys and malformed items are errors."""
+    from tadpole_b200 import Context
+    monkeypatch.setenv("TADPOLE_TUNE", "pca_block=288,iop_final_min_n=4096")
+    c = Context(0)
+    c.close()
+    for bad in ("no_such_key=1", "pca_block", "pca_block=abc", "=3"):
+        monkeypatch.setenv("TADPOLE_TUNE", bad)
+        with pytest.raises(Exception, match="TADPOLE_TUNE|unknown key"):
+            Context(0)
