@@ -421,6 +421,11 @@ def run_b200(args, rank, world, local_rank):
                     big["dgemm_roofline"] = {"kernel": "dgemm_kernel (FP64 DMMA)", "bound": "tensor", "achieved": a, "peak": fp64_peak,
                                              "unit": "TFLOP/s", "frac": a / fp64_peak,
                                              "peak_source": "cuBLAS DGEMM 4096^3 measured in this run"}
+                try:      # DRAM traffic per launch of the tcgen05 kernels from the ncu --set full capture at this size
+                    with open(os.path.join(ROOT, "profiles", f"r01_traffic_n{nl}.json")) as fh:
+                        big["traffic_bytes_per_launch_ncu"] = {k_: v for k_, v in json.load(fh).items() if not k_.startswith("_")}
+                except OSError:
+                    pass
                 line["large_n_call"] = big
                 del ml
             # input side: the same call starting from the matrix FILE, text parsed on the GPU
