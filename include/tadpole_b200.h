@@ -55,6 +55,7 @@ long long tp_ctx_launches(tp_ctx *ctx);
  * "jacobi_direct_max", "level_cap", "dist_min_n", "igemm_min_n" (smallest nf that takes the tcgen05 int8 Gram path
  * when the counts are integers; 0 = never), "iop_min_n" / "iop_switch" / "iop_final" (sliced int8 operator of the
  * subspace iteration; "iop_final_min_n" = smallest nf whose later rounds stay on the 8-plane sliced operator),
+ * "shard_sym" (0: ranks of a sharded call compute full-width row blocks of the symmetric products),
  * "mgram_min_n" (smallest nf whose M = Xc Xc^T is formed by the sliced int8 Gram; 0 = FP64 DMMA) */
 int tp_ctx_set(tp_ctx *ctx, const char *key, double value);
 /* The environment variable TADPOLE_TUNE="key=value,key=value" applies tp_ctx_set to every context at creation. */
@@ -145,6 +146,15 @@ int tp_test_igram(tp_ctx *ctx, const double *x, int n, double *gram_out, int *us
  * [row_begin, row_end) of a a^T for a general n x n FP64 matrix a; all rows = the symmetric launch (upper tiles mirrored),
  * a proper row block = what one rank of a sharded call computes.  Rows outside the block keep gram_out's values. */
 int tp_test_mgram(tp_ctx *ctx, const double *a, int n, int row_begin, int row_end, double *gram_out);
+/* test hook of the symmetric products of a call spread over `nranks` GPUs, emulated on one: each rank's launch computes
+ * the block pairs that are its share (every pair once), then the local transpose fills the rest; gram_out starts as `fill`.
+ * kind 0: exact Gram of a symmetric integer-count matrix (as tp_test_igram); kind 1: sliced a a^T (as tp_test_mgram).
+ * Must equal the one-GPU result bit for bit. */
+int tp_test_symshard(tp_ctx *ctx, const double *a, int n, int nranks, int kind, double fill, double *gram_out);
+/* host-only: the rule behind it.  Does the owner of row i compute element (i, j) (rows in blocks of rpr per rank)?  Does the
+ * 128 x 64 tile rows [r_lo, r_hi] x columns [c_lo, c_hi] hold any such element (i.e. is it launched)? */
+int tp_test_ss_need(int i, int j, int nranks, int rpr);
+int tp_test_ss_tile(int r_lo, int r_hi, int c_lo, int c_hi, int nranks, int rpr);
 
 /* ---- stages 4+5: the find_params sweep (R/TADpole.R:104-123) --------------------------------------
  * For candidates i = cand_begin + t*cand_stride < k (0-based: candidate i clusters on the first

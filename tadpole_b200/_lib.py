@@ -22,7 +22,7 @@ EXPORTED = [
     "tp_ctx_launches", "tp_ctx_set", "tp_ctx_timings", "tp_ctx_profile", "tp_filter", "tp_compact", "tp_set_filtered",
     "tp_get_filtered", "tp_correlation", "tp_get_correlation", "tp_set_correlation", "tp_pca",
     "tp_get_scores", "tp_set_scores", "tp_sweep", "tp_get_sweep_scores", "tp_get_dendro", "tp_select", "tp_call", "tp_call_arm",
-    "tp_difft_batch", "tp_assemble", "tp_assemble_levels", "tp_test_cholinv", "tp_test_eig", "tp_test_igram", "tp_test_mgram",
+    "tp_difft_batch", "tp_assemble", "tp_assemble_levels", "tp_test_cholinv", "tp_test_eig", "tp_test_igram", "tp_test_mgram", "tp_test_symshard", "tp_test_ss_need", "tp_test_ss_tile",
     "tp_comm_unique_id", "tp_ctx_comm_init", "tp_ctx_comm_select", "tp_ctx_comm_info",
     "tp_ingest_tsv", "tp_ingest_tsv_file", "tp_ingested", "tp_get_ingested", "tp_ingest_stats", "tp_test_parse_field",
     "tp_difft_null", "tp_recall",
@@ -82,6 +82,9 @@ def load():
         "tp_test_eig": (c_int, [vp, dp, c_int, c_double, dp, dp, ip]),
         "tp_test_igram": (c_int, [vp, dp, c_int, dp, ip]),
         "tp_test_mgram": (c_int, [vp, dp, c_int, c_int, c_int, dp]),
+        "tp_test_symshard": (c_int, [vp, dp, c_int, c_int, c_int, c_double, dp]),
+        "tp_test_ss_need": (c_int, [c_int, c_int, c_int, c_int]),
+        "tp_test_ss_tile": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
         "tp_get_scores": (c_int, [vp, dp]),
         "tp_set_scores": (c_int, [vp, dp, c_int, c_int]),
         "tp_sweep": (c_int, [vp, c_int, c_int, c_int, ip, dp, c_int, ip]),
@@ -302,6 +305,15 @@ class Context:
         n = a.shape[0]
         g = np.full((n, n), float(fill))
         check(self.lib.tp_test_mgram(self._h, _dp(a), n, int(row_begin), n if row_end is None else int(row_end), _dp(g)))
+        return g
+
+    def test_symshard(self, a, nranks, kind, fill=-7.0):
+        """a @ a.T as `nranks` ranks of a sharded call compute it (every block pair once + local transpose), emulated on
+        this GPU (test hook).  kind 0: exact integer Gram, kind 1: sliced FP64 Gram."""
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        n = a.shape[0]
+        g = np.zeros((n, n))
+        check(self.lib.tp_test_symshard(self._h, _dp(a), n, int(nranks), int(kind), float(fill), _dp(g)))
         return g
 
     def get_scores(self, nf, k):

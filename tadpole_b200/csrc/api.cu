@@ -149,6 +149,7 @@ extern "C" int tp_ctx_set(tp_ctx *ctx, const char *key, double value) {
     else if (k == "igemm_min_n") ctx->igemm_min_n = (int)value;
     else if (k == "iop_min_n") ctx->iop_min_n = (int)value;
     else if (k == "mgram_min_n") ctx->mgram_min_n = (int)value;
+    else if (k == "shard_sym") ctx->shard_sym = (int)value != 0;
     else if (k == "iop_switch") ctx->iop_switch = value;
     else if (k == "iop_final") ctx->iop_final = ((int)value == 8) ? 8 : 0;
     else if (k == "iop_final_min_n") ctx->iop_final_min_n = (int)value;
@@ -266,7 +267,7 @@ extern "C" int tp_test_eig(tp_ctx *ctx, const double *t, int b, double tol, doub
 }
 
 int tp_igram(tp_ctx *ctx, const double *X, int n, int ld, double *C, int ldc, const double *mean, const double *sd,
-             int raw, int *used_out);
+             int raw, int *used_out, int row_begin, int row_end, SymShard ss);
 
 // Gram matrix X X^T of a symmetric n x n matrix of integer counts through the tcgen05 int8 path (host in / out,
 // row-major); *used_out = 0 when the input is not integer-valued (gram_out untouched)
@@ -280,7 +281,8 @@ extern "C" int tp_test_igram(tp_ctx *ctx, const double *x, int n, double *gram_o
     TP_CUDA(cudaMemcpy2DAsync(ctx->X.p, (size_t)ld * sizeof(double), x, (size_t)n * sizeof(double),
                               (size_t)n * sizeof(double), n, cudaMemcpyHostToDevice, ctx->stream));
     ctx->have_X = ctx->have_C = false;
-    TP_TRY(tp_igram(ctx, ctx->X.as<double>(), n, ld, ctx->C.as<double>(), ld, nullptr, nullptr, 1, used_out));
+    TP_TRY(tp_igram(ctx, ctx->X.as<double>(), n, ld, ctx->C.as<double>(), ld, nullptr, nullptr, 1, used_out, 0, n,
+                    SymShard{1, 1 << 30}));
     if (*used_out)
         TP_CUDA(cudaMemcpy2DAsync(gram_out, (size_t)n * sizeof(double), ctx->C.p, (size_t)ld * sizeof(double),
                                   (size_t)n * sizeof(double), n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -288,7 +290,8 @@ extern "C" int tp_test_igram(tp_ctx *ctx, const double *x, int n, double *gram_o
     return TP_OK;
 }
 
-int tp_igram_sliced(tp_ctx *ctx, const double *A, int n, int ld, double *M, int ldm, int row_begin, int row_end);
+int tp_igram_sliced(tp_ctx *ctx, const double *A, int n, int ld, double *M, int ldm, int row_begin, int row_end,
+                    int sym, SymShard ss);
 
 // A A^T of a general n x n FP64 matrix through the sliced int8 Gram that forms M = Xc Xc^T in tp_pca (host in / out,
 // row-major); rows [row_begin, row_end) of the result are written, the others left as they are in gram_out
@@ -304,8 +307,52 @@ extern "C" int tp_test_mgram(tp_ctx *ctx, const double *a, int n, int row_begin,
     TP_CUDA(cudaMemcpy2DAsync(ctx->M.p, (size_t)ld * sizeof(double), gram_out, (size_t)n * sizeof(double),
                               (size_t)n * sizeof(double), n, cudaMemcpyHostToDevice, ctx->stream));
     ctx->have_C = ctx->have_scores = ctx->have_sweep = false;
-    TP_TRY(tp_igram_sliced(ctx, ctx->C.as<double>(), n, ld, ctx->M.as<double>(), ld, row_begin, row_end));
+    TP_TRY(tp_igram_sliced(ctx, ctx->C.as<double>(), n, ld, ctx->M.as<double>(), ld, row_begin, row_end,
+                           row_begin == 0 && row_end == n, SymShard{1, 1 << 30}));
     TP_CUDA(cudaMemcpy2DAsync(gram_out, (size_t)n * sizeof(double), ctx->M.p, (size_t)ld * sizeof(double),
+                              (size_t)n * sizeof(double), n, cudaMemcpyDeviceToHost, ctx->stream));
+    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return TP_OK;
+}
+
+// host-only views of the SymShard rule the kernels use (no GPU needed): element predicate and tile predicate
+extern "C" int tp_test_ss_need(int i, int j, int nranks, int rpr) { return ss_need(i, j, SymShard{nranks, rpr}) ? 1 : 0; }
+extern "C" int tp_test_ss_tile(int r_lo, int r_hi, int c_lo, int c_hi, int nranks, int rpr) {
+    return ss_tile_needed(r_lo, r_hi, c_lo, c_hi, SymShard{nranks, rpr}) ? 1 : 0;
+}
+
+// The symmetric products as `nranks` ranks of a sharded call would compute them (SymShard, common.cuh), emulated on this one
+// GPU: every emulated rank's launch writes its row block of one matrix pre-filled with `fill` (standing for the stale
+// contents of the other ranks' blocks before the all-gather), then tp_mirror_fill.  kind 0: exact integer Gram of a symmetric
+// count matrix (ig_gram_kernel, raw); kind 1: sliced FP64 Gram a a^T (io_gemm_kernel<8>).  The result must equal the
+// one-GPU launch bit for bit.
+extern "C" int tp_test_symshard(tp_ctx *ctx, const double *a, int n, int nranks, int kind, double fill, double *gram_out) {
+    TP_ARG(ctx && a && n >= 1 && nranks >= 1 && gram_out && (kind == 0 || kind == 1), "tp_test_symshard: bad arguments");
+    TP_CUDA(cudaSetDevice(ctx->device));
+    const int ld = round_up(n, 8);
+    const size_t bytes = (size_t)n * ld * sizeof(double);
+    DevBuf &in = kind == 0 ? ctx->X : ctx->C, &out = kind == 0 ? ctx->C : ctx->M;
+    TP_TRY(in.reserve(bytes)); TP_TRY(out.reserve(bytes));
+    TP_CUDA(cudaMemsetAsync(in.p, 0, bytes, ctx->stream));
+    TP_CUDA(cudaMemcpy2DAsync(in.p, (size_t)ld * sizeof(double), a, (size_t)n * sizeof(double),
+                              (size_t)n * sizeof(double), n, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<double> f((size_t)n * ld, fill);
+    TP_CUDA(cudaMemcpyAsync(out.p, f.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->have_X = ctx->have_C = ctx->have_scores = ctx->have_sweep = false;
+    const SymShard ss{nranks, round_up((n + nranks - 1) / nranks, 64)};
+    for (int r = 0; r < nranks; r++) {
+        const int r0 = std::min(r * ss.rpr, n), r1 = std::min(r0 + ss.rpr, n);
+        if (kind == 0) {
+            int used = 0;
+            TP_TRY(tp_igram(ctx, in.as<double>(), n, ld, out.as<double>(), ld, nullptr, nullptr, 1, &used, r0, r1, ss));
+            TP_ARG(used, "tp_test_symshard: kind 0 needs integer counts below 2^20");
+        } else {
+            TP_TRY(tp_igram_sliced(ctx, in.as<double>(), n, ld, out.as<double>(), ld, r0, r1, 1, ss));
+        }
+    }
+    TP_TRY(tp_mirror_fill(ctx, out.as<double>(), n, ld, ss));
+    TP_CUDA(cudaMemcpy2DAsync(gram_out, (size_t)n * sizeof(double), out.p, (size_t)ld * sizeof(double),
                               (size_t)n * sizeof(double), n, cudaMemcpyDeviceToHost, ctx->stream));
     TP_CUDA(cudaStreamSynchronize(ctx->stream));
     return TP_OK;

@@ -84,6 +84,7 @@ struct tp_ctx {
     int dist_min_n = 4096;
     int igemm_min_n = 1024;
     int iop_min_n = 1024;        // smallest nf whose early subspace-iteration rounds use the sliced int8 operator (0 = never)
+    int shard_sym = 1;           // several ranks: symmetric products computed once per block pair (SymShard); 0 = full-width row blocks
     int mgram_min_n = 1024;      // smallest nf whose M = Xc Xc^T is formed by the sliced int8 Gram (needs the sliced operator; 0 = FP64 DMMA)
     int iop_final_min_n = 1024;  // below this nf the later rounds use the FP64 DMMA operator whatever iop_final says (measured at N = 2000, 8 calls in flight: 224 -> 264 calls/s with the sliced operator)
     int iop_final = 8;           // operator of the later rounds where the sliced one is in use: 8 digit planes, or 0 = FP64 DMMA
@@ -171,6 +172,37 @@ static inline TpRows tp_rows(const tp_ctx *ctx, int n) {
     return t;
 }
 static inline bool tp_row_sharded(const tp_ctx *ctx, int n) { return tp_nranks(ctx) > 1 && n >= ctx->dist_min_n; }
+
+// Symmetric n x n products (Gram matrices) over R row-block owners.  Every off-diagonal pair of blocks (a, c) is computed
+// ONCE, by the owner of the block row that sees the other block within half a ring ((c - a) mod R < R / 2); the two
+// blocks half a ring apart (even R) share theirs along the anti-diagonal of local indices; inside its own diagonal block
+// a rank computes the tiles on and above the diagonal and mirrors them on store.  After the all-gather of the row blocks
+// every rank holds every computed element and fills the rest by a local transpose (tp_mirror_fill): no extra exchange,
+// each rank does 1 / R of the symmetric work, and every element is the same bits whoever computed it.
+// R == 1 is the plain symmetric launch.
+struct SymShard { int R, rpr; };
+// does the owner of row i compute element (i, j)?  (inside a diagonal block: the upper triangle; mirrored on store)
+__host__ __device__ inline bool ss_need(int i, int j, SymShard s) {
+    const int a = i / s.rpr, c = j / s.rpr;
+    int d = c - a; if (d < 0) d += s.R;
+    if (d == 0) return j >= i;
+    if (2 * d < s.R) return true;
+    if (2 * d > s.R) return false;
+    const int li = i - a * s.rpr, lj = j - c * s.rpr;
+    return a < c ? li + lj < s.rpr : li + lj >= s.rpr;
+}
+// any needed element in rows [r_lo, r_hi] x columns [c_lo, c_hi]?  (rows within one row block, columns within one column
+// block: rpr is a multiple of 64 and tiles are 64 columns wide)
+__host__ __device__ inline bool ss_tile_needed(int r_lo, int r_hi, int c_lo, int c_hi, SymShard s) {
+    const int a = r_lo / s.rpr, c = c_lo / s.rpr;
+    int d = c - a; if (d < 0) d += s.R;
+    if (d == 0) return c_hi >= r_lo;
+    if (2 * d < s.R) return true;
+    if (2 * d > s.R) return false;
+    return a < c ? (r_lo - a * s.rpr) + (c_lo - c * s.rpr) < s.rpr : (r_hi - a * s.rpr) + (c_hi - c * s.rpr) >= s.rpr;
+}
+// D[i][j] = D[j][i] wherever the owner of row i did not compute (i, j); every rank, on its gathered copy
+int tp_mirror_fill(tp_ctx *ctx, double *D, int n, int ld, SymShard s);
 int tp_comm_allgather(tp_ctx *ctx, double *buf, size_t chunk);          // in place, chunk doubles per rank
 int tp_comm_allreduce_sum(tp_ctx *ctx, void *buf, size_t count, int is_double);
 int tp_comm_bcast(tp_ctx *ctx, double *buf, size_t count, int root);

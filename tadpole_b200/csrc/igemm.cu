@@ -18,6 +18,7 @@
 #include "gemm.cuh"
 #include <cuda.h>
 #include <stdlib.h>
+#include <algorithm>
 
 #define IG_BM 128
 #define IG_BN 64
@@ -114,6 +115,8 @@ __device__ __forceinline__ unsigned long long ig_desc(unsigned smem_addr) {
 
 struct IgParams {
     int n;                 // valid rows / columns
+    int row_begin, row_end;   // rows of the output this launch computes (a rank's row block; all rows on one GPU)
+    SymShard ss;           // who computes which block pair (common.cuh); R = 1: plain symmetric launch
     int kblocks;           // Kp / 128
     double *C; long ldc;   // output, row-major
     const double *mean, *sd; double nrows;
@@ -122,8 +125,13 @@ struct IgParams {
 
 __global__ void __launch_bounds__(IG_THREADS, 1)
 ig_gram_kernel(const __grid_constant__ CUtensorMap tmap, IgParams p) {
-    const int m0 = blockIdx.y * IG_BM, n0 = blockIdx.x * IG_BN;
-    if (n0 + IG_BN <= m0 || m0 >= p.n || n0 >= p.n) return;          // below the diagonal (mirrored) or padding
+    const int m0 = p.row_begin + blockIdx.y * IG_BM, n0 = blockIdx.x * IG_BN;
+    if (m0 >= p.row_end || n0 >= p.n) return;                        // padding
+    {   // computed by another rank / mirrored from the tile above the diagonal (SymShard, common.cuh)
+        const int r_hi = m0 + IG_BM - 1 < p.row_end - 1 ? m0 + IG_BM - 1 : p.row_end - 1;
+        const int c_hi = n0 + IG_BN - 1 < p.n - 1 ? n0 + IG_BN - 1 : p.n - 1;
+        if (!ss_tile_needed(m0, r_hi, n0, c_hi, p.ss)) return;
+    }
     extern __shared__ unsigned char ig_raw[];
     unsigned char *tiles = (unsigned char *)(((uintptr_t)ig_raw + 1023) & ~(uintptr_t)1023);    // 1024-byte aligned
     __shared__ __align__(8) unsigned long long s_full[IG_STAGES], s_empty[IG_STAGES], s_done;
@@ -204,13 +212,15 @@ ig_gram_kernel(const __grid_constant__ CUtensorMap tmap, IgParams p) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int lg = warp & 3;                           // tensor-memory lane group this warp may read
         const int row = m0 + lg * 32 + lane;
-        const double mi = (row < p.n && !p.raw) ? p.mean[row] : 0.0, si = (row < p.n && !p.raw) ? p.sd[row] : 1.0;
+        const bool rok = row < p.row_end;
+        const int rblk = row / p.ss.rpr;
+        const double mi = (rok && !p.raw) ? p.mean[row] : 0.0, si = (rok && !p.raw) ? p.sd[row] : 1.0;
         for (int c0 = 0; c0 < IG_BN; c0 += 16) {
             unsigned r[5][16];
 #pragma unroll
             for (int s = 0; s < 5; s++) ig_tmem_ld16(tmem + ((unsigned)(lg * 32) << 16) + (unsigned)(s * IG_BN + c0), r[s]);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < p.n) {
+            if (rok) {
 #pragma unroll
                 for (int c = 0; c < 16; c++) {
                     const int col = n0 + c0 + c;
@@ -228,7 +238,8 @@ ig_gram_kernel(const __grid_constant__ CUtensorMap tmap, IgParams p) {
                         v = nan_to_zero(v);
                     }
                     p.C[(size_t)row * p.ldc + col] = v;
-                    if (col != row) p.C[(size_t)col * p.ldc + row] = v;      // mirror (the tile below the diagonal is skipped)
+                    // mirror inside the owner's diagonal block (its tiles below the diagonal are skipped)
+                    if (col != row && col / p.ss.rpr == rblk) p.C[(size_t)col * p.ldc + row] = v;
                 }
             }
         }
@@ -268,7 +279,7 @@ static int ig_encode(CUtensorMap *map, void *base, int rows_pad, int Kp) {
 // C = correlation (or raw Gram when raw != 0) of the n x n symmetric matrix X of integer counts.  *used_out = 0 when
 // the input is not integer (nothing written to C): the caller takes the FP64 DMMA path.
 int tp_igram(tp_ctx *ctx, const double *X, int n, int ld, double *C, int ldc, const double *mean, const double *sd,
-             int raw, int *used_out) {
+             int raw, int *used_out, int row_begin, int row_end, SymShard ss) {
     cudaStream_t st = ctx->stream;
     const int rows_pad = round_up(n, IG_BM), Kp = round_up(n, IG_BK);
     const size_t plane = (size_t)rows_pad * Kp;
@@ -290,17 +301,23 @@ int tp_igram(tp_ctx *ctx, const double *X, int n, int ld, double *C, int ldc, co
     TP_TRY(ig_encode(&map, S, rows_pad, Kp));
     IgParams p;
     p.n = n; p.kblocks = Kp / IG_BK; p.C = C; p.ldc = ldc; p.mean = mean; p.sd = sd; p.nrows = (double)n; p.raw = raw;
+    p.row_begin = row_begin; p.row_end = row_end; p.ss = ss;
     const size_t smem = (size_t)IG_STAGES * IG_STAGE_BYTES + 1024;
     TP_CUDA(cudaFuncSetAttribute(ig_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(rows_pad / IG_BN, rows_pad / IG_BM);
-    tp_prof_begin(ctx, PC_IGEMM);
-    if (ctx->prof) {       // executed: 9 digit products on the tiles of the upper triangle
-        const double tiles = 0.5 * ((double)rows_pad / IG_BM) * ((double)rows_pad / IG_BN);
-        ctx->prof_imma_ops += 2.0 * 9.0 * tiles * IG_BM * IG_BN * (double)Kp;
+    if (row_end > row_begin) {
+        dim3 grid(rows_pad / IG_BN, (row_end - row_begin + IG_BM - 1) / IG_BM);
+        tp_prof_begin(ctx, PC_IGEMM);
+        if (ctx->prof) {       // executed: 9 digit products on the tiles this launch computes
+            double tiles = 0.0;
+            for (int m0 = row_begin; m0 < row_end; m0 += IG_BM)
+                for (int n0 = 0; n0 < n; n0 += IG_BN)
+                    tiles += ss_tile_needed(m0, std::min(m0 + IG_BM, row_end) - 1, n0, std::min(n0 + IG_BN, n) - 1, ss);
+            ctx->prof_imma_ops += 2.0 * 9.0 * tiles * IG_BM * IG_BN * (double)Kp;
+        }
+        ig_gram_kernel<<<grid, IG_THREADS, smem, st>>>(map, p);
+        tp_prof_end(ctx);
+        ctx->launches += 1;
     }
-    ig_gram_kernel<<<grid, IG_THREADS, smem, st>>>(map, p);
-    tp_prof_end(ctx);
-    ctx->launches += 1;
     TP_CUDA(cudaGetLastError());
     *used_out = 1;
     return TP_OK;
@@ -457,8 +474,9 @@ struct IoParams {
     double alpha, beta, gamma;
     const double *rowscale, *colscale;       // 2^(e_i - 6), 2^(f_j - 6)
     int banded;            // 1: tile order in bands of 8 tile rows (see the kernel)
-    int sym;               // 1: symmetric product (B = A, square output): tiles below the diagonal are skipped and every
-                           // element is stored twice, as in ig_gram_kernel
+    int sym;               // 1: symmetric product (B = A, square output): only the tiles SymShard gives this row block are
+                           // computed, elements of the owner's diagonal block are stored twice, as in ig_gram_kernel
+    SymShard ss;
 };
 
 template <int NP>
@@ -475,7 +493,12 @@ io_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         by = band * 8u + in % h; bx = in / h;
     }
     const int m0 = p.row_begin + (int)by * IO_BM, n0 = (int)bx * IO_BN;
-    if (n0 >= p.b || (p.sym && n0 + IO_BN <= m0)) return;           // padding, or mirrored from the tile above the diagonal
+    if (n0 >= p.b || m0 >= p.row_end) return;                        // padding
+    if (p.sym) {    // computed by another rank / mirrored from the tile above the diagonal (SymShard, common.cuh)
+        const int r_hi = m0 + IO_BM - 1 < p.row_end - 1 ? m0 + IO_BM - 1 : p.row_end - 1;
+        const int c_hi = n0 + IO_BN - 1 < p.b - 1 ? n0 + IO_BN - 1 : p.b - 1;
+        if (!ss_tile_needed(m0, r_hi, n0, c_hi, p.ss)) return;
+    }
     extern __shared__ unsigned char ig_raw[];
     unsigned char *tiles = (unsigned char *)(((uintptr_t)ig_raw + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) unsigned long long s_full[IO_STAGES], s_empty[IO_STAGES], s_done;
@@ -568,7 +591,7 @@ io_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                     p.D[(size_t)row * p.ldd + col] = v;
                     // the digit sums are symmetric in (row, col) and the scales are powers of two: the mirrored
                     // element is the same bits
-                    if (p.sym && col != row) p.D[(size_t)col * p.ldd + row] = v;
+                    if (p.sym && col != row && col / p.ss.rpr == row / p.ss.rpr) p.D[(size_t)col * p.ldd + row] = v;
                 }
             }
         }
@@ -649,7 +672,7 @@ static int iop_apply_np(tp_ctx *ctx, const double *Yin, int b, int ldy, double *
     IoParams p;
     p.n = n; p.b = b; p.row_begin = row_begin; p.row_end = row_end; p.kblocks = Kp / IO_BK;
     p.D = D; p.ldd = ldd; p.E1 = E1; p.lde1 = lde1; p.E2 = E2; p.lde2 = lde2;
-    p.alpha = alpha; p.beta = beta; p.gamma = gamma; p.rowscale = rowscale; p.colscale = colscale; p.sym = 0; p.banded = 0;
+    p.alpha = alpha; p.beta = beta; p.gamma = gamma; p.rowscale = rowscale; p.colscale = colscale; p.sym = 0; p.banded = 0; p.ss = SymShard{1, 1 << 30};
     const size_t smem = (size_t)IoCfg<NP>::STAGES * IoCfg<NP>::STAGE_BYTES + 1024;
     TP_CUDA(cudaFuncSetAttribute(io_gemm_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(rows_padB / IO_BN, (row_end - row_begin + IO_BM - 1) / IO_BM);
@@ -677,7 +700,8 @@ int tp_iop_apply(tp_ctx *ctx, const double *Yin, int b, int ldy, double *D, int 
 // -- the FP64 DMMA Gram carries ~sqrt(n) ulp).  Used for M = Xc Xc^T of stage 3 (pca.cu).  With all rows requested only
 // the tiles on and above the diagonal are computed (36 digit products x n^3 / 2 MACs) and mirrored; a row block (rank
 // of a sharded call) computes its full width.  The planes share ctx->ioA with tp_iop_prepare, which runs after this.
-int tp_igram_sliced(tp_ctx *ctx, const double *A, int n, int ld, double *M, int ldm, int row_begin, int row_end) {
+int tp_igram_sliced(tp_ctx *ctx, const double *A, int n, int ld, double *M, int ldm, int row_begin, int row_end,
+                    int sym, SymShard ss) {
     constexpr int NP = IO_MAXNP;
     cudaStream_t st = ctx->stream;
     const int rows_pad = round_up(n, IO_BM), Kp = round_up(n, 128);
@@ -699,13 +723,15 @@ int tp_igram_sliced(tp_ctx *ctx, const double *A, int n, int ld, double *M, int 
         p.n = n; p.b = n; p.row_begin = row_begin; p.row_end = row_end; p.kblocks = Kp / IO_BK;
         p.D = M; p.ldd = ldm; p.E1 = nullptr; p.lde1 = 0; p.E2 = nullptr; p.lde2 = 0;
         p.alpha = 1.0; p.beta = 0.0; p.gamma = 0.0; p.rowscale = rowscale; p.colscale = rowscale;
-        p.sym = (row_begin == 0 && row_end == n) ? 1 : 0; p.banded = 1;
+        p.sym = sym; p.banded = 1; p.ss = ss;
         const size_t smem = (size_t)IoCfg<NP>::STAGES * IoCfg<NP>::STAGE_BYTES + 1024;
         TP_CUDA(cudaFuncSetAttribute(io_gemm_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(rows_pad / IO_BN, (row_end - row_begin + IO_BM - 1) / IO_BM);
         if (ctx->prof) {
-            double tiles = (double)grid.x * grid.y;
-            if (p.sym) tiles = 0.5 * tiles + 0.5 * grid.x;          // on and above the diagonal (128 x 64 tiles)
+            double tiles = 0.0;
+            for (int m0 = row_begin; m0 < row_end; m0 += IO_BM)
+                for (int n0 = 0; n0 < n; n0 += IO_BN)
+                    tiles += !sym || ss_tile_needed(m0, std::min(m0 + IO_BM, row_end) - 1, n0, std::min(n0 + IO_BN, n) - 1, ss);
             ctx->prof_imma_ops += 2.0 * (NP * (NP + 1) / 2) * tiles * IO_BM * IO_BN * (double)Kp;
         }
         tp_prof_begin(ctx, PC_IGEMM);
@@ -713,6 +739,39 @@ int tp_igram_sliced(tp_ctx *ctx, const double *A, int n, int ld, double *M, int 
         tp_prof_end(ctx);
         ctx->launches += 1;
     }
+    TP_CUDA(cudaGetLastError());
+    return TP_OK;
+}
+
+// ---- SymShard: fill the elements their row owner did not compute from the transposed ones (after the all-gather) -----------
+__global__ void __launch_bounds__(256)
+mirror_fill_kernel(double *__restrict__ D, int n, int ld, SymShard s) {
+    __shared__ double t[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    // 32 x 32 tiles lie within one block pair (rpr is a multiple of 64): nothing to do inside diagonal blocks, and a tile
+    // none of whose elements needs filling is skipped before the load
+    if (i0 / s.rpr == j0 / s.rpr) return;
+    const int i1 = i0 + 31 < n - 1 ? i0 + 31 : n - 1, j1 = j0 + 31 < n - 1 ? j0 + 31 : n - 1;
+    if (ss_need(i0, j0, s) && ss_need(i0, j1, s) && ss_need(i1, j0, s) && ss_need(i1, j1, s)) return;   // (half-planes: corners decide)
+    for (int r = ty; r < 32; r += 8) {          // t[r][c] = D[j0 + r][i0 + c]
+        const int j = j0 + r, i = i0 + tx;
+        t[r][tx] = (j < n && i < n) ? D[(size_t)j * ld + i] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r, j = j0 + tx;
+        if (i < n && j < n && !ss_need(i, j, s)) D[(size_t)i * ld + j] = t[tx][r];
+    }
+}
+
+int tp_mirror_fill(tp_ctx *ctx, double *D, int n, int ld, SymShard s) {
+    if (s.R <= 1) return TP_OK;
+    dim3 grid((n + 31) / 32, (n + 31) / 32);
+    tp_prof_begin(ctx, PC_ISLICE);
+    mirror_fill_kernel<<<grid, 256, 0, ctx->stream>>>(D, n, ld, s);
+    tp_prof_end(ctx);
+    ctx->launches += 1;
     TP_CUDA(cudaGetLastError());
     return TP_OK;
 }

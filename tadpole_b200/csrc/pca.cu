@@ -21,10 +21,11 @@
 int tp_jacobi(tp_ctx *ctx, double *A, int b, int ld, double *w, double *Vs, int lds, int ncols_out, int *sweeps_out,
               double tol);
 int tp_igram(tp_ctx *ctx, const double *X, int n, int ld, double *C, int ldc, const double *mean, const double *sd,
-             int raw, int *used_out);
+             int raw, int *used_out, int row_begin, int row_end, SymShard ss);
 int tp_chol_inv(tp_ctx *ctx, double *G, double *Linv, int b, int ld, int *bad_out);
 int tp_iop_prepare(tp_ctx *ctx, const double *S, int n, int ld);
-int tp_igram_sliced(tp_ctx *ctx, const double *A, int n, int ld, double *M, int ldm, int row_begin, int row_end);
+int tp_igram_sliced(tp_ctx *ctx, const double *A, int n, int ld, double *M, int ldm, int row_begin, int row_end,
+                    int sym, SymShard ss);
 int tp_iop_apply(tp_ctx *ctx, const double *Yin, int b, int ldy, double *D, int ldd, double alpha, const double *E1,
                  int lde1, double beta, const double *E2, int lde2, double gamma, int row_begin, int row_end, int np);
 
@@ -190,10 +191,23 @@ int tp_correlation(tp_ctx *ctx) {
     g.M = n; g.N = n; g.K = n;
     g.sym = 1; g.epi = EPI_CORR; g.mean = mean; g.sd = sd; g.nrows = (double)n;
     int igemm_used = 0;
-    if (ctx->igemm_min_n > 0 && n >= ctx->igemm_min_n)
-        // integer counts: exact Gram on the tcgen05 int8 path with the same epilogue (igemm.cu).  Several times
-        // faster than a row block of the FP64 path, so with more than one rank it simply runs replicated.
-        TP_TRY(tp_igram(ctx, ctx->X.as<double>(), n, ld, ctx->C.as<double>(), ld, mean, sd, 0, &igemm_used));
+    if (ctx->igemm_min_n > 0 && n >= ctx->igemm_min_n) {
+        // integer counts: exact Gram on the tcgen05 int8 path with the same epilogue (igemm.cu).  With several ranks
+        // every block pair is computed once (SymShard, common.cuh), the row blocks are all-gathered and the rest is a
+        // local transpose; the elements are the same bits as those of the one-GPU launch.
+        const bool ssym = shard && ctx->shard_sym;
+        if (ssym) {
+            const SymShard ss{tp_nranks(ctx), rw.rpr};
+            TP_TRY(tp_igram(ctx, ctx->X.as<double>(), n, ld, ctx->C.as<double>(), ld, mean, sd, 0, &igemm_used, rw.r0, rw.r1, ss));
+            if (igemm_used) {
+                TP_TRY(tp_comm_allgather(ctx, ctx->C.as<double>(), (size_t)rw.rpr * ld));
+                TP_TRY(tp_mirror_fill(ctx, ctx->C.as<double>(), n, ld, ss));
+            }
+        } else {
+            TP_TRY(tp_igram(ctx, ctx->X.as<double>(), n, ld, ctx->C.as<double>(), ld, mean, sd, 0, &igemm_used, 0, n,
+                            SymShard{1, 1 << 30}));
+        }
+    }
     if (igemm_used) {
     } else if (shard) {
         // row block [r0, r1) of the correlation matrix on this rank, then NCCL all-gather of the row blocks.  Every
@@ -306,9 +320,13 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
         g.D = M; g.ldd = ld; g.M = n; g.N = n; g.K = n; g.sym = 1;
         if (use_iop && ctx->mgram_min_n > 0 && n >= ctx->mgram_min_n) {
             // sliced int8 Gram on the tcgen05 tensor cores (8 digit planes of Xc, FP64 level); row blocks when sharded
+            // (several ranks: every block pair once, all-gather, local transpose -- SymShard in common.cuh)
             const int r0 = shard ? rw.r0 : 0, r1 = shard ? rw.r1 : n;
-            TP_TRY(tp_igram_sliced(ctx, C, n, ld, M, ld, r0, r1));
+            const bool ssym = shard && ctx->shard_sym;
+            const SymShard ss = ssym ? SymShard{tp_nranks(ctx), rw.rpr} : SymShard{1, 1 << 30};
+            TP_TRY(tp_igram_sliced(ctx, C, n, ld, M, ld, r0, r1, shard ? (ssym ? 1 : 0) : 1, ss));
             if (shard) TP_TRY(tp_comm_allgather(ctx, M, (size_t)rw.rpr * ld));
+            if (ssym) TP_TRY(tp_mirror_fill(ctx, M, n, ld, ss));
         } else if (shard) {      // row blocks of M = Xc Xc^T by their owner, all-gathered
             g.A += (size_t)rw.r0 * ld; g.D += (size_t)rw.r0 * ld; g.M = rw.r1 - rw.r0; g.sym = 0;
             if (g.M > 0) TP_TRY(tp_gemm(ctx, g));

@@ -106,3 +106,20 @@ def test_pca_scores_same_with_sliced_and_fp64_gram(ctx):
     a, b = out["fp64"], out["sliced"]
     sgn = np.sign((a * b).sum(axis=0)); sgn[sgn == 0] = 1
     assert np.abs(a - b * sgn).max() <= 1e-9 * np.abs(a).max()
+
+
+# ---- symmetric products of a call spread over several GPUs (SymShard), emulated rank by rank on one GPU ---------------
+@pytest.mark.parametrize("n,nranks", [(300, 2), (513, 3), (700, 4), (1000, 8), (1403, 5), (129, 2)])
+def test_symshard_integer_gram_equals_one_gpu(ctx, n, nranks):
+    a = _sym_counts(n, 30, seed=n + nranks)
+    ref = a @ a.T
+    g = ctx.test_symshard(a.astype(np.float64), nranks, kind=0)
+    assert np.array_equal(g.astype(np.int64), ref)          # nothing left at `fill`, every element exact
+
+
+@pytest.mark.parametrize("n,nranks", [(300, 2), (700, 4), (1000, 8), (1403, 3)])
+def test_symshard_sliced_gram_equals_one_gpu(ctx, n, nranks):
+    a = _centred_corr_like(n, seed=n)
+    one = ctx.test_mgram(a)
+    g = ctx.test_symshard(a, nranks, kind=1)
+    assert np.array_equal(g, one)                            # same bits whoever computed the block pair

@@ -161,3 +161,36 @@ def test_assemble_levels_matches_per_level_calls():
         for k in levels:
             ref, _ = _lib.assemble(seq, int(k), names, b)
             assert np.array_equal(got[int(k)], ref), (k, None if b is None else len(b))
+
+
+@pytest.mark.parametrize("n,nranks", [(300, 2), (500, 4), (700, 8), (513, 3), (640, 5), (129, 2), (260, 4)])
+def test_symshard_rule_computes_every_block_pair_once(n, nranks):
+    """The rule by which the ranks of a sharded call divide a symmetric product (csrc/common.cuh SymShard), through the
+    host-only hooks: replaying the tile launches of every rank, each element is written by its row owner or is the mirror
+    of an element written by ITS row owner; inside a diagonal block the upper triangle is computed and mirrored on store."""
+    from tadpole_b200 import _lib
+    lib = _lib.load()
+    rpr = -(-(-(-n // nranks)) // 64) * 64
+    who = np.full((n, n), -1)
+    tiles = np.zeros(nranks, dtype=int)
+    for rank in range(nranks):
+        r0 = min(rank * rpr, n); r1 = min(r0 + rpr, n)
+        for m0 in range(r0, r1, 128):
+            r_hi = min(m0 + 127, r1 - 1)
+            for n0 in range(0, n, 64):
+                c_hi = min(n0 + 63, n - 1)
+                if not lib.tp_test_ss_tile(m0, r_hi, n0, c_hi, nranks, rpr):
+                    continue
+                tiles[rank] += 1
+                who[m0:r_hi + 1, n0:c_hi + 1] = rank
+                if n0 // rpr == rank:                     # mirror on store inside the owner's diagonal block
+                    who[n0:c_hi + 1, m0:r_hi + 1] = np.where(who[n0:c_hi + 1, m0:r_hi + 1] < 0, rank, who[n0:c_hi + 1, m0:r_hi + 1])
+    own = np.arange(n) // rpr
+    need = np.array([[lib.tp_test_ss_need(i, j, nranks, rpr) for j in range(n)] for i in range(n)], dtype=bool)
+    diag = own[:, None] == own[None, :]
+    assert (who[diag] == np.broadcast_to(own[:, None], (n, n))[diag]).all()
+    off = ~diag
+    assert (need ^ need.T)[off].all()                                   # exactly one of (i, j), (j, i) is computed
+    assert (who[off & need] == np.broadcast_to(own[:, None], (n, n))[off & need]).all()
+    if n >= 128 * nranks:                                               # and the work is balanced
+        assert tiles.max() <= 1.6 * max(tiles.min(), 1) + 2
