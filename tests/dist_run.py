@@ -65,11 +65,11 @@ if cen:
     out["merged_tads"] = int(tp.merging_arms.shape[0])
 else:
     out["n_pcs"] = tp.n_pcs; out["optimal_n_clusters"] = tp.optimal_n_clusters
+# every rank must hold the same object
+summ = (tp.merging_arms.tobytes() if cen else (tp.n_pcs, tp.optimal_n_clusters, tp.scores.tobytes(), tp.dendro.seqdist.tobytes()))
+every = env.exchange(summ)
+out["all_ranks_identical"] = all(e == every[0] for e in every)
 if mode == "check":
-    # every rank must hold the same object
-    summ = (tp.merging_arms.tobytes() if cen else (tp.n_pcs, tp.optimal_n_clusters, tp.scores.tobytes(), tp.dendro.seqdist.tobytes()))
-    every = env.exchange(summ)
-    out["all_ranks_identical"] = all(e == every[0] for e in every)
     if rank == 0:
         ctx.comm_select(-1)
         ref = TADpole(m, centromere_search=cen, ctx=ctx)
