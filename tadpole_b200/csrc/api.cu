@@ -754,35 +754,24 @@ extern "C" int tp_assemble_levels(const double *seqdist, int nf, const int *leve
     } else {
         std::iota(src.begin(), src.end(), 0);
     }
-    std::vector<int> good(nf), fixed(total), vals, lens;
+    // Labels are non-decreasing along the good bins, so in the merged order a cluster's bins are interleaved only with
+    // zeros: fix_values (R/TADpole.R:503-510) absorbs the zero runs INSIDE a cluster (flanked by the same label) and leaves
+    // those between two clusters and at the ends, which the rle loop then drops.  A level's table is therefore one row
+    // per cluster, from the merged position of its first good bin to that of its last -- one pass over the boundaries
+    // instead of materialising the label vector, its run-length encoding and the fixed vector per level.
+    std::vector<int> pos(nf);
+    for (int p = 0; p < total; p++) if (src[p] >= 0) pos[src[p]] = p;
     int rows = 0;
     offsets_out[0] = 0;
     for (int l = 0; l < nlev; l++) {
         const int kc = levels[l];
         TP_ARG(kc >= 1 && kc <= nf, "tp_assemble_levels: level out of range");
-        int lab = 1;
+        int g0 = 0;
         for (int i = 0; i < nf; i++) {
-            good[i] = lab;
-            if (i < n1 && rank[i] < kc - 1) lab++;
-        }
-        for (int p = 0; p < total; p++) fixed[p] = src[p] >= 0 ? good[src[p]] : 0;
-        if (nbad >= 0) {      // fix_values on the run values, left to right (R/TADpole.R:503-510)
-            vals.clear(); lens.clear();
-            for (int p = 0; p < total; p++) {
-                if (p == 0 || fixed[p] != fixed[p - 1]) { vals.push_back(fixed[p]); lens.push_back(1); }
-                else lens.back()++;
+            if (i == n1 || rank[i] < kc - 1) {            // a cut after good bin i (or the last bin)
+                start_out[rows] = pos[g0] + 1; end_out[rows] = pos[i] + 1; rows++;
+                g0 = i + 1;
             }
-            for (size_t r = 1; r + 1 < vals.size(); r++)
-                if (vals[r] == 0 && vals[r - 1] == vals[r + 1]) vals[r] = vals[r - 1];
-            int p = 0;
-            for (size_t r = 0; r < vals.size(); r++) for (int t = 0; t < lens[r]; t++) fixed[p++] = vals[r];
-        }
-        int p = 0;
-        while (p < total) {
-            int q = p;
-            while (q + 1 < total && fixed[q + 1] == fixed[p]) q++;
-            if (fixed[p] != 0 || nbad < 0) { start_out[rows] = p + 1; end_out[rows] = q + 1; rows++; }
-            p = q + 1;
         }
         offsets_out[l + 1] = rows;
     }

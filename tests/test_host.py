@@ -194,3 +194,30 @@ def test_symshard_rule_computes_every_block_pair_once(n, nranks):
     assert (who[off & need] == np.broadcast_to(own[:, None], (n, n))[off & need]).all()
     if n >= 128 * nranks:                                               # and the work is balanced
         assert tiles.max() <= 1.6 * max(tiles.min(), 1) + 2
+
+
+def test_assemble_levels_random_against_per_level_reference():
+    """tp_assemble_levels builds every level's table from cluster intervals; tp_assemble materialises labels, applies
+    fix_values and run-length encodes (the reference's own order of steps, R/TADpole.R:470-497,503-510).  They must agree
+    on every level for arbitrary bad-bin patterns, including bad names that duplicate good ones (q-arm quirk Q3), bad bins
+    at both ends and adjacent bad runs."""
+    from tadpole_b200 import _lib
+    rng = np.random.default_rng(2024)
+    for trial in range(150):
+        nf = int(rng.integers(2, 50))
+        seq = rng.random(nf - 1)
+        if nf > 4 and trial % 3 == 0:
+            seq[1] = seq[2]                                   # a tie
+        total = nf + int(rng.integers(0, 25))
+        allbins = np.arange(1, total + 1)
+        nb = total - nf
+        bad = np.sort(rng.choice(allbins, nb, replace=False)).astype(np.int32)
+        names = np.setdiff1d(allbins, bad).astype(np.int32)
+        if trial % 5 == 0 and nb:                             # quirk Q3: bad names that were never removed from the arm
+            bad = np.sort(np.concatenate([bad, rng.choice(names, min(3, nf), replace=False)])).astype(np.int32)
+        levels = np.arange(1, nf + 1, dtype=np.int32)
+        for b in (bad, None):
+            got = _lib.assemble_levels(seq, levels, names, b)
+            for k in levels:
+                ref, _ = _lib.assemble(seq, int(k), names, b)
+                assert np.array_equal(got[int(k)], ref), (trial, nf, k, None if b is None else b.tolist())
