@@ -59,6 +59,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bins", type=int, default=N_BINS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync-blocking", default="auto", choices=["auto", "0", "1"],
+                    help="host threads sleep on a blocking-sync event while they wait for the GPU instead of spinning in "
+                         "cudaStreamSynchronize; auto = when ranks x calls in flight exceed half of the host's logical CPUs")
     ap.add_argument("--large-n", type=int, default=8000,
                     help="bins of one extra profiled call whose tensor-kernel rooflines are reported beside the workload's "
                          "(N = 1 only; 0 = skip)")
@@ -206,6 +209,13 @@ def run_b200(args, rank, world, local_rank):
     S = max(1, args.streams)
     pool = ContextPool(local_rank, S)
     ctx = pool.contexts[0]
+    # one host thread per call in flight waits for its stream most of the time; spinning waits (the CUDA default) need a
+    # core each, so with several ranks on one host the threads would outnumber the cores
+    ncpu = os.cpu_count() or 1
+    sync_blocking = (world * S > ncpu // 2) if args.sync_blocking == "auto" else args.sync_blocking == "1"
+    if sync_blocking:
+        for c in pool.contexts:
+            c.set("sync_blocking", 1)
     n = args.bins
 
     # synthetic inputs: POOL different matrices per rank; pinned host copies for e2e, device copies for value
@@ -370,6 +380,8 @@ def run_b200(args, rank, world, local_rank):
                        "l2": f"pool of {POOL} different {n}x{n} f64 matrices per rank ({POOL * n * n * 8 >> 20} MiB > L2) "
                              "cycled, no step re-reads a warm input",
                        "calls_in_flight_per_gpu": S,
+                       "host_wait": ("blocking-sync event (threads sleep)" if sync_blocking else "cudaStreamSynchronize (spin)")
+                                    + f", {ncpu} logical CPUs for {world * S} waiting threads",
                        "parallelism": f"{world} GPU(s) x {S} independent calls in flight (own context, stream and host thread "
                                       "each), no collective on the data path"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(n), "d2h_bytes_per_step": d2h,

@@ -55,6 +55,8 @@ long long tp_ctx_launches(tp_ctx *ctx);
  * "jacobi_direct_max", "level_cap", "dist_min_n", "igemm_min_n" (smallest nf that takes the tcgen05 int8 Gram path
  * when the counts are integers; 0 = never), "iop_min_n" / "iop_switch" / "iop_final" (sliced int8 operator of the
  * subspace iteration; "iop_final_min_n" = smallest nf whose later rounds stay on the 8-plane sliced operator),
+ * "sync_blocking" (1: the host thread sleeps on a blocking-sync event while it waits for the GPU instead of spinning
+ * in cudaStreamSynchronize; for hosts that run more calls in flight than they have cores),
  * "shard_sym" (0: ranks of a sharded call compute full-width row blocks of the symmetric products),
  * "mgram_min_n" (smallest nf whose M = Xc Xc^T is formed by the sliced int8 Gram; 0 = FP64 DMMA) */
 int tp_ctx_set(tp_ctx *ctx, const char *key, double value);

@@ -42,13 +42,20 @@ int tp_flags_enqueue(tp_ctx *ctx) {
 }
 int tp_flags_read(tp_ctx *ctx, int out[4]) {
     TP_TRY(tp_flags_enqueue(ctx));
-    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    TP_CUDA(tp_stream_sync(ctx));
     for (int i = 0; i < 4; i++) out[i] = ctx->pin_flags[i];
     return TP_OK;
 }
 
 extern "C" int tp_ctx_set(tp_ctx *ctx, const char *key, double value);
 extern "C" int tp_ctx_destroy(tp_ctx *ctx);
+
+cudaError_t tp_stream_sync(tp_ctx *ctx) {
+    if (!ctx->sync_blocking || !ctx->sync_ev) return cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaEventRecord(ctx->sync_ev, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ctx->sync_ev);
+}
 
 extern "C" int tp_ctx_create(int device, tp_ctx **out) {
     TP_ARG(out, "tp_ctx_create: null output pointer");
@@ -74,6 +81,7 @@ extern "C" int tp_ctx_create(int device, tp_ctx **out) {
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     TP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (int i = 0; i < EV_COUNT; i++) TP_CUDA(cudaEventCreate(&ctx->ev[i]));
+    TP_CUDA(cudaEventCreateWithFlags(&ctx->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
     TP_TRY(tp_pin_reserve(ctx, 1 << 16));
     TP_TRY(tp_flags_reset(ctx));
     // TADPOLE_TUNE="key=value,key=value": tp_ctx_set applied to every new context (for hosts that do not expose the
@@ -105,7 +113,7 @@ extern "C" int tp_ctx_create(int device, tp_ctx **out) {
 extern "C" int tp_ctx_destroy(tp_ctx *ctx) {
     if (!ctx) return TP_OK;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    tp_stream_sync(ctx);
     DevBuf *bufs[] = {&ctx->raw_own, &ctx->rowmean, &ctx->ranks, &ctx->flags, &ctx->qtmp, &ctx->keep, &ctx->X, &ctx->C,
                       &ctx->colstat, &ctx->scores, &ctx->M, &ctx->Y0, &ctx->Y1, &ctx->Y2, &ctx->W, &ctx->G, &ctx->T,
                       &ctx->Q, &ctx->Jw, &ctx->Jv, &ctx->Jt, &ctx->small1, &ctx->small2, &ctx->part, &ctx->resid,
@@ -116,6 +124,7 @@ extern "C" int tp_ctx_destroy(tp_ctx *ctx) {
     tp_comm_destroy_all(ctx);
     for (int i = 0; i < EV_COUNT; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+    if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
     for (int b = 0; b < 2; b++) {
         if (ctx->ipin[b]) cudaFreeHost(ctx->ipin[b]);
         if (ctx->ipin_ev[b]) cudaEventDestroy(ctx->ipin_ev[b]);
@@ -129,7 +138,7 @@ extern "C" int tp_ctx_destroy(tp_ctx *ctx) {
 
 extern "C" int tp_ctx_sync(tp_ctx *ctx) {
     TP_ARG(ctx, "tp_ctx_sync: null context");
-    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    TP_CUDA(tp_stream_sync(ctx));
     return TP_OK;
 }
 
@@ -150,6 +159,7 @@ extern "C" int tp_ctx_set(tp_ctx *ctx, const char *key, double value) {
     else if (k == "iop_min_n") ctx->iop_min_n = (int)value;
     else if (k == "mgram_min_n") ctx->mgram_min_n = (int)value;
     else if (k == "shard_sym") ctx->shard_sym = (int)value != 0;
+    else if (k == "sync_blocking") ctx->sync_blocking = (int)value != 0;
     else if (k == "iop_switch") ctx->iop_switch = value;
     else if (k == "iop_final") ctx->iop_final = ((int)value == 8) ? 8 : 0;
     else if (k == "iop_final_min_n") ctx->iop_final_min_n = (int)value;
@@ -166,7 +176,7 @@ static double ev_ms(tp_ctx *ctx, int a, int b) {
 
 extern "C" int tp_ctx_timings(tp_ctx *ctx, double *out10) {
     TP_ARG(ctx && out10, "tp_ctx_timings: null argument");
-    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    TP_CUDA(tp_stream_sync(ctx));
     out10[0] = ev_ms(ctx, EV_FILTER0, EV_FILTER1);
     out10[1] = ev_ms(ctx, EV_COMPACT0, EV_COMPACT1);
     out10[2] = ev_ms(ctx, EV_CORR0, EV_CORR1);
@@ -195,7 +205,7 @@ void tp_prof_end(tp_ctx *ctx) {
 
 extern "C" int tp_ctx_profile(tp_ctx *ctx, int enable, double *ms_out16, long long *count_out16) {
     TP_ARG(ctx, "tp_ctx_profile: null context");
-    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    TP_CUDA(tp_stream_sync(ctx));
     if (ms_out16 || count_out16) {
         double ms[PC_COUNT] = {};
         long long cnt[PC_COUNT] = {};
@@ -241,7 +251,7 @@ extern "C" int tp_test_cholinv(tp_ctx *ctx, const double *g, int b, int factor_o
     if (linv_out && !factor_only)
         TP_CUDA(cudaMemcpy2DAsync(linv_out, (size_t)b * sizeof(double), ctx->small1.p, (size_t)ld * sizeof(double),
                                   (size_t)b * sizeof(double), b, cudaMemcpyDeviceToHost, ctx->stream));
-    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    TP_CUDA(tp_stream_sync(ctx));
     return TP_OK;
 }
 
@@ -262,7 +272,7 @@ extern "C" int tp_test_eig(tp_ctx *ctx, const double *t, int b, double tol, doub
     TP_CUDA(cudaMemcpyAsync(w_out, ctx->Jw.p, (size_t)b * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     TP_CUDA(cudaMemcpy2DAsync(v_out, (size_t)b * sizeof(double), ctx->Jv.p, (size_t)ld * sizeof(double),
                               (size_t)b * sizeof(double), b, cudaMemcpyDeviceToHost, ctx->stream));
-    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    TP_CUDA(tp_stream_sync(ctx));
     return TP_OK;
 }
 
@@ -286,7 +296,7 @@ extern "C" int tp_test_igram(tp_ctx *ctx, const double *x, int n, double *gram_o
     if (*used_out)
         TP_CUDA(cudaMemcpy2DAsync(gram_out, (size_t)n * sizeof(double), ctx->C.p, (size_t)ld * sizeof(double),
                                   (size_t)n * sizeof(double), n, cudaMemcpyDeviceToHost, ctx->stream));
-    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    TP_CUDA(tp_stream_sync(ctx));
     return TP_OK;
 }
 
@@ -311,7 +321,7 @@ extern "C" int tp_test_mgram(tp_ctx *ctx, const double *a, int n, int row_begin,
                            row_begin == 0 && row_end == n, SymShard{1, 1 << 30}));
     TP_CUDA(cudaMemcpy2DAsync(gram_out, (size_t)n * sizeof(double), ctx->M.p, (size_t)ld * sizeof(double),
                               (size_t)n * sizeof(double), n, cudaMemcpyDeviceToHost, ctx->stream));
-    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    TP_CUDA(tp_stream_sync(ctx));
     return TP_OK;
 }
 
@@ -338,7 +348,7 @@ extern "C" int tp_test_symshard(tp_ctx *ctx, const double *a, int n, int nranks,
                               (size_t)n * sizeof(double), n, cudaMemcpyHostToDevice, ctx->stream));
     std::vector<double> f((size_t)n * ld, fill);
     TP_CUDA(cudaMemcpyAsync(out.p, f.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
-    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    TP_CUDA(tp_stream_sync(ctx));
     ctx->have_X = ctx->have_C = ctx->have_scores = ctx->have_sweep = false;
     const SymShard ss{nranks, round_up((n + nranks - 1) / nranks, 64)};
     for (int r = 0; r < nranks; r++) {
@@ -354,7 +364,7 @@ extern "C" int tp_test_symshard(tp_ctx *ctx, const double *a, int n, int nranks,
     TP_TRY(tp_mirror_fill(ctx, out.as<double>(), n, ld, ss));
     TP_CUDA(cudaMemcpy2DAsync(gram_out, (size_t)n * sizeof(double), out.p, (size_t)ld * sizeof(double),
                               (size_t)n * sizeof(double), n, cudaMemcpyDeviceToHost, ctx->stream));
-    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    TP_CUDA(tp_stream_sync(ctx));
     return TP_OK;
 }
 
@@ -364,13 +374,13 @@ static int upload_square(tp_ctx *ctx, DevBuf &buf, const double *h, int n, int l
     TP_CUDA(cudaMemsetAsync(buf.p, 0, (size_t)n * ld * sizeof(double), ctx->stream));
     TP_CUDA(cudaMemcpy2DAsync(buf.p, (size_t)ld * sizeof(double), h, (size_t)n * sizeof(double),
                               (size_t)n * sizeof(double), n, cudaMemcpyHostToDevice, ctx->stream));
-    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    TP_CUDA(tp_stream_sync(ctx));
     return TP_OK;
 }
 static int download(tp_ctx *ctx, const DevBuf &buf, double *h, int rows, int cols, int ld) {
     TP_CUDA(cudaMemcpy2DAsync(h, (size_t)cols * sizeof(double), buf.p, (size_t)ld * sizeof(double),
                               (size_t)cols * sizeof(double), rows, cudaMemcpyDeviceToHost, ctx->stream));
-    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    TP_CUDA(tp_stream_sync(ctx));
     return TP_OK;
 }
 
@@ -406,7 +416,7 @@ extern "C" int tp_set_scores(tp_ctx *ctx, const double *scores, int nf, int k) {
     TP_CUDA(cudaMemsetAsync(ctx->scores.p, 0, (size_t)nf * ctx->ldk * sizeof(double), ctx->stream));
     TP_CUDA(cudaMemcpy2DAsync(ctx->scores.p, (size_t)ctx->ldk * sizeof(double), scores, (size_t)k * sizeof(double),
                               (size_t)k * sizeof(double), nf, cudaMemcpyHostToDevice, ctx->stream));
-    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    TP_CUDA(tp_stream_sync(ctx));
     ctx->have_scores = true; ctx->have_sweep = false;
     return TP_OK;
 }
@@ -458,7 +468,7 @@ static int sweep_impl(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_st
             TP_TRY(tp_comm_allreduce_sum(ctx, ctx->chs.p, (size_t)k * ld, 1));
         }
         TP_CUDA(cudaMemcpyAsync(h_ncl, ctx->ncl.p, (size_t)k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        TP_CUDA(cudaStreamSynchronize(ctx->stream));
+        TP_CUDA(tp_stream_sync(ctx));
         maxlev = 0;
         for (int c = 0; c < k; c++) {
             if (h_ncl[c] < 0) {
@@ -485,7 +495,7 @@ static int sweep_impl(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_st
             TP_CUDA(cudaMemcpy2DAsync(scores_out, (size_t)ld_scores * sizeof(double), ctx->chs.p,
                                       (size_t)ctx->ld_chs * sizeof(double), (size_t)maxlev * sizeof(double), k,
                                       cudaMemcpyDeviceToHost, ctx->stream));
-        TP_CUDA(cudaStreamSynchronize(ctx->stream));
+        TP_CUDA(tp_stream_sync(ctx));
     }
     return TP_OK;
 }
@@ -500,7 +510,7 @@ extern "C" int tp_get_sweep_scores(tp_ctx *ctx, double *scores_out, int ld_score
         TP_CUDA(cudaMemcpy2DAsync(scores_out, (size_t)ld_scores * sizeof(double), ctx->chs.p,
                                   (size_t)ctx->ld_chs * sizeof(double), (size_t)maxlev * sizeof(double), k,
                                   cudaMemcpyDeviceToHost, ctx->stream));
-    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    TP_CUDA(tp_stream_sync(ctx));
     return TP_OK;
 }
 
@@ -524,7 +534,7 @@ extern "C" int tp_get_dendro(tp_ctx *ctx, int cand, double *seqdist_out, int *or
         TP_CUDA(cudaMemcpyAsync(tmp.data(), ctx->order.as<int4>() + (size_t)cand * ldd, (size_t)n1 * sizeof(int4),
                                 cudaMemcpyDeviceToHost, ctx->stream));
     }
-    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    TP_CUDA(tp_stream_sync(ctx));
     if (order_out) for (int t = 0; t < n1; t++) order_out[t] = tmp[(size_t)t * 4];
     return TP_OK;
 }

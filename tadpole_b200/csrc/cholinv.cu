@@ -304,7 +304,7 @@ static int launch_cholinv(tp_ctx *ctx, double *G, double *Linv, int b, int ld, i
     tp_prof_end(ctx);
     if (tr) {       // debugging aid: per-CTA phase clocks relative to the earliest one
         static long long h[CI_CLUSTER * 16 * 8];
-        TP_CUDA(cudaStreamSynchronize(ctx->stream));
+        TP_CUDA(tp_stream_sync(ctx));
         TP_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
         long long t0 = 0;
         for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;

@@ -84,6 +84,9 @@ struct tp_ctx {
     int dist_min_n = 4096;
     int igemm_min_n = 1024;
     int iop_min_n = 1024;        // smallest nf whose early subspace-iteration rounds use the sliced int8 operator (0 = never)
+    int sync_blocking = 0;       // 1: the host waits for the stream on a blocking-sync event (the thread sleeps) instead of
+                                 // cudaStreamSynchronize (which spins on a core): for hosts with more waiting threads than cores
+    cudaEvent_t sync_ev = nullptr;
     int shard_sym = 1;           // several ranks: symmetric products computed once per block pair (SymShard); 0 = full-width row blocks
     int mgram_min_n = 1024;      // smallest nf whose M = Xc Xc^T is formed by the sliced int8 Gram (needs the sliced operator; 0 = FP64 DMMA)
     int iop_final_min_n = 1024;  // below this nf the later rounds use the FP64 DMMA operator whatever iop_final says (measured at N = 2000, 8 calls in flight: 224 -> 264 calls/s with the sliced operator)
@@ -154,6 +157,8 @@ void tp_prof_begin(tp_ctx *ctx, int cls);
 void tp_prof_end(tp_ctx *ctx);
 
 int tp_pin_reserve(tp_ctx *ctx, size_t bytes);
+// wait for everything queued on the context stream (spinning or sleeping, see sync_blocking)
+cudaError_t tp_stream_sync(tp_ctx *ctx);
 
 // ---- multi-GPU (comm.cu) ----
 static inline int tp_nranks(const tp_ctx *ctx) { return ctx->comm_cur < 0 ? 1 : ctx->comm[ctx->comm_cur].nranks; }

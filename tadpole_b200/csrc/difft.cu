@@ -173,7 +173,7 @@ static int difft_device(tp_ctx *ctx, const int *dx, size_t xstride, const int *d
     TP_CUDA(cudaGetLastError());
     int nover = 0;
     TP_CUDA(cudaMemcpyAsync(&nover, d_over, sizeof(int), cudaMemcpyDeviceToHost, st));
-    TP_CUDA(cudaStreamSynchronize(st));
+    TP_CUDA(tp_stream_sync(ctx));
     if (nover > 0) {
         // pairs with more distinct labels than the shared table holds: global tables, <= 3L keys
         unsigned gslots = 1024;
@@ -211,7 +211,7 @@ int tp_difft_batch(tp_ctx *ctx, const int32_t *labels_x, const int32_t *labels_y
     }
     TP_TRY(difft_device(ctx, dx, (size_t)L, dy, L, npairs, dout, nullptr));
     if (!on_device) TP_CUDA(cudaMemcpyAsync(out, dout, nl * sizeof(double), cudaMemcpyDeviceToHost, st));
-    TP_CUDA(cudaStreamSynchronize(st));
+    TP_CUDA(tp_stream_sync(ctx));
     return TP_OK;
 }
 
@@ -364,6 +364,6 @@ int tp_difft_null(tp_ctx *ctx, const int32_t *labels_x, int L, int pad_left, int
     if (labels_out) TP_CUDA(cudaMemcpyAsync(labels_out, dy, nl * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (curves_out) TP_CUDA(cudaMemcpyAsync(curves_out, ctx->dout.p, nl * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (totals_out) TP_CUDA(cudaMemcpyAsync(totals_out, dtot, (size_t)nperm * sizeof(double), cudaMemcpyDeviceToHost, st));
-    TP_CUDA(cudaStreamSynchronize(st));
+    TP_CUDA(tp_stream_sync(ctx));
     return TP_OK;
 }

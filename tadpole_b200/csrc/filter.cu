@@ -238,7 +238,7 @@ int tp_filter(tp_ctx *ctx, const double *mat, int n, int colmajor, int on_device
     TP_CUDA(cudaMemcpyAsync(bad_out, bad, n, cudaMemcpyDeviceToHost, st));
     if (rowmeans_out) TP_CUDA(cudaMemcpyAsync(rowmeans_out, rm, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (thr_out) TP_CUDA(cudaMemcpyAsync(thr_out, xs + 2, sizeof(double), cudaMemcpyDeviceToHost, st));
-    TP_CUDA(cudaStreamSynchronize(st));
+    TP_CUDA(tp_stream_sync(ctx));
     return TP_OK;
 }
 

@@ -295,7 +295,7 @@ int tp_igram(tp_ctx *ctx, const double *X, int n, int ld, double *C, int ldc, co
     TP_TRY(tp_pin_reserve(ctx, 64));
     int *h = (int *)ctx->pin;
     TP_CUDA(cudaMemcpyAsync(h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-    TP_CUDA(cudaStreamSynchronize(st));
+    TP_CUDA(tp_stream_sync(ctx));
     if (h[0]) { *used_out = 0; return TP_OK; }
     CUtensorMap map;
     TP_TRY(ig_encode(&map, S, rows_pad, Kp));

@@ -287,7 +287,7 @@ static int ingest_core(tp_ctx *ctx, const TextSource &src, int sep, int *n_out) 
     TP_CUDA(cudaGetLastError());
     long long nrows_ll = 0;
     TP_CUDA(cudaMemcpyAsync(&nrows_ll, offs + nb, sizeof(long long), cudaMemcpyDeviceToHost, st));
-    TP_CUDA(cudaStreamSynchronize(st));
+    TP_CUDA(tp_stream_sync(ctx));
     ctx->launches += 2;
     TP_ARG(nrows_ll >= 2, "tp_ingest_tsv: the matrix must have at least 2 rows");
     TP_ARG(nrows_ll <= 200000, "tp_ingest_tsv: more than 200000 rows");
@@ -309,7 +309,7 @@ static int ingest_core(tp_ctx *ctx, const TextSource &src, int sep, int *n_out) 
     TP_MARK(ctx, EV_INGEST1);
     int hstat[16];
     TP_CUDA(cudaMemcpyAsync(hstat, status, 64, cudaMemcpyDeviceToHost, st));
-    TP_CUDA(cudaStreamSynchronize(st));
+    TP_CUDA(tp_stream_sync(ctx));
     ctx->raw = nullptr; ctx->n = 0;
     ctx->have_X = ctx->have_C = ctx->have_scores = ctx->have_sweep = false;
     if (hstat[1]) {                                         // little endian: hstat[1] is the high word
@@ -359,7 +359,7 @@ static int ingest_core(tp_ctx *ctx, const TextSource &src, int sep, int *n_out) 
         TP_CUDA(cudaMemcpyAsync(dval, val.data(), (size_t)nslow * sizeof(double), cudaMemcpyHostToDevice, st));
         scatter_kernel<<<(nslow + 255) / 256, 256, 0, st>>>(out, didx, dval, (int)nslow);
         TP_CUDA(cudaGetLastError());
-        TP_CUDA(cudaStreamSynchronize(st));
+        TP_CUDA(tp_stream_sync(ctx));
         ctx->launches += 1;
     }
     ctx->raw = out;
@@ -421,7 +421,7 @@ extern "C" int tp_get_ingested(tp_ctx *ctx, double *out) {
     TP_CUDA(cudaSetDevice(ctx->device));
     const size_t n = (size_t)ctx->ingested_n;
     TP_CUDA(cudaMemcpyAsync(out, ctx->raw_own.p, n * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    TP_CUDA(cudaStreamSynchronize(ctx->stream));
+    TP_CUDA(tp_stream_sync(ctx));
     return TP_OK;
 }
 

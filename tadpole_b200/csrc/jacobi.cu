@@ -298,7 +298,7 @@ int tp_jacobi(tp_ctx *ctx, double *A, int b, int ld, double *w, double *Vs, int 
     TP_TRY(tp_pin_reserve(ctx, 64));
     int *h = (int *)ctx->pin;
     TP_CUDA(cudaMemcpyAsync(h, info, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    TP_CUDA(cudaStreamSynchronize(st));
+    TP_CUDA(tp_stream_sync(ctx));
     if (sweeps_out) *sweeps_out = h[0];
     if (getenv("TADPOLE_DEBUG")) fprintf(stderr, "[tadpole] jacobi b=%d tol=%.1e sweeps=%d converged=%d\n", b, tol, h[0], h[2]);
     if (!h[2]) {

@@ -492,7 +492,7 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
                 // ---- bounds from the current Ritz values -----------------------------------------
                 TP_CUDA(cudaMemcpyAsync(hbuf, theta, (size_t)b * sizeof(double), cudaMemcpyDeviceToHost, st));
                 TP_TRY(tp_flags_enqueue(ctx));
-                TP_CUDA(cudaStreamSynchronize(st));
+                TP_CUDA(tp_stream_sync(ctx));
                 TP_TRY(poll());
                 hbuf = (double *)ctx->pin;
                 bd.top = hbuf[0]; bd.thk = hbuf[k - 1];
@@ -515,7 +515,7 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
                     ctx->launches += 1;
                     TP_CUDA(cudaMemcpyAsync(hbuf, res, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, st));
                     TP_TRY(tp_flags_enqueue(ctx));
-                    TP_CUDA(cudaStreamSynchronize(st));
+                    TP_CUDA(tp_stream_sync(ctx));
                     TP_TRY(poll());
                     rmax = 0.0;
                     for (int j = 0; j < k; j++) rmax = (hbuf[j] > rmax || hbuf[j] != hbuf[j]) ? hbuf[j] : rmax;
