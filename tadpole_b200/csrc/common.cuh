@@ -81,8 +81,8 @@ struct tp_ctx {
     // comm_cur = -1: no collective (single GPU, or replicated / independent work)
     TpCommSlot comm[TP_COMM_SLOTS];
     int comm_cur = -1;
-    int dist_min_n = 4096;
-    int igemm_min_n = 1024;
+    int dist_min_n = 4096;       // matrices smaller than this are not row-sharded over the ranks (only the candidate sweep is)
+    int igemm_min_n = 1024;      // integer-count matrices at least this large take the tcgen05 int8 Gram path (0 = never)
     int iop_min_n = 1024;        // smallest nf whose early subspace-iteration rounds use the sliced int8 operator (0 = never)
     int sync_blocking = 0;       // 1: the host waits for the stream on a blocking-sync event (the thread sleeps) instead of
                                  // cudaStreamSynchronize (which spins on a core): for hosts with more waiting threads than cores
@@ -91,7 +91,7 @@ struct tp_ctx {
     int mgram_min_n = 1024;      // smallest nf whose M = Xc Xc^T is formed by the sliced int8 Gram (needs the sliced operator; 0 = FP64 DMMA)
     int iop_final_min_n = 1024;  // below this nf the later rounds use the FP64 DMMA operator whatever iop_final says (measured at N = 2000, 8 calls in flight: 224 -> 264 calls/s with the sliced operator)
     int iop_final = 8;           // operator of the later rounds where the sliced one is in use: 8 digit planes, or 0 = FP64 DMMA
-    double iop_switch = 1e-3;    // relative residual below which the FP64 DMMA operator takes over (the first iteration always starts sliced)      // integer-count matrices at least this large take the tcgen05 int8 Gram path (0 = never)       // matrices smaller than this are not row-sharded (only the candidate sweep is)
+    double iop_switch = 1e-3;    // relative residual below which the 8-plane (or FP64 DMMA) operator takes over (the first iteration always starts with 5 planes)
 
     // tunables
     int pca_block = 0;
