@@ -106,3 +106,19 @@ def test_tadpole_tune_environment(monkeypatch):
         monkeypatch.setenv("TADPOLE_TUNE", bad)
         with pytest.raises(Exception, match="TADPOLE_TUNE|unknown key"):
             Context(0)
+
+
+def test_blocking_host_wait_gives_the_same_result(ctx):
+    """sync_blocking only changes HOW the host thread waits for the stream (sleeping on a blocking-sync event instead of
+    spinning in cudaStreamSynchronize): the call must return the same bits."""
+    from tadpole_b200.synth import synth_hic
+    m = synth_hic(700, seed=4)
+    a = ctx.call(m, max_pcs=80)
+    ctx.set("sync_blocking", 1)
+    try:
+        b = ctx.call(m, max_pcs=80)
+    finally:
+        ctx.set("sync_blocking", 0)
+    assert (a["n_pcs"], a["n_clusters"], a["nf"]) == (b["n_pcs"], b["n_clusters"], b["nf"])
+    assert np.array_equal(a["seqdist"], b["seqdist"])
+    assert np.array_equal(a["scores"], b["scores"], equal_nan=True)
