@@ -5,7 +5,10 @@ variants before spending GPU time on them.  `cost()` prices the counts with the 
 Findings, round 1 (N = 600..4000, seeds 1-5): the model reproduces the GPU's counts at N = 2000 (32 applications, 3 Rayleigh-
 Ritz steps, 3 iterations).  Replacing the start Rayleigh-Ritz step by Rayleigh quotients + a 1-norm bound for the top
 (start='norm1') saves one eigensolve and ~20 % of the modelled PCA time at N = 2000 / 3000, but costs one to two extra
-iterations at N = 600 / 1000 / 1200 / 4000: not a robust default.  inner = 4, cond cap 1e5, b = 256 stay the best all-round."""
+iterations at N = 600 / 1000 / 1200 / 4000: not a robust default.  inner = 4, cond cap 1e5, b = 256 stay the best all-round
+for N >= 1500.  Below that (Nf = 600..1200, where the 256-wide block is a quarter to a half of the spectrum) the degree rule
+leaves most filter rounds at degree 1 and the solve takes 4-6 iterations; a cond cap of 1e7 brings it back to 3 in the model
+(21 -> 11 modelled ms at N = 600), but one-pass Cholesky QR at that conditioning has to be checked on the GPU first."""
 import sys, os, numpy as np, math, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import tadpole_oracle as O
