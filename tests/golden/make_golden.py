@@ -6,7 +6,11 @@
                               reference's misc/DiffT_score.png (L = 194,
                               un-normalised total 1777, 0.064716@23, 0.881823@174, ...).
   pipeline_n160.json       -- a seeded 160-bin synthetic matrix and the oracle's TADpole() result.
+  pipeline_n1100.json      -- the oracle's TADpole(max_pcs = 40) result for synth_hic(1100, seed = 8): a size that takes the
+                              subspace iteration and the tcgen05 int8 kernels on the GPU (Nf >= 1024).  The matrix is not
+                              stored: (n, seed) and the SHA-256 of its bytes are, so a drift of the generator shows up as such.
 """
+import hashlib
 import json
 import os
 import sys
@@ -34,6 +38,15 @@ def main():
     r = O.tadpole(m)
     with open(os.path.join(HERE, "pipeline_n160.json"), "w") as fh:
         json.dump(dict(matrix=m.astype(int).tolist(), n_pcs=r.n_pcs, optimal_n_clusters=r.optimal_n_clusters,
+                       clusters={str(k): v.tolist() for k, v in r.clusters.items()},
+                       scores=[[None if np.isnan(x) else float(x) for x in row] for row in r.scores],
+                       seqdist=[float(v) for v in r.seqdist]), fh)
+    n, seed, max_pcs = 1100, 8, 40
+    m = synth_hic(n, seed=seed)
+    r = O.tadpole(m, max_pcs=max_pcs)
+    with open(os.path.join(HERE, "pipeline_n1100.json"), "w") as fh:
+        json.dump(dict(n=n, seed=seed, max_pcs=max_pcs, matrix_sha256=hashlib.sha256(np.ascontiguousarray(m).tobytes()).hexdigest(),
+                       n_pcs=r.n_pcs, optimal_n_clusters=r.optimal_n_clusters,
                        clusters={str(k): v.tolist() for k, v in r.clusters.items()},
                        scores=[[None if np.isnan(x) else float(x) for x in row] for row in r.scores],
                        seqdist=[float(v) for v in r.seqdist]), fh)

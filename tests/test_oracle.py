@@ -225,3 +225,20 @@ def test_bin_index_descending_range_quirk():
     # seq(a, b) with a > b counts down in R: the row [5, 4] labels bins 5 and 4; position 0 is a no-op
     assert O.bin_index(np.array([[3, 4], [7, 6], [8, 9]]), 7).tolist() == [1, 1, 0, 2, 2, 3, 3]
     assert O.bin_index(np.array([[1, 0], [1, 3]]), 3).tolist() == [2, 2, 2]
+
+
+def test_golden_pipeline_n1100_pins_oracle():
+    """The committed fixture of the iterative-path size (tests/golden/make_golden.py) is what the oracle computes today:
+    optimal n_pcs / level, every level's TAD table, CH scores."""
+    import hashlib
+    from tadpole_b200.synth import synth_hic
+    with open(os.path.join(GOLD, "pipeline_n1100.json")) as fh:
+        g = json.load(fh)
+    m = synth_hic(g["n"], seed=g["seed"])
+    assert hashlib.sha256(np.ascontiguousarray(m).tobytes()).hexdigest() == g["matrix_sha256"]
+    r = O.tadpole(m, max_pcs=g["max_pcs"])
+    assert (r.n_pcs, r.optimal_n_clusters) == (g["n_pcs"], g["optimal_n_clusters"])
+    for k, tab in g["clusters"].items():
+        assert np.array_equal(r.clusters[int(k)], np.array(tab))
+    ref = np.array([[np.nan if x is None else x for x in row] for row in g["scores"]])
+    assert np.allclose(r.scores, ref, rtol=1e-10, equal_nan=True)
