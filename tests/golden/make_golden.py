@@ -6,9 +6,10 @@
                               reference's misc/DiffT_score.png (L = 194,
                               un-normalised total 1777, 0.064716@23, 0.881823@174, ...).
   pipeline_n160.json       -- a seeded 160-bin synthetic matrix and the oracle's TADpole() result.
-  pipeline_n1100.json      -- the oracle's TADpole(max_pcs = 40) result for synth_hic(1100, seed = 8): a size that takes the
-                              subspace iteration and the tcgen05 int8 kernels on the GPU (Nf >= 1024).  The matrix is not
-                              stored: (n, seed) and the SHA-256 of its bytes are, so a drift of the generator shows up as such.
+  pipeline_n1100.json      -- the oracle's TADpole(max_pcs = 40) result for golden_int_matrix(1100, 8) (intgen.py: integer-only
+                              arithmetic, so the matrix is reproduced bit for bit on any machine): a size that takes the
+                              subspace iteration and the tcgen05 int8 kernels on the GPU (Nf = 1089 >= 1024).  The matrix is
+                              not stored: (n, seed) and the SHA-256 of its bytes are.
 """
 import hashlib
 import json
@@ -21,6 +22,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "..", ".."))
 from oracle import tadpole_oracle as O  # noqa: E402
 from tadpole_b200.synth import synth_hic  # noqa: E402
+sys.path.insert(0, HERE)
+from intgen import golden_int_matrix  # noqa: E402
 
 REF = "/root/reference/inst/extdata"
 
@@ -42,7 +45,7 @@ def main():
                        scores=[[None if np.isnan(x) else float(x) for x in row] for row in r.scores],
                        seqdist=[float(v) for v in r.seqdist]), fh)
     n, seed, max_pcs = 1100, 8, 40
-    m = synth_hic(n, seed=seed)
+    m = golden_int_matrix(n, seed)
     r = O.tadpole(m, max_pcs=max_pcs)
     with open(os.path.join(HERE, "pipeline_n1100.json"), "w") as fh:
         json.dump(dict(n=n, seed=seed, max_pcs=max_pcs, matrix_sha256=hashlib.sha256(np.ascontiguousarray(m).tobytes()).hexdigest(),

@@ -4,6 +4,7 @@ Bar: bit-exact for integer / index work (bad flags, merge order, n_cluster, opti
 level, TAD boundaries, diffT); stated tolerances for floating point (written next to each check).
 """
 import json
+import sys
 import os
 
 import numpy as np
@@ -279,13 +280,15 @@ def test_batch_of_calls_equals_sequential_calls():
 
 def test_golden_pipeline_iterative_path(ctx):
     """Committed fixture for a size that takes the subspace iteration and the tcgen05 int8 kernels (Nf >= 1024):
-    tests/golden/pipeline_n1100.json = the oracle's TADpole(max_pcs = 40) result for synth_hic(1100, seed = 8)."""
+    tests/golden/pipeline_n1100.json = the oracle's TADpole(max_pcs = 40) result for golden_int_matrix(1100, 8)."""
     import hashlib
     from tadpole_b200 import TADpole
     from tadpole_b200.synth import synth_hic
     with open(os.path.join(GOLD, "pipeline_n1100.json")) as fh:
         g = json.load(fh)
-    m = synth_hic(g["n"], seed=g["seed"])
+    sys.path.insert(0, GOLD)
+    from intgen import golden_int_matrix
+    m = golden_int_matrix(g["n"], g["seed"])                # integer-only arithmetic: the same bits on any machine
     assert hashlib.sha256(np.ascontiguousarray(m).tobytes()).hexdigest() == g["matrix_sha256"], "the generator drifted"
     tp = TADpole(m, max_pcs=g["max_pcs"], ctx=ctx)
     assert tp.n_pcs == g["n_pcs"] and tp.optimal_n_clusters == g["optimal_n_clusters"]

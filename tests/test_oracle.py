@@ -1,6 +1,7 @@
 """CPU tests of the oracle: golden vectors, cross-checks against independent implementations, and
 properties.  The reference has no tests; the diffT fixture pair is its only known-answer case."""
 import json
+import sys
 import os
 
 import numpy as np
@@ -234,7 +235,9 @@ def test_golden_pipeline_n1100_pins_oracle():
     from tadpole_b200.synth import synth_hic
     with open(os.path.join(GOLD, "pipeline_n1100.json")) as fh:
         g = json.load(fh)
-    m = synth_hic(g["n"], seed=g["seed"])
+    sys.path.insert(0, GOLD)
+    from intgen import golden_int_matrix
+    m = golden_int_matrix(g["n"], g["seed"])                # integer-only arithmetic: the same bits on any machine
     assert hashlib.sha256(np.ascontiguousarray(m).tobytes()).hexdigest() == g["matrix_sha256"]
     r = O.tadpole(m, max_pcs=g["max_pcs"])
     assert (r.n_pcs, r.optimal_n_clusters) == (g["n_pcs"], g["optimal_n_clusters"])
