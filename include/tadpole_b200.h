@@ -45,6 +45,23 @@ int tp_version(void);
 
 /* ---- context --------------------------------------------------------------------------- */
 int tp_ctx_create(int device, tp_ctx **out);
+/* One context over several GPUs of the box, driven from ONE host thread (R's .Call is single-threaded): the reference's
+ * TADpole() is one call that spreads over every core (registerDoParallel(detectCores()) + foreach %dopar%,
+ * R/TADpole.R:103-104); a multi-device context spreads the same one call over every device listed.  The library owns one
+ * host thread per device and the NCCL communicators between them (ncclCommInitAll); tp_filter / tp_compact /
+ * tp_correlation / tp_pca / tp_call / tp_call_arm / tp_call_arms / tp_recall on the returned handle run on all of them and
+ * return when all are done, with the results of a single-GPU call (bit-identical).  A host matrix is uploaded once: every
+ * device pulls a share of the upper-triangle bands over its own PCIe link and the bands are exchanged over NVLink.
+ * ndev = 1 gives a plain context.  Everything else (getters, diffT, ingest) runs on devices[0]. */
+int tp_ctx_create_multi(const int *devices, int ndev, tp_ctx **out);
+/* devices of the context (returns their number; fills at most `cap` entries) */
+int tp_ctx_devices(tp_ctx *ctx, int *devices_out, int cap);
+/* Counter that changes whenever the state resident in the context (matrix, PC scores, dendrograms) is replaced: a host
+ * object that kept a handle on that state compares it before tp_recall / tp_get_dendro. */
+long long tp_ctx_generation(tp_ctx *ctx);
+/* sizes of the resident state: bins of the input, good bins, PCs in use, PCs computed, levels of the last sweep
+ * (0 where that piece is absent); any pointer may be NULL */
+int tp_ctx_dims(tp_ctx *ctx, int *n_out, int *nf_out, int *k_out, int *k_full_out, int *maxlev_out);
 int tp_ctx_destroy(tp_ctx *ctx);
 int tp_ctx_sync(tp_ctx *ctx);
 /* cudaStream_t every kernel of this context is launched on (for CUDA-event timing by callers) */
@@ -171,7 +188,9 @@ int tp_sweep(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stride,
 /* score matrix of the last sweep (tp_sweep, tp_call, tp_call_arm): k x maxlev, NaN padded, row pitch ld_scores */
 int tp_get_sweep_scores(tp_ctx *ctx, double *scores_out, int ld_scores);
 /* seqdist (nf-1 doubles) and merge order (nf-1 ints: boundary removed at each step) of one
- * candidate of the last sweep; either pointer may be NULL */
+ * candidate of the last sweep; either pointer may be NULL.  After a sweep that was dealt out over several GPUs the
+ * dendrogram lives on the device that ran the candidate: a multi-device context fetches it from there; with one process
+ * per GPU the call is collective (every rank calls with the same `cand`, the owner broadcasts). */
 int tp_get_dendro(tp_ctx *ctx, int cand, double *seqdist_out, int *order_out);
 
 /* which.max(rowMeans(scores, na.rm=TRUE)) then which.max(scores[opt,]) (R/TADpole.R:134-135);
@@ -194,6 +213,36 @@ int tp_call(tp_ctx *ctx, const double *mat, int n, int colmajor, int on_device,
 int tp_call_arm(tp_ctx *ctx, const int *keep, int nf, int max_pcs, int min_clusters,
                 int *k_out, int *n_pcs_out, int *n_clusters_out,
                 double *scores_out, int ld_scores, int *maxlev_out, double *seqdist_out);
+
+/* Both chromosome arms of a centromere_search call (R/TADpole.R:357-374: the arms are independent from load_mat on), after
+ * tp_filter: on a multi-device context the first half of the devices works on p while the second half works on q; on one
+ * device p then q.  Outputs as tp_call_arm, element [0] / the _p buffers for p and [1] / _q for q; a too small ld_scores
+ * fails with TP_ERR_ARG and maxlev_out2 filled (call again with wider buffers). */
+int tp_call_arms(tp_ctx *ctx, const int *keep_p, int nf_p, const int *keep_q, int nf_q, int max_pcs, int min_clusters,
+                 int *k_out2, int *n_pcs_out2, int *n_clusters_out2, double *scores_p, double *scores_q, int ld_scores,
+                 int *maxlev_out2, double *seqdist_p, double *seqdist_q);
+
+/* ---- batches of independent calls (genome-wide use: one TADpole() per chromosome) -----------------------------------
+ * ncalls matrices (mats[i]: n[i] x n[i], host -- or device when on_device, single-device contexts only), same arguments
+ * as tp_call.  `inflight` calls per device are kept in flight by library-owned host threads, each on its own context and
+ * stream (a lone 2000-bin call leaves most of a B200 idle), over every device of the context; the caller's one thread
+ * just waits.  want_tables: also build the start / end table of every scored level of the optimal candidate
+ * (R/TADpole.R:470-497) in those threads.  Results are held by the returned tp_batch, in input order:
+ *   tp_batch_status / tp_batch_error  per-call return code and message (a failed call does not stop the others);
+ *   tp_batch_dims   sizes to allocate: n, nf, k, maxlev, number of scored levels, total table rows;
+ *   tp_batch_get    bad[n], n_pcs, n_clusters, scores[k x maxlev] row-major NaN padded, seqdist[nf-1], levels[nlevels],
+ *                   offsets[nlevels+1], start/end[nrows] (1-based inclusive), device ms of the call; NULL = skip. */
+typedef struct tp_batch tp_batch;
+int tp_call_batch(tp_ctx *ctx, int ncalls, const double *const *mats, const int *n, int colmajor, int on_device,
+                  int max_pcs, int min_clusters, double bad_frac, int inflight, int want_tables, tp_batch **out);
+int tp_batch_size(const tp_batch *b);
+int tp_batch_status(const tp_batch *b, int i);
+const char *tp_batch_error(const tp_batch *b, int i);
+int tp_batch_dims(const tp_batch *b, int i, int *n_out, int *nf_out, int *k_out, int *maxlev_out, int *nlevels_out,
+                  int *nrows_out);
+int tp_batch_get(const tp_batch *b, int i, uint8_t *bad_out, int *n_pcs_out, int *n_clusters_out, double *scores_out,
+                 double *seqdist_out, int *levels_out, int *offsets_out, int *start_out, int *end_out, double *device_ms_out);
+int tp_batch_free(tp_batch *b);
 
 /* The context is a device-resident pipeline handle: after tp_call / tp_call_arm / tp_pca the PC scores stay in HBM, and
  * after a sweep so do all k dendrograms (tp_get_dendro) and the score matrix (tp_get_sweep_scores).  tp_recall repeats
@@ -241,6 +290,12 @@ int tp_assemble(const double *seqdist, int nf, int n_clusters, const int *names,
  * sum(levels[i] + max(nbad, 0) + 1) rows */
 int tp_assemble_levels(const double *seqdist, int nf, const int *levels, int nlev, const int *names,
                        const int *bad, int nbad, int *start_out, int *end_out, int *offsets_out);
+
+/* rioja's .find.groups (the merge matrix of the chclust / hclust object, R/TADpole.R:108 -> dendro$merge): for step
+ * s = 1..n1 the boundary j = which.min(seqdist) (first index on ties) joins the groups of objects j and j+1; an operand is
+ * -object while that object is a singleton, else the step that last absorbed it.  merge_out: n1 x 2 ints, column-major
+ * (an R matrix).  Host only, O(n log n). */
+int tp_find_groups(const double *seqdist, int n1, int *merge_out);
 
 #ifdef __cplusplus
 }

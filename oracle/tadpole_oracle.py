@@ -262,29 +262,47 @@ def coniss_lw(pcs):
 
 
 def find_groups(seqdist):
-    """rioja's .find.groups: hclust merge matrix from seqdist by repeated which.min
-    (first index on ties).  Returns (merge[(n-1),2] R-style signed ints, height)."""
+    """rioja's .find.groups, literally: n-1 times j = which.min(x) (first index on ties, NA skipped); the two operands are
+    objects j and j+1 -- written -j / -(j+1) while they are singletons, else the number of the merge step their group was
+    formed by; every member of both groups is then relabelled with this step and x[j] becomes NA.  O(n^2) by design: it is
+    the checker of the product's O(n log n) union-find (tp_find_groups).  Returns (merge[(n-1), 2] R-style signed ints,
+    height = sort(seqdist))."""
     x = np.array(seqdist, dtype=np.float64)
     n1 = x.size
     merge = np.zeros((n1, 2), dtype=np.int64)
-    owner = np.zeros(n1 + 1, dtype=np.int64)  # 0 = singleton, else merge step that absorbed it
-    # union-find over objects so that "the merge step that last absorbed object j" is O(alpha)
-    parent = np.arange(n1 + 1)
+    group = np.zeros(n1 + 2, dtype=np.int64)          # group[obj] (1-based objects): 0 = singleton, else merge step
+    for step in range(1, n1 + 1):
+        j = int(np.nanargmin(x)) + 1                   # which.min: first minimum, 1-based boundary = left object
+        left, right = int(group[j]), int(group[j + 1])
+        merge[step - 1, 0] = -j if left == 0 else left
+        merge[step - 1, 1] = -(j + 1) if right == 0 else right
+        members = np.zeros(n1 + 2, dtype=bool)
+        members[j] = members[j + 1] = True
+        if left:
+            members |= group == left
+        if right:
+            members |= group == right
+        group[members] = step
+        x[j - 1] = np.nan
+    return merge, np.sort(np.asarray(seqdist, dtype=np.float64))
 
-    def root(a):
-        while parent[a] != a:
-            parent[a] = parent[parent[a]]
-            a = parent[a]
-        return a
 
-    idx = np.lexsort((np.arange(n1), x))  # ascending value, first index on ties
-    for step, j in enumerate(idx, start=1):
-        ra, rb = root(j), root(j + 1)
-        merge[step - 1, 0] = -(j + 1) if owner[ra] == 0 else owner[ra]
-        merge[step - 1, 1] = -(j + 2) if owner[rb] == 0 else owner[rb]
-        parent[rb] = ra
-        owner[ra] = step
-    return merge, np.sort(x)
+def cutree_from_merge(merge, k):
+    """stats::cutree(tree, k) from the hclust merge matrix alone: apply the first n-k merge steps, then number the
+    clusters by first appearance along the objects (an independent route to cutree(): no sorting of heights)."""
+    n = merge.shape[0] + 1
+    lab = np.arange(n, dtype=np.int64)                 # cluster id per object; merged clusters take the left id
+    step_id = {}
+    for s in range(n - k):
+        ids = []
+        for v in merge[s]:
+            ids.append(lab[-v - 1] if v < 0 else step_id[int(v)])
+        a, b = ids
+        lab[lab == b] = a
+        step_id[s + 1] = a
+    _, first = np.unique(lab, return_index=True)
+    order = {lab[i]: r + 1 for r, i in enumerate(np.sort(first))}
+    return np.array([order[v] for v in lab], dtype=np.int64)
 
 
 def cutree_boundaries(seqdist, k):

@@ -26,6 +26,8 @@ EXPORTED = [
     "tp_comm_unique_id", "tp_ctx_comm_init", "tp_ctx_comm_select", "tp_ctx_comm_info",
     "tp_ingest_tsv", "tp_ingest_tsv_file", "tp_ingested", "tp_get_ingested", "tp_ingest_stats", "tp_test_parse_field",
     "tp_difft_null", "tp_recall",
+    "tp_ctx_create_multi", "tp_ctx_devices", "tp_ctx_generation", "tp_ctx_dims", "tp_call_arms", "tp_call_batch",
+    "tp_batch_size", "tp_batch_status", "tp_batch_error", "tp_batch_dims", "tp_batch_get", "tp_batch_free", "tp_find_groups",
 ]
 
 
@@ -53,6 +55,19 @@ def load():
         "tp_last_error": (c_char_p, []),
         "tp_version": (c_int, []),
         "tp_ctx_create": (c_int, [c_int, POINTER(vp)]),
+        "tp_ctx_create_multi": (c_int, [ip, c_int, POINTER(vp)]),
+        "tp_ctx_devices": (c_int, [vp, ip, c_int]),
+        "tp_ctx_generation": (c_longlong, [vp]),
+        "tp_ctx_dims": (c_int, [vp, ip, ip, ip, ip, ip]),
+        "tp_call_arms": (c_int, [vp, ip, c_int, ip, c_int, c_int, c_int, ip, ip, ip, dp, dp, c_int, ip, dp, dp]),
+        "tp_call_batch": (c_int, [vp, c_int, POINTER(vp), ip, c_int, c_int, c_int, c_int, c_double, c_int, c_int, POINTER(vp)]),
+        "tp_batch_size": (c_int, [vp]),
+        "tp_batch_status": (c_int, [vp, c_int]),
+        "tp_batch_error": (c_char_p, [vp, c_int]),
+        "tp_batch_dims": (c_int, [vp, c_int, ip, ip, ip, ip, ip, ip]),
+        "tp_batch_get": (c_int, [vp, c_int, u8p, ip, ip, dp, dp, ip, ip, ip, ip, dp]),
+        "tp_batch_free": (c_int, [vp]),
+        "tp_find_groups": (c_int, [dp, c_int, ip]),
         "tp_ctx_destroy": (c_int, [vp]),
         "tp_ctx_sync": (c_int, [vp]),
         "tp_ctx_stream": (vp, [vp]),
@@ -121,14 +136,35 @@ def _ip(a):
 
 
 class Context:
-    """One GPU context (device buffers, stream).  Thin wrapper over tp_ctx."""
+    """One GPU context (device buffers, stream), or -- given a list of devices -- one multi-device context that spreads
+    every call over those GPUs from this one host thread (tp_ctx_create_multi).  Thin wrapper over tp_ctx."""
 
     def __init__(self, device=0):
         self.lib = load()
         self._h = c_void_p()
-        check(self.lib.tp_ctx_create(int(device), ctypes.byref(self._h)))
-        self.device = int(device)
-        self.generation = 0          # bumped whenever the resident matrix / scores are replaced (stale-handle check)
+        if isinstance(device, (list, tuple)):
+            devs = np.ascontiguousarray(device, dtype=np.int32)
+            check(self.lib.tp_ctx_create_multi(_ip(devs), devs.size, ctypes.byref(self._h)))
+            self.devices = [int(d) for d in devs]
+            self.device = self.devices[0]
+        else:
+            check(self.lib.tp_ctx_create(int(device), ctypes.byref(self._h)))
+            self.device = int(device)
+            self.devices = [self.device]
+
+    @property
+    def generation(self):
+        """changes whenever the state resident in the context is replaced (stale-handle check, tp_ctx_generation)"""
+        return int(self.lib.tp_ctx_generation(self._h))
+
+    @generation.setter
+    def generation(self, _):
+        pass                         # the library counts
+
+    def dims(self):
+        v = [c_int(0) for _ in range(5)]
+        check(self.lib.tp_ctx_dims(self._h, *[ctypes.byref(x) for x in v]))
+        return dict(zip(("n", "nf", "k", "k_full", "maxlev"), (x.value for x in v)))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -177,7 +213,6 @@ class Context:
     def ingest_tsv(self, src, sep="\t"):
         """Parse a header-less separator-delimited square matrix on the device (R/TADpole.R:17).  src: a path (str /
         os.PathLike) or the text itself (bytes).  Returns (device_ptr, n) for filter()/call() with device_ptr=."""
-        self.generation += 1
         n = c_int(0)
         if isinstance(src, (bytes, bytearray, memoryview)):
             buf = bytes(src)
@@ -211,7 +246,6 @@ class Context:
             ptr, ondev = mat.ctypes.data, 0
         else:
             ptr, ondev, colmajor = int(device_ptr), 1, int(bool(colmajor))
-        self.generation += 1
         bad = np.zeros(n, dtype=np.uint8)
         rm = np.zeros(n)
         thr = np.zeros(1)
@@ -220,13 +254,11 @@ class Context:
         return bad.astype(bool), rm, float(thr[0])
 
     def compact(self, keep):
-        self.generation += 1
         keep = np.ascontiguousarray(keep, dtype=np.int32)
         check(self.lib.tp_compact(self._h, _ip(keep), keep.size))
         return keep.size
 
     def set_filtered(self, x):
-        self.generation += 1
         x = np.ascontiguousarray(x, dtype=np.float64)
         check(self.lib.tp_set_filtered(self._h, _dp(x), x.shape[0]))
 
@@ -250,7 +282,6 @@ class Context:
 
     # ---- stage 3 ----
     def pca(self, max_pcs=200):
-        self.generation += 1
         k = c_int(0)
         check(self.lib.tp_pca(self._h, int(max_pcs), ctypes.byref(k)))
         return k.value
@@ -322,7 +353,6 @@ class Context:
         return out
 
     def set_scores(self, scores):
-        self.generation += 1
         scores = np.ascontiguousarray(scores, dtype=np.float64)
         check(self.lib.tp_set_scores(self._h, _dp(scores), scores.shape[0], scores.shape[1]))
 
@@ -366,7 +396,6 @@ class Context:
             ptr, ondev = mat.ctypes.data, 0
         else:
             ptr, ondev, colmajor = int(device_ptr), 1, int(bool(colmajor))
-        self.generation += 1
         bad = np.zeros(n, dtype=np.uint8)
         nf, k, npcs, ncl, maxlev = c_int(0), c_int(0), c_int(0), c_int(0), c_int(0)
         kmax = min(int(max_pcs), n)
@@ -390,7 +419,6 @@ class Context:
                     seqdist=seq[:nf.value - 1].copy())
 
     def call_arm(self, keep, max_pcs=200, min_clusters=2, ld=256):
-        self.generation += 1
         keep = np.ascontiguousarray(keep, dtype=np.int32)
         nf = keep.size
         k, npcs, ncl, maxlev = c_int(0), c_int(0), c_int(0), c_int(0)
@@ -410,9 +438,73 @@ class Context:
         return dict(nf=nf, k=k.value, n_pcs=npcs.value, n_clusters=ncl.value,
                     scores=sc[:k.value, :maxlev.value].copy(), seqdist=seq)
 
+    def call_arms(self, keep_p, keep_q, max_pcs=200, min_clusters=2, ld=256):
+        """tp_call_arms: both chromosome arms (on disjoint halves of the devices of a multi-device context).
+        Returns (result_p, result_q), each as call_arm returns."""
+        kp = np.ascontiguousarray(keep_p, dtype=np.int32)
+        kq = np.ascontiguousarray(keep_q, dtype=np.int32)
+        while True:
+            k, npcs, ncl, ml = (np.zeros(2, np.int32) for _ in range(4))
+            scs = [np.empty((min(int(max_pcs), kk.size), ld)) for kk in (kp, kq)]
+            sqs = [np.zeros(kk.size - 1) for kk in (kp, kq)]
+            rc = self.lib.tp_call_arms(self._h, _ip(kp), kp.size, _ip(kq), kq.size, int(max_pcs), int(min_clusters),
+                                       _ip(k), _ip(npcs), _ip(ncl), _dp(scs[0]), _dp(scs[1]), ld, _ip(ml), _dp(sqs[0]), _dp(sqs[1]))
+            if rc == TP_ERR_ARG and int(ml.max()) > ld:
+                ld = int(ml.max())
+                continue
+            check(rc)
+            break
+        return tuple(dict(nf=int(kk.size), k=int(k[a]), n_pcs=int(npcs[a]), n_clusters=int(ncl[a]),
+                          scores=scs[a][:k[a], :ml[a]].copy(), seqdist=sqs[a]) for a, kk in enumerate((kp, kq)))
+
+    def call_batch(self, mats, max_pcs=200, min_clusters=2, bad_frac=0.01, inflight=8, tables=True, device_ptrs=None, n=None):
+        """tp_call_batch: one tp_call per matrix, `inflight` calls per device kept in flight by library-owned threads over
+        every device of the context.  mats: list of square float64 arrays (all C or all F order); or device_ptrs + n
+        (row-major, single-device contexts).  Returns a list of dicts as call() returns, plus 'tables' {level: [rows, 2]}
+        and 'device_ms'; a failed call's entry is the TadpoleError."""
+        if device_ptrs is None:
+            mats = [m if (m.dtype == np.float64 and (m.flags.c_contiguous or m.flags.f_contiguous))
+                    else np.ascontiguousarray(m, dtype=np.float64) for m in (np.asarray(m) for m in mats)]
+            colmajor = 0 if all(m.flags.c_contiguous for m in mats) else 1
+            if colmajor:
+                mats = [m if m.flags.f_contiguous else np.asfortranarray(m) for m in mats]
+            ptrs = (c_void_p * max(len(mats), 1))(*[m.ctypes.data for m in mats])
+            ns = np.array([m.shape[0] for m in mats], dtype=np.int32)
+            ondev = 0
+        else:
+            ptrs = (c_void_p * max(len(device_ptrs), 1))(*[int(p) for p in device_ptrs])
+            ns = np.full(len(device_ptrs), int(n), dtype=np.int32)
+            colmajor, ondev = 0, 1
+        ncalls = int(ns.size)
+        h = c_void_p()
+        check(self.lib.tp_call_batch(self._h, ncalls, ptrs, _ip(ns), colmajor, ondev, int(max_pcs), int(min_clusters),
+                                     float(bad_frac), int(inflight), int(bool(tables)), ctypes.byref(h)))
+        out = []
+        try:
+            for i in range(ncalls):
+                rc = self.lib.tp_batch_status(h, i)
+                if rc != TP_OK:
+                    out.append(TadpoleError(rc, self.lib.tp_batch_error(h, i).decode("utf-8", "replace")))
+                    continue
+                d = [c_int(0) for _ in range(6)]
+                check(self.lib.tp_batch_dims(h, i, *[ctypes.byref(x) for x in d]))
+                nn, nf, k, ml, nlev, nrows = (x.value for x in d)
+                bad = np.zeros(nn, np.uint8); sc = np.empty((k, ml)); seq = np.empty(nf - 1)
+                lev = np.zeros(nlev, np.int32); off = np.zeros(nlev + 1, np.int32)
+                st = np.zeros(nrows, np.int32); en = np.zeros(nrows, np.int32)
+                npcs, ncl, ms = c_int(0), c_int(0), c_double(0.0)
+                check(self.lib.tp_batch_get(h, i, bad.ctypes.data_as(POINTER(c_uint8)), ctypes.byref(npcs), ctypes.byref(ncl),
+                                            _dp(sc), _dp(seq), _ip(lev), _ip(off), _ip(st), _ip(en), ctypes.byref(ms)))
+                tab = np.stack([st, en], axis=1).astype(np.int64)
+                out.append(dict(bad=bad.astype(bool), nf=nf, k=k, n_pcs=npcs.value, n_clusters=ncl.value, scores=sc, seqdist=seq,
+                                tables={int(l): tab[off[j]: off[j + 1]] for j, l in enumerate(lev)} if tables else None,
+                                device_ms=ms.value))
+        finally:
+            self.lib.tp_batch_free(h)
+        return out
+
     def recall(self, nf, max_pcs=200, min_clusters=2, ld=256):
         """tp_recall: the n_pcs sweep and the selection again on the PC scores resident in the context."""
-        self.generation += 1
         k, npcs, ncl, maxlev = c_int(0), c_int(0), c_int(0), c_int(0)
         kmax = min(int(max_pcs), nf)
         seq = np.zeros(nf - 1)
@@ -467,6 +559,15 @@ def parse_field(text):
     out = c_double(0.0)
     st = lib.tp_test_parse_field(b, len(b), ctypes.byref(out))
     return st, out.value
+
+
+def find_groups(seqdist):
+    """tp_find_groups: hclust merge matrix [n-1, 2] (R convention) of a chclust dendrogram (rioja's .find.groups rule)."""
+    lib = load()
+    x = np.ascontiguousarray(seqdist, dtype=np.float64)
+    out = np.zeros((2, x.size), dtype=np.int32)          # column-major n1 x 2
+    check(lib.tp_find_groups(_dp(x), x.size, _ip(out)))
+    return out.T.astype(np.int64)
 
 
 def assemble(seqdist, n_clusters, names, bad):

@@ -261,10 +261,13 @@ def TADpole(mat_file, max_pcs=200, min_clusters=2, bad_frac=0.01, chr=None, star
         every = dist.exchange((dist.my_arm, mine))
         for arm in ("p", "q"):
             arm_res[arm] = every[dist.arms[arm][0]][1]
+    else:
+        # tp_call_arms: on a multi-device context the two halves of the devices work on the two arms at the same time
+        arm_res["p"], arm_res["q"] = ctx.call_arms(lm.p.keep, lm.q.keep, max_pcs=max_pcs, min_clusters=min_clusters)
     for arm in ("p", "q"):
         message(f"Processing arm {arm}")
         la = getattr(lm, arm)
-        res = arm_res[arm] if arm in arm_res else ctx.call_arm(la.keep, max_pcs=max_pcs, min_clusters=min_clusters)
+        res = arm_res[arm]
         _messages_optimal(res)
         a = _Obj()
         a.n_pcs = res["n_pcs"]

@@ -112,6 +112,8 @@ extern "C" int tp_ctx_create(int device, tp_ctx **out) {
 
 extern "C" int tp_ctx_destroy(tp_ctx *ctx) {
     if (!ctx) return TP_OK;
+    tp_pool_destroy(ctx);
+    tp_group_destroy(ctx);           // a multi-device handle takes its member contexts and their threads with it
     cudaSetDevice(ctx->device);
     tp_stream_sync(ctx);
     DevBuf *bufs[] = {&ctx->raw_own, &ctx->rowmean, &ctx->ranks, &ctx->flags, &ctx->qtmp, &ctx->keep, &ctx->X, &ctx->C,
@@ -138,7 +140,11 @@ extern "C" int tp_ctx_destroy(tp_ctx *ctx) {
 
 extern "C" int tp_ctx_sync(tp_ctx *ctx) {
     TP_ARG(ctx, "tp_ctx_sync: null context");
-    TP_CUDA(tp_stream_sync(ctx));
+    for (int r = tp_group_size(ctx) - 1; r >= 0; r--) {
+        tp_ctx *m = tp_group_member(ctx, r);
+        TP_CUDA(cudaSetDevice(m->device));
+        TP_CUDA(tp_stream_sync(m));
+    }
     return TP_OK;
 }
 
@@ -147,6 +153,16 @@ extern "C" long long tp_ctx_launches(tp_ctx *ctx) { return ctx ? ctx->launches :
 
 extern "C" int tp_ctx_set(tp_ctx *ctx, const char *key, double value) {
     TP_ARG(ctx && key, "tp_ctx_set: null argument");
+    if (tp_group_dispatch(ctx)) {     // host-side fields only: no need for the member threads
+        for (int r = 1; r < tp_group_size(ctx); r++) {
+            tp_ctx *m = tp_group_member(ctx, r);
+            TpGroup *g = m->group;
+            m->group = nullptr;
+            const int rc = tp_ctx_set(m, key, value);
+            m->group = g;
+            TP_TRY(rc);
+        }
+    }
     std::string k(key);
     if (k == "pca_block") ctx->pca_block = (int)value;
     else if (k == "pca_tol") ctx->pca_tol = value;
@@ -386,7 +402,9 @@ static int download(tp_ctx *ctx, const DevBuf &buf, double *h, int rows, int col
 
 extern "C" int tp_set_filtered(tp_ctx *ctx, const double *x, int nf) {
     TP_ARG(ctx && x && nf >= 2, "tp_set_filtered: bad arguments");
+    if (tp_group_dispatch(ctx)) return tp_group_run(ctx, [&](tp_ctx *gc, int) -> int { return tp_set_filtered(gc, x, nf); });
     TP_CUDA(cudaSetDevice(ctx->device));
+    ctx->generation++;
     ctx->nf = nf; ctx->ldx = round_up(nf, 8);
     TP_TRY(upload_square(ctx, ctx->X, x, nf, ctx->ldx));
     ctx->have_X = true; ctx->have_C = ctx->have_scores = ctx->have_sweep = false;
@@ -398,7 +416,9 @@ extern "C" int tp_get_filtered(tp_ctx *ctx, double *x_out) {
 }
 extern "C" int tp_set_correlation(tp_ctx *ctx, const double *cor, int nf) {
     TP_ARG(ctx && cor && nf >= 2, "tp_set_correlation: bad arguments");
+    if (tp_group_dispatch(ctx)) return tp_group_run(ctx, [&](tp_ctx *gc, int) -> int { return tp_set_correlation(gc, cor, nf); });
     TP_CUDA(cudaSetDevice(ctx->device));
+    ctx->generation++;
     ctx->nf = nf; ctx->ldx = round_up(nf, 8);
     TP_TRY(upload_square(ctx, ctx->C, cor, nf, ctx->ldx));
     ctx->have_C = true; ctx->have_scores = ctx->have_sweep = false;
@@ -410,7 +430,9 @@ extern "C" int tp_get_correlation(tp_ctx *ctx, double *cor_out) {
 }
 extern "C" int tp_set_scores(tp_ctx *ctx, const double *scores, int nf, int k) {
     TP_ARG(ctx && scores && nf >= 3 && k >= 1 && k <= nf, "tp_set_scores: bad arguments");
+    if (tp_group_dispatch(ctx)) return tp_group_run(ctx, [&](tp_ctx *gc, int) -> int { return tp_set_scores(gc, scores, nf, k); });
     TP_CUDA(cudaSetDevice(ctx->device));
+    ctx->generation++;
     ctx->nf = nf; ctx->k = ctx->k_full = k; ctx->ldk = round_up(k, 8);
     TP_TRY(ctx->scores.reserve((size_t)nf * ctx->ldk * sizeof(double)));
     TP_CUDA(cudaMemsetAsync(ctx->scores.p, 0, (size_t)nf * ctx->ldk * sizeof(double), ctx->stream));
@@ -443,10 +465,9 @@ static int sweep_impl(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_st
                       int *n_cluster_out, double *scores_out, int ld_scores, int *maxlev_out, bool collective = false) {
     int ncand = 0;
     collective = collective && tp_nranks(ctx) > 1;
-    if (collective) {
-        TP_ARG(ctx->k >= tp_nranks(ctx), "tp_sweep: fewer candidates than ranks");
-        cand_begin = tp_rank(ctx); cand_stride = tp_nranks(ctx);
-    }
+    if (collective) { cand_begin = tp_rank(ctx); cand_stride = tp_nranks(ctx); }    // (a rank may end up with no candidate)
+    ctx->generation++;
+    ctx->last_sweep_ranks = collective ? tp_nranks(ctx) : 1;
     TP_TRY(tp_sweep_device(ctx, min_clusters, cand_begin, cand_stride, &ncand));
     const int k = ctx->k;
     if (maxlev_out) *maxlev_out = 0;
@@ -525,16 +546,33 @@ extern "C" int tp_get_dendro(tp_ctx *ctx, int cand, double *seqdist_out, int *or
     TP_ARG(ctx && ctx->have_sweep, "tp_get_dendro: run tp_sweep first");
     TP_ARG(cand >= 0 && cand < ctx->k, "tp_get_dendro: candidate out of range");
     const int n1 = ctx->nf - 1, ldd = round_up(n1, 8);
+    // after a sweep dealt out over several GPUs the dendrogram lives on the device that ran the candidate
+    const int owner = cand % ctx->last_sweep_ranks;
+    tp_ctx *src = ctx;
+    if (ctx->last_sweep_ranks > 1 && tp_group_dispatch(ctx)) {
+        // multi-device context, called by the user (the member threads are idle): read the owner's copy, ordered after
+        // whatever is still queued on the owner's stream.  (Inside a grouped call the caller has broadcast what it reads.)
+        src = tp_group_member(ctx, owner);
+        TP_ARG(src && src->have_sweep && src->nf == ctx->nf && src->k == ctx->k, "tp_get_dendro: the owner device no longer holds this sweep");
+    } else if (ctx->last_sweep_ranks > 1 && !ctx->group) {
+        // one process per GPU: collective, the owner broadcasts (every rank calls with the same cand)
+        TP_ARG(tp_nranks(ctx) == ctx->last_sweep_ranks, "tp_get_dendro: select the communicator the sweep ran over");
+        TP_CUDA(cudaSetDevice(ctx->device));
+        if (seqdist_out) TP_TRY(tp_comm_bcast(ctx, ctx->seqdist.as<double>() + (size_t)cand * ldd, (size_t)n1, owner));
+        if (order_out) TP_TRY(tp_comm_bcast_bytes(ctx, ctx->order.as<int4>() + (size_t)cand * ldd, (size_t)n1 * sizeof(int4), owner));
+    }
+    TP_CUDA(cudaSetDevice(src->device));
     if (seqdist_out)
-        TP_CUDA(cudaMemcpyAsync(seqdist_out, ctx->seqdist.as<double>() + (size_t)cand * ldd, (size_t)n1 * sizeof(double),
-                                cudaMemcpyDeviceToHost, ctx->stream));
+        TP_CUDA(cudaMemcpyAsync(seqdist_out, src->seqdist.as<double>() + (size_t)cand * ldd, (size_t)n1 * sizeof(double),
+                                cudaMemcpyDeviceToHost, src->stream));
     std::vector<int> tmp;
     if (order_out) {
         tmp.resize((size_t)n1 * 4);
-        TP_CUDA(cudaMemcpyAsync(tmp.data(), ctx->order.as<int4>() + (size_t)cand * ldd, (size_t)n1 * sizeof(int4),
-                                cudaMemcpyDeviceToHost, ctx->stream));
+        TP_CUDA(cudaMemcpyAsync(tmp.data(), src->order.as<int4>() + (size_t)cand * ldd, (size_t)n1 * sizeof(int4),
+                                cudaMemcpyDeviceToHost, src->stream));
     }
-    TP_CUDA(tp_stream_sync(ctx));
+    TP_CUDA(tp_stream_sync(src));
+    if (src != ctx) TP_CUDA(cudaSetDevice(ctx->device));
     if (order_out) for (int t = 0; t < n1; t++) order_out[t] = tmp[(size_t)t * 4];
     return TP_OK;
 }
@@ -626,6 +664,11 @@ static int call_from_compacted(tp_ctx *ctx, int max_pcs, int min_clusters, int *
 extern "C" int tp_recall(tp_ctx *ctx, int max_pcs, int min_clusters, int *k_out, int *n_pcs_out, int *n_clusters_out,
                          double *scores_out, int ld_scores, int *maxlev_out, double *seqdist_out) {
     TP_ARG(ctx, "tp_recall: null context");
+    if (tp_group_dispatch(ctx))
+        return tp_group_run(ctx, [&](tp_ctx *gc, int gr) -> int {
+            return gr ? tp_recall(gc, max_pcs, min_clusters, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr)
+                      : tp_recall(gc, max_pcs, min_clusters, k_out, n_pcs_out, n_clusters_out, scores_out, ld_scores, maxlev_out, seqdist_out);
+        });
     TP_ARG(ctx->have_scores && ctx->k_full >= 1, "tp_recall: no PC scores in the context (run tp_call / tp_call_arm / tp_pca first)");
     TP_ARG(max_pcs >= 1, "tp_recall: max_pcs must be positive");
     const int want = max_pcs < ctx->nf ? max_pcs : ctx->nf;
@@ -646,6 +689,15 @@ extern "C" int tp_call(tp_ctx *ctx, const double *mat, int n, int colmajor, int 
                        uint8_t *bad_out, int *nf_out, int *k_out, int *n_pcs_out, int *n_clusters_out,
                        double *scores_out, int ld_scores, int *maxlev_out, double *seqdist_out) {
     TP_ARG(ctx && mat && bad_out, "tp_call: null argument");
+    if (tp_group_dispatch(ctx))
+        return tp_group_run(ctx, [&](tp_ctx *gc, int gr) -> int {
+            if (gr == 0)
+                return tp_call(gc, mat, n, colmajor, on_device, max_pcs, min_clusters, bad_frac, bad_out, nf_out, k_out, n_pcs_out,
+                               n_clusters_out, scores_out, ld_scores, maxlev_out, seqdist_out);
+            std::vector<uint8_t> tmp((size_t)(n > 0 ? n : 1));
+            return tp_call(gc, mat, n, colmajor, on_device, max_pcs, min_clusters, bad_frac, tmp.data(), nullptr, nullptr, nullptr,
+                           nullptr, nullptr, 0, nullptr, nullptr);
+        });
     TP_CUDA(cudaSetDevice(ctx->device));
     TP_MARK(ctx, EV_TOTAL0);
     TP_TRY(tp_filter(ctx, mat, n, colmajor, on_device, bad_frac, bad_out, nullptr, nullptr));
@@ -663,6 +715,12 @@ extern "C" int tp_call_arm(tp_ctx *ctx, const int *keep, int nf, int max_pcs, in
                            int *k_out, int *n_pcs_out, int *n_clusters_out,
                            double *scores_out, int ld_scores, int *maxlev_out, double *seqdist_out) {
     TP_ARG(ctx && keep, "tp_call_arm: null argument");
+    if (tp_group_dispatch(ctx))
+        return tp_group_run(ctx, [&](tp_ctx *gc, int gr) -> int {
+            return gr ? tp_call_arm(gc, keep, nf, max_pcs, min_clusters, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr)
+                      : tp_call_arm(gc, keep, nf, max_pcs, min_clusters, k_out, n_pcs_out, n_clusters_out, scores_out, ld_scores,
+                                    maxlev_out, seqdist_out);
+        });
     TP_CUDA(cudaSetDevice(ctx->device));
     TP_MARK(ctx, EV_TOTAL0);
     TP_TRY(tp_compact(ctx, keep, nf));

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include <dlfcn.h>
 #include <nccl.h>
+#include <mutex>
 
 struct TpNccl {
     void *lib = nullptr;
@@ -23,10 +24,15 @@ struct TpNccl {
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
 };
 static TpNccl g_nccl;
 
 static int nccl_bind() {
+    static std::mutex mu;                 // several rank threads of one process may arrive together
+    std::lock_guard<std::mutex> lock(mu);
     if (g_nccl.lib) return TP_OK;
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
     void *h = nullptr;
@@ -39,7 +45,7 @@ static int nccl_bind() {
         if (!g_nccl.f) { tp_set_error("NCCL symbol nccl" #f " missing"); return TP_ERR_CUDA; } \
     } while (0)
     BIND(GetUniqueId); BIND(CommInitRank); BIND(CommDestroy); BIND(GetErrorString);
-    BIND(AllGather); BIND(AllReduce); BIND(Broadcast);
+    BIND(AllGather); BIND(AllReduce); BIND(Broadcast); BIND(CommInitAll); BIND(GroupStart); BIND(GroupEnd);
 #undef BIND
     g_nccl.lib = h;
     return TP_OK;
@@ -124,5 +130,49 @@ int tp_comm_bcast(tp_ctx *ctx, double *buf, size_t count, int root) {
     tp_prof_begin(ctx, PC_COMM);
     TP_NCCL(g_nccl.Broadcast(buf, buf, count, ncclDouble, root, (ncclComm_t)c.handle, ctx->stream));
     tp_prof_end(ctx);
+    return TP_OK;
+}
+
+// raw bytes, in place (the root's buffer is the source, everyone else's the destination)
+int tp_comm_bcast_bytes(tp_ctx *ctx, void *buf, size_t bytes, int root) {
+    if (tp_nranks(ctx) == 1) return TP_OK;
+    const TpCommSlot &c = ctx->comm[ctx->comm_cur];
+    if (!ctx->comm_grouped) tp_prof_begin(ctx, PC_COMM);
+    TP_NCCL(g_nccl.Broadcast(buf, buf, bytes, ncclChar, root, (ncclComm_t)c.handle, ctx->stream));
+    if (!ctx->comm_grouped) tp_prof_end(ctx);
+    return TP_OK;
+}
+// the collectives between begin and end are issued as one NCCL group (timed as one)
+int tp_comm_group_begin(tp_ctx *ctx) {
+    if (tp_nranks(ctx) == 1) return TP_OK;
+    tp_prof_begin(ctx, PC_COMM);
+    ctx->comm_grouped = true;
+    TP_NCCL(g_nccl.GroupStart());
+    return TP_OK;
+}
+int tp_comm_group_end(tp_ctx *ctx) {
+    if (tp_nranks(ctx) == 1) return TP_OK;
+    ctx->comm_grouped = false;
+    TP_NCCL(g_nccl.GroupEnd());
+    tp_prof_end(ctx);
+    return TP_OK;
+}
+
+// One process driving several GPUs (multi-device contexts, group.cu): all communicators of the group at once, member i = rank i
+int tp_comm_init_all(tp_ctx **members, int nmembers, int slot) {
+    TP_ARG(members && nmembers >= 2 && slot >= 0 && slot < TP_COMM_SLOTS, "tp_comm_init_all: bad arguments");
+    TP_TRY(nccl_bind());
+    std::vector<int> devs(nmembers);
+    std::vector<ncclComm_t> comms(nmembers, nullptr);
+    for (int i = 0; i < nmembers; i++) {
+        TP_ARG(!members[i]->comm[slot].handle, "tp_comm_init_all: slot already holds a communicator");
+        devs[i] = members[i]->device;
+    }
+    TP_NCCL(g_nccl.CommInitAll(comms.data(), nmembers, devs.data()));
+    for (int i = 0; i < nmembers; i++) {
+        members[i]->comm[slot].handle = (void *)comms[i];
+        members[i]->comm[slot].rank = i;
+        members[i]->comm[slot].nranks = nmembers;
+    }
     return TP_OK;
 }

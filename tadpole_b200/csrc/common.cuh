@@ -7,6 +7,7 @@
 #include <math.h>
 #include <string>
 #include <vector>
+#include <functional>
 #include "../../include/tadpole_b200.h"
 
 void tp_set_error(const char *fmt, ...);
@@ -40,7 +41,10 @@ struct DevBuf {
     size_t cap = 0;
     int reserve(size_t bytes) {
         if (bytes <= cap) return TP_OK;
-        if (p) cudaFree(p);
+        // cudaFree waits for the device; with several devices driven by one process (multi-device contexts, group.cu) that
+        // wait must not happen inside the runtime call, where it could hold up another thread's launch of the collective
+        // this device is waiting for: drain the device first, then free
+        if (p) { cudaDeviceSynchronize(); cudaFree(p); }
         p = nullptr; cap = 0;
         size_t want = bytes + (bytes >> 3);
         cudaError_t e = cudaMalloc(&p, want);
@@ -68,7 +72,17 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 #define TP_COMM_SLOTS 4
 struct TpCommSlot { void *handle = nullptr; int rank = 0, nranks = 1; };
 
+struct TpGroup;
+struct TpPool;
+
 struct tp_ctx {
+    // multi-device context (group.cu): every member points to the group; the member with group_rank 0 is the handle the
+    // caller holds.  One host thread per member device runs the members' calls (the members are the "ranks" of comm.cu).
+    TpGroup *group = nullptr;
+    int group_rank = 0;
+    TpPool *pool = nullptr;        // contexts of tp_call_batch, owned by the context the batch was first run on
+    long long generation = 0;      // bumped whenever the resident matrix / scores / sweep state are replaced
+
     int device = 0;
     int sm_count = 148;
     int max_smem_optin = 0;
@@ -81,6 +95,8 @@ struct tp_ctx {
     // comm_cur = -1: no collective (single GPU, or replicated / independent work)
     TpCommSlot comm[TP_COMM_SLOTS];
     int comm_cur = -1;
+    bool comm_grouped = false;   // between tp_comm_group_begin / end
+    int last_sweep_ranks = 1;    // ranks the candidates of the last sweep were dealt out over (owner of candidate c: c % ranks)
     int dist_min_n = 4096;       // matrices smaller than this are not row-sharded over the ranks (only the candidate sweep is)
     int igemm_min_n = 1024;      // integer-count matrices at least this large take the tcgen05 int8 Gram path (0 = never)
     int iop_min_n = 1024;        // smallest nf whose early subspace-iteration rounds use the sliced int8 operator (0 = never)
@@ -212,6 +228,21 @@ int tp_comm_allgather(tp_ctx *ctx, double *buf, size_t chunk);          // in pl
 int tp_comm_allreduce_sum(tp_ctx *ctx, void *buf, size_t count, int is_double);
 int tp_comm_bcast(tp_ctx *ctx, double *buf, size_t count, int root);
 int tp_comm_destroy_all(tp_ctx *ctx);
+int tp_comm_bcast_bytes(tp_ctx *ctx, void *buf, size_t bytes, int root);            // in place
+int tp_comm_group_begin(tp_ctx *ctx);                                               // ncclGroupStart / End around several
+int tp_comm_group_end(tp_ctx *ctx);                                                 // collectives of one rank
+int tp_comm_init_all(tp_ctx **members, int nmembers, int slot);                     // ncclCommInitAll over the members' devices
+// ---- multi-device contexts (group.cu) ----
+// true when `ctx` is the handle of a multi-device context and the caller is not one of its own rank threads: the entry
+// point then runs itself once per member device (tp_group_run) instead of on this context alone
+bool tp_group_dispatch(const tp_ctx *ctx);
+// fn(member, rank) on every member concurrently (rank 0 on the calling thread); first failure wins, its message becomes
+// the calling thread's tp_last_error()
+int tp_group_run(tp_ctx *ctx, const std::function<int(tp_ctx *, int)> &fn);
+int tp_group_size(const tp_ctx *ctx);
+tp_ctx *tp_group_member(const tp_ctx *ctx, int rank);
+void tp_group_destroy(tp_ctx *leader);
+void tp_pool_destroy(tp_ctx *ctx);
 int tp_flags_reset(tp_ctx *ctx);                 // zero the status words (stream ordered)
 int tp_flags_read(tp_ctx *ctx, int out[4]);      // copy them to the host (synchronises the stream)
 int tp_flags_enqueue(tp_ctx *ctx);               // async copy into ctx->pin_flags; valid after the next stream sync

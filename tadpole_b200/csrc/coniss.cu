@@ -396,8 +396,17 @@ int tp_sweep_device(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stri
     std::vector<int> cands;
     const int ncand = build_cand_list(k, cand_begin, cand_stride, cands);
     *ncand_out = ncand;
-    if (ncand == 0) return TP_OK;
     cudaStream_t st = ctx->stream;
+    if (ncand == 0) {          // a rank of a sharded sweep with more ranks than candidates: nothing to run, rows stay empty
+        TP_TRY(ctx->ncl.reserve((size_t)(2 * k + 8) * sizeof(int)));
+        TP_CUDA(cudaMemsetAsync(ctx->ncl.p, 0, k * sizeof(int), st));
+        TP_TRY(ctx->seqdist.reserve((size_t)k * ldd * sizeof(double)));
+        TP_TRY(ctx->order.reserve((size_t)k * ldd * sizeof(int4)));
+        TP_MARK(ctx, EV_SWEEP0);
+        TP_MARK(ctx, EV_SWEEP1);
+        ctx->have_sweep = true;
+        return TP_OK;
+    }
 
     TP_TRY(ctx->P.reserve((size_t)(n + 1) * ldk * sizeof(double)));
     TP_TRY(ctx->Qp.reserve((size_t)(n + 2) * sizeof(double) * 2));
@@ -475,6 +484,7 @@ int tp_ch_device(tp_ctx *ctx, int min_clusters, int ncand, int ld_chs) {
     int *d_cands = ctx->ncl.as<int>() + k;
     // rows of candidates that are not run must read as NaN too
     TP_CUDA(cudaMemsetAsync(ctx->chs.p, 0xff, (size_t)k * ld_chs * sizeof(double), st));
+    if (ncand == 0) { TP_MARK(ctx, EV_CH1); return TP_OK; }
     tp_prof_begin(ctx, PC_CH);
     ch_kernel<<<ncand, 32, 0, st>>>(ctx->P.as<double>(), ctx->Qp.as<double>(), ldk, n, k,
                                     ctx->seqdist.as<double>(), ctx->order.as<int4>(), ldd, d_cands, min_clusters,

@@ -174,21 +174,44 @@ int tp_filter(tp_ctx *ctx, const double *mat, int n, int colmajor, int on_device
     TP_ARG(ctx && mat && bad_out, "tp_filter: null argument");
     TP_ARG(n >= 2, "tp_filter: matrix must be at least 2 x 2");
     TP_ARG(bad_frac >= 0.0 && bad_frac <= 1.0, "tp_filter: bad_frac must be in [0, 1]");
+    if (tp_group_dispatch(ctx))      // multi-device context: every member device runs the stage; rank 0 reports
+        return tp_group_run(ctx, [&](tp_ctx *gc, int gr) -> int {
+            std::vector<uint8_t> tmp;
+            if (gr) tmp.resize((size_t)n);
+            return tp_filter(gc, mat, n, colmajor, on_device, bad_frac, gr ? tmp.data() : bad_out, gr ? nullptr : rowmeans_out,
+                             gr ? nullptr : thr_out);
+        });
     TP_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    ctx->generation++;
     const size_t bytes = (size_t)n * n * sizeof(double);
-    if (on_device) {
+    const int R = tp_nranks(ctx), rank = tp_rank(ctx);
+    if (on_device && ctx->group && R > 1) {
+        // multi-device context: `mat` lives on the first device; the others receive it over NVLink
+        ctx->ingested_n = rank == 0 ? ctx->ingested_n : 0;
+        double *dst = const_cast<double *>(mat);
+        if (rank != 0) { TP_TRY(ctx->raw_own.reserve(bytes)); dst = ctx->raw_own.as<double>(); }
+        TP_TRY(tp_comm_bcast_bytes(ctx, dst, bytes, 0));
+        ctx->raw = dst;
+    } else if (on_device) {
         ctx->raw = mat;
     } else {
         // Only the upper triangle is ever read (forceSymmetric(uplo = 'U')), so only it crosses PCIe: ~32 band copies
         // (row bands from the diagonal to the right edge; column bands from the top to the diagonal for R's layout),
         // 52 % of the bytes of the full matrix.
+        // Several ranks working on the same matrix (a call spread over GPUs) upload it ONCE between them: the bands are
+        // dealt out boustrophedon (equal bytes per rank), every rank pulls its bands over its own PCIe link, then each
+        // band is broadcast from its owner over NVLink.
         ctx->ingested_n = 0;                       // raw_own is about to be overwritten
         TP_TRY(ctx->raw_own.reserve(bytes));
         double *dst = ctx->raw_own.as<double>();
         const int band = n / 32 > 64 ? n / 32 : 64;
         const size_t pitch = (size_t)n * sizeof(double);
-        for (int r = 0; r < n; r += band) {
+        const bool share = R > 1 && n >= ctx->dist_min_n;
+        auto owner_of = [&](int bi) { const int blk = bi / R, pos = bi % R; return (blk & 1) ? R - 1 - pos : pos; };
+        int bi = 0;
+        for (int r = 0; r < n; r += band, bi++) {
+            if (share && owner_of(bi) != rank) continue;
             const int h = n - r < band ? n - r : band;
             if (!colmajor)   // rows [r, r + h), columns [r, n)
                 TP_CUDA(cudaMemcpy2DAsync(dst + (size_t)r * n + r, pitch, mat + (size_t)r * n + r, pitch,
@@ -196,6 +219,18 @@ int tp_filter(tp_ctx *ctx, const double *mat, int n, int colmajor, int on_device
             else             // columns [r, r + h), rows [0, r + h)
                 TP_CUDA(cudaMemcpy2DAsync(dst + (size_t)r * n, pitch, mat + (size_t)r * n, pitch,
                                           (size_t)(r + h) * sizeof(double), h, cudaMemcpyHostToDevice, st));
+        }
+        if (share) {
+            // the memory between the first and the last uploaded element of a band is one contiguous range
+            TP_TRY(tp_comm_group_begin(ctx));
+            bi = 0;
+            for (int r = 0; r < n; r += band, bi++) {
+                const int h = n - r < band ? n - r : band;
+                double *b0 = colmajor ? dst + (size_t)r * n : dst + (size_t)r * n + r;
+                double *b1 = colmajor ? dst + (size_t)(r + h - 1) * n + (r + h) : dst + (size_t)(r + h) * n;
+                TP_TRY(tp_comm_bcast_bytes(ctx, b0, (size_t)(b1 - b0) * sizeof(double), owner_of(bi)));
+            }
+            TP_TRY(tp_comm_group_end(ctx));
         }
         ctx->raw = dst;
     }
@@ -244,8 +279,10 @@ int tp_filter(tp_ctx *ctx, const double *mat, int n, int colmajor, int on_device
 
 int tp_compact(tp_ctx *ctx, const int *keep, int nf) {
     TP_ARG(ctx && keep, "tp_compact: null argument");
+    if (tp_group_dispatch(ctx)) return tp_group_run(ctx, [&](tp_ctx *gc, int) -> int { return tp_compact(gc, keep, nf); });
     TP_ARG(ctx->raw && ctx->n > 0, "tp_compact: call tp_filter first");
     TP_ARG(nf >= 2 && nf <= ctx->n, "tp_compact: bad keep count");
+    ctx->generation++;
     for (int i = 0; i < nf; i++)
         TP_ARG(keep[i] >= 0 && keep[i] < ctx->n, "tp_compact: keep index out of range");
     TP_CUDA(cudaSetDevice(ctx->device));

@@ -366,6 +366,7 @@ static int ingest_core(tp_ctx *ctx, const TextSource &src, int sep, int *n_out) 
     ctx->n = n;
     ctx->colmajor = 0;
     ctx->ingested_n = n;
+    ctx->generation++;
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev[EV_INGEST0], ctx->ev[EV_INGEST1]);
     ctx->ingest_stats[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();

@@ -172,6 +172,7 @@ __global__ void scores_kernel(const double *__restrict__ U, int ldu, const doubl
 
 // ---- stage 2 -------------------------------------------------------------------------------------
 int tp_correlation(tp_ctx *ctx) {
+    if (tp_group_dispatch(ctx)) return tp_group_run(ctx, [&](tp_ctx *gc, int) -> int { return tp_correlation(gc); });
     TP_ARG(ctx && ctx->have_X, "tp_correlation: no filtered matrix in the context");
     TP_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -285,9 +286,12 @@ static int small_gemm(tp_ctx *ctx, const double *A, int a_kc, const double *B, i
 }
 
 int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
+    if (tp_group_dispatch(ctx))
+        return tp_group_run(ctx, [&](tp_ctx *gc, int gr) -> int { return tp_pca(gc, max_pcs, gr ? nullptr : k_out); });
     TP_ARG(ctx && ctx->have_C, "tp_pca: no correlation matrix in the context");
     TP_ARG(max_pcs >= 1, "tp_pca: max_pcs must be >= 1");
     TP_CUDA(cudaSetDevice(ctx->device));
+    ctx->generation++;
     cudaStream_t st = ctx->stream;
     const int n = ctx->nf, ld = ctx->ldx;
     const int k = max_pcs < n ? max_pcs : n;       // number_pca <- min(max_pcs, nrow(mat))

@@ -13,26 +13,10 @@ __all__ = ["Dendro", "find_groups", "cutree"]
 
 
 def find_groups(seqdist):
-    """hclust merge matrix, R convention: negative = singleton object, positive = earlier step."""
-    x = np.asarray(seqdist, dtype=np.float64)
-    n1 = x.size
-    merge = np.zeros((n1, 2), dtype=np.int64)
-    parent = np.arange(n1 + 1)
-    owner = np.zeros(n1 + 1, dtype=np.int64)
-
-    def root(a):
-        while parent[a] != a:
-            parent[a] = parent[parent[a]]
-            a = parent[a]
-        return a
-
-    for step, j in enumerate(np.lexsort((np.arange(n1), x)), start=1):
-        ra, rb = root(j), root(j + 1)
-        merge[step - 1, 0] = -(j + 1) if owner[ra] == 0 else owner[ra]
-        merge[step - 1, 1] = -(j + 2) if owner[rb] == 0 else owner[rb]
-        parent[rb] = ra
-        owner[ra] = step
-    return merge
+    """hclust merge matrix, R convention: negative = singleton object, positive = earlier step (tp_find_groups in the
+    library: union-find over the boundaries in rioja's .find.groups order)."""
+    from . import _lib
+    return _lib.find_groups(seqdist)
 
 
 def cutree(seqdist, k):

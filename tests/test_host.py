@@ -116,6 +116,13 @@ def test_python_host_helpers_match_oracle():
     rng = np.random.default_rng(2)
     seq = rng.random(40)
     assert hclust.find_groups(seq).tolist() == O.find_groups(seq)[0].tolist()
+    # the library's union-find against the oracle's literal repeated-which.min loop, ties and long chains included
+    for n1, levels in ((1, 3), (2, 2), (257, 4), (1500, 50)):
+        s2 = np.round(rng.random(n1) * levels)
+        assert hclust.find_groups(s2).tolist() == O.find_groups(s2)[0].tolist(), n1
+    s3 = np.cumsum(rng.random(300))                       # one chain growing to the right, then to the left
+    assert hclust.find_groups(s3).tolist() == O.find_groups(s3)[0].tolist()
+    assert hclust.find_groups(s3[::-1]).tolist() == O.find_groups(s3[::-1])[0].tolist()
     for k in (1, 2, 7, 41):
         assert hclust.cutree(seq, k).tolist() == O.cutree(seq, k).tolist()
     bed = np.array([[5, 9], [10, 20], [18, 25]])

@@ -139,6 +139,16 @@ def test_find_groups_and_cutree():
     assert O.cutree(seq, 3).tolist() == [1, 1, 1, 2, 2, 3]
 
 
+def test_cutree_from_merge_matrix_agrees_with_sorted_heights():
+    """two independent routes to stats::cutree: undoing merges of the literal .find.groups matrix vs ranking the heights"""
+    rng = np.random.default_rng(11)
+    for n1 in (1, 2, 17, 130):
+        seq = np.round(rng.random(n1) * 6)            # many exact ties
+        merge, _ = O.find_groups(seq)
+        for k in sorted({1, 2, min(5, n1 + 1), n1 + 1}):
+            assert O.cutree_from_merge(merge, k).tolist() == O.cutree(seq, k).tolist(), (n1, k)
+
+
 def test_bstick_and_first_true_run():
     seq = np.cumsum(np.arange(1.0, 11.0))               # heights 1,3,6,...,55
     disp, bs = O.bstick_table(seq)
