@@ -54,6 +54,8 @@ int tp_ctx_create(int device, tp_ctx **out);
  * device pulls a share of the upper-triangle bands over its own PCIe link and the bands are exchanged over NVLink.
  * ndev = 1 gives a plain context.  Everything else (getters, diffT, ingest) runs on devices[0]. */
 int tp_ctx_create_multi(const int *devices, int ndev, tp_ctx **out);
+/* CUDA devices visible to the process (0 when there is none or no driver) */
+int tp_device_count(void);
 /* devices of the context (returns their number; fills at most `cap` entries) */
 int tp_ctx_devices(tp_ctx *ctx, int *devices_out, int cap);
 /* Counter that changes whenever the state resident in the context (matrix, PC scores, dendrograms) is replaced: a host

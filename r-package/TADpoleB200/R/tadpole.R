@@ -3,33 +3,28 @@
 # Written against the C ABI in include/tadpole_b200.h; the same logic runs (and is tested) as tadpole_b200/api.py.
 # NOTE: R is not available in the build image, so this file is exercised only through its .Call targets
 # (tests/test_r_shim_*.py drive src/r_shim.c with a stand-in R runtime); it has not been run under R.
+# plot_hierarchy() and CH_map() of the reference only read the returned object: source them from the reference
+# package unchanged (they are graphics, outside this package).
 
 .tp_state <- new.env(parent = emptyenv())
 
-.tp_ctx <- function(device = 0L) {
-    key <- paste0("ctx", device)
-    if (is.null(.tp_state[[key]])) .tp_state[[key]] <- .Call(C_tp_ctx, as.integer(device))
+# One context per device set.  options(tadpole.gpus = 0:7) makes every call of this session spread over those GPUs: the
+# library then owns one host thread per GPU (R stays single-threaded), as registerDoParallel(detectCores()) made the
+# reference spread over every core.
+.tp_ctx <- function(devices = getOption("tadpole.gpus", 0L)) {
+    devices <- as.integer(devices)
+    key <- paste0("ctx", paste(devices, collapse = "_"))
+    if (is.null(.tp_state[[key]])) .tp_state[[key]] <- .Call(C_tp_ctx, devices)
     .tp_state[[key]]
 }
 
-# chclust / hclust object from the seqdist vector the GPU returns (rioja builds the same fields from its C result)
+# chclust / hclust object from the seqdist vector the GPU returns (rioja builds the same fields from its C result);
+# merge = rioja's .find.groups rule, computed in the library (union-find, O(n log n): the interpreted loop of repeated
+# which.min is minutes at 25k bins)
 .tp_dendro <- function(seqdist, labels) {
     n <- length(seqdist) + 1L
-    merge <- matrix(0L, n - 1L, 2L)
-    owner <- integer(n)                       # merge step that last absorbed object j (0: still a singleton)
-    x <- seqdist
-    for (step in seq_len(n - 1L)) {
-        j <- which.min(x)
-        left <- if (owner[j] == 0L) -j else owner[j]
-        right <- if (owner[j + 1L] == 0L) -(j + 1L) else owner[j + 1L]
-        merge[step, ] <- c(left, right)
-        members <- which(owner == owner[j] & owner != 0L | seq_len(n) == j |
-                         owner == owner[j + 1L] & owner != 0L | seq_len(n) == j + 1L)
-        owner[members] <- step
-        x[j] <- NA
-    }
-    structure(list(merge = merge, height = sort(seqdist), seqdist = seqdist, order = seq_len(n),
-                   labels = as.character(labels), method = "coniss",
+    structure(list(merge = .Call(C_tp_find_groups, as.numeric(seqdist)), height = sort(seqdist), seqdist = seqdist,
+                   order = seq_len(n), labels = as.character(labels), method = "coniss",
                    call = quote(rioja::chclust(d = dist(pcs))), dist.method = "euclidean"),
               class = c("chclust", "hclust"))
 }
@@ -60,23 +55,35 @@
          centromere = cs:ce)
 }
 
-load_mat <- function(mat_file, chr, start, end, resol, bad_frac = 0.01, centromere_search = FALSE) {
-    ctx <- .tp_ctx()
+# the numeric core of load_mat on the GPU: which bins stay (index lists; the matrix itself stays in HBM)
+.tp_load <- function(ctx, mat_file, bad_frac, centromere_search) {
     if (is.character(mat_file)) {
         .Call(C_tp_ingest, ctx, path.expand(mat_file))          # the file's text is parsed on the GPU
         bad <- .Call(C_tp_filter, ctx, NULL, as.numeric(bad_frac))
     } else {
         bad <- .Call(C_tp_filter, ctx, as.matrix(mat_file) + 0, as.numeric(bad_frac))
     }
-    structure(.tp_split(bad, centromere_search), n_bins = length(bad), class = "tadpole_matrix")
+    structure(.tp_split(bad, centromere_search), n_bins = length(bad))
+}
+
+# mat[keep, keep] as the reference returns it: dimnames = original bin numbers, attr 'bad_columns'
+.tp_part_matrix <- function(ctx, part) {
+    m <- .Call(C_tp_get_filtered, ctx, as.integer(part$keep - 1L))
+    dimnames(m) <- list(as.character(part$keep), as.character(part$keep))
+    attr(m, "bad_columns") <- part$bad_columns
+    m
+}
+
+# Same return value as the reference (R/TADpole.R:85,88-90): the filtered numeric matrix carrying attr 'bad_columns', or
+# list(p = , q = , centromere = ) of such matrices.  (The plots of R/TADpole.R:24-53 are not drawn.)
+load_mat <- function(mat_file, chr, start, end, resol, bad_frac = 0.01, centromere_search = FALSE) {
+    ctx <- .tp_ctx()
+    parts <- .tp_load(ctx, mat_file, bad_frac, centromere_search)
+    if (is.null(parts$p)) return(.tp_part_matrix(ctx, parts))
+    list(p = .tp_part_matrix(ctx, parts$p), q = .tp_part_matrix(ctx, parts$q), centromere = parts$centromere)
 }
 
 # one matrix or one arm: list(n_pcs, optimal_n_clusters, dendro, clusters, scores, labels_optimal)
-.tp_call_part <- function(ctx, part, max_pcs, min_clusters) {
-    res <- .Call(C_tp_call_arm, ctx, as.integer(part$keep - 1L), as.integer(max_pcs), as.integer(min_clusters))
-    .tp_pack_part(res, part)
-}
-
 .tp_pack_part <- function(res, part) {
     n_pcs <- res[[1L]]; n_clusters <- res[[2L]]; seqdist <- res[[3L]]; scores <- res[[4L]]
     dimnames(scores) <- list(as.character(seq_len(nrow(scores))), as.character(seq_len(ncol(scores))))
@@ -96,20 +103,25 @@ load_mat <- function(mat_file, chr, start, end, resol, bad_frac = 0.01, centrome
 TADpole <- function(mat_file, max_pcs = 200, min_clusters = 2, bad_frac = 0.01,
                     chr, start, end, resol, centromere_search = FALSE) {
     ctx <- .tp_ctx()
-    mat <- load_mat(mat_file, chr, start, end, resol, bad_frac = bad_frac, centromere_search = centromere_search)
+    mat <- .tp_load(ctx, mat_file, bad_frac, centromere_search)
     if (!centromere_search) {
-        r <- .tp_call_part(ctx, mat, max_pcs, min_clusters)
+        res <- .Call(C_tp_call_arm, ctx, as.integer(mat$keep - 1L), as.integer(max_pcs), as.integer(min_clusters))
+        r <- .tp_pack_part(res, mat)
         out <- structure(list(n_pcs = r$n_pcs, optimal_n_clusters = r$optimal_n_clusters, dendro = r$dendro,
                               clusters = r$clusters, scores = r$scores), class = "tadpole")
-        attr(out, "resident") <- list(ctx = ctx, part = mat[c("keep", "bad_columns")])
+        attr(out, "resident") <- list(ctx = ctx, generation = res[[5L]], part = mat[c("keep", "bad_columns")])
         return(out)
     }
     if (is.null(mat$p)) stop("centromere_search = TRUE but load_mat did not split the matrix")
+    # both arms in one .Call: on several GPUs the two halves of the devices work on the two arms at the same time
+    both <- .Call(C_tp_call_arms, ctx, as.integer(mat$p$keep - 1L), as.integer(mat$q$keep - 1L),
+                  as.integer(max_pcs), as.integer(min_clusters))
+    names(both) <- c("p", "q")
     out <- structure(list(), class = "tadpole")
     joined <- integer(0)
     for (arm in c("p", "q")) {
         message(paste("Processing arm", arm))
-        r <- .tp_call_part(ctx, mat[[arm]], max_pcs, min_clusters)
+        r <- .tp_pack_part(both[[arm]], mat[[arm]])
         out[[arm]] <- list(n_pcs = r$n_pcs, optimal_n_clusters = r$optimal_n_clusters, dendro = r$dendro,
                            cluster = r$clusters)
         joined <- c(joined, r$labels_optimal, rep(0L, length(mat$centromere)))
@@ -122,14 +134,36 @@ TADpole <- function(mat_file, max_pcs = 200, min_clusters = 2, bad_frac = 0.01,
     out
 }
 
+# TADpole() on a list of matrices (genome-wide use: one per chromosome), `inflight` calls per GPU kept in flight by the
+# library's own threads over every GPU of options(tadpole.gpus); same objects, same order, as calling TADpole() on each
+TADpole_batch <- function(mats, max_pcs = 200, min_clusters = 2, bad_frac = 0.01, inflight = 8L) {
+    ctx <- .tp_ctx()
+    mats <- lapply(mats, function(m) if (is.character(m)) {
+        .Call(C_tp_ingest, ctx, path.expand(m)); .Call(C_tp_ingested_matrix, ctx) } else as.matrix(m) + 0)
+    res <- .Call(C_tp_call_batch, ctx, mats, as.integer(max_pcs), as.integer(min_clusters), as.numeric(bad_frac),
+                 as.integer(inflight))
+    lapply(res, function(r) {
+        if (is.character(r)) stop(r)
+        bad <- r[[1L]]; scores <- r[[5L]]; keep <- which(!bad)
+        dimnames(scores) <- list(as.character(seq_len(nrow(scores))), as.character(seq_len(ncol(scores))))
+        clusters <- lapply(r[[7L]], function(m) data.frame(start = m[, 1L], end = m[, 2L]))
+        names(clusters) <- as.character(r[[6L]])
+        structure(list(n_pcs = r[[2L]], optimal_n_clusters = r[[3L]], dendro = .tp_dendro(r[[4L]], keep),
+                       clusters = clusters, scores = scores), class = "tadpole")
+    })
+}
+
 # the n_pcs sweep again with another max_pcs / min_clusters on the PC scores that are still on the GPU
 tadpole_recall <- function(tadpole, max_pcs = 200, min_clusters = 2) {
     h <- attr(tadpole, "resident")
     if (is.null(h)) stop("this tadpole object carries no device handle")
-    res <- .Call(C_tp_recall, h$ctx, length(h$part$keep), as.integer(max_pcs), as.integer(min_clusters))
+    # the shim stops when the context has been used for another matrix since (generation), and sizes every buffer from
+    # the context, never from this object
+    res <- .Call(C_tp_recall, h$ctx, h$generation, as.integer(max_pcs), as.integer(min_clusters))
     r <- .tp_pack_part(res, h$part)
     out <- structure(list(n_pcs = r$n_pcs, optimal_n_clusters = r$optimal_n_clusters, dendro = r$dendro,
                           clusters = r$clusters, scores = r$scores), class = "tadpole")
+    h$generation <- res[[5L]]               # the sweep state was replaced: `tadpole` itself is stale from here on
     attr(out, "resident") <- h
     out
 }
@@ -138,7 +172,7 @@ tadpole_recall <- function(tadpole, max_pcs = 200, min_clusters = 2) {
 tadpole_dendro <- function(tadpole, n_pcs) {
     h <- attr(tadpole, "resident")
     if (is.null(h)) stop("this tadpole object carries no device handle")
-    .tp_dendro(.Call(C_tp_dendro, h$ctx, length(h$part$keep), as.integer(n_pcs)), h$part$keep)
+    .tp_dendro(.Call(C_tp_dendro, h$ctx, h$generation, as.integer(n_pcs)), h$part$keep)
 }
 
 .tp_bin_index <- function(bed, size) {

@@ -31,13 +31,33 @@ static void ctx_finalizer(SEXP p) {
     }
 }
 
-SEXP C_tp_ctx(SEXP device) {
+/* devices: one index, or several -> one context over those GPUs driven from this one thread (options(tadpole.gpus=)) */
+SEXP C_tp_ctx(SEXP devices) {
     tp_ctx *c = NULL;
-    if (tp_ctx_create(asInteger(device), &c) != TP_OK) error("%s", tp_last_error());
+    int ndev = length(devices);
+    if (ndev < 1) error("TADpole: no device given");
+    int *devs = (int *)R_alloc((size_t)ndev, sizeof(int));
+    if (ndev == 1) devs[0] = asInteger(devices);
+    else for (int i = 0; i < ndev; i++) devs[i] = isReal(devices) ? (int)REAL(devices)[i] : INTEGER(devices)[i];
+    if (tp_ctx_create_multi(devs, ndev, &c) != TP_OK) error("%s", tp_last_error());
     SEXP p = PROTECT(R_MakeExternalPtr(c, R_NilValue, R_NilValue));
     R_RegisterCFinalizerEx(p, ctx_finalizer, TRUE);
     UNPROTECT(1);
     return p;
+}
+
+/* the counter that changes whenever the state resident in the context is replaced (kept in attr(, 'resident')) */
+SEXP C_tp_generation(SEXP ctx) {
+    SEXP g = PROTECT(allocVector(REALSXP, 1));
+    REAL(g)[0] = (double)tp_ctx_generation(ctx_of(ctx));
+    UNPROTECT(1);
+    return g;
+}
+
+/* stop() unless the context still holds the state the R object was made from */
+static void check_generation(tp_ctx *c, SEXP generation) {
+    if ((double)tp_ctx_generation(c) != asReal(generation))
+        error("TADpole: the GPU context has been used for another matrix since this call; its resident state is gone");
 }
 
 /* read.big.matrix(mat_file, type = 'double', sep = '\t') on the device (R/TADpole.R:17): returns N */
@@ -109,12 +129,15 @@ static SEXP pack_call(tp_ctx *c, int rc, int k, int npcs, int ncl, int maxlev, i
             double v = sc[(size_t)r * ld + l];
             REAL(scores)[r + (size_t)l * k] = ISNAN(v) ? NA_REAL : v;
         }
-    SEXP out = PROTECT(allocVector(VECSXP, 4));
+    SEXP out = PROTECT(allocVector(VECSXP, 5));
     SET_VECTOR_ELT(out, 0, ScalarInteger(npcs));
     SET_VECTOR_ELT(out, 1, ScalarInteger(ncl));
     SET_VECTOR_ELT(out, 2, seq);
     SET_VECTOR_ELT(out, 3, scores);
-    UNPROTECT(2);
+    SEXP gen = PROTECT(allocVector(REALSXP, 1));
+    REAL(gen)[0] = (double)tp_ctx_generation(c);          /* the state this result was read from */
+    SET_VECTOR_ELT(out, 4, gen);
+    UNPROTECT(3);
     return out;
 }
 
@@ -134,11 +157,16 @@ SEXP C_tp_call_arm(SEXP ctx, SEXP keep, SEXP max_pcs, SEXP min_clusters) {
     return out;
 }
 
-/* the sweep again on the resident PC scores with another max_pcs / min_clusters (no reference counterpart) */
-SEXP C_tp_recall(SEXP ctx, SEXP nf_, SEXP max_pcs, SEXP min_clusters) {
+/* the sweep again on the resident PC scores with another max_pcs / min_clusters (no reference counterpart).  The sizes
+ * come from the context, never from the R object: `generation` proves the object and the context still belong together. */
+SEXP C_tp_recall(SEXP ctx, SEXP generation, SEXP max_pcs, SEXP min_clusters) {
     tp_ctx *c = ctx_of(ctx);
-    int nf = asInteger(nf_), k = 0, npcs = 0, ncl = 0, maxlev = 0, ld = 256;
+    check_generation(c, generation);
+    int nf = 0, kfull = 0, k = 0, npcs = 0, ncl = 0, maxlev = 0, ld = 256;
+    if (tp_ctx_dims(c, NULL, &nf, NULL, &kfull, NULL) != TP_OK) error("%s", tp_last_error());
+    if (nf < 3 || kfull < 1) error("TADpole: the context holds no PC scores");
     int kmax = asInteger(max_pcs) < nf ? asInteger(max_pcs) : nf;
+    if (kmax < 1) error("TADpole: max_pcs must be positive");
     SEXP seq = PROTECT(allocVector(REALSXP, nf - 1));
     double *sc = (double *)R_alloc((size_t)kmax * ld, sizeof(double));
     int rc = tp_recall(c, asInteger(max_pcs), asInteger(min_clusters), &k, &npcs, &ncl, sc, ld, &maxlev, REAL(seq));
@@ -148,15 +176,148 @@ SEXP C_tp_recall(SEXP ctx, SEXP nf_, SEXP max_pcs, SEXP min_clusters) {
 }
 
 /* seqdist of the candidate that clusters on the first n_pcs PCs (1-based), for CH_map / plot_hierarchy browsing */
-SEXP C_tp_dendro(SEXP ctx, SEXP nf_, SEXP n_pcs) {
-    int nf = asInteger(nf_);
+SEXP C_tp_dendro(SEXP ctx, SEXP generation, SEXP n_pcs) {
+    tp_ctx *c = ctx_of(ctx);
+    check_generation(c, generation);
+    int nf = 0, k = 0, maxlev = 0;
+    if (tp_ctx_dims(c, NULL, &nf, &k, NULL, &maxlev) != TP_OK) error("%s", tp_last_error());
+    if (nf < 3 || maxlev < 1) error("TADpole: the context holds no sweep");
+    if (asInteger(n_pcs) < 1 || asInteger(n_pcs) > k) error("TADpole: n_pcs must be between 1 and %d", k);
     SEXP seq = PROTECT(allocVector(REALSXP, nf - 1));
-    if (tp_get_dendro(ctx_of(ctx), asInteger(n_pcs) - 1, REAL(seq), NULL) != TP_OK) {
+    if (tp_get_dendro(c, asInteger(n_pcs) - 1, REAL(seq), NULL) != TP_OK) {
         UNPROTECT(1);
         error("%s", tp_last_error());
     }
     UNPROTECT(1);
     return seq;
+}
+
+/* mat[keep, keep] after NA -> 0 and forceSymmetric(uplo = 'U'): the matrix load_mat() returns (R/TADpole.R:85,88-90);
+ * keep = 0-based original indices.  Symmetric, so the row-major device copy is also the column-major R matrix. */
+SEXP C_tp_get_filtered(SEXP ctx, SEXP keep) {
+    tp_ctx *c = ctx_of(ctx);
+    int nf = length(keep);
+    if (nf < 2) error("TADpole: fewer than 2 good bins left after filtering");
+    if (tp_compact(c, INTEGER(keep), nf) != TP_OK) error("%s", tp_last_error());
+    SEXP m = PROTECT(allocMatrix(REALSXP, nf, nf));
+    if (tp_get_filtered(c, REAL(m)) != TP_OK) {
+        UNPROTECT(1);
+        error("%s", tp_last_error());
+    }
+    UNPROTECT(1);
+    return m;
+}
+
+/* dendro$merge of the chclust object: rioja's .find.groups on seqdist, in C (O(n log n)) */
+SEXP C_tp_find_groups(SEXP seqdist) {
+    int n1 = length(seqdist);
+    SEXP m = PROTECT(allocMatrix(INTSXP, n1, 2));
+    if (n1 > 0 && tp_find_groups(REAL(seqdist), n1, INTEGER(m)) != TP_OK) {
+        UNPROTECT(1);
+        error("%s", tp_last_error());
+    }
+    UNPROTECT(1);
+    return m;
+}
+
+/* both arms of a centromere_search call at once (R/TADpole.R:357-374); on a multi-device context the two halves of the
+ * devices work on the two arms at the same time.  list(p = <as C_tp_call_arm>, q = ...) */
+SEXP C_tp_call_arms(SEXP ctx, SEXP keep_p, SEXP keep_q, SEXP max_pcs, SEXP min_clusters) {
+    tp_ctx *c = ctx_of(ctx);
+    SEXP keep[2] = {keep_p, keep_q};
+    int nf[2] = {length(keep_p), length(keep_q)}, kmax[2], k[2], npcs[2], ncl[2], maxlev[2] = {0, 0}, ld = 256, rc;
+    if (nf[0] < 3 || nf[1] < 3) error("TADpole: fewer than 3 good bins left in an arm after filtering");
+    SEXP seq0 = PROTECT(allocVector(REALSXP, nf[0] - 1)), seq1 = PROTECT(allocVector(REALSXP, nf[1] - 1));
+    SEXP seq[2] = {seq0, seq1};
+    double *sc[2];
+    for (;;) {
+        for (int a = 0; a < 2; a++) {
+            kmax[a] = asInteger(max_pcs) < nf[a] ? asInteger(max_pcs) : nf[a];
+            sc[a] = (double *)R_alloc((size_t)kmax[a] * ld, sizeof(double));
+        }
+        rc = tp_call_arms(c, INTEGER(keep[0]), nf[0], INTEGER(keep[1]), nf[1], asInteger(max_pcs), asInteger(min_clusters),
+                          k, npcs, ncl, sc[0], sc[1], ld, maxlev, REAL(seq[0]), REAL(seq[1]));
+        int need = maxlev[0] > maxlev[1] ? maxlev[0] : maxlev[1];
+        if (rc == TP_ERR_ARG && need > ld) { ld = need; continue; }       /* rare: more levels than the buffers hold */
+        break;
+    }
+    if (rc != TP_OK) {
+        UNPROTECT(2);
+        error("%s", tp_last_error());
+    }
+    SEXP out = PROTECT(allocVector(VECSXP, 2));
+    for (int a = 0; a < 2; a++)
+        SET_VECTOR_ELT(out, a, pack_call(c, TP_OK, k[a], npcs[a], ncl[a], maxlev[a], ld, sc[a], kmax[a], seq[a]));
+    UNPROTECT(3);
+    return out;
+}
+
+/* TADpole() on a list of matrices, `inflight` calls per device kept in flight by the library's own threads over every
+ * device of the context (tp_call_batch); this thread only waits.  Per matrix: list(bad, n_pcs, optimal_n_clusters,
+ * seqdist, scores, levels, tables = list of 2-column (start, end) matrices), or a character error message. */
+SEXP C_tp_call_batch(SEXP ctx, SEXP mats, SEXP max_pcs, SEXP min_clusters, SEXP bad_frac, SEXP inflight) {
+    tp_ctx *c = ctx_of(ctx);
+    int nc = length(mats);
+    const double **ptr = (const double **)R_alloc((size_t)(nc ? nc : 1), sizeof(double *));
+    int *n = (int *)R_alloc((size_t)(nc ? nc : 1), sizeof(int));
+    for (int i = 0; i < nc; i++) {
+        SEXP m = VECTOR_ELT(mats, i);
+        if (!isReal(m) || nrows(m) != ncols(m)) error("TADpole: element %d is not a square numeric matrix", i + 1);
+        ptr[i] = REAL(m);
+        n[i] = nrows(m);
+    }
+    tp_batch *b = NULL;
+    if (tp_call_batch(c, nc, ptr, n, 1, 0, asInteger(max_pcs), asInteger(min_clusters), asReal(bad_frac), asInteger(inflight),
+                      1, &b) != TP_OK)
+        error("%s", tp_last_error());
+    /* (an R allocation failure below longjmps past tp_batch_free: the batch, plain host memory, is then leaked) */
+    SEXP out = PROTECT(allocVector(VECSXP, nc));
+    for (int i = 0; i < nc; i++) {
+        if (tp_batch_status(b, i) != TP_OK) {
+            SEXP msg = PROTECT(allocVector(STRSXP, 1));
+            SET_STRING_ELT(msg, 0, mkChar(tp_batch_error(b, i)));
+            SET_VECTOR_ELT(out, i, msg);
+            UNPROTECT(1);
+            continue;
+        }
+        int nn, nf, k, maxlev, nlev, nrow;
+        tp_batch_dims(b, i, &nn, &nf, &k, &maxlev, &nlev, &nrow);
+        SEXP bad = PROTECT(allocVector(LGLSXP, nn)), seq = PROTECT(allocVector(REALSXP, nf - 1));
+        SEXP scores = PROTECT(allocMatrix(REALSXP, k, maxlev)), levels = PROTECT(allocVector(INTSXP, nlev));
+        SEXP tables = PROTECT(allocVector(VECSXP, nlev));
+        unsigned char *tb = (unsigned char *)R_alloc((size_t)nn, 1);
+        double *sc = (double *)R_alloc((size_t)k * maxlev + 1, sizeof(double));
+        int *off = (int *)R_alloc((size_t)nlev + 1, sizeof(int)), *st = (int *)R_alloc((size_t)nrow + 1, sizeof(int)),
+            *en = (int *)R_alloc((size_t)nrow + 1, sizeof(int));
+        int npcs = 0, ncl = 0;
+        tp_batch_get(b, i, tb, &npcs, &ncl, sc, REAL(seq), INTEGER(levels), off, st, en, NULL);
+        for (int j = 0; j < nn; j++) LOGICAL(bad)[j] = tb[j];
+        for (int r = 0; r < k; r++)
+            for (int l = 0; l < maxlev; l++) {
+                double v = sc[(size_t)r * maxlev + l];
+                REAL(scores)[r + (size_t)l * k] = ISNAN(v) ? NA_REAL : v;
+            }
+        for (int l = 0; l < nlev; l++) {
+            int rows = off[l + 1] - off[l];
+            SEXP m = PROTECT(allocMatrix(INTSXP, rows, 2));
+            for (int r = 0; r < rows; r++) { INTEGER(m)[r] = st[off[l] + r]; INTEGER(m)[r + rows] = en[off[l] + r]; }
+            SET_VECTOR_ELT(tables, l, m);
+            UNPROTECT(1);
+        }
+        SEXP item = PROTECT(allocVector(VECSXP, 7));
+        SET_VECTOR_ELT(item, 0, bad);
+        SET_VECTOR_ELT(item, 1, ScalarInteger(npcs));
+        SET_VECTOR_ELT(item, 2, ScalarInteger(ncl));
+        SET_VECTOR_ELT(item, 3, seq);
+        SET_VECTOR_ELT(item, 4, scores);
+        SET_VECTOR_ELT(item, 5, levels);
+        SET_VECTOR_ELT(item, 6, tables);
+        SET_VECTOR_ELT(out, i, item);
+        UNPROTECT(6);
+    }
+    tp_batch_free(b);
+    UNPROTECT(1);
+    return out;
 }
 
 /* the cutree / fix_values / rle loop of R/TADpole.R:470-497 for many levels at once: list of 2-column integer
@@ -266,6 +427,11 @@ static const R_CallMethodDef call_table[] = {
     {"C_tp_call_arm", (DL_FUNC)&C_tp_call_arm, 4},
     {"C_tp_recall", (DL_FUNC)&C_tp_recall, 4},
     {"C_tp_dendro", (DL_FUNC)&C_tp_dendro, 3},
+    {"C_tp_generation", (DL_FUNC)&C_tp_generation, 1},
+    {"C_tp_get_filtered", (DL_FUNC)&C_tp_get_filtered, 2},
+    {"C_tp_find_groups", (DL_FUNC)&C_tp_find_groups, 1},
+    {"C_tp_call_arms", (DL_FUNC)&C_tp_call_arms, 5},
+    {"C_tp_call_batch", (DL_FUNC)&C_tp_call_batch, 6},
     {"C_tp_levels", (DL_FUNC)&C_tp_levels, 5},
     {"C_tp_labels", (DL_FUNC)&C_tp_labels, 5},
     {"C_tp_difft", (DL_FUNC)&C_tp_difft, 5},

@@ -26,7 +26,7 @@ EXPORTED = [
     "tp_comm_unique_id", "tp_ctx_comm_init", "tp_ctx_comm_select", "tp_ctx_comm_info",
     "tp_ingest_tsv", "tp_ingest_tsv_file", "tp_ingested", "tp_get_ingested", "tp_ingest_stats", "tp_test_parse_field",
     "tp_difft_null", "tp_recall",
-    "tp_ctx_create_multi", "tp_ctx_devices", "tp_ctx_generation", "tp_ctx_dims", "tp_call_arms", "tp_call_batch",
+    "tp_ctx_create_multi", "tp_device_count", "tp_ctx_devices", "tp_ctx_generation", "tp_ctx_dims", "tp_call_arms", "tp_call_batch",
     "tp_batch_size", "tp_batch_status", "tp_batch_error", "tp_batch_dims", "tp_batch_get", "tp_batch_free", "tp_find_groups",
 ]
 
@@ -56,6 +56,7 @@ def load():
         "tp_version": (c_int, []),
         "tp_ctx_create": (c_int, [c_int, POINTER(vp)]),
         "tp_ctx_create_multi": (c_int, [ip, c_int, POINTER(vp)]),
+        "tp_device_count": (c_int, []),
         "tp_ctx_devices": (c_int, [vp, ip, c_int]),
         "tp_ctx_generation": (c_longlong, [vp]),
         "tp_ctx_dims": (c_int, [vp, ip, ip, ip, ip, ip]),
@@ -120,6 +121,10 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def device_count():
+    return int(load().tp_device_count())
 
 
 def check(rc):

@@ -161,6 +161,12 @@ extern "C" int tp_ctx_create_multi(const int *devices, int ndev, tp_ctx **out) {
     return TP_OK;
 }
 
+extern "C" int tp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+
 extern "C" int tp_ctx_devices(tp_ctx *ctx, int *devices_out, int cap) {
     TP_ARG(ctx, "tp_ctx_devices: null context");
     const int n = tp_group_size(ctx);

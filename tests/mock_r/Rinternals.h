@@ -41,6 +41,9 @@ SEXP Rf_ScalarInteger(int);
 SEXP SET_VECTOR_ELT(SEXP, ptrdiff_t, SEXP);
 SEXP VECTOR_ELT(SEXP, ptrdiff_t);
 SEXP STRING_ELT(SEXP, ptrdiff_t);
+void SET_STRING_ELT(SEXP, ptrdiff_t, SEXP);
+SEXP Rf_mkChar(const char *);
+#define mkChar Rf_mkChar
 const char *CHAR(SEXP);
 int Rf_length(SEXP);
 int Rf_nrows(SEXP);

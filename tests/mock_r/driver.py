@@ -54,6 +54,10 @@ class MockR:
             return int(x)                                         # already a SEXP (external pointer, ...)
         if isinstance(x, str):
             return L.mock_string(x.encode())
+        if isinstance(x, list):                                   # an R list (VECSXP)
+            elts = [self.to_r(e) for e in x]
+            arr = (ctypes.c_void_p * max(len(elts), 1))(*elts)
+            return L.mock_vector(VECSXP, len(elts), ctypes.cast(arr, ctypes.c_void_p))
         if isinstance(x, bool):
             return L.mock_vector(LGLSXP, 1, np.array([int(x)], np.int32).ctypes.data)
         if isinstance(x, int):
@@ -81,6 +85,8 @@ class MockR:
             return [self.from_r(L.mock_elt(s, i)) for i in range(n)]
         if t == 22:
             return Sexp(s)
+        if t == STRSXP:
+            return [ctypes.string_at(L.mock_data(L.mock_elt(s, i))).decode() for i in range(n)]
         dt = {LGLSXP: np.int32, INTSXP: np.int32, REALSXP: np.float64, RAWSXP: np.uint8}[t]
         if n == 0:
             flat = np.zeros(0, dt)

@@ -68,6 +68,12 @@ SEXP Rf_ScalarInteger(int v) { SEXP s = Rf_allocVector(INTSXP, 1); ((int *)s->da
 SEXP SET_VECTOR_ELT(SEXP v, ptrdiff_t i, SEXP x) { ((SEXP *)v->data)[i] = x; return x; }
 SEXP VECTOR_ELT(SEXP v, ptrdiff_t i) { return ((SEXP *)v->data)[i]; }
 SEXP STRING_ELT(SEXP v, ptrdiff_t i) { return ((SEXP *)v->data)[i]; }
+void SET_STRING_ELT(SEXP v, ptrdiff_t i, SEXP x) { ((SEXP *)v->data)[i] = x; }
+SEXP Rf_mkChar(const char *str) {
+    SEXP c = new_obj(CHARSXP, (int)strlen(str), strlen(str) + 1);
+    strcpy((char *)c->data, str);
+    return c;
+}
 const char *CHAR(SEXP s) { return (const char *)s->data; }
 int Rf_length(SEXP s) { return s->n; }
 int Rf_nrows(SEXP s) { return s->nrow; }
@@ -110,6 +116,7 @@ int mock_registered(const char *name) {                     /* number of argumen
 SEXP mock_dot_call(const char *name, int nargs, SEXP *a, const char **err) {
     typedef SEXP (*f0)(void); typedef SEXP (*f1)(SEXP); typedef SEXP (*f2)(SEXP, SEXP); typedef SEXP (*f3)(SEXP, SEXP, SEXP);
     typedef SEXP (*f4)(SEXP, SEXP, SEXP, SEXP); typedef SEXP (*f5)(SEXP, SEXP, SEXP, SEXP, SEXP);
+    typedef SEXP (*f6)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
     typedef SEXP (*f8)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
     *err = NULL;
     const R_CallMethodDef *m = registered;
@@ -128,6 +135,7 @@ SEXP mock_dot_call(const char *name, int nargs, SEXP *a, const char **err) {
             case 3: out = ((f3)f)(a[0], a[1], a[2]); break;
             case 4: out = ((f4)f)(a[0], a[1], a[2], a[3]); break;
             case 5: out = ((f5)f)(a[0], a[1], a[2], a[3], a[4]); break;
+            case 6: out = ((f6)f)(a[0], a[1], a[2], a[3], a[4], a[5]); break;
             case 8: out = ((f8)f)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]); break;
             default: snprintf(errbuf, sizeof(errbuf), "arity %d not supported by the mock", nargs); *err = errbuf;
         }

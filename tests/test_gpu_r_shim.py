@@ -35,7 +35,8 @@ def test_filter_and_call_arm_through_the_shim(R, rctx, ctx):
     want_bad, _, _ = ctx.filter(m, bad_frac=0.01)
     assert bad.dtype == bool and np.array_equal(bad, want_bad)
     keep = np.flatnonzero(~bad)
-    n_pcs, n_cl, seq, scores = R.call("C_tp_call_arm", rctx, keep, 200, 2)
+    n_pcs, n_cl, seq, scores, gen = R.call("C_tp_call_arm", rctx, keep, 200, 2)
+    assert gen[0] == R.call("C_tp_generation", rctx)[0]
     want = ctx.call_arm(keep.astype(np.int32))
     assert n_pcs[0] == want["n_pcs"] and n_cl[0] == want["n_clusters"]
     assert np.array_equal(seq, want["seqdist"])
@@ -55,12 +56,65 @@ def test_filter_and_call_arm_through_the_shim(R, rctx, ctx):
     labels = R.call("C_tp_labels", seq, int(n_cl[0]), keep + 1, np.flatnonzero(bad) + 1, False)
     assert labels.size == m.shape[0] and labels.max() <= n_cl[0]
     # recall and any candidate's dendrogram from the resident state
-    r2 = R.call("C_tp_recall", rctx, int(keep.size), 50, 3)
+    r2 = R.call("C_tp_recall", rctx, float(gen[0]), 50, 3)
     ref2 = O.tadpole(m, max_pcs=50, min_clusters=3)
     assert r2[0][0] == ref2.n_pcs and r2[1][0] == ref2.optimal_n_clusters
-    d7 = R.call("C_tp_dendro", rctx, int(keep.size), 7)
+    assert r2[4][0] != gen[0]                                # the sweep state was replaced: a new generation
+    d7 = R.call("C_tp_dendro", rctx, float(r2[4][0]), 7)
     oseq, _ = O.coniss_lw(ref.pcs[:, :7])
     assert (np.argsort(d7, kind="stable") == np.argsort(oseq, kind="stable")).all()
+    # dendro$merge through the shim = the oracle's literal .find.groups loop
+    merge = R.call("C_tp_find_groups", seq)
+    assert merge.shape == (seq.size, 2) and np.array_equal(merge, O.find_groups(seq)[0])
+    # load_mat()'s return value: mat[keep, keep] of the symmetrised matrix
+    filt = R.call("C_tp_get_filtered", rctx, keep)
+    assert np.array_equal(filt, O.symmetrise_upper(m)[np.ix_(keep, keep)])
+
+
+def test_stale_handle_is_refused_and_buffers_follow_the_context(R, rctx):
+    """a <- TADpole(A); b <- TADpole(B); tadpole_recall(a): the context now holds B (more good bins than A).  The shim must
+    refuse A's handle instead of packing B's sweep into A-sized buffers."""
+    from mock_r.driver import RError
+    from tadpole_b200.synth import synth_hic
+    a, b = synth_hic(300, seed=3), synth_hic(420, seed=4)
+    bad_a = R.call("C_tp_filter", rctx, a, 0.01)
+    res_a = R.call("C_tp_call_arm", rctx, np.flatnonzero(~bad_a), 200, 2)
+    bad_b = R.call("C_tp_filter", rctx, b, 0.01)
+    res_b = R.call("C_tp_call_arm", rctx, np.flatnonzero(~bad_b), 200, 2)
+    with pytest.raises(RError, match="used for another matrix"):
+        R.call("C_tp_recall", rctx, float(res_a[4][0]), 100, 2)
+    with pytest.raises(RError, match="used for another matrix"):
+        R.call("C_tp_dendro", rctx, float(res_a[4][0]), 5)
+    # B's own handle works, and every buffer has B's sizes
+    r = R.call("C_tp_recall", rctx, float(res_b[4][0]), 100, 2)
+    assert r[2].size == int((~bad_b).sum()) - 1 and r[3].shape[0] == 100
+    ref = O.tadpole(b, max_pcs=100)
+    assert r[0][0] == ref.n_pcs and r[1][0] == ref.optimal_n_clusters
+    with pytest.raises(RError, match="n_pcs must be between"):
+        R.call("C_tp_dendro", rctx, float(r[4][0]), 101)
+
+
+def test_arms_and_batch_through_the_shim(R, rctx):
+    from tadpole_b200.synth import synth_hic
+    m = synth_hic(700, seed=5, centromere=True)
+    ref = O.tadpole(m, centromere_search=True)
+    bad = R.call("C_tp_filter", rctx, m, 0.01)
+    lm = O.load_mat_numeric(m, centromere_search=True)
+    kp, kq = np.asarray(lm.p.names) - 1, np.asarray(lm.q.names) - 1
+    p, q = R.call("C_tp_call_arms", rctx, kp, kq, 200, 2)
+    for got, arm in ((p, ref.p), (q, ref.q)):
+        assert got[0][0] == arm.n_pcs and got[1][0] == arm.optimal_n_clusters
+    # a batch: results in input order, one failing matrix does not stop the others
+    mats = [synth_hic(260, seed=s) for s in (1, 2, 3)] + [np.zeros((50, 50))]
+    out = R.call("C_tp_call_batch", rctx, mats, 200, 2, 0.01, 3)
+    assert len(out) == 4 and isinstance(out[3][0], str)
+    for mm, item in zip(mats[:3], out[:3]):
+        o = O.tadpole(mm)
+        badv, npcs, ncl, seq, scores, levels, tables = item
+        assert npcs[0] == o.n_pcs and ncl[0] == o.optimal_n_clusters and badv.dtype == bool
+        assert sorted(int(l) for l in levels) == sorted(o.clusters)
+        for lv, t in zip(levels, tables):
+            assert np.array_equal(t, o.clusters[int(lv)])
 
 
 def test_ingest_through_the_shim(R, rctx, tmp_path):
