@@ -89,3 +89,95 @@ int oracle_difft(const int *tx, const int *ty, int L, double *out) {
     if (mx != 0) { double t = out[L - 1]; for (int b = 0; b < L; b++) out[b] /= t; }
     return 0;
 }
+
+/* ---- one candidate of the find_params sweep, start to end (R/TADpole.R:105-122) --------------------------------
+ *     pcs <- pca$x[, 1:i];  clust <- rioja::chclust(dist(pcs))                      -> oracle_coniss_lw above
+ *     bs <- rioja::bstick(clust, ng = nrow(mat) - 1);  n_cluster = first TRUE run of dispersion > bstick  (quirk Q1)
+ *     for (n in min(min_clusters, n_cluster):n_cluster)
+ *         score[n] <- fpc::calinhara(pca$x, cutree(clust, n), n)                   on ALL k columns (quirk Q2)
+ * in plain C so that the timed CPU arm (bench.py --impl reference, cpu_baseline) runs every candidate in full on every
+ * host core (ctypes releases the GIL).  calinhara is evaluated in trace form, two passes per level (cluster means, then
+ * squared deviations): the reference's fpc forms k x k covariance matrices per cluster, O(n k^2) per level, so this port
+ * UNDER-states the reference's cost; it never over-states it.
+ * x: n x ld row-major PC scores, k_all columns in use.  seqdist[n-1]; scores[cap] (NaN padded).
+ * returns 0, 1 = out of memory, 2 = no significant broken-stick level (the reference errors), 3 = cap too small
+ * (*ncl_out tells the width needed). */
+static const double *g_sort_key;
+static int cmp_desc(const void *a, const void *b) {
+    const int ia = *(const int *)a, ib = *(const int *)b;
+    if (g_sort_key[ia] > g_sort_key[ib]) return -1;
+    if (g_sort_key[ia] < g_sort_key[ib]) return 1;
+    return ib - ia;                                   /* later boundary first: the merge order is (value, index) ascending */
+}
+
+int oracle_candidate(const double *x, int n, int ld, int k_all, int i, int min_clusters, double *seqdist, double *scores,
+                     int cap, int *ncl_out) {
+    const int n1 = n - 1;
+    int *order = (int *)malloc((size_t)n1 * sizeof(int));
+    double *bs = (double *)malloc((size_t)n1 * sizeof(double));
+    double *height = (double *)malloc((size_t)n1 * sizeof(double));
+    int *rank = (int *)malloc((size_t)n1 * sizeof(int));
+    int *idx = (int *)malloc((size_t)n1 * sizeof(int));
+    double *mean = (double *)malloc((size_t)n * k_all * sizeof(double));     /* at most n clusters */
+    int *lab = (int *)malloc((size_t)n * sizeof(int)), *cnt = (int *)malloc((size_t)n * sizeof(int));
+    int rc = 1;
+    if (!order || !bs || !height || !rank || !idx || !mean || !lab || !cnt) goto done;
+    if (oracle_coniss_lw(x, n, ld, i, seqdist, order)) goto done;
+    /* height = sort(seqdist) = the running total in merge order */
+    for (int t = 0; t < n1; t++) height[t] = seqdist[order[t]];
+    {   /* vegan::bstick.default(n1, tot) = rev(cumsum(tot / n1:1) / n1) */
+        const double tot = height[n1 - 1];
+        double c = 0.0;
+        for (int m = n1; m >= 1; m--) { c += tot / (double)m; bs[m - 1] = c / (double)n1; }
+    }
+    int first = -1, run = 0;
+    for (int j = 1; j <= n1 - 1; j++) {               /* dispersion_j = |disp[j+1] - disp[j]|, disp = rev(height) */
+        const int f = fabs(height[n1 - j - 1] - height[n1 - j]) > bs[j - 1];
+        if (first < 0) { if (f) { first = j; run = 1; } }
+        else if (f) run++;
+        else break;
+    }
+    if (first < 0) { rc = 2; goto done; }
+    *ncl_out = run;
+    if (run > cap) { rc = 3; goto done; }
+    for (int l = 0; l < cap; l++) scores[l] = NAN;
+    /* cutree: the boundaries ranked by (seqdist descending, index descending); level m keeps the first m - 1 */
+    for (int j = 0; j < n1; j++) idx[j] = j;
+    g_sort_key = seqdist;
+    qsort(idx, (size_t)n1, sizeof(int), cmp_desc);
+    for (int r = 0; r < n1; r++) rank[idx[r]] = r;
+    {
+        double trs = 0.0;                              /* tr(S): total SS about the column means, all k columns */
+        for (int c = 0; c < k_all; c++) {
+            double m = 0.0;
+            for (int r = 0; r < n; r++) m += x[(size_t)r * ld + c];
+            m /= (double)n;
+            for (int r = 0; r < n; r++) { const double t = x[(size_t)r * ld + c] - m; trs += t * t; }
+        }
+        const int mc = min_clusters < run ? min_clusters : run;
+        for (int lev = mc; lev <= run; lev++) {
+            int cl = 0;
+            for (int r = 0; r < n; r++) { lab[r] = cl; if (r < n1 && rank[r] < lev - 1) cl++; }
+            memset(mean, 0, (size_t)lev * k_all * sizeof(double));
+            memset(cnt, 0, (size_t)lev * sizeof(int));
+            for (int r = 0; r < n; r++) {
+                double *m = mean + (size_t)lab[r] * k_all;
+                const double *row = x + (size_t)r * ld;
+                for (int c = 0; c < k_all; c++) m[c] += row[c];
+                cnt[lab[r]]++;
+            }
+            for (int g = 0; g < lev; g++) for (int c = 0; c < k_all; c++) mean[(size_t)g * k_all + c] /= (double)cnt[g];
+            double trw = 0.0;
+            for (int r = 0; r < n; r++) {
+                if (cnt[lab[r]] < 2) continue;         /* clusters of one object contribute 0 */
+                const double *m = mean + (size_t)lab[r] * k_all, *row = x + (size_t)r * ld;
+                for (int c = 0; c < k_all; c++) { const double t = row[c] - m[c]; trw += t * t; }
+            }
+            scores[lev - 1] = (double)(n - lev) * (trs - trw) / ((double)(lev - 1) * trw);
+        }
+    }
+    rc = 0;
+done:
+    free(order); free(bs); free(height); free(rank); free(idx); free(mean); free(lab); free(cnt);
+    return rc;
+}

@@ -386,6 +386,53 @@ def candidate_scores(scores_all, i, min_clusters, coniss=coniss_lw):
     return score, n_cluster, seq
 
 
+def candidate_scores_c(scores_all, i, min_clusters, cap=1024):
+    """candidate_scores in plain C end to end (oracle/coniss_lw.c: oracle_candidate), GIL released: the body of the foreach
+    as the timed CPU arm runs it on every host core.  Same return value as candidate_scores."""
+    x = np.ascontiguousarray(scores_all, dtype=np.float64)
+    n, k_all = x.shape
+    lib = _oracle_lib()
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+    lib.oracle_candidate.argtypes = [dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp, ctypes.c_int, ip]
+    lib.oracle_candidate.restype = ctypes.c_int
+    seq = np.zeros(n - 1)
+    while True:
+        sc = np.empty(cap)
+        ncl = ctypes.c_int(0)
+        rc = lib.oracle_candidate(x.ctypes.data_as(dp), n, k_all, k_all, int(i), int(min_clusters), seq.ctypes.data_as(dp),
+                                  sc.ctypes.data_as(dp), cap, ctypes.byref(ncl))
+        if rc == 3:
+            cap = ncl.value
+            continue
+        if rc == 2:
+            raise ValueError("no broken-stick level is significant (reference errors here, quirk Q1)")
+        if rc != 0:
+            raise MemoryError("oracle_candidate failed")
+        return sc[: ncl.value].copy(), ncl.value, seq
+
+
+def tadpole_cpu_full(mat, max_pcs=200, min_clusters=2, bad_frac=0.01, threads=1):
+    """The whole non-centromere call on the host cores, every candidate in full: load_mat numeric core, sparse_cor, prcomp
+    (LAPACK SVD), then the foreach over candidates on `threads` threads (each candidate in C with the GIL released; the
+    reference forks detectCores() workers, R/TADpole.R:103-104), score reduction.  Returns (n_pcs, n_clusters, scores,
+    stage seconds)."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+    t0 = time.perf_counter()
+    lm = load_mat_numeric(mat, bad_frac)
+    cor = sparse_cor(lm.mat)
+    k = min(max_pcs, lm.mat.shape[0])
+    pcs = np.ascontiguousarray(prcomp_scores(cor, k))
+    t1 = time.perf_counter()
+    cands = list(range(k, 0, -1))                          # most expensive first
+    with ThreadPoolExecutor(max_workers=max(1, int(threads))) as ex:
+        per = list(ex.map(lambda i: candidate_scores_c(pcs, i, min_clusters), cands))
+    per = per[::-1]
+    scores, opt_pcs, opt_k = reduce_scores([p[0] for p in per])
+    t2 = time.perf_counter()
+    return opt_pcs, opt_k, scores, dict(front_s=t1 - t0, sweep_s=t2 - t1, k=k, nf=int(lm.mat.shape[0]))
+
+
 def reduce_scores(score_list):
     """NA-padded score matrix and the two which.max (R/TADpole.R:125-135).
     Returns (scores[k, maxlev] NaN padded, optimal_PCs, optimal_n_clusters), 1-based."""

@@ -102,7 +102,7 @@ def test_arms_and_batch_through_the_shim(R, rctx):
     lm = O.load_mat_numeric(m, centromere_search=True)
     kp, kq = np.asarray(lm.p.names) - 1, np.asarray(lm.q.names) - 1
     p, q = R.call("C_tp_call_arms", rctx, kp, kq, 200, 2)
-    for got, arm in ((p, ref.p), (q, ref.q)):
+    for got, arm in ((p, ref.arms["p"]), (q, ref.arms["q"])):
         assert got[0][0] == arm.n_pcs and got[1][0] == arm.optimal_n_clusters
     # a batch: results in input order, one failing matrix does not stop the others
     mats = [synth_hic(260, seed=s) for s in (1, 2, 3)] + [np.zeros((50, 50))]
