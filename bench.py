@@ -4,33 +4,37 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference
 
-A "step" is one full TADpole() call on one synthetic matrix: bad-column filter, Pearson
-correlation, PCA to max_pcs = 200 components, the n_pcs sweep (CONISS per candidate), broken
-stick + Calinski-Harabasz, selection.  Workload at N = 1: BASELINE.json configs[1], a 2,000-bin
-matrix with nested block TADs and power-law decay.  With N > 1 every rank calls its own
-matrices (multi-chromosome batch, no data-path collective): weak scaling.
+Workload: BASELINE.json configs[1], synthetic 2,000-bin Hi-C matrices with nested block TADs and power-law decay,
+max_pcs = 200.  One TADpole() call = bad-column filter, Pearson correlation, PCA to 200 components, the n_pcs sweep
+(CONISS per candidate), broken stick + Calinski-Harabasz, selection.  A "step" is one pass of the hot path over one
+BATCH of --batch (16) different matrices -- genome-wide use is one call per chromosome, and a lone 2000-bin call leaves
+most of a B200 idle -- handed to the library in one tp_call_batch, which keeps --streams calls in flight with its own
+host threads (one Python / R thread just waits).  With N > 1 every rank runs its own batches (no data-path
+collective): weak scaling.
 
-value  : calls/s with the input matrices already resident in HBM (device pointers through the
-         C ABI), timed with CUDA events on the library's streams, max over ranks.  A single 2000-bin call
-         leaves most of the GPU idle (its b x b eigen / Cholesky kernels run on one 8-CTA cluster), so, as a
-         genome-wide run over many chromosomes would, --streams S independent calls are in flight per GPU
-         (tadpole_b200.batch: one context, stream and host thread each); the K steps are dealt out to them.
-         `single_call` in the JSON line is the same measured with one call at a time (latency), and the
-         per-kernel rooflines are taken from that pass.
-e2e    : the same through the public API TADpole(matrix) with the matrix in pinned HOST memory;
-         H2D copy of the matrix and D2H of the results are inside the timed region.
-A pool of different matrices larger than L2 (5 x 32 MB) is cycled, so no step re-reads a warm input.
+value  : calls/s with the input matrices already resident in HBM (device pointers through the C ABI), CUDA events on
+         the library's streams (tp_batch_device_ms), max over ranks.
+e2e    : the same through the public API TADpole_batch(matrices) with the matrices in pinned HOST memory: H2D copy,
+         D2H of the results, per-level tables and object assembly inside the timed (wall clock) region.
+single_call : one call at a time (latency); the per-kernel rooflines are taken from that pass (CUDA events around
+         every launch of a class).
+strong_scaling : ONE chromosome-wide call (BASELINE configs[3], 25,000 bins) spread over all N ranks -- row blocks of
+         the symmetric products and of every operator application by their owner + NCCL all-gather, candidates of the
+         sweep rank-interleaved -- and the 15,000-bin centromere_search call with the arms on disjoint halves of the ranks
+         (configs[2]); at N > 1 rank 0 repeats the call alone and the results must be identical bit for bit.
+The step's inputs (16 x 32 MB) are larger than L2, so no step re-reads a warm input.
 
-The reference is a pure-R package and R is not installed here or on the GPU box, so
-`--impl reference` and `cpu_baseline` time oracle/ (numpy + C restatement in the reference's
-algorithmic shape: full LAPACK SVD, per-candidate O(N^2) dist + Lance-Williams CONISS, per-level
-Calinski-Harabasz) on the host cores, on a bounded sample of candidates extrapolated to all 200.
+The reference is a pure-R package and R is not installed here or on the GPU box (probed: `Rscript`), so
+`--impl reference` and `cpu_baseline` time oracle/ (numpy + C restatement in the reference's algorithmic shape: full
+LAPACK SVD, per-candidate O(N^2) dist + Lance-Williams CONISS, per-level Calinski-Harabasz) on all host cores, every
+one of the 200 candidates in full; a reference step is a bounded sample of the GPU arm's step: ONE of the batch's calls.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
 import tempfile
@@ -44,7 +48,6 @@ if ROOT not in sys.path:
 
 N_BINS = 2000
 MAX_PCS = 200
-POOL = 5
 METRIC = "tadpole_calls_per_sec"
 UNIT = "calls/s"
 
@@ -52,44 +55,57 @@ UNIT = "calls/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--streams", type=int, default=8,
-                    help="independent calls in flight per GPU (own context / stream / host thread each)")
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--batch", type=int, default=16, help="calls per step (one tp_call_batch of that many different matrices)")
+    ap.add_argument("--streams", type=int, default=8, help="calls kept in flight per GPU by the library's own threads")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bins", type=int, default=N_BINS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sync-blocking", default="auto", choices=["auto", "0", "1"],
-                    help="host threads sleep on a blocking-sync event while they wait for the GPU instead of spinning in "
-                         "cudaStreamSynchronize; auto = when ranks x calls in flight exceed half of the host's logical CPUs")
     ap.add_argument("--large-n", type=int, default=8000,
                     help="bins of one extra profiled call whose tensor-kernel rooflines are reported beside the workload's "
                          "(N = 1 only; 0 = skip)")
-    ap.add_argument("--cpu-sample", type=int, default=8, help="candidates timed per CPU sample")
+    ap.add_argument("--strong-bins", type=int, default=25000, help="bins of the one call spread over all ranks (0 = skip)")
+    ap.add_argument("--arm-bins", type=int, default=15000, help="bins of the centromere_search call, arms sharded (0 = skip)")
     return ap.parse_args()
+
+
+def workload_text(bins):
+    return (f"synthetic {bins}-bin Hi-C matrix, nested block TADs, power-law decay, max_pcs=200 "
+            "(BASELINE.json configs[1]); one TADpole() call per matrix")
+
+
+def r_probe():
+    """if Rscript with rioja + fpc ever appears, the real reference supersedes the restatement."""
+    rs = shutil.which("Rscript")
+    if not rs:
+        return {"Rscript": None, "note": "R is not installed: CPU arm = oracle/ port"}
+    try:
+        ok = subprocess.run([rs, "-e", "stopifnot(requireNamespace('rioja'), requireNamespace('fpc'))"],
+                            capture_output=True, timeout=60).returncode == 0
+    except Exception:
+        ok = False
+    return {"Rscript": rs, "rioja_fpc": ok,
+            "note": "R found: run tests/golden/make_r_golden.R to pin the oracle to the real reference" if ok
+                    else "R found but rioja / fpc are missing"}
 
 
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle, timed (the only place besides tests/ and smoke() that touches oracle/)
 # ---------------------------------------------------------------------------------------------
-def cpu_sample(mat, ncand_sample, threads):
-    """One bounded sample of the reference-shaped CPU path.  Returns (estimated seconds for the
-    full call, detail dict)."""
-    from concurrent.futures import ThreadPoolExecutor
+def cpu_full_call(mat, threads):
+    """One FULL call of the reference-shaped CPU path: every one of the 200 candidates, all host cores."""
     from oracle import tadpole_oracle as O
     t0 = time.perf_counter()
-    lm = O.load_mat_numeric(mat)
-    cor = O.sparse_cor(lm.mat)
-    k = min(MAX_PCS, lm.mat.shape[0])
-    pcs = O.prcomp_scores(cor, k)
-    t_front = time.perf_counter() - t0
-    cands = np.unique(np.linspace(1, k, ncand_sample).round().astype(int))
-    t1 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=threads) as ex:      # foreach %dopar% over candidates
-        list(ex.map(lambda i: O.candidate_scores(pcs, int(i), 2), cands))
-    t_sweep = time.perf_counter() - t1
-    est = t_front + t_sweep * (k / len(cands))
-    return est, dict(front_s=round(t_front, 3), sweep_sample_s=round(t_sweep, 3), candidates=len(cands), k=int(k))
+    n_pcs, n_cl, _, st = O.tadpole_cpu_full(mat, max_pcs=MAX_PCS, threads=threads)
+    return time.perf_counter() - t0, dict(front_s=round(st["front_s"], 3), sweep_s=round(st["sweep_s"], 3), k=st["k"],
+                                          n_pcs=int(n_pcs), n_clusters=int(n_cl))
+
+
+def cpu_sample_text(detail, threads):
+    return (f"one full call per step (1 of the GPU arm's batch): filter + correlation + full LAPACK SVD ({detail['front_s']} s) "
+            f"and ALL {detail['k']} candidates (dist + Lance-Williams CONISS + broken stick + per-level CH, plain C, "
+            f"{detail['sweep_s']} s) on {threads} threads; nothing extrapolated")
 
 
 def run_reference(args, rank, world):
@@ -97,31 +113,28 @@ def run_reference(args, rank, world):
         return
     from tadpole_b200.synth import synth_hic
     threads = os.cpu_count() or 1
-    mats = [synth_hic(args.bins, seed=1 + s) for s in range(min(POOL, max(1, args.steps)))]
-    for w in range(min(args.warmup, 1)):
-        cpu_sample(mats[0], 2, threads)
-    ests, detail = [], None
+    mats = [synth_hic(args.bins, seed=1 + s) for s in range(min(4, max(1, args.steps)))]
+    if args.warmup > 0:          # ONE untimed call whatever W is: page-in and thread start-up are all this path has to warm,
+        cpu_full_call(mats[0], threads)      # and every further warm-up call would cost as much as a timed step
+    secs, detail = [], None
     t0 = time.perf_counter()
     for s in range(args.steps):
-        est, detail = cpu_sample(mats[s % len(mats)], args.cpu_sample, threads)
-        ests.append(est)
+        sec, detail = cpu_full_call(mats[s % len(mats)], threads)
+        secs.append(sec)
     wall = time.perf_counter() - t0
-    sec = float(np.mean(ests))
+    sec = wall / args.steps
     val = 1.0 / sec
-    sample = (f"per step: filter+correlation+full SVD timed in full, {detail['candidates']} of {detail['k']} candidates "
-              f"(dist + Lance-Williams CONISS + broken stick + per-level CH) on {threads} threads, sweep time "
-              f"scaled by k/candidates; wall for {args.steps} sampled steps {wall:.1f} s")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic {args.bins}-bin Hi-C matrix, nested block TADs, power-law decay, max_pcs=200 "
-                               "(BASELINE.json configs[1])", "bins": args.bins, "max_pcs": MAX_PCS,
-                   "note": "reference is pure R and R is not installed: CPU restatement (oracle/) in the "
-                           "reference's algorithmic shape, runs on rank 0 only"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": workload_text(args.bins), "bins": args.bins, "max_pcs": MAX_PCS,
+                   "calls_per_step": 1,
+                   "note": "reference is pure R and R is not installed: CPU restatement (oracle/) in the reference's "
+                           "algorithmic shape, every step one full call, runs on rank 0 only"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample_text(detail, threads)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "r_probe": r_probe(),
     }
     print(json.dumps(line), flush=True)
 
@@ -196,38 +209,128 @@ def measure_fp64_peak(torch):
     return best
 
 
+def measure_int8_peak(torch):
+    """Library int8 GEMM (torch._int_mm -> cuBLASLt, int32 accumulation) 8192^3, best of 10, TOP/s (2 per multiply-add):
+    the measured denominator of the tcgen05 kind::i8 kernels.  None when the library call is unavailable."""
+    try:
+        a = torch.randint(-127, 127, (8192, 8192), dtype=torch.int8, device="cuda")
+        b = torch.randint(-127, 127, (8192, 8192), dtype=torch.int8, device="cuda")
+        torch._int_mm(a, b)
+        best = 0.0
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch._int_mm(a, b); e1.record(); torch.cuda.synchronize()
+            best = max(best, 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        return best
+    except Exception:
+        return None
+
+
+def strong_scaling(args, torch, dist, rank, world, local_rank, Context, sharding, api):
+    """One chromosome-wide call over all ranks (configs[3]) and the arm-sharded centromere call (configs[2])."""
+    from tadpole_b200 import TADpole
+    from tadpole_b200.synth import synth_hic_gpu
+    out = {}
+    ctx = Context(local_rank)
+    env = sharding.DistEnv(ctx) if world > 1 else None
+
+    def sync_all():
+        ctx.sync(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for key, bins, cen in (("chr", args.strong_bins, False), ("arms", args.arm_bins, True)):
+        if bins <= 0:
+            continue
+        dev = synth_hic_gpu(bins, seed=7 if cen else 3, device=local_rank, centromere=cen)
+        if world > 1:
+            sums = env.exchange(float(dev.sum()))
+            assert all(v == sums[0] for v in sums), "ranks drew different matrices"
+        host = dev.cpu().numpy()                                   # pageable host memory, as an R matrix is
+        del dev
+        torch.cuda.empty_cache()
+        walls, tp = [], None
+        for rep in range(3):                                       # first call allocates; the last two are timed
+            sync_all()
+            t0 = time.perf_counter()
+            tp = TADpole(host, max_pcs=MAX_PCS, centromere_search=cen, ctx=ctx, dist=env)
+            sync_all()
+            walls.append((time.perf_counter() - t0) * 1e3)
+        stages = ctx.timings()
+        ctx.profile(1)
+        TADpole(host, max_pcs=MAX_PCS, centromere_search=cen, ctx=ctx, dist=env)
+        prof = ctx.profile(0)
+        t = torch.tensor([min(walls[1:]), stages["total_ms"]] + [stages[k] for k in ("filter_ms", "compact_ms", "correlation_ms", "pca_ms", "sweep_ms", "ch_ms")],
+                         dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = [float(v) for v in t]
+        r = {"bins": bins, "centromere_search": cen, "ranks": world,
+             "wall_ms": round(t[0], 2), "device_total_ms": round(t[1], 2),
+             "stages_ms": dict(zip(("filter", "compact", "correlation", "pca", "sweep", "ch"), (round(v, 2) for v in t[2:]))),
+             "stages_sum_ms": round(sum(t[2:]), 2),
+             "comm_ms": round(prof["comm"][0], 2), "islice_ms": round(prof["islice"][0], 2),
+             "igemm_ms": round(prof["igemm"][0], 2), "sweep_kernel_ms": round(prof["coniss_sweep"][0], 2),
+             "pca_applications": int(stages["pca_applications"]), "pca_iterations": int(stages["pca_iterations"]),
+             "timing": "max over ranks; wall = host matrix (pageable) in, tadpole object out, best of 2 after one warm call; "
+                       "stages = CUDA events on the library stream; comm / islice / igemm / sweep = rank 0 CUDA events around "
+                       "every launch of the class in one extra profiled call"}
+        if cen:
+            r["result"] = {"p": [tp.p.n_pcs, tp.p.optimal_n_clusters], "q": [tp.q.n_pcs, tp.q.optimal_n_clusters],
+                           "tads": int(tp.merging_arms.shape[0])}
+            summ = tp.merging_arms.tobytes() + tp.p.dendro.seqdist.tobytes() + tp.q.dendro.seqdist.tobytes()
+        else:
+            r["result"] = {"n_pcs": tp.n_pcs, "optimal_n_clusters": tp.optimal_n_clusters, "levels": len(tp.clusters)}
+            summ = tp.scores.tobytes() + tp.dendro.seqdist.tobytes()
+        big = max(("comm", "islice", "sweep"), key=lambda k_: {"comm": r["comm_ms"], "islice": r["islice_ms"], "sweep": r["stages_ms"]["sweep"]}[k_])
+        r["largest_non_gemm_cost"] = big
+        if world > 1:
+            every = env.exchange(summ)
+            r["all_ranks_identical"] = all(e == every[0] for e in every)
+            if rank == 0:                                           # the same call on this GPU alone
+                ctx.comm_select(-1)
+                ref = TADpole(host, max_pcs=MAX_PCS, centromere_search=cen, ctx=ctx)
+                ctx.comm_select(env.world_slot)
+                if cen:
+                    same = (np.array_equal(ref.merging_arms, tp.merging_arms) and all(
+                        np.array_equal(ref[a].dendro.seqdist, tp[a].dendro.seqdist) and ref[a].n_pcs == tp[a].n_pcs for a in "pq"))
+                else:
+                    same = (ref.n_pcs == tp.n_pcs and ref.optimal_n_clusters == tp.optimal_n_clusters
+                            and np.array_equal(ref.dendro.seqdist, tp.dendro.seqdist)
+                            and np.array_equal(ref.scores, tp.scores, equal_nan=True))
+                r["identical_to_1gpu"] = bool(same)
+                r["one_gpu_stages_sum_ms"] = round(sum(ctx.timings()[k] for k in ("filter_ms", "compact_ms", "correlation_ms", "pca_ms", "sweep_ms", "ch_ms")), 2)
+            dist.barrier()
+        out[key] = r
+        del host, tp
+    ctx.close()
+    return out
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from tadpole_b200 import ContextPool, TADpole, api
+    from tadpole_b200 import Context, TADpole_batch, api, sharding
     from tadpole_b200.synth import synth_hic
 
     api.QUIET = True
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    S = max(1, args.streams)
-    pool = ContextPool(local_rank, S)
-    ctx = pool.contexts[0]
-    # one host thread per call in flight waits for its stream most of the time; spinning waits (the CUDA default) need a
-    # core each, so with several ranks on one host the threads would outnumber the cores
-    ncpu = os.cpu_count() or 1
-    sync_blocking = (world * S > ncpu // 2) if args.sync_blocking == "auto" else args.sync_blocking == "1"
-    if sync_blocking:
-        for c in pool.contexts:
-            c.set("sync_blocking", 1)
-    n = args.bins
+    S, B, n = max(1, args.streams), max(1, args.batch), args.bins
+    ctx = Context(local_rank)
 
-    # synthetic inputs: POOL different matrices per rank; pinned host copies for e2e, device copies for value
+    # synthetic inputs: B different matrices per rank; pinned host copies for e2e, device copies for value
     host = []
-    for s in range(POOL):
+    for s in range(B):
         m = synth_hic(n, seed=1000 * rank + 1 + s)
         t = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
         t.numpy()[:] = m
         host.append(t)
     dev = [t.cuda(non_blocking=False) for t in host]
     torch.cuda.synchronize()
-    streams = [torch.cuda.ExternalStream(c.stream, device=torch.device("cuda", local_rank)) for c in pool.contexts]
+    ptrs = [d.data_ptr() for d in dev]
+    host_np = [t.numpy() for t in host]
 
     def barrier():
         torch.cuda.synchronize()
@@ -235,66 +338,69 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_dev(c, i):
-        d = dev[i % POOL]
-        return c.call(device_ptr=d.data_ptr(), n=n, colmajor=0, max_pcs=MAX_PCS)
-
-    def step_e2e(c, i):
-        return TADpole(host[i % POOL].numpy(), max_pcs=MAX_PCS, ctx=c)
-
-    def timed_pass(fn, steps, contexts, event_streams):
-        """`steps` calls dealt out to the contexts; device time from a CUDA event recorded before the first call to the
-        last end event over the contexts' streams; also wall seconds."""
-        sub = ContextPool.__new__(ContextPool)
-        sub.device, sub.contexts = local_rank, contexts
-        e0 = torch.cuda.Event(enable_timing=True)
-        ends = [torch.cuda.Event(enable_timing=True) for _ in contexts]
-        barrier()
-        e0.record(event_streams[0])
-        t0 = time.perf_counter()
-        out = sub.map(fn, range(steps))
-        for c, ev, st in zip(contexts, ends, event_streams):
-            ev.record(st)
-        for c in contexts:
-            c.sync()
-        wall = time.perf_counter() - t0
-        barrier()
-        return max(e0.elapsed_time(ev) for ev in ends), wall, out
-
-    # ---- warm-up: every context allocates its buffers --------------------------------------------
-    for w in range(max(args.warmup, 3)):
-        pool.map(lambda c, i: step_dev(c, i), range(S))
+    # ---- warm-up: the pool's contexts allocate their buffers -----------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        ctx.call_batch(None, device_ptrs=ptrs, n=n, inflight=S, tables=False, max_pcs=MAX_PCS)
     # ---- single call at a time: latency, per-kernel device times (CUDA events around each launch) ----
-    lat_steps = max(5, min(args.steps, 20))
+    lat_steps = 20
+    for i in range(3):
+        ctx.call(device_ptr=ptrs[i % B], n=n, colmajor=0, max_pcs=MAX_PCS)
+    lstream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
     clocks = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
     ctx.profile(1)
-    l0 = sum(c.launches for c in pool.contexts)
-    ms, _, outs = timed_pass(lambda c, i: step_dev(c, args.warmup + i), lat_steps, [ctx], streams[:1])
-    res = outs[-1]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(lstream)
+    for i in range(lat_steps):
+        res = ctx.call(device_ptr=ptrs[i % B], n=n, colmajor=0, max_pcs=MAX_PCS)
+    e1.record(lstream)
+    ctx.sync()
+    ms_single = e0.elapsed_time(e1)
     prof = ctx.profile(0)
     stage = ctx.timings()
-    # ---- value: S calls in flight ------------------------------------------------------------------
-    ms_thr, _, _ = timed_pass(lambda c, i: step_dev(c, args.warmup + i), args.steps, pool.contexts, streams)
-    launches = sum(c.launches for c in pool.contexts) - l0
+    # ---- value: K steps of B device-resident calls, S in flight ------------------------------------
+    barrier()
+    ctx.call_batch(None, device_ptrs=ptrs * args.steps, n=n, inflight=S, tables=False, max_pcs=MAX_PCS)
+    ms_thr, launches = ctx.last_batch_device_ms, ctx.last_batch_launches
+    barrier()
     clk = clocks.stop() if clocks else None
-    # ---- e2e: public API, pinned host input, copies inside the timed region -----------------------
-    pool.map(lambda c, i: step_e2e(c, i), range(S))
-    _, t_e2e, tps = timed_pass(lambda c, i: step_e2e(c, args.warmup + i), args.steps, pool.contexts, streams)
-    _, t_e2e_single, _ = timed_pass(lambda c, i: step_e2e(c, args.warmup + i), lat_steps, [ctx], streams[:1])
+    # ---- e2e: public API, pinned host input, copies + tables + objects inside the timed region ----
+    TADpole_batch(host_np, max_pcs=MAX_PCS, ctx=ctx, streams=S)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tps = TADpole_batch(host_np, max_pcs=MAX_PCS, ctx=ctx, streams=S)
+    ctx.sync()
+    t_e2e = time.perf_counter() - t0
+    barrier()
     tp = tps[-1]
-    d2h = int(n + tp.scores.size * 8 + (res["nf"] - 1) * 8)
+    d2h = int(n + tp.scores.size * 8 + (res["nf"] - 1) * 8) * B
+    # one call at a time through the public API (what a plain TADpole() in a loop costs)
+    from tadpole_b200 import TADpole
+    t0 = time.perf_counter()
+    for i in range(lat_steps):
+        TADpole(host_np[i % B], max_pcs=MAX_PCS, ctx=ctx)
+    t_e2e_single = time.perf_counter() - t0
 
-    tmax = torch.tensor([ms_thr, t_e2e * 1e3, ms, t_e2e_single * 1e3], dtype=torch.float64, device="cuda")
+    tmax = torch.tensor([ms_thr, t_e2e * 1e3, ms_single, t_e2e_single * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_all, e2e_ms_all, ms_single_all, e2e_single_all = (float(v) for v in tmax)
-    args_steps_single = lat_steps
+    ctx.close()
+
+    strong = None
+    if args.strong_bins > 0 or args.arm_bins > 0:
+        try:
+            strong = strong_scaling(args, torch, dist, rank, world, local_rank, Context, sharding, api)
+        except Exception as e:                                      # the headline line must still be printed
+            if world > 1:
+                raise
+            strong = {"failed": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
-        value = world * args.steps / (ms_all * 1e-3)
-        e2e_val = world * args.steps / (e2e_ms_all * 1e-3)
-        # roofline of the dominant kernel class (device time measured live with CUDA events around
-        # every launch of the class, in the timed region above)
+        ncalls = args.steps * B
+        value = world * ncalls / (ms_all * 1e-3)
+        e2e_val = world * ncalls / (e2e_ms_all * 1e-3)
         peaks = {}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -302,9 +408,14 @@ def run_b200(args, rank, world, local_rank):
         except OSError:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         nf, k = res["nf"], res["k"]
         fp64_peak = measure_fp64_peak(torch)
+        int8_peak = measure_int8_peak(torch)
+        int8_src = ("measured in this run: torch._int_mm (cuBLASLt int8 -> int32) 8192^3, best of 10; executed digit-product "
+                    "operations, not FP64 flops")
+        if not int8_peak:
+            int8_peak, int8_src = 4500.0, "nominal B200 dense int8 (4.5 POP/s): torch._int_mm unavailable"
         b_blk = -(-(k + max(32, k // 4)) // 32) * 32 if nf > 512 else nf      # width of the Rayleigh-Ritz problems
         nlev = float(np.count_nonzero(~np.isnan(res["scores"]))) if res.get("scores") is not None else 0.0
 
@@ -315,18 +426,13 @@ def run_b200(args, rank, world, local_rank):
             per = t_ms / cnt                                   # ms per launch (CUDA events around each launch)
             src = peak_src
             if cls == "dgemm":
-                # algorithmic flops summed by the library per launch (2MNK; M N (K+1) for SYRK shapes);
-                # denominator: cuBLAS DGEMM measured in this same run (no FP64 peak in MEASURED_PEAKS.json)
                 r = {"kernel": "dgemm_kernel (FP64 DMMA mma.sync m8n8k4)", "bound": "tensor",
                      "achieved": prof["gemm_gflop"][0] / t_ms, "peak": fp64_peak, "unit": "TFLOP/s", "traffic": None}
                 src = "cuBLAS DGEMM 4096^3 via torch.matmul, best of 6, measured in this run"
             elif cls == "igemm":
-                # tcgen05 int8 launches (exact Gram of the correlation, sliced operator of the PCA; the class also
-                # holds their digit-slicing kernels): executed int8 operations / class time against the NOMINAL dense
-                # int8 rate (no measured int8 peak in MEASURED_PEAKS.json)
                 r = {"kernel": "ig_gram_kernel + io_gemm_kernel (tcgen05.mma kind::i8; digit slicing timed apart as islice)", "bound": "tensor",
-                     "achieved": prof["igemm_gop"][0] / t_ms, "peak": 4500.0, "unit": "TOP/s", "traffic": None}
-                src = "nominal B200 dense int8 (4.5 POP/s); executed digit-product operations, not FP64 flops"
+                     "achieved": prof["igemm_gop"][0] / t_ms, "peak": int8_peak, "unit": "TOP/s", "traffic": None}
+                src = int8_src
             else:
                 if cls == "coniss_sweep":      # 8 Nf k(k+1)/2 read + 8 k (Nf-1) written per sweep
                     alg, name = 8.0 * nf * k * (k + 1) / 2 + 8.0 * k * (nf - 1), "coniss_sweep_kernel"
@@ -338,6 +444,8 @@ def run_b200(args, rank, world, local_rank):
                     alg, name = 8.0 * nf * nf, "compact_kernel"
                 elif cls == "chol":            # read G, write L and L^-1 (lower triangles): 3 * 8 * b(b+1)/2
                     alg, name = 12.0 * b_blk * (b_blk + 1), "cholinv8_kernel"
+                elif cls == "islice":
+                    return None
                 else:                          # eigensolver: read T, write V: 2 * 8 * b^2
                     alg, name = 16.0 * b_blk * b_blk, "osj_kernel"
                 r = {"kernel": name, "bound": "hbm", "achieved": alg / (per * 1e-3) / 1e9, "peak": hbm_peak,
@@ -348,24 +456,25 @@ def run_b200(args, rank, world, local_rank):
                     r["note"] = "latency-bound: serial dependent steps on L2 / shared-memory resident data"
             r["frac"] = r["achieved"] / r["peak"]
             r["peak_source"] = src
-            r["share_of_step"] = t_ms / ms          # of the one-call-at-a-time pass the classes were timed in
+            r["share_of_step"] = t_ms / ms_single          # of the one-call-at-a-time pass the classes were timed in
             r["avg_launch_ms"] = per
-            r["launches_per_step"] = cnt / args_steps_single
+            r["launches_per_call"] = cnt / lat_steps
             return r
 
         classes = ("dgemm", "igemm", "jacobi", "chol", "coniss_sweep", "ch", "rowmean", "compact")
         roofs = {c: roof_of(c) for c in classes}
         roofs = {c: r for c, r in roofs.items() if r}
-        try:        # DRAM traffic per launch measured by ncu --set full (profiles/), N = 2000 workload only
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-                traffic = json.load(fh)
+        for fn in ("r02_traffic.json", "r01_traffic.json"):     # DRAM bytes per launch from the ncu --set full captures
+            try:
+                with open(os.path.join(ROOT, "profiles", fn)) as fh:
+                    traffic = json.load(fh)
+            except OSError:
+                continue
             if n == 2000:
                 for r in roofs.values():
-                    if r["kernel"] in traffic:
+                    if r["traffic"] is None and r["kernel"] in traffic:
                         r["traffic"] = traffic[r["kernel"]]
-                        r["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
-        except OSError:
-            pass
+                        r["traffic_unit"] = f"bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/{fn})"
         top = max(roofs, key=lambda c: roofs[c]["share_of_step"])
         roof = roofs[top]
 
@@ -373,45 +482,45 @@ def run_b200(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"synthetic {n}-bin Hi-C matrix, nested block TADs, power-law decay, max_pcs=200 "
-                                   "(BASELINE.json configs[1]); one TADpole() call per step",
-                       "bins": n, "good_bins": nf, "max_pcs": MAX_PCS, "n_pcs_found": res["n_pcs"],
-                       "optimal_n_clusters": res["n_clusters"],
-                       "l2": f"pool of {POOL} different {n}x{n} f64 matrices per rank ({POOL * n * n * 8 >> 20} MiB > L2) "
-                             "cycled, no step re-reads a warm input",
+            "config": {"workload": workload_text(n), "bins": n, "good_bins": nf, "max_pcs": MAX_PCS,
+                       "calls_per_step": B, "calls_timed": ncalls * world,
+                       "n_pcs_found": res["n_pcs"], "optimal_n_clusters": res["n_clusters"],
+                       "l2": f"every step passes over {B} different {n}x{n} f64 matrices ({B * n * n * 8 >> 20} MiB > L2): "
+                             "no step re-reads a warm input",
                        "calls_in_flight_per_gpu": S,
-                       "host_wait": ("blocking-sync event (threads sleep)" if sync_blocking else "cudaStreamSynchronize (spin)")
-                                    + f", {ncpu} logical CPUs for {world * S} waiting threads",
-                       "parallelism": f"{world} GPU(s) x {S} independent calls in flight (own context, stream and host thread "
-                                      "each), no collective on the data path"},
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(n), "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms_all / args.steps},
-            "single_call": {"ms_per_call": ms_single_all / args_steps_single, "calls_per_s": world * args_steps_single / (ms_single_all * 1e-3),
-                            "e2e_ms_per_call": e2e_single_all / args_steps_single,
-                            "note": "one call at a time per GPU (latency); rooflines and kernel_ms_per_step are from this pass"},
+                       "parallelism": f"{world} GPU(s) x {S} independent calls in flight, kept in flight by tp_call_batch's own host "
+                                      "threads (one context + stream each); no collective on the data path"},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(n) * B, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms_all / args.steps,
+                    "api": "TADpole_batch(list of pinned host matrices): one host thread -> tp_call_batch; returns tadpole objects"},
+            "single_call": {"ms_per_call": ms_single_all / lat_steps, "calls_per_s": world * lat_steps / (ms_single_all * 1e-3),
+                            "e2e_ms_per_call": e2e_single_all / lat_steps,
+                            "note": "one call at a time per GPU (latency); rooflines and kernel_ms_per_call are from this pass"},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": roof,
             "roofline_all_kernels": roofs,
             "fp64_dgemm_peak_tflops_measured": fp64_peak,
-            "stage_ms_last_step": {k_: round(v, 4) for k_, v in stage.items()},
-            "kernel_ms_per_step": {c: round(v[0] / args_steps_single, 4) for c, v in prof.items() if v[1]},
+            "int8_peak_tops": int8_peak,
+            "stage_ms_last_call": {k_: round(v, 4) for k_, v in stage.items()},
+            "kernel_ms_per_call": {c: round(v[0] / lat_steps, 4) for c, v in prof.items() if v[1]},
             "h2d_note": "only the upper triangle of the matrix is uploaded (band copies)",
-            "kernel_launches_per_step": {c: v[1] / args_steps_single for c, v in prof.items() if v[1]},
+            "kernel_launches_per_call": {c: v[1] / lat_steps for c, v in prof.items() if v[1]},
+            "r_probe": r_probe(),
         }
+        if strong is not None:
+            line["strong_scaling"] = strong
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            est, detail = cpu_sample(host[0].numpy().copy(), args.cpu_sample, threads)
-            line["cpu_baseline"] = {
-                "value": 1.0 / est, "unit": UNIT, "cores": threads, "kind": "port",
-                "sample": (f"oracle/ (numpy + C restatement; R unavailable): filter+correlation+full SVD timed in full "
-                           f"({detail['front_s']} s), {detail['candidates']} of {detail['k']} candidates on {threads} "
-                           f"threads ({detail['sweep_sample_s']} s) scaled by k/candidates")}
+            sec, detail = cpu_full_call(host_np[0].copy(), threads)
+            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "oracle/ (numpy + C restatement; R unavailable): " + cpu_sample_text(detail, threads),
+                                    "same_result_as_gpu": bool(detail["n_pcs"] == tps[0].n_pcs and detail["n_clusters"] == tps[0].optimal_n_clusters)}
+            c0 = Context(local_rank)
             # the tensor-core kernels at a size where they are the step (the 2000-bin workload leaves them 64-CTA grids)
             if args.large_n > 0:
                 nl = args.large_n
                 ml = synth_hic(nl, seed=77)
-                c0 = pool.contexts[0]
                 for _ in range(2):
                     rl = c0.call(ml, max_pcs=MAX_PCS)
                 c0.profile(1)
@@ -425,29 +534,29 @@ def run_b200(args, rank, world, local_rank):
                 if pl["igemm"][1]:
                     a = pl["igemm_gop"][0] / pl["igemm"][0]
                     big["igemm_roofline"] = {"kernel": "ig_gram_kernel + io_gemm_kernel<5|8> (tcgen05.mma kind::i8)", "bound": "tensor",
-                                             "achieved": a, "peak": 4500.0, "unit": "TOP/s", "frac": a / 4500.0,
-                                             "peak_source": "nominal B200 dense int8; executed digit-product operations over the "
-                                                            "CUDA-event time of the tcgen05 launches of one call"}
+                                             "achieved": a, "peak": int8_peak, "unit": "TOP/s", "frac": a / int8_peak,
+                                             "peak_source": int8_src}
                 if pl["dgemm"][1]:
                     a = pl["gemm_gflop"][0] / pl["dgemm"][0]
                     big["dgemm_roofline"] = {"kernel": "dgemm_kernel (FP64 DMMA)", "bound": "tensor", "achieved": a, "peak": fp64_peak,
                                              "unit": "TFLOP/s", "frac": a / fp64_peak,
                                              "peak_source": "cuBLAS DGEMM 4096^3 measured in this run"}
-                try:      # DRAM traffic per launch of the tcgen05 kernels from the ncu --set full capture at this size
-                    with open(os.path.join(ROOT, "profiles", f"r01_traffic_n{nl}.json")) as fh:
-                        big["traffic_bytes_per_launch_ncu"] = {k_: v for k_, v in json.load(fh).items() if not k_.startswith("_")}
-                except OSError:
-                    pass
+                for fn in (f"r02_traffic_n{nl}.json", f"r01_traffic_n{nl}.json"):
+                    try:
+                        with open(os.path.join(ROOT, "profiles", fn)) as fh:
+                            big["traffic_bytes_per_launch_ncu"] = {k_: v for k_, v in json.load(fh).items() if not k_.startswith("_")}
+                            big["traffic_source"] = f"profiles/{fn}"
+                        break
+                    except OSError:
+                        pass
                 line["large_n_call"] = big
                 del ml
             # input side: the same call starting from the matrix FILE, text parsed on the GPU
             try:
-                import tempfile
-                hm = host[0].numpy()
+                hm = host_np[0]
                 text = "\n".join("\t".join(map(str, row)) for row in hm.astype(np.int64).tolist()) + "\n"
                 with tempfile.NamedTemporaryFile("w", suffix=".tsv", delete=False) as fh:
                     fh.write(text)
-                c0 = pool.contexts[0]
                 t_file = []
                 for _ in range(6):
                     t0 = time.perf_counter()
@@ -467,9 +576,10 @@ def run_b200(args, rank, world, local_rank):
                     "note": "wall clock from the open() of the TSV file to the returned result, page cache warm"}
             except OSError as e:
                 line["from_file"] = {"unavailable": str(e)}
+            c0.close()
         print(json.dumps(line), flush=True)
-    pool.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

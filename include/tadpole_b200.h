@@ -238,6 +238,11 @@ typedef struct tp_batch tp_batch;
 int tp_call_batch(tp_ctx *ctx, int ncalls, const double *const *mats, const int *n, int colmajor, int on_device,
                   int max_pcs, int min_clusters, double bad_frac, int inflight, int want_tables, tp_batch **out);
 int tp_batch_size(const tp_batch *b);
+/* device milliseconds of the whole batch: CUDA events, from the start of the batch to the end of the last call, max over
+ * the streams and devices it ran on */
+double tp_batch_device_ms(const tp_batch *b);
+/* kernels launched by the calls of the batch */
+long long tp_batch_launches(const tp_batch *b);
 int tp_batch_status(const tp_batch *b, int i);
 const char *tp_batch_error(const tp_batch *b, int i);
 int tp_batch_dims(const tp_batch *b, int i, int *n_out, int *nf_out, int *k_out, int *maxlev_out, int *nlevels_out,

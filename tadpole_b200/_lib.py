@@ -27,7 +27,7 @@ EXPORTED = [
     "tp_ingest_tsv", "tp_ingest_tsv_file", "tp_ingested", "tp_get_ingested", "tp_ingest_stats", "tp_test_parse_field",
     "tp_difft_null", "tp_recall",
     "tp_ctx_create_multi", "tp_device_count", "tp_ctx_devices", "tp_ctx_generation", "tp_ctx_dims", "tp_call_arms", "tp_call_batch",
-    "tp_batch_size", "tp_batch_status", "tp_batch_error", "tp_batch_dims", "tp_batch_get", "tp_batch_free", "tp_find_groups",
+    "tp_batch_size", "tp_batch_device_ms", "tp_batch_launches", "tp_batch_status", "tp_batch_error", "tp_batch_dims", "tp_batch_get", "tp_batch_free", "tp_find_groups",
 ]
 
 
@@ -63,6 +63,8 @@ def load():
         "tp_call_arms": (c_int, [vp, ip, c_int, ip, c_int, c_int, c_int, ip, ip, ip, dp, dp, c_int, ip, dp, dp]),
         "tp_call_batch": (c_int, [vp, c_int, POINTER(vp), ip, c_int, c_int, c_int, c_int, c_double, c_int, c_int, POINTER(vp)]),
         "tp_batch_size": (c_int, [vp]),
+        "tp_batch_device_ms": (c_double, [vp]),
+        "tp_batch_launches": (c_longlong, [vp]),
         "tp_batch_status": (c_int, [vp, c_int]),
         "tp_batch_error": (c_char_p, [vp, c_int]),
         "tp_batch_dims": (c_int, [vp, c_int, ip, ip, ip, ip, ip, ip]),
@@ -485,6 +487,8 @@ class Context:
         check(self.lib.tp_call_batch(self._h, ncalls, ptrs, _ip(ns), colmajor, ondev, int(max_pcs), int(min_clusters),
                                      float(bad_frac), int(inflight), int(bool(tables)), ctypes.byref(h)))
         out = []
+        self.last_batch_device_ms = float(self.lib.tp_batch_device_ms(h))
+        self.last_batch_launches = int(self.lib.tp_batch_launches(h))
         try:
             for i in range(ncalls):
                 rc = self.lib.tp_batch_status(h, i)

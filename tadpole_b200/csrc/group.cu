@@ -257,12 +257,15 @@ struct TpBatchItem {
     std::vector<double> scores, seqdist;          // scores: k x maxlev row-major, NaN padded
     std::vector<int> levels, offsets, start, end; // per-level start / end tables (R/TADpole.R:470-497)
     double device_ms = 0.0;
+    long long launches = 0;
 };
-struct tp_batch { std::vector<TpBatchItem> items; };
+struct tp_batch { std::vector<TpBatchItem> items; double device_ms = 0.0; };
 
 static int batch_one(tp_ctx *c, const double *mat, int n, int colmajor, int on_device, int max_pcs, int min_clusters,
                      double bad_frac, int want_tables, TpBatchItem &it) {
     it.n = n;
+    const long long launches0 = c->launches;
+    struct Count { TpBatchItem &it; tp_ctx *c; long long l0; ~Count() { it.launches = c->launches - l0; } } count{it, c, launches0};
     it.bad.assign((size_t)n, 0);
     int ld = c->level_cap > 8 ? c->level_cap : 8;
     const int kmax = max_pcs < n ? max_pcs : n;
@@ -332,29 +335,57 @@ extern "C" int tp_call_batch(tp_ctx *ctx, int ncalls, const double *const *mats,
     for (int d = 0; d < ndev; d++) for (tp_ctx *c : pool->ctxs[d]) c->sync_blocking = blocking || ctx->sync_blocking;
     tp_batch *b = new tp_batch();
     b->items.resize((size_t)ncalls);
+    // device time of the whole batch: one start event per device (its streams are idle: the previous batch was joined), one
+    // end event per worker on its own stream after its last call; the batch took max(end - start) over the workers
+    std::vector<cudaEvent_t> ev_start((size_t)ndev), ev_end((size_t)ndev * per_dev);
+    for (int d = 0; d < ndev; d++) {
+        cudaSetDevice(pool->devices[d]);
+        cudaEventCreate(&ev_start[d]);
+        for (int s2 = 0; s2 < per_dev; s2++) cudaEventCreate(&ev_end[(size_t)d * per_dev + s2]);
+        cudaEventRecord(ev_start[d], pool->ctxs[d][0]->stream);
+    }
     std::atomic<int> next(0);
-    auto worker = [&](tp_ctx *c) {
+    auto worker = [&](tp_ctx *c, cudaEvent_t done) {
         cudaSetDevice(c->device);
         for (;;) {
             const int i = next.fetch_add(1);
-            if (i >= ncalls) return;
+            if (i >= ncalls) break;
             TpBatchItem &it = b->items[(size_t)i];
             it.rc = mats[i] ? batch_one(c, mats[i], n[i], colmajor, on_device, max_pcs, min_clusters, bad_frac, want_tables, it)
                             : (tp_set_error("tp_call_batch: matrix %d is null", i), (int)TP_ERR_ARG);
             if (it.rc != TP_OK) it.err = tp_last_error();
         }
+        cudaEventRecord(done, c->stream);
     };
     std::vector<std::thread> threads;
-    for (int s = 0; s < per_dev; s++)
+    for (int s2 = 0; s2 < per_dev; s2++)
         for (int d = 0; d < ndev; d++)
-            if (!(s == 0 && d == 0)) threads.emplace_back(worker, pool->ctxs[d][s]);
-    worker(pool->ctxs[0][0]);
+            if (!(s2 == 0 && d == 0)) threads.emplace_back(worker, pool->ctxs[d][s2], ev_end[(size_t)d * per_dev + s2]);
+    worker(pool->ctxs[0][0], ev_end[0]);
     for (std::thread &t : threads) t.join();
+    for (int d = 0; d < ndev; d++) {
+        cudaSetDevice(pool->devices[d]);
+        for (int s2 = 0; s2 < per_dev; s2++) {
+            cudaEvent_t e = ev_end[(size_t)d * per_dev + s2];
+            float ms = 0.f;
+            if (cudaEventSynchronize(e) == cudaSuccess && cudaEventElapsedTime(&ms, ev_start[d], e) == cudaSuccess)
+                b->device_ms = std::max(b->device_ms, (double)ms);
+            else (void)cudaGetLastError();
+            cudaEventDestroy(e);
+        }
+        cudaEventDestroy(ev_start[d]);
+    }
     cudaSetDevice(ctx->device);
     *out = b;
     return TP_OK;
 }
 
+extern "C" double tp_batch_device_ms(const tp_batch *b) { return b ? b->device_ms : 0.0; }
+extern "C" long long tp_batch_launches(const tp_batch *b) {
+    long long s = 0;
+    if (b) for (const TpBatchItem &it : b->items) s += it.launches;
+    return s;
+}
 extern "C" int tp_batch_size(const tp_batch *b) { return b ? (int)b->items.size() : 0; }
 extern "C" int tp_batch_status(const tp_batch *b, int i) {
     if (!b || i < 0 || i >= (int)b->items.size()) return TP_ERR_ARG;

@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["synth_hic", "synth_partition_pairs", "write_tsv"]
+__all__ = ["synth_hic", "synth_hic_gpu", "synth_partition_pairs", "write_tsv"]
 
 
 def _random_blocks(rng, n, mean_len):
@@ -69,6 +69,47 @@ def synth_hic(n, seed=1, amp=200.0, alpha=1.0, levels=((None, 1.5), (40, 3.0), (
         z = rng.choice(n, size=nz, replace=False)
         mat[z, :] = 0.0
         mat[:, z] = 0.0
+    if centromere:
+        ln = max(2, int(round(centromere_frac * n)))
+        c0 = n // 2 - ln // 2 + int(rng.integers(-n // 50 - 1, n // 50 + 2))
+        c0 = min(max(c0, 2), n - ln - 2)
+        mat[c0:c0 + ln, :] = 0.0
+        mat[:, c0:c0 + ln] = 0.0
+    return mat
+
+
+def synth_hic_gpu(n, seed=1, device=0, centromere=False, centromere_frac=0.03, zero_frac=0.005):
+    """The same lambda structure drawn on the GPU with torch.poisson (numpy's generator needs ~26 s at 25 000 bins): for
+    the chromosome-sized configurations of bench.py and the GPU tests.  The block structure comes from numpy's seeded
+    generator, the Poisson draws from torch's (same seed + same GPU model = same matrix on every rank; callers that need
+    that compare a checksum).  Returns an n x n float64 CUDA tensor (symmetric integer counts)."""
+    import torch
+    rng = np.random.default_rng(seed)
+    dev = torch.device("cuda", device)
+    idx = torch.arange(n, device=dev)
+    blocks = [(torch.from_numpy(_random_blocks(rng, n, n / 5.0 if ml is None else float(ml))).to(dev), bo)
+              for ml, bo in ((None, 1.5), (40, 3.0), (10, 6.0))]
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    mat = torch.empty((n, n), dtype=torch.float64, device=dev)
+    step = max(1, (1 << 26) // n)
+    for r0 in range(0, n, step):
+        r1 = min(n, r0 + step)
+        lam = 200.0 / ((idx[r0:r1, None] - idx[None, :]).abs().float() + 1.0)
+        for ids, bo in blocks:
+            lam = torch.where(ids[r0:r1, None] == ids[None, :], lam * bo, lam)
+        mat[r0:r1] = torch.poisson(lam, generator=g).double()
+        del lam
+    for r0 in range(0, n, step):            # lower := upper^T, in row blocks (no second n x n temporary)
+        r1 = min(n, r0 + step)
+        blk = mat[:, r0:r1].T.contiguous()                    # blk[i, j] = mat[j, r0 + i]
+        cols = torch.arange(n, device=dev)[None, :]
+        rows = torch.arange(r0, r1, device=dev)[:, None]
+        mat[r0:r1] = torch.where(cols < rows, blk, mat[r0:r1])
+        del blk
+    z = torch.from_numpy(rng.choice(n, size=int(round(zero_frac * n)), replace=False)).to(dev)
+    mat[z, :] = 0.0
+    mat[:, z] = 0.0
     if centromere:
         ln = max(2, int(round(centromere_frac * n)))
         c0 = n // 2 - ln // 2 + int(rng.integers(-n // 50 - 1, n // 50 + 2))

@@ -1,0 +1,162 @@
+"""GPU tests at the chromosome sizes of BASELINE.json configs[2] (15 000 bins, centromere_search) and configs[3]
+(25 000 bins): the code paths that only exist up there (two-wave sweeps, boundary links in global memory, 8-plane int8
+convergence checks, >= 12 288-bin operator form) run under the driver's `pytest -m gpu`, checked through
+
+  * the C oracle (Lance-Williams CONISS on a full distance matrix) on the GPU's own PC scores of a ~7k-bin arm:
+    the merge order must be identical                                                       (rioja::chclust, R/TADpole.R:108)
+  * eigen-residuals of the returned PC scores recomputed in FP64 on the host                 (prcomp, R/TADpole.R:366-367)
+  * last CONISS height = total sum of squares of the clustered columns                       (chclust)
+  * broken-stick level count and Calinski-Harabasz recomputed on the host from the returned dendrogram
+                                                                                              (R/TADpole.R:111-120)
+  * TAD tables partition the good bins                                                       (R/TADpole.R:470-497)
+and, when the box has >= 2 GPUs, one call spread over 2 ranks (torchrun) must equal the one-GPU call bit for bit.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import tadpole_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _host_matrix(n, seed, centromere=False):
+    import torch
+    from tadpole_b200.synth import synth_hic_gpu
+    d = synth_hic_gpu(n, seed=seed, device=0, centromere=centromere)
+    h = d.cpu().numpy()
+    del d
+    torch.cuda.empty_cache()
+    return h
+
+
+def _check_scores_are_eigenvectors(cor, s, cols):
+    xc = cor - cor.mean(axis=0, keepdims=True)               # prcomp centres the columns
+    lam = (s * s).sum(axis=0)
+    assert np.all(np.diff(lam) <= 1e-9 * lam[0])             # descending
+    sc = s[:, cols]
+    ms = xc @ (xc.T @ sc)                                    # M s_j = lambda_j s_j
+    resid = np.linalg.norm(ms - sc * lam[cols], axis=0) / (lam[0] * np.sqrt(lam[cols]))
+    assert resid.max() <= 1e-10, resid
+
+
+def _check_levels(seq, s, row, i):
+    """last height, n_cluster and three CH values of candidate i (1-based) from its dendrogram `seq`"""
+    pcs = s[:, :i]
+    tss = ((pcs - pcs.mean(axis=0)) ** 2).sum()
+    assert seq.max() == pytest.approx(tss, rel=1e-9)
+    disp, bs = O.bstick_table(seq)
+    ncl = O.first_true_run(disp > bs)
+    levels = np.flatnonzero(~np.isnan(row)) + 1
+    assert ncl == levels[-1]                                 # broken stick + first-TRUE-run rule (quirk Q1)
+    n = s.shape[0]
+    tot = ((s - s.mean(axis=0)) ** 2).sum()                  # CH on ALL k columns (quirk Q2)
+    for lv in (levels[0], levels[len(levels) // 2], levels[-1]):
+        lab = O.cutree(seq, int(lv))
+        edges = np.flatnonzero(np.diff(lab)) + 1
+        w = sum(((blk - blk.mean(axis=0)) ** 2).sum() for blk in np.split(s, edges))
+        assert row[lv - 1] == pytest.approx((n - lv) * (tot - w) / ((lv - 1) * w), rel=1e-8)
+
+
+@pytest.fixture(scope="module")
+def arms15k(ctx):
+    """configs[2]: 15 000 bins, centromere_search = TRUE"""
+    from tadpole_b200 import TADpole, api
+    api.QUIET = True
+    m = _host_matrix(15000, seed=7, centromere=True)
+    tp = TADpole(m, centromere_search=True, ctx=ctx)
+    return dict(m=m, tp=tp)
+
+
+def test_15k_arms_tables(arms15k):
+    tp, n = arms15k["tp"], 15000
+    ma = tp.merging_arms
+    assert np.all(ma[:, 0] <= ma[:, 1]) and np.all(ma[1:, 0] > ma[:-1, 1])
+    assert ma.shape[0] == tp.p.cluster[str(tp.p.optimal_n_clusters)].shape[0] + tp.q.cluster[str(tp.q.optimal_n_clusters)].shape[0]
+    for arm in (tp.p, tp.q):
+        assert 1 <= arm.n_pcs <= 200 and str(arm.optimal_n_clusters) in arm.cluster
+        for key, tab in arm.cluster.items():
+            assert np.all(tab[:, 0] <= tab[:, 1]) and np.all(tab[1:, 0] > tab[:-1, 1]) and tab.shape[0] <= int(key)
+    assert ma[0, 0] >= 1 and ma[-1, 1] <= n + 1000
+
+
+def test_7k_arm_against_the_c_oracle(ctx, arms15k):
+    """the q arm (~7k bins) stage by stage; the C oracle clusters the GPU's own scores: identical merge order"""
+    lm = O.load_mat_numeric(arms15k["m"], centromere_search=True)
+    keep = (np.asarray(lm.q.names) - 1).astype(np.int32)
+    nf = keep.size
+    assert nf > 6000
+    bad, _, _ = ctx.filter(arms15k["m"])
+    ctx.compact(keep)
+    ctx.correlation()
+    cor = ctx.get_correlation(nf)
+    k = ctx.pca(200)
+    s = ctx.get_scores(nf, k)
+    _check_scores_are_eigenvectors(cor, s, [0, 1, 57, 199])
+    del cor
+    ncl, sc = ctx.sweep(k)
+    for cand in (1, 12, 40):                                 # number of PCs of the candidate
+        seq, order = ctx.dendro(cand - 1, nf)
+        oseq, oorder = O.coniss_lw(s[:, :cand])
+        assert np.array_equal(order, oorder), f"merge order differs from the oracle at {cand} PCs"
+        np.testing.assert_allclose(seq, oseq, rtol=1e-10)
+        _check_levels(seq, s, sc[cand - 1], cand)
+    # the arm's own result: same optimum as the full call found for q
+    oc, ol = ctx.select(sc)
+    tp = arms15k["tp"]
+    assert (oc + 1, ol + 1) == (tp.q.n_pcs, tp.q.optimal_n_clusters)
+
+
+def test_25k_chromosome_call(ctx):
+    """configs[3] on one GPU: the whole call, then its pieces recomputed on the host"""
+    from tadpole_b200 import TADpole, api
+    api.QUIET = True
+    n = 25000
+    m = _host_matrix(n, seed=3)
+    tp = TADpole(m, ctx=ctx)
+    h = object.__getattribute__(tp, "__dict__")["_handle"]
+    nf, bad = h["nf"], h["bad"]
+    assert nf > 24000 and 1 <= tp.n_pcs <= 200
+    s = ctx.get_scores(nf, 200)
+    st = ctx.timings()
+    assert st["pca_applications"] > 0
+    # tables partition the good bins at every level
+    for key, tab in tp.clusters.items():
+        assert np.all(tab[:, 0] <= tab[:, 1]) and np.all(tab[1:, 0] > tab[:-1, 1]) and tab.shape[0] <= int(key)
+        covered = np.zeros(n, bool)
+        covered[np.concatenate([np.arange(a - 1, b) for a, b in tab])] = True
+        assert covered[~bad].all()
+    # the optimal candidate and two others: height, level count, CH
+    for cand in sorted({tp.n_pcs, 3, 120}):
+        seq, order = ctx.dendro(cand - 1, nf)
+        assert sorted(order.tolist()) == list(range(nf - 1))           # every boundary removed exactly once
+        assert np.all(np.diff(seq[order]) >= 0)                        # heights grow along the merge order
+        _check_levels(seq, s, tp.scores[cand - 1], cand)
+    assert np.array_equal(ctx.dendro(tp.n_pcs - 1, nf)[0], tp.dendro.seqdist)
+    # eigen-residuals need the correlation matrix again (tp_pca consumed it): stage calls on the resident matrix
+    ctx.compact(np.flatnonzero(~bad).astype(np.int32))
+    ctx.correlation()
+    cor = ctx.get_correlation(nf)
+    assert np.array_equal(cor[:2000, :2000], cor[:2000, :2000].T)
+    np.testing.assert_allclose(np.diag(cor), 1.0, atol=1e-12)
+    _check_scores_are_eigenvectors(cor, s, [0, 100, 199])
+
+
+@pytest.mark.skipif("__import__('tadpole_b200')._lib.device_count() < 2", reason="needs >= 2 GPUs")
+def test_two_ranks_equal_one_gpu():
+    """one process per GPU (torchrun), NCCL path: row-sharded Gram + all-gathered operator applications + dealt-out sweep;
+    rank 0 repeats the call alone and compares (tests/dist_run.py check)"""
+    port = 29500 + os.getpid() % 400
+    for extra in ([], ["centromere"]):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), os.path.join(ROOT, "tests", "dist_run.py"), "check", "4500"] + extra
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        assert p.returncode == 0, p.stderr[-2000:]
+        out = json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1])
+        assert out["all_ranks_identical"] and out["same_as_single_gpu"], out
+        port += 1
