@@ -103,6 +103,8 @@ template <typename LinkT, bool SMEM> struct Links {
 };
 
 #define CS_CHUNK 8     // 8 x 32 = 256 score columns loaded per batch
+#define TIE_REL 1e-11  // increases this close (relative) to the minimum are tied: the lowest index is merged
+#define TIE_ABS 1e-24  // ... or this close in units of the total squared norm of the scores (exact-zero ties)
 
 // INV_SMEM: a table of 1/m, m = 0..n, sits in shared memory (cluster sizes are integers), replacing
 // the five FP64 divisions of a merge step by loads
@@ -110,13 +112,16 @@ template <typename LinkT, bool SMEM> struct Links {
 // reciprocal table shared by the CTA after them).  Packing several candidates into one CTA keeps the sweep on few SMs:
 // 200 one-warp CTAs would be spread over all 148 SMs, and their 25-40 KB of shared memory each would keep the
 // ~200 KB CTAs of the tcgen05 kernels of OTHER calls in flight on the same GPU off every SM for the whole sweep.
-template <typename LinkT, bool LINKS_SMEM, bool INV_SMEM>
+// TRACE: cycles of one merge step by phase, summed over the merge loop of the first candidate of the list (the widest),
+// written to trace[0..5] = find, links, P rows + dot products, shuffle reduce + scale, write back + level-1 re-reduce,
+// level-2 re-reduce; trace[6] = steps (TADPOLE_SWEEP_TRACE; profiles/r02_coniss_merge_step.md)
+template <typename LinkT, bool LINKS_SMEM, bool INV_SMEM, bool TRACE>
 __global__ void __launch_bounds__(256)
 coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
                     const double *__restrict__ d0, int ldd,
                     const int *__restrict__ cand_list, int ncand, unsigned cand_smem,
                     double *__restrict__ seqdist, int4 *__restrict__ merges,
-                    LinkT *__restrict__ glinks) {
+                    LinkT *__restrict__ glinks, const double *__restrict__ qtot, long long *__restrict__ trace) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const int slot = blockIdx.x * wpc + warp;
@@ -169,30 +174,47 @@ coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
     __syncwarp();
 
     auto inv_of = [&](int m) -> double { return INV_SMEM ? lds_f64(sinv + 8u * m) : 1.0 / (double)m; };
+    const double tie_abs = TIE_ABS * __ldg(qtot);       // qtot: sum of the squared norms of all score rows
     const double *Plane = P + lane;
     double total = 0.0;
+    long long tr_acc[6] = {0, 0, 0, 0, 0, 0}, tr_t = 0;
+#define CS_TR(ph) do { if (TRACE) { const long long t_ = clock64(); tr_acc[ph] += t_ - tr_t; tr_t = t_; } } while (0)
     for (int t = 0; t < n1; t++) {
-        // ---- find the lowest-index minimum ------------------------------------------------
+        if (TRACE) tr_t = clock64();
+        // ---- find the minimum; among increases equal to it, the lowest index ---------------------------
+        // The reference's scan keeps the first of EQUAL increases (strict '<').  Equal means equal in exact arithmetic:
+        // bins with identical score rows (zero-variance bins all map to one row of the correlation matrix, quirk Q9) give
+        // families of exactly tied increases, which Lance-Williams arithmetic on the distance matrix reproduces bit for bit
+        // while differences of prefix sums taken at different offsets differ in their last bits.  So an increase within
+        // TIE_REL (relative, two orders above the rounding of this kernel's arithmetic) + tie_abs (for exact zeros: identical
+        // adjacent rows) of the minimum counts as tied.  Two increases that close without being structurally equal are
+        // ordered by rounding noise in the reference too.
         double mn;
         int b2 = 0;
         if (B2p == 32) {
             const double v = lds_f64(sm2 + 8u * lane);
             mn = warp_min_nonneg(v);
-            b2 = __ffs(__ballot_sync(0xffffffffu, v == mn)) - 1;
+            const double thr = fma(mn, TIE_REL, mn) + tie_abs;
+            b2 = __ffs(__ballot_sync(0xffffffffu, v <= thr)) - 1;
         } else {
             double v = INF_D;
             for (int q = lane; q < B2p; q += 32) v = fmin(v, lds_f64(sm2 + 8u * q));
             mn = warp_min_nonneg(v);
+            const double thr = fma(mn, TIE_REL, mn) + tie_abs;
             for (int q0 = 0; q0 < B2p; q0 += 32) {
-                unsigned bal = __ballot_sync(0xffffffffu, lds_f64(sm2 + 8u * (q0 + lane)) == mn);
+                unsigned bal = __ballot_sync(0xffffffffu, lds_f64(sm2 + 8u * (q0 + lane)) <= thr);
                 if (bal) { b2 = q0 + __ffs(bal) - 1; break; }
             }
         }
-        const unsigned bal1 = __ballot_sync(0xffffffffu, lds_f64(sm1 + 8u * ((b2 << 5) + lane)) == mn);
+        const double thr = fma(mn, TIE_REL, mn) + tie_abs;
+        const unsigned bal1 = __ballot_sync(0xffffffffu, lds_f64(sm1 + 8u * ((b2 << 5) + lane)) <= thr);
         const int b1 = (b2 << 5) + __ffs(bal1) - 1;
-        const unsigned bal0 = __ballot_sync(0xffffffffu, lds_f64(sd + 8u * ((b1 << 5) + lane)) == mn);
+        const double leaf = lds_f64(sd + 8u * ((b1 << 5) + lane));
+        const unsigned bal0 = __ballot_sync(0xffffffffu, leaf <= thr);
         const int j = (b1 << 5) + __ffs(bal0) - 1;
+        mn = __shfl_sync(0xffffffffu, leaf, j & 31);          // the increase of the boundary that is merged
 
+        CS_TR(0);
         // ---- neighbours ---------------------------------------------------------------------
         const int pj = lk.prv(j) - 1;            // previous live boundary or -1
         const int nj = lk.nxt(j);                // next live boundary or n1
@@ -206,6 +228,7 @@ coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
         const int cC = c - b, cLL = b - a, cRR = e - c;
         const double iC = inv_of(cC), iLL = inv_of(cLL), iRR = inv_of(cRR);
         double accL = 0.0, accR = 0.0;
+        if (TRACE) { asm volatile("" ::"d"(iC), "d"(iLL), "d"(iRR)); CS_TR(1); }
         for (int c0 = 0; c0 < ncol; c0 += 32 * CS_CHUNK) {
             double va[CS_CHUNK], vb[CS_CHUNK], vc[CS_CHUNK], ve[CS_CHUNK];
             // all loads of the batch first: one L2 round trip per step instead of one per 32 columns
@@ -229,6 +252,7 @@ coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
                 accR = fma(tR, tR, accR);
             }
         }
+        if (TRACE) { asm volatile("" ::"d"(accL), "d"(accR)); CS_TR(2); }
         total += mn;
         if (lane == 0) {
             seq[j] = total;
@@ -243,6 +267,7 @@ coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
         accL *= (double)cLL * (double)cC * inv_of(cLL + cC);
         accR *= (double)cC * (double)cRR * inv_of(cC + cRR);
 
+        if (TRACE) { asm volatile("" ::"d"(accL), "d"(accR)); CS_TR(3); }
         // ---- write back: boundary j dies, its neighbours get new increases ---------------
         if (lane == 0) {
             sts_f64(sd + 8u * j, INF_D);
@@ -266,6 +291,7 @@ coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
             if (k2 != k0) sts_f64(sm1 + 8u * k2, r2);
         }
         __syncwarp();
+        CS_TR(4);
         const int g0 = k0 >> 5, g1 = k1 >> 5, g2 = k2 >> 5;
         const double y0 = warp_min_nonneg(lds_f64(sm1 + 8u * ((g0 << 5) + lane)));
         if (lane == 0) sts_f64(sm2 + 8u * g0, y0);
@@ -278,7 +304,14 @@ coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
             if (lane == 0) sts_f64(sm2 + 8u * g2, y2);
         }
         __syncwarp();
+        CS_TR(5);
     }
+    if (TRACE && slot == 0 && lane == 0) {
+        for (int p = 0; p < 6; p++) trace[p] = tr_acc[p];
+        trace[6] = n1;
+        trace[7] = ncol;
+    }
+#undef CS_TR
 }
 
 // ------------------------------------------------------------------------------------------
@@ -451,25 +484,40 @@ int tp_sweep_device(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stri
         TP_TRY(ctx->links.reserve((size_t)ncand * link_bytes));
         glinks = ctx->links.p;
     }
-#define LAUNCH_SWEEP(LT, LS, IS)                                                                          \
+    long long *trace = nullptr;
+    DevBuf trbuf;
+    if (getenv("TADPOLE_SWEEP_TRACE")) { TP_TRY(trbuf.reserve(8 * sizeof(long long))); trace = trbuf.as<long long>(); }
+#define LAUNCH_SWEEP2(LT, LS, IS, TR)                                                                     \
     do {                                                                                                  \
-        TP_CUDA(cudaFuncSetAttribute(coniss_sweep_kernel<LT, LS, IS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        TP_CUDA(cudaFuncSetAttribute(coniss_sweep_kernel<LT, LS, IS, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         tp_prof_begin(ctx, PC_SWEEP);                                                                     \
-        coniss_sweep_kernel<LT, LS, IS><<<nblocks, 32 * wpc, smem, st>>>(ctx->P.as<double>(), ldk, n, ctx->d0.as<double>(), ldd, \
+        coniss_sweep_kernel<LT, LS, IS, TR><<<nblocks, 32 * wpc, smem, st>>>(ctx->P.as<double>(), ldk, n, ctx->d0.as<double>(), ldd, \
                                                                  d_cands, ncand, (unsigned)cand_smem, ctx->seqdist.as<double>(), \
-                                                                 ctx->order.as<int4>(), (LT *)glinks);     \
+                                                                 ctx->order.as<int4>(), (LT *)glinks, ctx->Qp.as<double>() + n, trace); \
         tp_prof_end(ctx);                                                                                 \
     } while (0)
+#define LAUNCH_SWEEP(LT, LS, IS) do { if (trace) LAUNCH_SWEEP2(LT, LS, IS, true); else LAUNCH_SWEEP2(LT, LS, IS, false); } while (0)
     if (small_links) {
         if (links_smem) { if (inv_smem) LAUNCH_SWEEP(unsigned short, true, true); else LAUNCH_SWEEP(unsigned short, true, false); }
         else LAUNCH_SWEEP(unsigned short, false, false);
     } else {
         if (links_smem) LAUNCH_SWEEP(int, true, false); else LAUNCH_SWEEP(int, false, false);
     }
+#undef LAUNCH_SWEEP2
 #undef LAUNCH_SWEEP
     ctx->launches += 1;
     TP_CUDA(cudaGetLastError());
     TP_MARK(ctx, EV_SWEEP1);
+    if (trace) {
+        long long h[8];
+        TP_CUDA(cudaStreamSynchronize(st));
+        TP_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
+        static const char *ph[6] = {"find", "links", "p_rows_dot", "reduce_scale", "writeback_l1", "l2"};
+        fprintf(stderr, "[sweep trace] n=%d cols=%lld wpc=%d links_smem=%d inv_smem=%d cycles per merge step:", n, h[7], wpc, (int)links_smem, (int)inv_smem);
+        for (int p = 0; p < 6; p++) fprintf(stderr, " %s %.0f", ph[p], (double)h[p] / (double)h[6]);
+        fprintf(stderr, "\n");
+        trbuf.release();
+    }
     ctx->have_sweep = true;
     (void)min_clusters;
     return TP_OK;

@@ -113,7 +113,11 @@ __device__ __forceinline__ void osj_rotate(unsigned sA, unsigned sN, int BP, int
 template <int RL>
 __global__ void __cluster_dims__(OSJ_CLUSTER, 1, 1) __launch_bounds__(OSJ_THREADS, 1)
 osj_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol,
-           double *cmax, double *w_out, int *info) {
+           double *cmax, double *w_out, int *info, long long *trace) {
+    // optional phase trace (TADPOLE_OSJ_TRACE): cycles of thread 0 of every CTA summed per phase over the whole solve
+    long long tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tr_t = 0;
+#define OSJ_TR0() do { if (trace && threadIdx.x == 0) tr_t = clock64(); } while (0)
+#define OSJ_TR(ph) do { if (trace && threadIdx.x == 0) { const long long t_ = clock64(); tr_acc[ph] += t_ - tr_t; tr_t = t_; } } while (0)
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) double s_osj[];
     double *sA = s_osj;                       // 2H columns x BP
@@ -132,6 +136,7 @@ osj_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol,
         for (int bs = 0; bs < OSJ_NHP - 1; bs++) {
             int hI, hJ;
             osj_pair(crank, bs, OSJ_NHP, hI, hJ);
+            OSJ_TR0();
             // ---- load the two half-panels (columns contiguous in global: coalesced) -----------
             const int colsz = H * BP;
             for (int i0 = 0; i0 < colsz; i0 += OSJ_THREADS * 8) {       // all loads of a batch in flight together
@@ -148,6 +153,7 @@ osj_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol,
                 }
             }
             __syncthreads();
+            OSJ_TR(0);
             // squared column norms, recomputed every block step (no drift)
             for (int c = wid; c < 2 * H; c += OSJ_THREADS / 32) {
                 double a = 0.0;
@@ -157,6 +163,7 @@ osj_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol,
                 if (lane == 0) s_norm[c] = a;
             }
             __syncthreads();
+            OSJ_TR(1);
             // ---- pairs inside each half-panel, once per sweep ---------------------------------
             if (bs == 0) {
                 for (int st = 0; st < Hm - 1; st++) {
@@ -169,6 +176,7 @@ osj_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol,
                     __syncthreads();
                 }
             }
+            OSJ_TR(2);
             // ---- all pairs across the two half-panels: H sub-steps of H disjoint pairs ----------
             for (int st = 0; st < H; st++) {
                 for (int pw = wid; pw < H; pw += OSJ_THREADS / 32) {
@@ -177,6 +185,7 @@ osj_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol,
                 }
                 __syncthreads();
             }
+            OSJ_TR(3);
             // ---- write back ---------------------------------------------------------------------------
             for (int idx = tid; idx < colsz; idx += OSJ_THREADS) {
                 Ac[(size_t)hI * colsz + idx] = sA[idx];
@@ -188,9 +197,12 @@ osj_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol,
                     w_out[gcol] = s_norm[c];
                 }
             }
+            OSJ_TR(4);
             cluster.sync();
+            OSJ_TR(5);
         }
         sweeps++;
+        OSJ_TR0();
         // largest scaled cosine seen by this CTA -> cluster-wide maximum through global memory
         rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, 16));   // only lane values of the warp matter
 #pragma unroll
@@ -206,6 +218,11 @@ osj_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol,
         double v = 0.0;
         for (int r = 0; r < OSJ_CLUSTER; r++) v = fmax(v, __ldcg(&cmax[(sweeps & 1) * OSJ_CLUSTER + r]));
         converged = v <= tol2;          // squared scaled cosines
+        OSJ_TR(6);
+    }
+    if (trace && threadIdx.x == 0) {
+        for (int p = 0; p < 7; p++) trace[crank * 8 + p] = tr_acc[p];
+        trace[crank * 8 + 7] = sweeps;
     }
     if (crank == 0 && tid == 0) { if (!converged) info[1] = 1; info[2] += sweeps; }     // sticky status words
 }
@@ -256,10 +273,13 @@ int tp_osj(tp_ctx *ctx, double *T, int b, int ld, double *w, double *Vs, int lds
     osj_init_kernel<<<(unsigned)(((size_t)NC * BP + 255) / 256), 256, 0, st>>>(T, b, ld, BP, NC, Ac);
     const size_t smem = (size_t)2 * H * BP * sizeof(double);
     const double otol = tol > 2e-15 ? tol : 2e-15;
+    long long *trace = nullptr;
+    DevBuf trbuf;
+    if (getenv("TADPOLE_OSJ_TRACE")) { TP_TRY(trbuf.reserve(OSJ_CLUSTER * 8 * sizeof(long long))); trace = trbuf.as<long long>(); }
 #define OSJ_LAUNCH(R)                                                                                         \
     case R:                                                                                                   \
         TP_CUDA(cudaFuncSetAttribute(osj_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        osj_kernel<R><<<OSJ_CLUSTER, OSJ_THREADS, smem, st>>>(Ac, b, BP, H, 30, otol, cmax, wtmp, info);      \
+        osj_kernel<R><<<OSJ_CLUSTER, OSJ_THREADS, smem, st>>>(Ac, b, BP, H, 30, otol, cmax, wtmp, info, trace); \
         break;
     switch (BP / 32) {
         OSJ_LAUNCH(1) OSJ_LAUNCH(2) OSJ_LAUNCH(3) OSJ_LAUNCH(4) OSJ_LAUNCH(5) OSJ_LAUNCH(6)
@@ -272,6 +292,18 @@ int tp_osj(tp_ctx *ctx, double *T, int b, int ld, double *w, double *Vs, int lds
     tp_prof_end(ctx);
     ctx->launches += 3;
     TP_CUDA(cudaGetLastError());
+    if (trace) {
+        long long h[OSJ_CLUSTER * 8];
+        TP_CUDA(cudaStreamSynchronize(st));
+        TP_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
+        static const char *ph[7] = {"load", "norms", "intra", "cross", "writeback", "cluster_sync", "converge"};
+        for (int c = 0; c < OSJ_CLUSTER; c += 7) {
+            fprintf(stderr, "[osj trace] b=%d tol=%.1e cta %d sweeps %lld:", b, otol, c, h[c * 8 + 7]);
+            for (int p = 0; p < 7; p++) fprintf(stderr, " %s %lld", ph[p], h[c * 8 + p]);
+            fprintf(stderr, "\n");
+        }
+        trbuf.release();
+    }
     if (sweeps_out) {        // synchronous use: status read back now; otherwise the caller polls tp_flags_read
         int f[4];
         TP_TRY(tp_flags_read(ctx, f));

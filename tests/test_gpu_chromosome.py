@@ -121,6 +121,10 @@ def test_7k_arm_against_the_c_oracle(ctx, arms15k):
     _check_scores_are_eigenvectors(cor, s, [0, 1, 57, 199])
     del cor
     ncl, sc = ctx.sweep(k)
+    dump = os.environ.get("TADPOLE_DUMP_7K")                 # ad-hoc: keep the inputs of a failing comparison for offline study
+    if dump:
+        np.savez_compressed(dump, s=s[:, :40], **{f"seq{c}": ctx.dendro(c - 1, nf)[0] for c in (1, 12, 40)},
+                            **{f"order{c}": ctx.dendro(c - 1, nf)[1] for c in (1, 12, 40)})
     for cand in (1, 12, 40):                                 # number of PCs of the candidate
         seq, order = ctx.dendro(cand - 1, nf)
         oseq, oorder = O.coniss_lw(s[:, :cand])

@@ -163,6 +163,71 @@ def test_sweep_ties_lowest_index_first(ctx):
         assert (order == oorder).all()
 
 
+def test_sweep_structural_ties_follow_the_reference(ctx):
+    """Bins with IDENTICAL score rows (every zero-variance bin maps to the same row of the correlation matrix, quirk Q9;
+    the q arm keeps its all-zero bins, quirk Q3) make exactly tied increases: two single bins on either side of a cluster,
+    runs of identical neighbours whose merged cluster ties again with the next one (zero ties that only appear AFTER a
+    merge), identical bins far apart.  Lance-Williams arithmetic on the distance matrix (the reference) keeps those ties bit
+    for bit and merges the lowest index; the product must produce the same merge order and the same heights."""
+    rng = np.random.default_rng(7)
+    n, k = 900, 24
+    pcs = np.cumsum(rng.standard_normal((n, k)), axis=0) * (1.0 + np.arange(k)) ** -0.7
+    v = rng.standard_normal(k) * 3.0                        # the row every "zero-variance" bin gets
+    w = rng.standard_normal(k) * 0.5
+    dup = [5, 40, 41, 42, 43, 100, 123, 124, 300, 301, 302, 500, 520, 521, 640, 641, 642, 643, 644, 777, 898]
+    pcs[dup] = v
+    pcs[[200, 230, 231, 260]] = w                          # a second family
+    pcs[600:606] = pcs[600]                                 # a run of six identical ordinary rows
+    pcs -= pcs.mean(0)
+    ctx.set_scores(pcs)
+    try:
+        ctx.sweep(k)
+    except Exception:
+        pass                                                # (a candidate without a significant level: the dendrograms exist)
+    for i in (1, 2, 7, 24):
+        seq, order = ctx.dendro(i - 1, n)
+        oseq, oorder = O.coniss_lw(pcs[:, :i])
+        assert np.array_equal(order, oorder), f"merge order differs from the reference's at {i} PCs"
+        np.testing.assert_allclose(seq, oseq, rtol=1e-9, atol=1e-18 * oseq.max())
+
+
+def test_zero_variance_bins_tie_family(ctx):
+    """The q arm of a centromere_search call keeps its all-zero bins (quirk Q3): their columns have zero variance, the whole
+    row of the correlation matrix becomes 0 (0/0 = NaN -> 0, quirk Q9) and all of them get the same PC scores -- a family
+    of exactly tied increases in every candidate's merge loop.  (In the reference the scores of such bins come out of a BLAS
+    product and can differ in the last bit from row to row, so R's own order among them is rounding noise; the product gives
+    them bitwise identical scores and merges the lowest index, which is what the reference's scan does on equal values.)
+    Here: the product's scores of those bins are bitwise identical, and the reference's merge loop (C oracle) run on the
+    product's own scores gives the same merge order, level counts and CH rows for EVERY candidate, hence the same optimum."""
+    from tadpole_b200.synth import synth_hic
+    m = synth_hic(900, seed=9, zero_frac=0.03, centromere=True)
+    lm = O.load_mat_numeric(m, centromere_search=True)
+    keep = (np.asarray(lm.q.names) - 1).astype(np.int32)
+    nf = keep.size
+    ctx.filter(m)
+    ctx.compact(keep)
+    ctx.correlation()
+    cor = ctx.get_correlation(nf)
+    zero = np.flatnonzero(np.all(cor == 0.0, axis=1))
+    assert zero.size >= 8
+    k = ctx.pca(200)
+    s = ctx.get_scores(nf, k)
+    assert all(np.array_equal(s[zero[0]], s[z]) for z in zero), "zero-variance bins must share one row of scores"
+    ncl, sc = ctx.sweep(k)
+    per = []
+    for i in range(1, k + 1):
+        score, n_cluster, oseq = O.candidate_scores_c(s, i, 2)
+        seq, order = ctx.dendro(i - 1, nf)
+        _, oorder = O.coniss_lw(s[:, :i])
+        assert np.array_equal(order, oorder), f"merge order differs at {i} PCs"
+        assert n_cluster == ncl[i - 1]
+        np.testing.assert_allclose(sc[i - 1, :n_cluster][1:], score[1:], rtol=1e-9)
+        per.append(score)
+    _, opt_pcs, opt_k = O.reduce_scores(per)
+    oc, ol = ctx.select(sc)
+    assert (oc + 1, ol + 1) == (opt_pcs, opt_k)
+
+
 # ---- full pipeline --------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,seed", [(200, 1), (200, 2), (601, 1), (2000, 1)])
 def test_tadpole_end_to_end(ctx, n, seed):
