@@ -245,7 +245,7 @@ extern "C" int tp_ctx_profile(tp_ctx *ctx, int enable, double *ms_out16, long lo
 int tp_chol_inv(tp_ctx *ctx, double *G, double *Linv, int b, int ld, int *bad_out);
 int tp_chol_factor(tp_ctx *ctx, double *G, int b, int ld);
 int tp_jacobi(tp_ctx *ctx, double *A, int b, int ld, double *w, double *Vs, int lds, int ncols_out, int *sweeps_out,
-              double tol);
+              double tol, double predict = 0.0);
 
 extern "C" int tp_test_cholinv(tp_ctx *ctx, const double *g, int b, int factor_only, double *l_out, double *linv_out,
                                int *bad_out) {

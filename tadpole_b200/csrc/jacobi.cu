@@ -262,16 +262,16 @@ __global__ void sort_eig_kernel(const double *__restrict__ A, const double *__re
 }
 
 int tp_osj(tp_ctx *ctx, double *T, int b, int ld, double *w, double *Vs, int lds, int ncols_out, int *sweeps_out,
-           double tol);
+           double tol, double predict);
 
 // Eigen-decomposition of the symmetric b x b matrix in A (row-major, ld).  A is destroyed.
 // On return w[0..b) holds the eigenvalues in descending order and Vs (b x lds) the matching
 // eigenvectors in its first ncols_out columns.
 int tp_jacobi(tp_ctx *ctx, double *A, int b, int ld, double *w, double *Vs, int lds, int ncols_out, int *sweeps_out,
-              double tol) {
+              double tol, double predict) {
     TP_ARG(b >= 1 && (b + 1) / 2 <= JC_MAXPAIRS, "tp_jacobi: matrix too large for the cluster Jacobi solver");
     if (b >= 2 && b <= 384 && !getenv("TADPOLE_TWOSIDED"))
-        return tp_osj(ctx, A, b, ld, w, Vs, lds, ncols_out, sweeps_out, tol);
+        return tp_osj(ctx, A, b, ld, w, Vs, lds, ncols_out, sweeps_out, tol, predict);
     cudaStream_t st = ctx->stream;
     const int max_sweeps = 40;
     const int m = (b + 1) & ~1, np = m / 2;

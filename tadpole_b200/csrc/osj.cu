@@ -16,7 +16,7 @@
 namespace cg = cooperative_groups;
 
 #define OSJ_CLUSTER 8
-#define OSJ_THREADS 512
+#define OSJ_THREADS 256             // 16 half-warps: one column pair per half-warp and sub-step
 #define OSJ_NHP 16              // half-panels
 #define OSJ_MAXH 24             // columns per half-panel
 #define OSJ_MAX_B 384            // 2 * 24 columns x 384 rows x 8 B = 147 KB of shared memory
@@ -55,64 +55,140 @@ __global__ void osj_init_kernel(const double *__restrict__ L, int b, int ld, int
 __device__ __forceinline__ double osj_lds(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void osj_sts(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 
-// rotate columns ix and iy of the shared-memory panel; one warp, RL rows per lane
-template <int RL>
-__device__ __forceinline__ void osj_rotate(unsigned sA, unsigned sN, int BP, int ix, int iy,
-                                           int lane, double skip2, double &rmax2) {
-    const unsigned ax = sA + 8u * (ix * BP + lane), ay = sA + 8u * (iy * BP + lane);
-    double xa[RL], ya[RL];
-    double g0 = 0.0, g1 = 0.0;
-#pragma unroll
-    for (int u = 0; u < RL; u++) { xa[u] = osj_lds(ax + 256u * u); ya[u] = osj_lds(ay + 256u * u); }
-    const double al = osj_lds(sN + 8u * ix), be = osj_lds(sN + 8u * iy);
-#pragma unroll
-    for (int u = 0; u < RL; u += 2) {
-        g0 = fma(xa[u], ya[u], g0);
-        if (u + 1 < RL) g1 = fma(xa[u + 1], ya[u + 1], g1);
-    }
-    double g = g0 + g1;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
-    const double ab = al * be;
-    if (!(ab > 0.0)) return;
-    // squared scaled cosine g^2 / (al be): the convergence measure; a crude reciprocal is enough
+// (c, s) of the rotation that makes two columns with squared norms al, be and inner product g orthogonal; false = leave the
+// pair alone (a zero column, or already orthogonal to working precision).  rmax2 collects the squared scaled cosines.
+__device__ __forceinline__ bool osj_cs(double g, double al, double be, double skip2, double &rmax2, double &c, double &sn) {
+    const double ab = al * be, gg = g * g;
+    if (!(ab > 0.0)) return false;
+    // squared scaled cosine g^2 / (al be): the convergence measure (off the critical path; a crude reciprocal is enough)
     double rab;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rab) : "d"(ab));
-    const double rel2 = g * g * rab;
-    rmax2 = fmax(rmax2, rel2);
-    if (!(rel2 > skip2)) return;
-    // t = sgn(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (be - al) / (2 g), without the division.
-    // t only steers convergence; (c, s) is renormalised to c^2 + s^2 = 1 in full precision.
-    // The tangent only steers convergence (an error of 2^-22 in t leaves 2^-22 of the pair's cosine behind, far below
-    // what the other rotations of the sweep put back), so h and the quotient come from the bare MUFU approximations;
-    // (c, s) is then normalised to c^2 + s^2 = 1 in full precision: two Newton steps take 2^-22.9 to 2^-89.
+    rmax2 = fmax(rmax2, gg * rab);
+    if (!(gg > skip2 * ab)) return false;
+    // Tangent t = sgn(dd) 2 g / (|dd| + sqrt(dd^2 + 4 g^2)), dd = be - al.  t only steers convergence (an error of 2^-20 in
+    // t leaves 2^-20 of the pair's cosine behind, far below what the other rotations of the sweep put back), so it is
+    // computed in FP32 on operands scaled into range by a power of two; (c, s) is then normalised to c^2 + s^2 = 1 in
+    // full precision: two Newton steps take the FP32 reciprocal square root to 2^-80.
     const double dd = be - al;
-    const double hh = fma(dd, dd, 4.0 * g * g);
-    double rh;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rh) : "d"(hh));
-    double rden;
-    const double den = fma(hh, rh, fabs(dd));
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rden) : "d"(den));
-    double t = 2.0 * g * rden;
-    if (dd < 0.0) t = -t;
-    const double tt = fma(t, t, 1.0);
-    double c;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(c) : "d"(tt));
-    const double htt = 0.5 * tt;
+    const int hm = max(__double2hiint(dd) & 0x7ff00000, __double2hiint(g) & 0x7ff00000);
+    const double scl = __hiloint2double(0x7fd00000 - hm, 0);            // 2^(1021 - E): the larger operand lands in [1/4, 1/2)
+    const float df = __double2float_rn(dd * scl), gf = __double2float_rn(g * scl);
+    const float hh = fmaf(df, df, 4.0f * gf * gf);                      // >= 1/16: the larger operand is >= 1/4
+    const float hf = hh * rsqrtf(hh);
+    float tf = __fdividef(2.0f * gf, fabsf(df) + hf);
+    if (df < 0.0f) tf = -tf;
+    const float cf = rsqrtf(fmaf(tf, tf, 1.0f));
+    const double t = (double)tf;
+    const double htt = 0.5 * fma(t, t, 1.0);
+    c = (double)cf;
     c = c * fma(-htt * c, c, 1.5);
     c = c * fma(-htt * c, c, 1.5);
-    const double sn = t * c;
+    sn = t * c;
+    return true;
+}
+
+// Rotate columns ix and iy of the shared-memory panel: one HALF-warp (16 lanes, RL rows per lane), so that a warp works on
+// two pairs at once: the scalar chain between the dot product and the rotation (the latency of a sub-step) is issued once
+// for both, the reduction tree is four levels, and 8 warps per CTA (2 per scheduler) contend less for the FP64 pipe than
+// 16 did.  hmask = the lanes of this half; the two halves of a warp may diverge.
+template <int RL>
+__device__ __forceinline__ void osj_rotate(unsigned sA, unsigned sN, int BP, int ix, int iy,
+                                           int hl, unsigned hmask, double skip2, double &rmax2) {
+    const unsigned ax = sA + 8u * (ix * BP + hl), ay = sA + 8u * (iy * BP + hl);
+    double xa[RL], ya[RL];
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+#pragma unroll
+    for (int u = 0; u < RL; u++) { xa[u] = osj_lds(ax + 128u * u); ya[u] = osj_lds(ay + 128u * u); }
+    const double al = osj_lds(sN + 8u * ix), be = osj_lds(sN + 8u * iy);
+#pragma unroll
+    for (int u = 0; u < RL; u += 4) {
+        g0 = fma(xa[u], ya[u], g0);
+        if (u + 1 < RL) g1 = fma(xa[u + 1], ya[u + 1], g1);
+        if (u + 2 < RL) g2 = fma(xa[u + 2], ya[u + 2], g2);
+        if (u + 3 < RL) g3 = fma(xa[u + 3], ya[u + 3], g3);
+    }
+    double g = (g0 + g1) + (g2 + g3);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) g += __shfl_xor_sync(hmask, g, o);
+    double c, sn;
+    if (!osj_cs(g, al, be, skip2, rmax2, c, sn)) return;
 #pragma unroll
     for (int u = 0; u < RL; u++) {
-        osj_sts(ax + 256u * u, c * xa[u] - sn * ya[u]);
-        osj_sts(ay + 256u * u, sn * xa[u] + c * ya[u]);
+        osj_sts(ax + 128u * u, c * xa[u] - sn * ya[u]);
+        osj_sts(ay + 128u * u, sn * xa[u] + c * ya[u]);
     }
-    if (lane == 0) { osj_sts(sN + 8u * ix, al - t * g); osj_sts(sN + 8u * iy, be + t * g); }
+    // new squared norms (the tangent is only approximately Jacobi's, so from c and s): c^2 al - 2 c s g + s^2 be and mirror
+    if (hl == 0) {
+        const double cc = c * c, ss = sn * sn, cs2 = 2.0 * c * sn * g;
+        osj_sts(sN + 8u * ix, fma(cc, al, fma(ss, be, -cs2)));
+        osj_sts(sN + 8u * iy, fma(ss, al, fma(cc, be, cs2)));
+    }
+}
+
+// All pairs across the two half-panels, H sub-steps of H disjoint pairs (x_p, y_(p + st) mod H), H <= 16: half-warp p keeps its
+// x column in REGISTERS over the H sub-steps and only the y columns travel through shared memory.  (With both columns
+// round-tripping through shared memory every sub-step moved the whole 64 KB panel in and out: 128 KB at 128 B / clock =
+// 1024 of the ~1850 cycles a sub-step took -- profiles/r02_osj_trace.md.)
+template <int RL>
+__device__ __forceinline__ void osj_cross_xreg(unsigned sA, unsigned sN, int BP, int H, int hwid, int hl, unsigned hmask,
+                                               double skip2, double &rmax2) {
+    const bool act = hwid < H;
+    const unsigned ax = sA + 8u * (hwid * BP + hl);
+    double xa[RL], al = 0.0;
+    if (act) {
+#pragma unroll
+        for (int u = 0; u < RL; u++) xa[u] = osj_lds(ax + 128u * u);
+        al = osj_lds(sN + 8u * hwid);
+    }
+    // (Splitting the ring into four groups of four pairs that synchronise among themselves only -- named barriers, so that one
+    // group's shared-memory bursts overlap another's arithmetic -- changed nothing: a sub-step is one dependent chain, not a
+    // contended pipe.)
+    for (int st = 0; st < H; st++) {
+        if (act) {
+            int jj = hwid + st; if (jj >= H) jj -= H;
+            const int iy = H + jj;
+            const unsigned ay = sA + 8u * (iy * BP + hl);
+            double ya[RL];
+            double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+#pragma unroll
+            for (int u = 0; u < RL; u++) ya[u] = osj_lds(ay + 128u * u);
+            const double be = osj_lds(sN + 8u * iy);
+#pragma unroll
+            for (int u = 0; u < RL; u += 4) {
+                g0 = fma(xa[u], ya[u], g0);
+                if (u + 1 < RL) g1 = fma(xa[u + 1], ya[u + 1], g1);
+                if (u + 2 < RL) g2 = fma(xa[u + 2], ya[u + 2], g2);
+                if (u + 3 < RL) g3 = fma(xa[u + 3], ya[u + 3], g3);
+            }
+            double g = (g0 + g1) + (g2 + g3);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) g += __shfl_xor_sync(hmask, g, o);
+            double c, sn;
+            if (osj_cs(g, al, be, skip2, rmax2, c, sn)) {
+#pragma unroll
+                for (int u = 0; u < RL; u++) {
+                    const double x = xa[u], y = ya[u];
+                    xa[u] = c * x - sn * y;
+                    osj_sts(ay + 128u * u, sn * x + c * y);
+                }
+                const double cc = c * c, ss = sn * sn, cs2 = 2.0 * c * sn * g;
+                if (hl == 0) osj_sts(sN + 8u * iy, fma(ss, al, fma(cc, be, cs2)));
+                al = fma(cc, al, fma(ss, be, -cs2));
+            }
+        }
+        __syncthreads();
+    }
+    if (act) {
+#pragma unroll
+        for (int u = 0; u < RL; u++) osj_sts(ax + 128u * u, xa[u]);
+        if (hl == 0) osj_sts(sN + 8u * hwid, al);
+    }
+    __syncthreads();
 }
 
 template <int RL>
 __global__ void __cluster_dims__(OSJ_CLUSTER, 1, 1) __launch_bounds__(OSJ_THREADS, 1)
-osj_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol,
+osj_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol, double predict,
            double *cmax, double *w_out, int *info, long long *trace) {
     // optional phase trace (TADPOLE_OSJ_TRACE): cycles of thread 0 of every CTA summed per phase over the whole solve
     long long tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tr_t = 0;
@@ -125,6 +201,8 @@ osj_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol,
     const double tol2 = tol * tol;
     __shared__ double s_red[OSJ_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int hwid = tid >> 4, hl = tid & 15;                       // half-warp index (one column pair each) and lane in it
+    const unsigned hmask = (lane & 16) ? 0xffff0000u : 0x0000ffffu;
     const int crank = cluster.block_rank();
     const unsigned uA = (unsigned)__cvta_generic_to_shared(sA), uN = (unsigned)__cvta_generic_to_shared(s_norm);
     const int Hm = (H + 1) & ~1;
@@ -167,23 +245,27 @@ osj_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol,
             // ---- pairs inside each half-panel, once per sweep ---------------------------------
             if (bs == 0) {
                 for (int st = 0; st < Hm - 1; st++) {
-                    for (int pw = wid; pw < Hm; pw += OSJ_THREADS / 32) {      // Hm pair slots over the warps
+                    for (int pw = hwid; pw < Hm; pw += OSJ_THREADS / 16) {     // Hm pair slots over the half-warps
                         const int half = pw / (Hm / 2), slot = pw % (Hm / 2);
                         int p, q;
                         osj_pair(slot, st, Hm, p, q);
-                        if (q < H) osj_rotate<RL>(uA, uN, BP, half * H + p, half * H + q, lane, skip2, rmax);
+                        if (q < H) osj_rotate<RL>(uA, uN, BP, half * H + p, half * H + q, hl, hmask, skip2, rmax);
                     }
                     __syncthreads();
                 }
             }
             OSJ_TR(2);
             // ---- all pairs across the two half-panels: H sub-steps of H disjoint pairs ----------
-            for (int st = 0; st < H; st++) {
-                for (int pw = wid; pw < H; pw += OSJ_THREADS / 32) {
-                    int jj = pw + st; if (jj >= H) jj -= H;
-                    osj_rotate<RL>(uA, uN, BP, pw, H + jj, lane, skip2, rmax);
+            if (H <= OSJ_THREADS / 16) {
+                osj_cross_xreg<RL>(uA, uN, BP, H, hwid, hl, hmask, skip2, rmax);
+            } else {
+                for (int st = 0; st < H; st++) {
+                    for (int pw = hwid; pw < H; pw += OSJ_THREADS / 16) {
+                        int jj = pw + st; if (jj >= H) jj -= H;
+                        osj_rotate<RL>(uA, uN, BP, pw, H + jj, hl, hmask, skip2, rmax);
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
             OSJ_TR(3);
             // ---- write back ---------------------------------------------------------------------------
@@ -217,7 +299,12 @@ osj_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol,
         cluster.sync();
         double v = 0.0;
         for (int r = 0; r < OSJ_CLUSTER; r++) v = fmax(v, __ldcg(&cmax[(sweeps & 1) * OSJ_CLUSTER + r]));
-        converged = v <= tol2;          // squared scaled cosines
+        // squared scaled cosines, as they were BEFORE this sweep's rotations.  Jacobi converges quadratically once the
+        // cosines are below the relative gaps of the eigenvalues: with predict > 0 (callers that check the result
+        // themselves: the Rayleigh-Ritz steps of the subspace iteration, whose residual test follows) the sweep that would
+        // only confirm convergence is not run when predict * v^2 -- what this sweep leaves behind for relative gaps down to
+        // predict^(-1/2) -- is already below the tolerance.
+        converged = v <= tol2 || (predict > 0.0 && predict * v * v <= tol2);
         OSJ_TR(6);
     }
     if (trace && threadIdx.x == 0) {
@@ -257,7 +344,7 @@ int tp_chol_factor(tp_ctx *ctx, double *G, int b, int ld);
 // Eigen-decomposition of the symmetric positive semi-definite b x b matrix T (row-major, ld), b <= 384.
 // T is destroyed.  w[0..b) descending, Vs (b x lds) eigenvectors in its first ncols_out columns.
 int tp_osj(tp_ctx *ctx, double *T, int b, int ld, double *w, double *Vs, int lds, int ncols_out, int *sweeps_out,
-           double tol) {
+           double tol, double predict) {
     TP_ARG(b >= 2 && b <= OSJ_MAX_B, "tp_osj: b out of range");
     cudaStream_t st = ctx->stream;
     const int H = (b + OSJ_NHP - 1) / OSJ_NHP, NC = H * OSJ_NHP, BP = round_up(b, 32);
@@ -278,8 +365,8 @@ int tp_osj(tp_ctx *ctx, double *T, int b, int ld, double *w, double *Vs, int lds
     if (getenv("TADPOLE_OSJ_TRACE")) { TP_TRY(trbuf.reserve(OSJ_CLUSTER * 8 * sizeof(long long))); trace = trbuf.as<long long>(); }
 #define OSJ_LAUNCH(R)                                                                                         \
     case R:                                                                                                   \
-        TP_CUDA(cudaFuncSetAttribute(osj_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        osj_kernel<R><<<OSJ_CLUSTER, OSJ_THREADS, smem, st>>>(Ac, b, BP, H, 30, otol, cmax, wtmp, info, trace); \
+        TP_CUDA(cudaFuncSetAttribute(osj_kernel<2 * R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        osj_kernel<2 * R><<<OSJ_CLUSTER, OSJ_THREADS, smem, st>>>(Ac, b, BP, H, 30, otol, predict, cmax, wtmp, info, trace); \
         break;
     switch (BP / 32) {
         OSJ_LAUNCH(1) OSJ_LAUNCH(2) OSJ_LAUNCH(3) OSJ_LAUNCH(4) OSJ_LAUNCH(5) OSJ_LAUNCH(6)
