@@ -330,9 +330,9 @@ int tp_igram(tp_ctx *ctx, const double *X, int n, int ld, double *C, int ldc, co
 // a = 2^e sum_s d_s 2^(-6-7s), |d_s| <= 64; column j of Yin likewise with exponent f_j (planes stored transposed,
 // K-major).  The digit products with s + t <= NP - 1 are accumulated exactly in INT32 by tcgen05.mma.kind::i8, one
 // accumulator per scale g = s + t, and recombined in FP64 in the epilogue.  The digit pairs left out are below
-// 2^(-7 NP) of the row scale x column scale (NP = 5: 3e-11), so this operator carries the early filter rounds of the
-// subspace iteration while the residual is far above that; the last rounds and every residual check use the FP64 DMMA
-// operator (pca.cu).
+// 2^(-7 NP) of the row scale x column scale: NP = 5 (3e-11) carries the early filter rounds of the subspace iteration
+// while the residual is far above that; NP = 8 (1.4e-17, FP64 level) carries the last rounds and the residual checks
+// that decide convergence where nf >= iop_final_min_n (default), the FP64 DMMA operator elsewhere (pca.cu).
 // Tiles 128 x 64 x 64 (SWIZZLE_64B rows of 64 bytes), stage = NP x (8 KB + 4 KB), 3 stages.
 // =====================================================================================================================
 #define IO_BM 128

@@ -308,7 +308,18 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
     ctx->have_C = false;                               // C now holds Xc
     ctx->timing[7] = ctx->timing[8] = ctx->timing[9] = 0.0;
 
+    // block width: k wanted vectors + a guard band (a quarter of k, at least 32).  The b x b Rayleigh-Ritz, Cholesky and
+    // eigen problems are solved on chip (shared-memory panels): b <= 832, so above 1024 bins (where the direct solver no
+    // longer applies) the guard band narrows for large k and max_pcs stops at 800.  prcomp(rank. = ) has no such limit.
     int b = ctx->pca_block > 0 ? ctx->pca_block : round_up(k + (k / 4 > 32 ? k / 4 : 32), 32);
+    if (n > 1024 && n > ctx->jacobi_direct_max) {
+        if (b > 832) b = 832;
+        if (k + 32 > b) {
+            tp_set_error("tp_pca: max_pcs = %d is not supported for matrices above 1024 bins (this one has %d good bins): the "
+                         "subspace iteration keeps k + 32 <= 832 vectors on chip, so max_pcs <= 800", max_pcs, n);
+            return TP_ERR_ARG;
+        }
+    }
     const bool direct = n <= ctx->jacobi_direct_max || b >= n;
     const bool use_iop = !direct && ctx->iop_min_n > 0 && n >= ctx->iop_min_n;
     const bool explicitM = direct || n <= 12288 || use_iop;
@@ -340,7 +351,7 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
         }
     }
     if (direct) {
-        TP_ARG(n <= 1024, "tp_pca: direct eigensolver limited to 1024 bins; lower pca_block");
+        TP_ARG(n <= 1024, "tp_pca: direct eigensolver limited to 1024 bins (jacobi_direct_max / pca_block set too high)");
         TP_TRY(ctx->W.reserve((size_t)n * ld * sizeof(double)));
         TP_TRY(ctx->Jw.reserve((size_t)n * sizeof(double)));
         int sweeps = 0;
@@ -529,8 +540,12 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
                     if (getenv("TADPOLE_DEBUG"))
                         fprintf(stderr, "[tadpole] pca it=%d res=%.3e top=%.4e thk=%.4e cut=%.4e deg=%d %s eig_sweeps_so_far=%d apps=%d\n", it, last_res,
                                 bd.top, bd.thk, bd.cut, bd.deg, op.np == 5 ? "int8x5" : (op.np == 8 ? "int8x8" : "fp64"), sweeps_total, op.applications);
-                    // the sliced operator carries the iteration down to iop_switch (or until it stops helping); from
-                    // there on, and for every decision about convergence, the FP64 operator is used
+                    // the 5-plane sliced operator (terms below 2^-35 of row scale x column scale left out) carries the
+                    // iteration down to iop_switch (or until it stops helping).  From there on, and for the residual that
+                    // decides convergence, the operator is the 8-plane sliced one (terms below 2^-56 left out: FP64 level,
+                    // every product kept is exact; nf >= iop_final_min_n and iop_final = 8, the defaults) or else the FP64
+                    // DMMA GEMM.  The 8-plane residual agrees with the FP64 DMMA one to ~1e-16 of theta_1, four orders
+                    // below pca_tol (tests/iop_compare.py; scores vs the pure FP64 solve: 1.3e-11 of the largest score).
                     if (op.np != 5 || !(last_res <= ctx->iop_switch || last_res > 0.1 * prev_res)) break;
                     op.np = n >= ctx->iop_final_min_n ? ctx->iop_final : 0;
                 }

@@ -232,6 +232,35 @@ def test_zero_variance_bins_tie_family(ctx):
     assert (oc + 1, ol + 1) == (opt_pcs, opt_k)
 
 
+def test_large_max_pcs(ctx, synth_cache):
+    """prcomp(rank. = min(max_pcs, n)) accepts any max_pcs (R/TADpole.R:366-367).  Here: every max_pcs up to n for matrices
+    up to 1024 bins (direct eigensolver), up to 800 above that, with an error that says so beyond."""
+    from tadpole_b200 import TadpoleError
+    from tadpole_b200.synth import synth_hic
+    m = synth_hic(1300, seed=4)
+    lm = O.load_mat_numeric(m)
+    cor = O.sparse_cor(lm.mat)
+    ref = O.prcomp_scores(cor, 600)
+    ctx.set_correlation(cor)
+    assert ctx.pca(600) == 600
+    got = ctx.get_scores(cor.shape[0], 600)
+    sgn = np.sign((got * ref).sum(axis=0))
+    assert np.abs(got * sgn - ref).max() <= 1e-9 * np.abs(ref).max()
+    ctx.set_correlation(cor)
+    with pytest.raises(TadpoleError, match="max_pcs <= 800"):
+        ctx.pca(1000)
+    # at most 1024 bins: all of them
+    c = synth_cache(601)
+    ctx.set_correlation(c["cor"])
+    nf = c["cor"].shape[0]
+    assert ctx.pca(5000) == nf
+    ref = O.prcomp_scores(c["cor"], nf)
+    got = ctx.get_scores(nf, nf)
+    keep = np.linalg.norm(ref, axis=0) > 1e-6 * np.linalg.norm(ref[:, 0])      # (the last components are rounding noise)
+    sgn = np.sign((got * ref).sum(axis=0))
+    assert np.abs(got * sgn - ref)[:, keep].max() <= 1e-9 * np.abs(ref).max()
+
+
 # ---- full pipeline --------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,seed", [(200, 1), (200, 2), (601, 1), (2000, 1)])
 def test_tadpole_end_to_end(ctx, n, seed):

@@ -255,3 +255,39 @@ def test_golden_pipeline_n1100_pins_oracle():
         assert np.array_equal(r.clusters[int(k)], np.array(tab))
     ref = np.array([[np.nan if x is None else x for x in row] for row in g["scores"]])
     assert np.allclose(r.scores, ref, rtol=1e-10, equal_nan=True)
+
+
+def test_oracle_against_r_golden(tmp_path):
+    """SURVEY 8(c), last row: wherever Rscript with the reference's dependencies exists, the real reference supersedes the
+    restatement.  Compares the oracle with every tests/golden/r_pipeline_*.json (made by tests/golden/r_golden.py from the
+    reference's own TADpole()); makes them first when R is found.  Skipped -- and parity of stages 1-5 stays 'unpinned' --
+    while neither exists."""
+    import glob
+    import sys
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    sys.path.insert(0, gold)
+    import r_golden
+    from intgen import golden_int_matrix
+    files = sorted(glob.glob(os.path.join(gold, "r_pipeline_*.json")))
+    rs = r_golden.r_available()
+    if not files and rs:
+        files = [r_golden.make(c, rs, str(tmp_path)) for c in r_golden.CASES]
+    if not files:
+        pytest.skip("no R (Rscript + rioja + fpc) here and no committed r_pipeline_*.json: parity of stages 1-5 is unpinned")
+    for f in files:
+        with open(f) as fh:
+            g = json.load(fh)
+        c = g["case"]
+        ref = O.tadpole(golden_int_matrix(c["n"], c["seed"]), max_pcs=c["max_pcs"])
+        assert (ref.n_pcs, ref.optimal_n_clusters) == (g["n_pcs"], g["optimal_n_clusters"]), f
+        assert sorted(int(k) for k in g["clusters"]) == sorted(ref.clusters)
+        for k, tab in g["clusters"].items():
+            assert np.array_equal(np.array(tab).reshape(-1, 2), ref.clusters[int(k)]), (f, k)
+        # heights up to the one open constant (SURVEY Appendix A: rioja's height scale)
+        h = np.array(g["dendro"]["height"], dtype=float)
+        mine = np.sort(ref.seqdist)
+        np.testing.assert_allclose(h / h[-1], mine / mine[-1], rtol=1e-8)
+        assert np.array_equal(np.array(g["dendro"]["merge"]).reshape(-1, 2), O.find_groups(ref.seqdist)[0])
+        sc = np.array([[np.nan if v is None else v for v in row] for row in g["scores"]], dtype=float)
+        assert sc.shape == ref.scores.shape and np.array_equal(np.isnan(sc), np.isnan(ref.scores))
+        np.testing.assert_allclose(sc[~np.isnan(sc)], ref.scores[~np.isnan(sc)], rtol=1e-7)
