@@ -177,6 +177,7 @@ extern "C" int tp_ctx_set(tp_ctx *ctx, const char *key, double value) {
     else if (k == "shard_sym") ctx->shard_sym = (int)value != 0;
     else if (k == "sync_blocking") ctx->sync_blocking = (int)value != 0;
     else if (k == "iop_switch") ctx->iop_switch = value;
+    else if (k == "io_bn32") ctx->io_bn32 = (int)value;
     else if (k == "iop_final") ctx->iop_final = ((int)value == 8) ? 8 : 0;
     else if (k == "iop_final_min_n") ctx->iop_final_min_n = (int)value;
     else { tp_set_error("tp_ctx_set: unknown key '%s'", key); return TP_ERR_ARG; }

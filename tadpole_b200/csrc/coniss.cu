@@ -78,6 +78,8 @@ __device__ __forceinline__ double lds_f64(unsigned a) { double v; asm volatile("
 __device__ __forceinline__ void sts_f64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 __device__ __forceinline__ int lds_u16(unsigned a) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts_u16(unsigned a, int v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ unsigned lds_u32(unsigned a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_u32(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ int lds_s32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts_s32(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
@@ -145,20 +147,55 @@ coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
     const unsigned sd = sbase;                       // d[n1p]
     const unsigned sm1 = sd + 8u * n1p;              // m1[B1p]
     const unsigned sm2 = sm1 + 8u * B1p;             // m2[B2p]
-    Links<LinkT, LINKS_SMEM> lk;
+    // Neighbours of a boundary (previous / next boundary still alive).  LINKS_SMEM: two link arrays in shared memory, two
+    // dependent loads per merge.  Otherwise (the arrays do not fit beside the dSS array: above ~18k bins; or they would push
+    // the reciprocal table out): one BIT per boundary in shared memory, 32 x smaller; the previous / next set bit is found
+    // by the warp together (one word per lane covers 1024 boundaries per step).  The links used to go to global memory
+    // here: two dependent L2 round trips, 1100 of the 3800 cycles of a merge step at 25k bins (profiles/r02_coniss_merge_step.md).
+    Links<LinkT, true> lk;
     lk.sp = lk.sn = 0; lk.gp = lk.gn = nullptr;
-    if (LINKS_SMEM) {
-        lk.sp = sm2 + 8u * B2p; lk.sn = lk.sp + (unsigned)sizeof(LinkT) * n1;
-    } else {
-        lk.gp = glinks + (size_t)slot * 2 * n1;
-        lk.gn = lk.gp + n1;
-    }
+    const unsigned sbits = sm2 + 8u * B2p;
+    const int W = (n1 + 31) >> 5;
+    if (LINKS_SMEM) { lk.sp = sbits; lk.sn = lk.sp + (unsigned)sizeof(LinkT) * n1; }
+    // one word per lane: the word of j (only its bits below / above j) and the 31 words before / after it, 1024 boundaries
+    // per step; a second step only when a cluster is longer than that (the last few dozen merges of a chromosome)
+    auto bm_prev = [&](int j) -> int {             // largest live boundary below j, or -1 (warp-collective, uniform j)
+        for (int w0 = j >> 5; w0 >= 0; w0 -= 32) {
+            const int wi = w0 - lane;
+            unsigned v = wi >= 0 ? lds_u32(sbits + 4u * wi) : 0u;
+            if (wi == (j >> 5)) v &= (1u << (j & 31)) - 1u;
+            const unsigned bal = __ballot_sync(0xffffffffu, v != 0u);
+            if (bal) {
+                const int src = __ffs(bal) - 1;
+                return ((w0 - src) << 5) + 31 - __clz(__shfl_sync(0xffffffffu, v, src));
+            }
+        }
+        return -1;
+    };
+    auto bm_next = [&](int j) -> int {             // smallest live boundary above j, or n1
+        for (int w0 = j >> 5; w0 < W; w0 += 32) {
+            const int wi = w0 + lane;
+            unsigned v = wi < W ? lds_u32(sbits + 4u * wi) : 0u;
+            if (wi == (j >> 5)) v &= ~((2u << (j & 31)) - 1u);
+            const unsigned bal = __ballot_sync(0xffffffffu, v != 0u);
+            if (bal) {
+                const int src = __ffs(bal) - 1;
+                return ((w0 + src) << 5) + __ffs(__shfl_sync(0xffffffffu, v, src)) - 1;
+            }
+        }
+        return n1;
+    };
     const double *d0row = d0 + (size_t)cand * ldd;
     double *seq = seqdist + (size_t)cand * ldd;
     int4 *mrg = merges + (size_t)cand * ldd;
 
     for (int j = lane; j < n1p; j += 32) sts_f64(sd + 8u * j, (j < n1) ? d0row[j] : INF_D);
-    for (int j = lane; j < n1; j += 32) { lk.set_prv(j, j); lk.set_nxt(j, j + 1); }   // prv holds index+1, 0 = none
+    if (LINKS_SMEM) {
+        for (int j = lane; j < n1; j += 32) { lk.set_prv(j, j); lk.set_nxt(j, j + 1); }   // prv holds index+1, 0 = none
+    } else {
+        for (int w = lane; w < W; w += 32)
+            sts_u32(sbits + 4u * w, (w << 5) + 32 <= n1 ? 0xffffffffu : ((1u << (n1 - (w << 5))) - 1u));
+    }
     for (int b = lane; b < B1p; b += 32) sts_f64(sm1 + 8u * b, INF_D);
     for (int b = lane; b < B2p; b += 32) sts_f64(sm2 + 8u * b, INF_D);
     __syncwarp();
@@ -216,11 +253,17 @@ coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
 
         CS_TR(0);
         // ---- neighbours ---------------------------------------------------------------------
-        const int pj = lk.prv(j) - 1;            // previous live boundary or -1
-        const int nj = lk.nxt(j);                // next live boundary or n1
+        int pj, nj, ppj, nnj;                    // previous / next live boundary (-1 / n1: none) and theirs
+        if (LINKS_SMEM) {
+            pj = lk.prv(j) - 1; nj = lk.nxt(j);
+            ppj = pj >= 0 ? lk.prv(pj) - 1 : -1;
+            nnj = nj < n1 ? lk.nxt(nj) : n1;
+        } else {
+            pj = bm_prev(j); nj = bm_next(j);
+            ppj = pj >= 0 ? bm_prev(pj) : -1;
+            nnj = nj < n1 ? bm_next(nj) : n1;
+        }
         const bool hasL = pj >= 0, hasR = nj < n1;
-        const int ppj = hasL ? lk.prv(pj) - 1 : -1;
-        const int nnj = hasR ? lk.nxt(nj) : n1;
         // P rows: LL = [a, b), C = [b, c), RR = [c, e)
         const int a = ppj + 1, b = pj + 1, c = nj + 1, e = nnj + 1;
         const double *Pa = Plane + (size_t)a * ldk, *Pb = Plane + (size_t)b * ldk;
@@ -271,8 +314,9 @@ coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
         // ---- write back: boundary j dies, its neighbours get new increases ---------------
         if (lane == 0) {
             sts_f64(sd + 8u * j, INF_D);
-            if (hasL) { sts_f64(sd + 8u * pj, accL); lk.set_nxt(pj, nj); }
-            if (hasR) { sts_f64(sd + 8u * nj, accR); lk.set_prv(nj, pj + 1); }
+            if (hasL) { sts_f64(sd + 8u * pj, accL); if (LINKS_SMEM) lk.set_nxt(pj, nj); }
+            if (hasR) { sts_f64(sd + 8u * nj, accR); if (LINKS_SMEM) lk.set_prv(nj, pj + 1); }
+            if (!LINKS_SMEM) sts_u32(sbits + 4u * (j >> 5), lds_u32(sbits + 4u * (j >> 5)) & ~(1u << (j & 31)));
         }
         __syncwarp();
         const int k0 = j >> 5;
@@ -466,11 +510,17 @@ int tp_sweep_device(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stri
     const size_t base = (size_t)(n1p + B1p + B2p) * sizeof(double);
     const bool small_links = n <= 65535;
     const size_t link_bytes = round_up((int)((size_t)2 * n1 * (small_links ? 2 : 4)), 8);
+    const size_t bitmap_bytes = (size_t)round_up(((n1 + 31) / 32) * 4, 16);
     const size_t inv_bytes = (size_t)(n + 1) * sizeof(double);
     const size_t limit = (size_t)ctx->max_smem_optin;
-    TP_ARG(base <= limit, "tp_sweep: matrix too large for the shared-memory dSS array (n > ~28k bins); split by centromere");
-    const bool links_smem = base + link_bytes <= limit;
-    const size_t cand_smem = round_up((int)(links_smem ? base + link_bytes : base), 16);
+    TP_ARG(base + bitmap_bytes <= limit, "tp_sweep: matrix too large for the shared-memory dSS array (n > ~28k bins); split by centromere");
+    // link arrays while they fit (two dependent loads: ~90 cycles per merge against ~400 for the bitmap searches), else the
+    // bitmap (32 x smaller: above ~18k bins)
+    const char *force = getenv("TADPOLE_SWEEP_LINKS");           // "bitmap" / "array": experiments
+    bool links_smem = base + link_bytes <= limit;
+    if (force && force[0] == 'b') links_smem = false;
+    if (force && force[0] == 'a' && base + link_bytes <= limit) links_smem = true;
+    const size_t cand_smem = round_up((int)(links_smem ? base + link_bytes : base + bitmap_bytes), 16);
     // the reciprocal table goes to shared memory while at least two candidates still fit beside it
     const bool inv_smem = 2 * cand_smem + inv_bytes <= limit;
     int wpc = (int)((limit - (inv_smem ? inv_bytes : 0)) / cand_smem);
@@ -480,10 +530,6 @@ int tp_sweep_device(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stri
     const size_t smem = (size_t)wpc * cand_smem + (inv_smem ? inv_bytes : 0);
     const int nblocks = (ncand + wpc - 1) / wpc;
     void *glinks = nullptr;
-    if (!links_smem) {
-        TP_TRY(ctx->links.reserve((size_t)ncand * link_bytes));
-        glinks = ctx->links.p;
-    }
     long long *trace = nullptr;
     DevBuf trbuf;
     if (getenv("TADPOLE_SWEEP_TRACE")) { TP_TRY(trbuf.reserve(8 * sizeof(long long))); trace = trbuf.as<long long>(); }
@@ -497,11 +543,11 @@ int tp_sweep_device(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stri
         tp_prof_end(ctx);                                                                                 \
     } while (0)
 #define LAUNCH_SWEEP(LT, LS, IS) do { if (trace) LAUNCH_SWEEP2(LT, LS, IS, true); else LAUNCH_SWEEP2(LT, LS, IS, false); } while (0)
-    if (small_links) {
-        if (links_smem) { if (inv_smem) LAUNCH_SWEEP(unsigned short, true, true); else LAUNCH_SWEEP(unsigned short, true, false); }
-        else LAUNCH_SWEEP(unsigned short, false, false);
+    if (links_smem) {
+        if (small_links) { if (inv_smem) LAUNCH_SWEEP(unsigned short, true, true); else LAUNCH_SWEEP(unsigned short, true, false); }
+        else { if (inv_smem) LAUNCH_SWEEP(int, true, true); else LAUNCH_SWEEP(int, true, false); }
     } else {
-        if (links_smem) LAUNCH_SWEEP(int, true, false); else LAUNCH_SWEEP(int, false, false);
+        if (inv_smem) LAUNCH_SWEEP(unsigned short, false, true); else LAUNCH_SWEEP(unsigned short, false, false);
     }
 #undef LAUNCH_SWEEP2
 #undef LAUNCH_SWEEP

@@ -336,15 +336,20 @@ int tp_igram(tp_ctx *ctx, const double *X, int n, int ld, double *C, int ldc, co
 // Tiles 128 x 64 x 64 (SWIZZLE_64B rows of 64 bytes), stage = NP x (8 KB + 4 KB), 3 stages.
 // =====================================================================================================================
 #define IO_BM 128
-#define IO_BN 64
+#define IO_BN 64                  // widest output tile (the planes of the block are padded to multiples of it)
 #define IO_BK 64
-#define IO_NGROUP 4               // adjacent B digit planes multiplied by one MMA (N = 64 x group, at most 256)
 #define IO_MAXNP 8                // digit planes kept of the operator; a product uses the first NP of them (5 or 8)
 #define IO_A_BYTES (IO_BM * IO_BK)
-#define IO_B_BYTES (IO_BN * IO_BK)
-template <int NP> struct IoCfg {
-    static constexpr int STAGES = NP <= 5 ? 3 : 2;
-    static constexpr int STAGE_BYTES = NP * (IO_A_BYTES + IO_B_BYTES);
+// BN = 64: one CTA per SM (all 512 tensor-memory columns at NP = 8).  BN = 32: half the tensor memory and half the B tile,
+// so at NP = 5 two CTAs share an SM (one's epilogue under the other's MMAs) and a 2000 x 256 application is 128 CTAs
+// instead of 64 on the 148 SMs; used for the small applications (tiles of 64 columns would not fill the GPU).
+template <int NP, int BN> struct IoCfg {
+    static constexpr int STAGES = BN == 64 ? (NP <= 5 ? 3 : 2) : 2;
+    static constexpr int B_BYTES = BN * IO_BK;
+    static constexpr int STAGE_BYTES = NP * (IO_A_BYTES + B_BYTES);
+    static constexpr int TMEM_COLS = NP * BN <= 256 ? 256 : 512;
+    static constexpr int NGROUP = 256 / BN;      // adjacent B digit planes multiplied by one MMA (N = BN x group <= 256)
+    static constexpr int CTAS_PER_SM = (BN == 32 && NP <= 5) ? 2 : 1;
 };
 
 // exponent e with max < 2^e (max > 0), else 0; scale arrays hold 2^(e-6)
@@ -479,10 +484,11 @@ struct IoParams {
     SymShard ss;
 };
 
-template <int NP>
-__global__ void __launch_bounds__(IG_THREADS, 1)
+template <int NP, int BN>
+__global__ void __launch_bounds__(IG_THREADS, (IoCfg<NP, BN>::CTAS_PER_SM))
 io_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, IoParams p) {
-    constexpr int IO_STAGES = IoCfg<NP>::STAGES, IO_STAGE_BYTES = IoCfg<NP>::STAGE_BYTES, IO_NP = NP;
+    constexpr int IO_STAGES = IoCfg<NP, BN>::STAGES, IO_STAGE_BYTES = IoCfg<NP, BN>::STAGE_BYTES, IO_NP = NP;
+    constexpr int IO_B_BYTES = IoCfg<NP, BN>::B_BYTES, IO_NGROUP = IoCfg<NP, BN>::NGROUP, TMEM_COLS = IoCfg<NP, BN>::TMEM_COLS;
     unsigned bx = blockIdx.x, by = blockIdx.y;
     if (p.banded) {
         // wide outputs (Gram): bands of 8 tile rows walked column by column, so that the CTAs resident together share
@@ -492,11 +498,11 @@ io_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         const unsigned h = gridDim.y - band * 8u < 8u ? gridDim.y - band * 8u : 8u;
         by = band * 8u + in % h; bx = in / h;
     }
-    const int m0 = p.row_begin + (int)by * IO_BM, n0 = (int)bx * IO_BN;
+    const int m0 = p.row_begin + (int)by * IO_BM, n0 = (int)bx * BN;
     if (n0 >= p.b || m0 >= p.row_end) return;                        // padding
     if (p.sym) {    // computed by another rank / mirrored from the tile above the diagonal (SymShard, common.cuh)
         const int r_hi = m0 + IO_BM - 1 < p.row_end - 1 ? m0 + IO_BM - 1 : p.row_end - 1;
-        const int c_hi = n0 + IO_BN - 1 < p.b - 1 ? n0 + IO_BN - 1 : p.b - 1;
+        const int c_hi = n0 + BN - 1 < p.b - 1 ? n0 + BN - 1 : p.b - 1;
         if (!ss_tile_needed(m0, r_hi, n0, c_hi, p.ss)) return;
     }
     extern __shared__ unsigned char ig_raw[];
@@ -511,7 +517,7 @@ io_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ig_smem(&s_tmem)), "n"(IG_TMEM_COLS));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ig_smem(&s_tmem)), "n"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -554,10 +560,10 @@ io_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 #pragma unroll
                         for (int b0 = 0; b0 < IO_NP - a; b0 += IO_NGROUP) {
                             const int m = IO_NP - a - b0 < IO_NGROUP ? IO_NP - a - b0 : IO_NGROUP;
-                            const unsigned idm = (2u << 4) | (1u << 7) | (1u << 10) | (((unsigned)(m * IO_BN) >> 3) << 17) | ((IO_BM >> 4) << 24);
+                            const unsigned idm = (2u << 4) | (1u << 7) | (1u << 10) | (((unsigned)(m * BN) >> 3) << 17) | ((IO_BM >> 4) << 24);
                             const unsigned long long bd = io_desc(base + IO_NP * IO_A_BYTES + b0 * IO_B_BYTES) + (unsigned long long)(kk * 32 >> 4);
                             const bool first = kb == 0 && kk == 0 && a == 0;      // a = 0 touches every accumulator
-                            ig_mma_i8(tmem + (unsigned)(a + b0) * IO_BN, ad, bd, idm, first ? 0u : 1u);
+                            ig_mma_i8(tmem + (unsigned)(a + b0) * BN, ad, bd, idm, first ? 0u : 1u);
                         }
                     }
                 }
@@ -572,10 +578,10 @@ io_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         const int row = m0 + lg * 32 + lane;
         const bool rok = row < p.row_end && row < p.n;
         const double rs = rok ? p.alpha * p.rowscale[row] : 0.0;
-        for (int c0 = 0; c0 < IO_BN; c0 += 16) {
+        for (int c0 = 0; c0 < BN; c0 += 16) {
             unsigned r[IO_NP][16];
 #pragma unroll
-            for (int s = 0; s < IO_NP; s++) ig_tmem_ld16(tmem + ((unsigned)(lg * 32) << 16) + (unsigned)(s * IO_BN + c0), r[s]);
+            for (int s = 0; s < IO_NP; s++) ig_tmem_ld16(tmem + ((unsigned)(lg * 32) << 16) + (unsigned)(s * BN + c0), r[s]);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (rok) {
 #pragma unroll
@@ -600,11 +606,11 @@ io_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(IG_TMEM_COLS));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
     }
 }
 
-static int io_encode(CUtensorMap *map, void *base, int rows_pad, int Kp, int planes) {
+static int io_encode(CUtensorMap *map, void *base, int rows_pad, int Kp, int planes, int box_rows = 64) {
     static PFN_encodeTiled fn = nullptr;
     if (!fn) {
         void *sym = nullptr;
@@ -615,7 +621,7 @@ static int io_encode(CUtensorMap *map, void *base, int rows_pad, int Kp, int pla
     }
     const cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows_pad, (cuuint64_t)planes};
     const cuuint64_t strides[2] = {(cuuint64_t)Kp, (cuuint64_t)Kp * rows_pad};
-    const cuuint32_t box[3] = {IO_BK, 64, 1};
+    const cuuint32_t box[3] = {IO_BK, (cuuint32_t)box_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -645,7 +651,7 @@ int tp_iop_prepare(tp_ctx *ctx, const double *S, int n, int ld) {
 
 // D[rows] = alpha S[rows, :] Yin + beta E1[rows] + gamma E2[rows], rows = [row_begin, row_end); NP = 5 (digit pairs
 // left out below 2^-35 of row scale x column scale) or 8 (2^-56: FP64 level)
-template <int NP>
+template <int NP, int BN>
 static int iop_apply_np(tp_ctx *ctx, const double *Yin, int b, int ldy, double *D, int ldd, double alpha, const double *E1,
                         int lde1, double beta, const double *E2, int lde2, double gamma, int row_begin, int row_end) {
     cudaStream_t st = ctx->stream;
@@ -668,17 +674,17 @@ static int iop_apply_np(tp_ctx *ctx, const double *Yin, int b, int ldy, double *
     tp_prof_end(ctx);
     CUtensorMap mapA, mapB;
     TP_TRY(io_encode(&mapA, ctx->ioA.p, rows_padA, Kp, NP));        // the first NP of the IO_MAXNP planes
-    TP_TRY(io_encode(&mapB, ctx->ioB.p, rows_padB, Kp, NP));
+    TP_TRY(io_encode(&mapB, ctx->ioB.p, rows_padB, Kp, NP, BN));
     IoParams p;
     p.n = n; p.b = b; p.row_begin = row_begin; p.row_end = row_end; p.kblocks = Kp / IO_BK;
     p.D = D; p.ldd = ldd; p.E1 = E1; p.lde1 = lde1; p.E2 = E2; p.lde2 = lde2;
     p.alpha = alpha; p.beta = beta; p.gamma = gamma; p.rowscale = rowscale; p.colscale = colscale; p.sym = 0; p.banded = 0; p.ss = SymShard{1, 1 << 30};
-    const size_t smem = (size_t)IoCfg<NP>::STAGES * IoCfg<NP>::STAGE_BYTES + 1024;
-    TP_CUDA(cudaFuncSetAttribute(io_gemm_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(rows_padB / IO_BN, (row_end - row_begin + IO_BM - 1) / IO_BM);
-    if (ctx->prof) ctx->prof_imma_ops += 2.0 * (NP * (NP + 1) / 2) * (double)grid.x * grid.y * IO_BM * IO_BN * (double)Kp;
+    const size_t smem = (size_t)IoCfg<NP, BN>::STAGES * IoCfg<NP, BN>::STAGE_BYTES + 1024;
+    TP_CUDA(cudaFuncSetAttribute(io_gemm_kernel<NP, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(rows_padB / BN, (row_end - row_begin + IO_BM - 1) / IO_BM);
+    if (ctx->prof) ctx->prof_imma_ops += 2.0 * (NP * (NP + 1) / 2) * (double)grid.x * grid.y * IO_BM * BN * (double)Kp;
     tp_prof_begin(ctx, PC_IGEMM);
-    io_gemm_kernel<NP><<<grid, IG_THREADS, smem, st>>>(mapA, mapB, p);
+    io_gemm_kernel<NP, BN><<<grid, IG_THREADS, smem, st>>>(mapA, mapB, p);
     tp_prof_end(ctx);
     ctx->launches += 4;
     TP_CUDA(cudaGetLastError());
@@ -690,8 +696,13 @@ int tp_iop_apply(tp_ctx *ctx, const double *Yin, int b, int ldy, double *D, int 
     TP_ARG(ctx->io_n > 0, "tp_iop_apply: tp_iop_prepare first");
     TP_ARG(b <= 1024, "tp_iop_apply: block wider than 1024 columns");
     TP_ARG(np == 5 || np == 8, "tp_iop_apply: 5 or 8 digit planes");
-    if (np == 5) return iop_apply_np<5>(ctx, Yin, b, ldy, D, ldd, alpha, E1, lde1, beta, E2, lde2, gamma, row_begin, row_end);
-    return iop_apply_np<8>(ctx, Yin, b, ldy, D, ldd, alpha, E1, lde1, beta, E2, lde2, gamma, row_begin, row_end);
+    // tiles of 64 columns while they fill the GPU; otherwise 32 (twice the CTAs, two per SM at 5 planes)
+    const long tiles64 = (long)((row_end - row_begin + IO_BM - 1) / IO_BM) * ((b + 63) / 64);
+    const bool narrow = ctx->io_bn32 >= 0 ? ctx->io_bn32 != 0 : tiles64 < ctx->sm_count;
+    if (np == 5) return narrow ? iop_apply_np<5, 32>(ctx, Yin, b, ldy, D, ldd, alpha, E1, lde1, beta, E2, lde2, gamma, row_begin, row_end)
+                               : iop_apply_np<5, 64>(ctx, Yin, b, ldy, D, ldd, alpha, E1, lde1, beta, E2, lde2, gamma, row_begin, row_end);
+    return narrow ? iop_apply_np<8, 32>(ctx, Yin, b, ldy, D, ldd, alpha, E1, lde1, beta, E2, lde2, gamma, row_begin, row_end)
+                  : iop_apply_np<8, 64>(ctx, Yin, b, ldy, D, ldd, alpha, E1, lde1, beta, E2, lde2, gamma, row_begin, row_end);
 }
 
 // M[rows] = A[rows, :] A^T for an FP64 matrix A (n x n, ld), rows = [row_begin, row_end): the sliced product above with
@@ -724,8 +735,8 @@ int tp_igram_sliced(tp_ctx *ctx, const double *A, int n, int ld, double *M, int 
         p.D = M; p.ldd = ldm; p.E1 = nullptr; p.lde1 = 0; p.E2 = nullptr; p.lde2 = 0;
         p.alpha = 1.0; p.beta = 0.0; p.gamma = 0.0; p.rowscale = rowscale; p.colscale = rowscale;
         p.sym = sym; p.banded = 1; p.ss = ss;
-        const size_t smem = (size_t)IoCfg<NP>::STAGES * IoCfg<NP>::STAGE_BYTES + 1024;
-        TP_CUDA(cudaFuncSetAttribute(io_gemm_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t smem = (size_t)IoCfg<NP, IO_BN>::STAGES * IoCfg<NP, IO_BN>::STAGE_BYTES + 1024;
+        TP_CUDA(cudaFuncSetAttribute(io_gemm_kernel<NP, IO_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(rows_pad / IO_BN, (row_end - row_begin + IO_BM - 1) / IO_BM);
         if (ctx->prof) {
             double tiles = 0.0;
@@ -735,7 +746,7 @@ int tp_igram_sliced(tp_ctx *ctx, const double *A, int n, int ld, double *M, int 
             ctx->prof_imma_ops += 2.0 * (NP * (NP + 1) / 2) * tiles * IO_BM * IO_BN * (double)Kp;
         }
         tp_prof_begin(ctx, PC_IGEMM);
-        io_gemm_kernel<NP><<<grid, IG_THREADS, smem, st>>>(map, map, p);
+        io_gemm_kernel<NP, IO_BN><<<grid, IG_THREADS, smem, st>>>(map, map, p);
         tp_prof_end(ctx);
         ctx->launches += 1;
     }

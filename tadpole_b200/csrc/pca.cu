@@ -309,14 +309,15 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
     ctx->timing[7] = ctx->timing[8] = ctx->timing[9] = 0.0;
 
     // block width: k wanted vectors + a guard band (a quarter of k, at least 32).  The b x b Rayleigh-Ritz, Cholesky and
-    // eigen problems are solved on chip (shared-memory panels): b <= 832, so above 1024 bins (where the direct solver no
-    // longer applies) the guard band narrows for large k and max_pcs stops at 800.  prcomp(rank. = ) has no such limit.
+    // eigen problems are solved on chip (the cluster Jacobi solver keeps its share of the b x b matrix in registers): b <= 704,
+    // so above 1024 bins (where the direct solver no longer applies) the guard band narrows for large k and max_pcs stops at
+    // 672.  prcomp(rank. = ) has no such limit.
     int b = ctx->pca_block > 0 ? ctx->pca_block : round_up(k + (k / 4 > 32 ? k / 4 : 32), 32);
     if (n > 1024 && n > ctx->jacobi_direct_max) {
-        if (b > 832) b = 832;
+        if (b > 704) b = 704;
         if (k + 32 > b) {
             tp_set_error("tp_pca: max_pcs = %d is not supported for matrices above 1024 bins (this one has %d good bins): the "
-                         "subspace iteration keeps k + 32 <= 832 vectors on chip, so max_pcs <= 800", max_pcs, n);
+                         "subspace iteration keeps k + 32 <= 704 vectors on chip, so max_pcs <= 672", max_pcs, n);
             return TP_ERR_ARG;
         }
     }

@@ -1,19 +1,20 @@
-"""Ad-hoc (not a test): calls/s at N bins with 1, 2, 4, 8 calls in flight on one GPU.  python tests/batch_throughput.py [N]"""
-import sys, os, time
+"""Ad-hoc (not a test): calls/s of tp_call_batch against the number of calls in flight.  python tests/batch_throughput.py [N]"""
+import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
-from tadpole_b200 import ContextPool
+import numpy as np, torch
+from tadpole_b200 import Context
 from tadpole_b200.synth import synth_hic
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
-mats = [synth_hic(n, seed=1 + i) for i in range(4)]
-for streams in (1, 2, 4, 8):
-    pool = ContextPool(0, streams)
-    work = [mats[i % 4] for i in range(8 * streams)]
-    fn = lambda ctx, m: ctx.call(m, want_scores=True)["n_pcs"]
-    pool.map(fn, work[: 2 * streams])                 # warm-up: buffers allocated
-    for c in pool.contexts: c.sync()
-    t = time.perf_counter(); pool.map(fn, work)
-    for c in pool.contexts: c.sync()
-    dt = time.perf_counter() - t
-    print(f"N={n} streams={streams} calls={len(work)} {len(work) / dt:.1f} calls/s ({1e3 * dt / len(work):.2f} ms per call amortised)", flush=True)
-    pool.close()
+mats = [synth_hic(n, seed=1 + s) for s in range(16)]
+dev = [torch.as_tensor(m, device="cuda") for m in mats]
+torch.cuda.synchronize()
+ptrs = [d.data_ptr() for d in dev]
+ctx = Context(0)
+for s in (1, 2, 4, 6, 8, 12, 16, 24, 32):
+    ctx.call_batch(None, device_ptrs=ptrs, n=n, inflight=s, tables=False)
+    ctx.call_batch(None, device_ptrs=ptrs * 10, n=n, inflight=s, tables=False)
+    ms = ctx.last_batch_device_ms
+    t0 = time.perf_counter()
+    ctx.call_batch(mats * 5, inflight=s)
+    wall = time.perf_counter() - t0
+    print(f"in flight {s:2d}: device-resident {160 / ms * 1e3:7.1f} calls/s   host matrices + tables {80 / wall:7.1f} calls/s", flush=True)

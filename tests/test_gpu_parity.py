@@ -234,7 +234,7 @@ def test_zero_variance_bins_tie_family(ctx):
 
 def test_large_max_pcs(ctx, synth_cache):
     """prcomp(rank. = min(max_pcs, n)) accepts any max_pcs (R/TADpole.R:366-367).  Here: every max_pcs up to n for matrices
-    up to 1024 bins (direct eigensolver), up to 800 above that, with an error that says so beyond."""
+    up to 1024 bins (direct eigensolver), up to 672 above that, with an error that says so beyond."""
     from tadpole_b200 import TadpoleError
     from tadpole_b200.synth import synth_hic
     m = synth_hic(1300, seed=4)
@@ -247,7 +247,7 @@ def test_large_max_pcs(ctx, synth_cache):
     sgn = np.sign((got * ref).sum(axis=0))
     assert np.abs(got * sgn - ref).max() <= 1e-9 * np.abs(ref).max()
     ctx.set_correlation(cor)
-    with pytest.raises(TadpoleError, match="max_pcs <= 800"):
+    with pytest.raises(TadpoleError, match="max_pcs <= 672"):
         ctx.pca(1000)
     # at most 1024 bins: all of them
     c = synth_cache(601)
