@@ -319,6 +319,13 @@ def run_b200(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     S, B, n = max(1, args.streams), max(1, args.batch), args.bins
     ctx = Context(local_rank)
+    # the library's batch threads wait for their streams most of the time; a spinning wait (the CUDA default) needs a core
+    # each, so with several ranks on one host they sleep on blocking-sync events instead (tp_call_batch decides this for
+    # the threads of ONE process; it cannot see the other ranks)
+    ncpu = os.cpu_count() or 1
+    sync_blocking = world * S > ncpu // 2
+    if sync_blocking:
+        ctx.set("sync_blocking", 1)
 
     # synthetic inputs: B different matrices per rank; pinned host copies for e2e, device copies for value
     host = []
@@ -488,6 +495,8 @@ def run_b200(args, rank, world, local_rank):
                        "l2": f"every step passes over {B} different {n}x{n} f64 matrices ({B * n * n * 8 >> 20} MiB > L2): "
                              "no step re-reads a warm input",
                        "calls_in_flight_per_gpu": S,
+                       "host_wait": ("blocking-sync events (threads sleep)" if sync_blocking else "cudaStreamSynchronize (spin)")
+                                    + f", {ncpu} logical CPUs for {world * S} batch threads",
                        "parallelism": f"{world} GPU(s) x {S} independent calls in flight, kept in flight by tp_call_batch's own host "
                                       "threads (one context + stream each); no collective on the data path"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(n) * B, "d2h_bytes_per_step": d2h,

@@ -66,18 +66,40 @@ def launches(path):
         print(f"| `{k}` | {a[0]} | {a[1]:.1f} | {100 * a[1] / tot:.1f}% | {a[1] / a[0]:.1f} | {a[2]} | {a[3]} |")
 
 
-def full(paths):
+def full(paths, dedupe=False):
+    """paths: .ncu-rep reports, or the `ncu -i ... --page raw --csv` text already made on the GPU box (*.csv; gpurun brings
+    back at most 64 MiB, a --set full report of a whole call is larger).  dedupe: one table per distinct kernel and launch
+    shape (the launch with the median duration) plus the launch count and the duration range."""
     for p in paths:
-        out = subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        if p.endswith(".csv"):
+            with open(p) as fh:
+                out = fh.read()
+        else:
+            out = subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader([l for l in out.splitlines() if l.startswith('"')]))
         if len(rows) < 3:
             print(f"## {p}: no data\n")
             continue
         hdr, units = rows[0], rows[1]
         print(f"## {p}\n")
-        for r in rows[2:]:
+        body = rows[2:]
+        note = {}
+        if dedupe:
+            di = hdr.index("gpu__time_duration.sum")
+            groups = OrderedDict()
+            for r in body:
+                groups.setdefault((r[hdr.index("Kernel Name")], r[hdr.index("Grid Size")], r[hdr.index("Block Size")]), []).append(r)
+            body = []
+            for key, rs in groups.items():
+                rs = sorted(rs, key=lambda r: float(r[di].replace(",", "")))
+                pick = rs[len(rs) // 2]
+                body.append(pick)
+                note[id(pick)] = f"{len(rs)} launches of this shape in the call, duration {rs[0][di]} .. {rs[-1][di]} {units[di]}; the median one:"
+        for r in body:
             name = r[hdr.index("Kernel Name")]
             print(f"### `{simplify(name)}`  grid {r[hdr.index('Grid Size')]} block {r[hdr.index('Block Size')]}\n")
+            if id(r) in note:
+                print(note[id(r)] + "\n")
             print("| counter | value |")
             print("|---|---|")
             for key, label in WANT:
@@ -90,5 +112,7 @@ def full(paths):
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "full1":
+        full(sys.argv[2:], dedupe=True)
     else:
         full(sys.argv[2:])

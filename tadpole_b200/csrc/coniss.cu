@@ -33,24 +33,47 @@ __global__ void rownorm2_kernel(const double *__restrict__ s, int n, int k, int 
     if (lane == 0) out[w] = a;
 }
 
-__global__ void prefix_kernel(const double *__restrict__ s, const double *__restrict__ rn2, int n, int k, int ldk,
-                              double *__restrict__ P, double *__restrict__ Qp) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+// Blocked scan over the bins: rows are cut into chunks of PF_CHUNK; (1) every (chunk, column) sums its rows, (2) every
+// (chunk, column) adds up the sums of the chunks before it and writes its rows' prefixes.  Two launches of Nf / 128 x k / 64
+// CTAs instead of one thread per column walking all Nf rows (0.40 ms at 2000 bins, ~5 ms at 25 000: the dependent adds of one
+// thread); the order of the additions is fixed by the chunking, so every rank and every run gets the same bits.
+// Column ldk is the squared row norms (rn2 -> Qp); columns k..ldk-1 are padding (zero).
+#define PF_CHUNK 128
+__global__ void __launch_bounds__(64)
+prefix_sums_kernel(const double *__restrict__ s, const double *__restrict__ rn2, int n, int k, int ldk,
+                   double *__restrict__ csum) {
+    const int c = blockIdx.y * 64 + threadIdx.x, ch = blockIdx.x;
+    if (c > ldk) return;
+    const int r0 = ch * PF_CHUNK, r1 = min(n, r0 + PF_CHUNK);
+    double a0 = 0.0, a1 = 0.0;
     if (c < k) {
-        double acc = 0.0;
-        P[c] = 0.0;
-#pragma unroll 8
-        for (int r = 0; r < n; r++) {
-            acc += s[(size_t)r * ldk + c];
-            P[(size_t)(r + 1) * ldk + c] = acc;
-        }
-    } else if (c < ldk) {
-        for (int r = 0; r <= n; r++) P[(size_t)r * ldk + c] = 0.0;   // padding columns
+        int r = r0;
+        for (; r + 1 < r1; r += 2) { a0 += s[(size_t)r * ldk + c]; a1 += s[(size_t)(r + 1) * ldk + c]; }
+        if (r < r1) a0 += s[(size_t)r * ldk + c];
     } else if (c == ldk) {
-        double acc = 0.0;
-        Qp[0] = 0.0;
-#pragma unroll 8
-        for (int r = 0; r < n; r++) { acc += rn2[r]; Qp[r + 1] = acc; }
+        int r = r0;
+        for (; r + 1 < r1; r += 2) { a0 += rn2[r]; a1 += rn2[r + 1]; }
+        if (r < r1) a0 += rn2[r];
+    }
+    csum[(size_t)ch * (ldk + 1) + c] = a0 + a1;
+}
+__global__ void __launch_bounds__(64)
+prefix_write_kernel(const double *__restrict__ s, const double *__restrict__ rn2, const double *__restrict__ csum, int n, int k,
+                    int ldk, double *__restrict__ P, double *__restrict__ Qp) {
+    const int c = blockIdx.y * 64 + threadIdx.x, ch = blockIdx.x;
+    if (c > ldk) return;
+    const int r0 = ch * PF_CHUNK, r1 = min(n, r0 + PF_CHUNK);
+    double acc = 0.0;
+    for (int q = 0; q < ch; q++) acc += csum[(size_t)q * (ldk + 1) + c];
+    if (c < k) {
+        if (ch == 0) P[c] = 0.0;
+        for (int r = r0; r < r1; r++) { acc += s[(size_t)r * ldk + c]; P[(size_t)(r + 1) * ldk + c] = acc; }
+    } else if (c < ldk) {
+        if (ch == 0) P[c] = 0.0;
+        for (int r = r0; r < r1; r++) P[(size_t)(r + 1) * ldk + c] = 0.0;
+    } else {
+        if (ch == 0) Qp[0] = 0.0;
+        for (int r = r0; r < r1; r++) { acc += rn2[r]; Qp[r + 1] = acc; }
     }
 }
 
@@ -361,13 +384,19 @@ coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
 // ------------------------------------------------------------------------------------------
 // stage 5: rioja::bstick + first-TRUE-run rule + fpc::calinhara per level (R/TADpole.R:111-120)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
+#define CH_WARPS 4
+__global__ void __launch_bounds__(32 * CH_WARPS)
 ch_kernel(const double *__restrict__ P, const double *__restrict__ Qp, int ldk, int n, int k,
           const double *__restrict__ seqdist, const int4 *__restrict__ merges, int ldd,
           const int *__restrict__ cand_list, int min_clusters,
           double *__restrict__ bs_scratch, int *__restrict__ ncl_out,
           double *__restrict__ chs, int ld_chs) {
-    const int lane = threadIdx.x;
+    // One CTA of CH_WARPS warps per candidate.  What is serial in the reference's arithmetic stays serial on one thread, in
+    // the reference's order (the cumulative sum of the broken stick, the running within-cluster dispersion); what feeds
+    // those chains is computed by all warps first: the quotients tot / m, and the dispersion each level undoes.
+    extern __shared__ double s_dl[];                  // s_dl[lev]: decrease of W when level lev undoes its merge
+    __shared__ int s_ncl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cand = cand_list[blockIdx.x];
     const int n1 = n - 1;                 // nobj = number of merges = length(height)
     const double *seq = seqdist + (size_t)cand * ldd;
@@ -375,64 +404,62 @@ ch_kernel(const double *__restrict__ P, const double *__restrict__ Qp, int ldk, 
     double *bs = bs_scratch + (size_t)blockIdx.x * ldd;
     double *out = chs + (size_t)cand * ld_chs;
 
-    for (int l = lane; l < ld_chs; l += 32) out[l] = __longlong_as_double(0x7ff8000000000000LL);
+    for (int l = tid; l < ld_chs; l += blockDim.x) out[l] = __longlong_as_double(0x7ff8000000000000LL);
 
     // height[t] = cumulative dispersion after merge t; tot = height[n1-1]
     const double tot = seq[mrg[n1 - 1].x];
-    // vegan::bstick.default(nobj, tot) = rev(cumsum(tot / nobj:1) / nobj): the cumulative sum runs
-    // from m = nobj down to 1 in this order, one thread, to round exactly as R does.
-    if (lane == 0) {
+    // vegan::bstick.default(nobj, tot) = rev(cumsum(tot / nobj:1) / nobj): the quotients in parallel, then the cumulative
+    // sum from m = nobj down to 1 on one thread, so that it rounds exactly as R's cumsum does, then the division by nobj.
+    const double dn = (double)n1;
+    for (int m = 1 + tid; m <= n1; m += blockDim.x) bs[m - 1] = tot / (double)m;
+    __syncthreads();
+    if (tid == 0) {
         double c = 0.0;
-        const double dn = (double)n1;
-        for (int m = n1; m >= 1; m--) {
-            c += tot / (double)m;
-            bs[m - 1] = c / dn;
-        }
+        for (int m = n1; m >= 1; m--) { c += bs[m - 1]; bs[m - 1] = c; }
     }
-    __syncwarp();
+    __syncthreads();
+    for (int m = 1 + tid; m <= n1; m += blockDim.x) bs[m - 1] = bs[m - 1] / dn;
+    __syncthreads();
     // dispersion_j = |disp[j+1] - disp[j]|, disp = rev(height), j = 1..n1-1;  flag_j = dispersion_j > bs_j
-    int first = -1, runlen = 0;
-    bool done = false;
-    for (int j0 = 1; j0 <= n1 - 1 && !done; j0 += 32) {
-        const int j = j0 + lane;
-        bool f = false;
-        if (j <= n1 - 1) {
-            const double hi = seq[mrg[n1 - j].x];        // disp[j]   = height[n1 - j]
-            const double lo = seq[mrg[n1 - j - 1].x];    // disp[j+1] = height[n1 - j - 1]
-            f = fabs(lo - hi) > bs[j - 1];
-        }
-        unsigned bal = __ballot_sync(0xffffffffu, f);
-        unsigned valid = (j0 + 31 <= n1 - 1) ? 0xffffffffu : ((1u << (n1 - j0)) - 1u);
-        if (first < 0) {
-            if (bal) {
-                int s = __ffs(bal) - 1;
-                first = j0 + s;
-                unsigned rest = (~bal & valid) >> s;      // first FALSE at or after s
-                if (rest) { runlen = __ffs(rest) - 1; done = true; }
-                else if (valid != 0xffffffffu) { runlen = (n1 - 1) - first + 1; done = true; }
-                else runlen = 32 - s;
+    if (warp == 0) {
+        int first = -1, runlen = 0;
+        bool done = false;
+        for (int j0 = 1; j0 <= n1 - 1 && !done; j0 += 32) {
+            const int j = j0 + lane;
+            bool f = false;
+            if (j <= n1 - 1) {
+                const double hi = seq[mrg[n1 - j].x];        // disp[j]   = height[n1 - j]
+                const double lo = seq[mrg[n1 - j - 1].x];    // disp[j+1] = height[n1 - j - 1]
+                f = fabs(lo - hi) > bs[j - 1];
             }
-        } else {
-            unsigned nb = ~bal & valid;
-            if (nb) { runlen += __ffs(nb) - 1; done = true; }
-            else if (valid != 0xffffffffu) { runlen += n1 - j0; done = true; }
-            else runlen += 32;
+            unsigned bal = __ballot_sync(0xffffffffu, f);
+            unsigned valid = (j0 + 31 <= n1 - 1) ? 0xffffffffu : ((1u << (n1 - j0)) - 1u);
+            if (first < 0) {
+                if (bal) {
+                    int sft = __ffs(bal) - 1;
+                    first = j0 + sft;
+                    unsigned rest = (~bal & valid) >> sft;      // first FALSE at or after sft
+                    if (rest) { runlen = __ffs(rest) - 1; done = true; }
+                    else if (valid != 0xffffffffu) { runlen = (n1 - 1) - first + 1; done = true; }
+                    else runlen = 32 - sft;
+                }
+            } else {
+                unsigned nb = ~bal & valid;
+                if (nb) { runlen += __ffs(nb) - 1; done = true; }
+                else if (valid != 0xffffffffu) { runlen += n1 - j0; done = true; }
+                else runlen += 32;
+            }
         }
+        if (lane == 0) { s_ncl = (first < 0) ? -1 : runlen; ncl_out[cand] = s_ncl; }
     }
-    const int ncl = (first < 0) ? -1 : runlen;
-    if (lane == 0) ncl_out[cand] = ncl;
+    __syncthreads();
+    const int ncl = s_ncl;
     if (ncl < 1) return;
 
-    // Calinski-Harabasz on all k columns; level n is reached by undoing the last n-1 merges.
-    double ssq = 0.0;
-    for (int c = lane; c < k; c += 32) { double v = P[(size_t)n * ldk + c]; ssq += v * v; }
-    ssq = warp_sum(ssq);
-    const double trS = Qp[n] - ssq / (double)n;
-    double W = trS;
-    const int mc = min(min_clusters, ncl);
-    const double dN = (double)n;
-    if (mc <= 1 && lane == 0 && ld_chs > 0) out[0] = (dN - 1.0) * (trS - W) / (0.0 * W);
-    for (int lev = 2; lev <= ncl; lev++) {
+    // Calinski-Harabasz on all k columns; level lev is reached by undoing the last lev - 1 merges.  The merge undone by
+    // level lev lowers W by n_a n_b / (n_a + n_b) |c_a - c_b|^2: one warp per level (only levels the caller's row holds)
+    const int nlev = min(ncl, ld_chs);
+    for (int lev = 2 + warp; lev <= nlev; lev += CH_WARPS) {
         const int4 mg = mrg[n1 - (lev - 1)];
         const int a = mg.y + 1, b = mg.x + 1, c = mg.z + 1;   // A = [a, b), B = [b, c) in P rows
         const double nA = (double)(b - a), nB = (double)(c - b);
@@ -445,9 +472,24 @@ ch_kernel(const double *__restrict__ P, const double *__restrict__ Qp, int ldk, 
             acc += tt * tt;
         }
         acc = warp_sum(acc);
-        W -= acc * (nA * nB / (nA + nB));
-        if (lev >= mc && lev <= ld_chs && lane == 0)
-            out[lev - 1] = (dN - (double)lev) * (trS - W) / ((double)(lev - 1) * W);
+        if (lane == 0) s_dl[lev] = acc * (nA * nB / (nA + nB));
+    }
+    double ssq = 0.0;
+    if (warp == 0) {
+        for (int c = lane; c < k; c += 32) { double v = P[(size_t)n * ldk + c]; ssq += v * v; }
+        ssq = warp_sum(ssq);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const double trS = Qp[n] - ssq / (double)n;
+        double W = trS;
+        const int mc = min(min_clusters, ncl);
+        const double dN = (double)n;
+        if (mc <= 1 && ld_chs > 0) out[0] = (dN - 1.0) * (trS - W) / (0.0 * W);
+        for (int lev = 2; lev <= nlev; lev++) {
+            W -= s_dl[lev];
+            if (lev >= mc) out[lev - 1] = (dN - (double)lev) * (trS - W) / ((double)(lev - 1) * W);
+        }
     }
 }
 
@@ -499,10 +541,16 @@ int tp_sweep_device(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stri
     double *rn2 = ctx->Qp.as<double>() + (n + 2);
     TP_MARK(ctx, EV_SWEEP0);
     rownorm2_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(ctx->scores.as<double>(), n, k, ldk, rn2);
-    prefix_kernel<<<(ldk + 1 + 63) / 64, 64, 0, st>>>(ctx->scores.as<double>(), rn2, n, k, ldk,
-                                                     ctx->P.as<double>(), ctx->Qp.as<double>());
+    {
+        const int nch = (n + PF_CHUNK - 1) / PF_CHUNK;
+        TP_TRY(ctx->harm.reserve((size_t)nch * (ldk + 1) * sizeof(double)));
+        const dim3 pg(nch, (ldk + 1 + 63) / 64);
+        prefix_sums_kernel<<<pg, 64, 0, st>>>(ctx->scores.as<double>(), rn2, n, k, ldk, ctx->harm.as<double>());
+        prefix_write_kernel<<<pg, 64, 0, st>>>(ctx->scores.as<double>(), rn2, ctx->harm.as<double>(), n, k, ldk,
+                                               ctx->P.as<double>(), ctx->Qp.as<double>());
+    }
     d0_kernel<<<(n1 + 127) / 128, 128, 0, st>>>(ctx->scores.as<double>(), n, k, ldk, ctx->d0.as<double>(), ldd);
-    ctx->launches += 3;
+    ctx->launches += 4;
 
     // shared memory plan: per candidate the dSS array with its min tree (+ the boundary links when they fit); several
     // candidates per CTA (one warp each) sharing one reciprocal table while that fits
@@ -535,7 +583,7 @@ int tp_sweep_device(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stri
     if (getenv("TADPOLE_SWEEP_TRACE")) { TP_TRY(trbuf.reserve(8 * sizeof(long long))); trace = trbuf.as<long long>(); }
 #define LAUNCH_SWEEP2(LT, LS, IS, TR)                                                                     \
     do {                                                                                                  \
-        TP_CUDA(cudaFuncSetAttribute(coniss_sweep_kernel<LT, LS, IS, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        TP_CUDA(cudaFuncSetAttribute(coniss_sweep_kernel<LT, LS, IS, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, tp_smem_optin(ctx))); \
         tp_prof_begin(ctx, PC_SWEEP);                                                                     \
         coniss_sweep_kernel<LT, LS, IS, TR><<<nblocks, 32 * wpc, smem, st>>>(ctx->P.as<double>(), ldk, n, ctx->d0.as<double>(), ldd, \
                                                                  d_cands, ncand, (unsigned)cand_smem, ctx->seqdist.as<double>(), \
@@ -580,7 +628,7 @@ int tp_ch_device(tp_ctx *ctx, int min_clusters, int ncand, int ld_chs) {
     TP_CUDA(cudaMemsetAsync(ctx->chs.p, 0xff, (size_t)k * ld_chs * sizeof(double), st));
     if (ncand == 0) { TP_MARK(ctx, EV_CH1); return TP_OK; }
     tp_prof_begin(ctx, PC_CH);
-    ch_kernel<<<ncand, 32, 0, st>>>(ctx->P.as<double>(), ctx->Qp.as<double>(), ldk, n, k,
+    ch_kernel<<<ncand, 32 * CH_WARPS, (size_t)(ld_chs + 2) * sizeof(double), st>>>(ctx->P.as<double>(), ctx->Qp.as<double>(), ldk, n, k,
                                     ctx->seqdist.as<double>(), ctx->order.as<int4>(), ldd, d_cands, min_clusters,
                                     ctx->bsbuf.as<double>(), ctx->ncl.as<int>(), ctx->chs.as<double>(), ld_chs);
     tp_prof_end(ctx);

@@ -317,7 +317,25 @@ extern "C" int tp_call_batch(tp_ctx *ctx, int ncalls, const double *const *mats,
         ctx->pool->ctxs.resize(ndev);
     }
     TpPool *pool = ctx->pool;
-    const int per_dev = std::max(1, std::min(inflight, (ncalls + ndev - 1) / ndev));
+    int per_dev = std::max(1, std::min(inflight, (ncalls + ndev - 1) / ndev));
+    {   // every call in flight holds its own working set in HBM (raw + filtered + correlation + M + digit planes +
+        // blocks: ~48 bytes per matrix element, 30 GB at 25k bins): do not keep more in flight than the device has room for
+        size_t nmax = 0;
+        for (int i = 0; i < ncalls; i++) nmax = std::max(nmax, (size_t)(n[i] > 0 ? n[i] : 0));
+        const double need = 48.0 * (double)nmax * (double)nmax + 64e6;
+        for (int d = 0; d < ndev; d++) {
+            size_t fr = 0, tot = 0;
+            cudaSetDevice(pool->devices[d]);
+            if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { (void)cudaGetLastError(); continue; }
+            // memory the pool's contexts on this device already hold counts as available to them
+            double have = 0.8 * (double)fr;
+            for (tp_ctx *c : pool->ctxs[d])
+                for (const DevBuf *bf : {&c->raw_own, &c->X, &c->C, &c->M, &c->ioA, &c->ioB, &c->islices, &c->Y0, &c->Y1, &c->Y2, &c->W})
+                    have += (double)bf->cap;
+            per_dev = std::max(1, std::min(per_dev, (int)(have / need)));
+        }
+        cudaSetDevice(ctx->device);
+    }
     const unsigned hw = std::thread::hardware_concurrency();
     // a waiting host thread spins on a core in cudaStreamSynchronize; with more threads than spare cores they sleep instead
     const bool blocking = hw > 0 && (unsigned)(per_dev * ndev) > hw / 2;

@@ -314,6 +314,232 @@ osj_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol, double 
     if (crank == 0 && tid == 0) { if (!converged) info[1] = 1; info[2] += sweeps; }     // sticky status words
 }
 
+// =====================================================================================================================
+// The same solver in FP32, for solves whose tolerance is loose (the start Rayleigh-Ritz step of the subspace iteration, of
+// which only the Ritz VALUES are used: 1e-2).  A sub-step is one dependent chain (profiles/r02_osj_trace.md); in FP32 its
+// links cost ~4 cycles instead of ~20 and the y columns are half the shared-memory bytes.  The factor stays FP64 in global
+// memory: a half-panel is converted on load (scaled by a power of two so that the largest diagonal entry of L is in [1, 2):
+// squared norms stay far from the FP32 range limits) and converted back on write-back.
+// =====================================================================================================================
+__device__ __forceinline__ float osj_ldsf(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void osj_stsf(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+
+__device__ __forceinline__ bool osj_csf(float g, float al, float be, float skip2, float &rmax2, float &c, float &sn) {
+    const float ab = al * be, gg = g * g;
+    if (!(ab > 0.0f)) return false;
+    rmax2 = fmaxf(rmax2, __fdividef(gg, ab));
+    if (!(gg > skip2 * ab)) return false;
+    const float dd = be - al;
+    const float hh = fmaf(dd, dd, 4.0f * gg);
+    const float hf = hh * rsqrtf(hh);
+    float t = __fdividef(2.0f * g, fabsf(dd) + hf);
+    if (dd < 0.0f) t = -t;
+    const float tt = fmaf(t, t, 1.0f);
+    c = rsqrtf(tt);
+    c = c * fmaf(-0.5f * tt * c, c, 1.5f);          // c^2 + s^2 = 1 to FP32 rounding
+    sn = t * c;
+    return true;
+}
+
+template <int RL>
+__device__ __forceinline__ void osj_rotatef(unsigned sA, unsigned sN, int BP, int ix, int iy, int hl, unsigned hmask,
+                                            float skip2, float &rmax2) {
+    const unsigned ax = sA + 4u * (ix * BP + hl), ay = sA + 4u * (iy * BP + hl);
+    float xa[RL], ya[RL];
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+#pragma unroll
+    for (int u = 0; u < RL; u++) { xa[u] = osj_ldsf(ax + 64u * u); ya[u] = osj_ldsf(ay + 64u * u); }
+    const float al = osj_ldsf(sN + 4u * ix), be = osj_ldsf(sN + 4u * iy);
+#pragma unroll
+    for (int u = 0; u < RL; u += 4) {
+        g0 = fmaf(xa[u], ya[u], g0);
+        if (u + 1 < RL) g1 = fmaf(xa[u + 1], ya[u + 1], g1);
+        if (u + 2 < RL) g2 = fmaf(xa[u + 2], ya[u + 2], g2);
+        if (u + 3 < RL) g3 = fmaf(xa[u + 3], ya[u + 3], g3);
+    }
+    float g = (g0 + g1) + (g2 + g3);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) g += __shfl_xor_sync(hmask, g, o);
+    float c, sn;
+    if (!osj_csf(g, al, be, skip2, rmax2, c, sn)) return;
+#pragma unroll
+    for (int u = 0; u < RL; u++) {
+        osj_stsf(ax + 64u * u, c * xa[u] - sn * ya[u]);
+        osj_stsf(ay + 64u * u, sn * xa[u] + c * ya[u]);
+    }
+    if (hl == 0) {
+        const float cc = c * c, ss = sn * sn, cs2 = 2.0f * c * sn * g;
+        osj_stsf(sN + 4u * ix, fmaf(cc, al, fmaf(ss, be, -cs2)));
+        osj_stsf(sN + 4u * iy, fmaf(ss, al, fmaf(cc, be, cs2)));
+    }
+}
+
+template <int RL>
+__global__ void __cluster_dims__(OSJ_CLUSTER, 1, 1) __launch_bounds__(OSJ_THREADS, 1)
+osj32_kernel(double *Ac, int b, int BP, int H, int max_sweeps, double tol, const double *scale_p,
+             double *cmax, double *w_out, int *info) {
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) float s_osjf[];
+    float *sA = s_osjf;                        // 2H columns x BP
+    __shared__ float s_norm[2 * OSJ_MAXH];
+    __shared__ float s_red[OSJ_THREADS / 32];
+    const float tol2 = (float)(tol * tol);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int hwid = tid >> 4, hl = tid & 15;
+    const unsigned hmask = (lane & 16) ? 0xffff0000u : 0x0000ffffu;
+    const int crank = cluster.block_rank();
+    const unsigned uA = (unsigned)__cvta_generic_to_shared(sA), uN = (unsigned)__cvta_generic_to_shared(s_norm);
+    const int Hm = (H + 1) & ~1;
+    const float skip2 = 1e-13f;
+    const double scl = __ldg(scale_p), iscl = 1.0 / scl;          // powers of two
+    int sweeps = 0;
+    bool converged = false;
+    while (!converged && sweeps < max_sweeps) {
+        float rmax = 0.f;
+        for (int bs = 0; bs < OSJ_NHP - 1; bs++) {
+            int hI, hJ;
+            osj_pair(crank, bs, OSJ_NHP, hI, hJ);
+            const int colsz = H * BP;
+            for (int i0 = 0; i0 < colsz; i0 += OSJ_THREADS * 8) {
+                double ti[8], tj[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int idx = i0 + u * OSJ_THREADS + tid;
+                    if (idx < colsz) { ti[u] = __ldcg(&Ac[(size_t)hI * colsz + idx]); tj[u] = __ldcg(&Ac[(size_t)hJ * colsz + idx]); }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int idx = i0 + u * OSJ_THREADS + tid;
+                    if (idx < colsz) { sA[idx] = (float)(ti[u] * scl); sA[colsz + idx] = (float)(tj[u] * scl); }
+                }
+            }
+            __syncthreads();
+            for (int c = wid; c < 2 * H; c += OSJ_THREADS / 32) {
+                float a = 0.f;
+                for (int r = lane; r < BP; r += 32) { const float v = sA[c * BP + r]; a = fmaf(v, v, a); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (lane == 0) s_norm[c] = a;
+            }
+            __syncthreads();
+            if (bs == 0) {
+                for (int st = 0; st < Hm - 1; st++) {
+                    for (int pw = hwid; pw < Hm; pw += OSJ_THREADS / 16) {
+                        const int half = pw / (Hm / 2), slot = pw % (Hm / 2);
+                        int p, q;
+                        osj_pair(slot, st, Hm, p, q);
+                        if (q < H) osj_rotatef<RL>(uA, uN, BP, half * H + p, half * H + q, hl, hmask, skip2, rmax);
+                    }
+                    __syncthreads();
+                }
+            }
+            if (H <= OSJ_THREADS / 16) {       // x column of every pair in registers over the H sub-steps
+                const bool act = hwid < H;
+                const unsigned ax = uA + 4u * (hwid * BP + hl);
+                float xa[RL], al = 0.f;
+                if (act) {
+#pragma unroll
+                    for (int u = 0; u < RL; u++) xa[u] = osj_ldsf(ax + 64u * u);
+                    al = osj_ldsf(uN + 4u * hwid);
+                }
+                for (int st = 0; st < H; st++) {
+                    if (act) {
+                        int jj = hwid + st; if (jj >= H) jj -= H;
+                        const int iy = H + jj;
+                        const unsigned ay = uA + 4u * (iy * BP + hl);
+                        float ya[RL];
+                        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+#pragma unroll
+                        for (int u = 0; u < RL; u++) ya[u] = osj_ldsf(ay + 64u * u);
+                        const float be = osj_ldsf(uN + 4u * iy);
+#pragma unroll
+                        for (int u = 0; u < RL; u += 4) {
+                            g0 = fmaf(xa[u], ya[u], g0);
+                            if (u + 1 < RL) g1 = fmaf(xa[u + 1], ya[u + 1], g1);
+                            if (u + 2 < RL) g2 = fmaf(xa[u + 2], ya[u + 2], g2);
+                            if (u + 3 < RL) g3 = fmaf(xa[u + 3], ya[u + 3], g3);
+                        }
+                        float g = (g0 + g1) + (g2 + g3);
+#pragma unroll
+                        for (int o = 8; o > 0; o >>= 1) g += __shfl_xor_sync(hmask, g, o);
+                        float c, sn;
+                        if (osj_csf(g, al, be, skip2, rmax, c, sn)) {
+#pragma unroll
+                            for (int u = 0; u < RL; u++) {
+                                const float x = xa[u], y = ya[u];
+                                xa[u] = c * x - sn * y;
+                                osj_stsf(ay + 64u * u, sn * x + c * y);
+                            }
+                            const float cc = c * c, ss = sn * sn, cs2 = 2.0f * c * sn * g;
+                            if (hl == 0) osj_stsf(uN + 4u * iy, fmaf(ss, al, fmaf(cc, be, cs2)));
+                            al = fmaf(cc, al, fmaf(ss, be, -cs2));
+                        }
+                    }
+                    __syncthreads();
+                }
+                if (act) {
+#pragma unroll
+                    for (int u = 0; u < RL; u++) osj_stsf(ax + 64u * u, xa[u]);
+                    if (hl == 0) osj_stsf(uN + 4u * hwid, al);
+                }
+                __syncthreads();
+            } else {
+                for (int st = 0; st < H; st++) {
+                    for (int pw = hwid; pw < H; pw += OSJ_THREADS / 16) {
+                        int jj = pw + st; if (jj >= H) jj -= H;
+                        osj_rotatef<RL>(uA, uN, BP, pw, H + jj, hl, hmask, skip2, rmax);
+                    }
+                    __syncthreads();
+                }
+            }
+            for (int idx = tid; idx < colsz; idx += OSJ_THREADS) {
+                Ac[(size_t)hI * colsz + idx] = (double)sA[idx] * iscl;
+                Ac[(size_t)hJ * colsz + idx] = (double)sA[colsz + idx] * iscl;
+            }
+            if (bs == OSJ_NHP - 2 && w_out) {
+                for (int c = tid; c < 2 * H; c += OSJ_THREADS) {
+                    const int gcol = (c < H ? hI : hJ) * H + (c < H ? c : c - H);
+                    w_out[gcol] = (double)s_norm[c] * iscl * iscl;
+                }
+            }
+            cluster.sync();
+        }
+        sweeps++;
+        rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 16));
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+        if (lane == 0) s_red[wid] = rmax;
+        __syncthreads();
+        if (tid == 0) {
+            float v = 0.f;
+            for (int w = 0; w < OSJ_THREADS / 32; w++) v = fmaxf(v, s_red[w]);
+            cmax[(sweeps & 1) * OSJ_CLUSTER + crank] = (double)v;
+        }
+        cluster.sync();
+        float v = 0.f;
+        for (int r = 0; r < OSJ_CLUSTER; r++) v = fmaxf(v, (float)__ldcg(&cmax[(sweeps & 1) * OSJ_CLUSTER + r]));
+        converged = v <= tol2;
+    }
+    if (crank == 0 && tid == 0) { if (!converged) info[1] = 1; info[2] += sweeps; }
+}
+
+// scale = 2^-e with max_i L_ii in [2^e, 2^(e+1)) (1 when the factor is zero)
+__global__ void osj_scale_kernel(const double *__restrict__ L, int b, int ld, double *__restrict__ scale) {
+    __shared__ double s[32];
+    double mx = 0.0;
+    for (int i = threadIdx.x; i < b; i += blockDim.x) mx = fmax(mx, fabs(L[(size_t)i * ld + i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (unsigned w = 1; w < (blockDim.x >> 5); w++) mx = fmax(mx, s[w]);
+        int e = 0;
+        if (mx > 0.0 && isfinite(mx)) frexp(mx, &e);            // mx = f 2^e, f in [0.5, 1)
+        *scale = ldexp(1.0, 1 - e);
+    }
+}
+
 // eigenvalues w (unsorted, one per column) -> descending order; eigenvector = normalised column of the
 // rotated factor: Vs[r][rank(c)] = Ac[c * BP + r] / sqrt(w_c)
 __global__ void osj_sort_kernel(const double *__restrict__ w_in, const double *__restrict__ Vc, int b, int BP,
@@ -349,7 +575,7 @@ int tp_osj(tp_ctx *ctx, double *T, int b, int ld, double *w, double *Vs, int lds
     cudaStream_t st = ctx->stream;
     const int H = (b + OSJ_NHP - 1) / OSJ_NHP, NC = H * OSJ_NHP, BP = round_up(b, 32);
     const size_t panel = (size_t)NC * BP * sizeof(double);
-    TP_TRY(ctx->Jt.reserve(panel + (size_t)(NC + 64) * sizeof(double) + 64));
+    TP_TRY(ctx->Jt.reserve(panel + (size_t)(NC + 64) * sizeof(double) + 128));
     double *Ac = ctx->Jt.as<double>();
     double *wtmp = Ac + (size_t)NC * BP, *cmax = wtmp + NC;
     TP_TRY(ctx->status.reserve(64));
@@ -358,6 +584,25 @@ int tp_osj(tp_ctx *ctx, double *T, int b, int ld, double *w, double *Vs, int lds
     TP_TRY(tp_chol_factor(ctx, T, b, ld));
     tp_prof_begin(ctx, PC_JACOBI);
     osj_init_kernel<<<(unsigned)(((size_t)NC * BP + 255) / 256), 256, 0, st>>>(T, b, ld, BP, NC, Ac);
+    // loose tolerances (>= 1e-4: the start Rayleigh-Ritz step) are solved in FP32
+    const bool f32 = tol >= 1e-4 && !getenv("TADPOLE_OSJ_NOF32");
+    if (f32) {
+        double *scale = cmax + 2 * OSJ_CLUSTER;
+        osj_scale_kernel<<<1, 256, 0, st>>>(T, b, ld, scale);
+        const size_t smem32 = (size_t)2 * H * BP * sizeof(float);
+#define OSJ32_LAUNCH(R)                                                                                         \
+    case R:                                                                                                     \
+        TP_CUDA(cudaFuncSetAttribute(osj32_kernel<2 * R>, cudaFuncAttributeMaxDynamicSharedMemorySize, tp_smem_optin(ctx))); \
+        osj32_kernel<2 * R><<<OSJ_CLUSTER, OSJ_THREADS, smem32, st>>>(Ac, b, BP, H, 30, tol, scale, cmax, wtmp, info); \
+        break;
+        switch (BP / 32) {
+            OSJ32_LAUNCH(1) OSJ32_LAUNCH(2) OSJ32_LAUNCH(3) OSJ32_LAUNCH(4) OSJ32_LAUNCH(5) OSJ32_LAUNCH(6)
+            OSJ32_LAUNCH(7) OSJ32_LAUNCH(8) OSJ32_LAUNCH(9) OSJ32_LAUNCH(10) OSJ32_LAUNCH(11) OSJ32_LAUNCH(12)
+            default: tp_set_error("tp_osj: unsupported panel height"); return TP_ERR_ARG;
+        }
+#undef OSJ32_LAUNCH
+        ctx->launches += 1;
+    }
     const size_t smem = (size_t)2 * H * BP * sizeof(double);
     const double otol = tol > 2e-15 ? tol : 2e-15;
     long long *trace = nullptr;
@@ -365,10 +610,10 @@ int tp_osj(tp_ctx *ctx, double *T, int b, int ld, double *w, double *Vs, int lds
     if (getenv("TADPOLE_OSJ_TRACE")) { TP_TRY(trbuf.reserve(OSJ_CLUSTER * 8 * sizeof(long long))); trace = trbuf.as<long long>(); }
 #define OSJ_LAUNCH(R)                                                                                         \
     case R:                                                                                                   \
-        TP_CUDA(cudaFuncSetAttribute(osj_kernel<2 * R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        TP_CUDA(cudaFuncSetAttribute(osj_kernel<2 * R>, cudaFuncAttributeMaxDynamicSharedMemorySize, tp_smem_optin(ctx))); \
         osj_kernel<2 * R><<<OSJ_CLUSTER, OSJ_THREADS, smem, st>>>(Ac, b, BP, H, 30, otol, predict, cmax, wtmp, info, trace); \
         break;
-    switch (BP / 32) {
+    if (!f32) switch (BP / 32) {
         OSJ_LAUNCH(1) OSJ_LAUNCH(2) OSJ_LAUNCH(3) OSJ_LAUNCH(4) OSJ_LAUNCH(5) OSJ_LAUNCH(6)
         OSJ_LAUNCH(7) OSJ_LAUNCH(8) OSJ_LAUNCH(9) OSJ_LAUNCH(10) OSJ_LAUNCH(11) OSJ_LAUNCH(12)
         default: tp_set_error("tp_osj: unsupported panel height"); return TP_ERR_ARG;

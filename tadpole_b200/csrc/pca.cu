@@ -136,17 +136,22 @@ __global__ void scale_rows_kernel(double *__restrict__ Q, int b, int ld, const d
     Q[(size_t)i * ld + j] *= d[i];
 }
 
-// residual_j = || MY_j - theta_j Y_j ||_2 where MY = (e / sigma1) Y1 + c Y0 (first filter step)
+// residual_j = || MY_j - theta_j Y_j ||_2 where MY = (e / sigma1) Y1 + c Y0 (first filter step).  Two stages with a fixed
+// summation order (every rank, every run: the same bits): RS_SLABS row slabs x 32-column groups of partial sums of squares,
+// then one thread per column adds the slabs.  (One CTA per 32 columns walking all the rows was 7 CTAs and 0.13 ms at
+// 2000 bins, four times per call.)
+#define RS_SLABS 32
 __global__ void __launch_bounds__(256)
-residual_kernel(const double *__restrict__ Y0, const double *__restrict__ Y1, int n, int ld, int k,
-                const double *__restrict__ theta, double e_over_sig, double c, double *__restrict__ res) {
+residual_partial_kernel(const double *__restrict__ Y0, const double *__restrict__ Y1, int n, int ld, int k,
+                        const double *__restrict__ theta, double e_over_sig, double c, double *__restrict__ part) {
     __shared__ double s[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + tx;
+    const int rows = (n + RS_SLABS - 1) / RS_SLABS, r0 = blockIdx.y * rows, r1 = min(n, r0 + rows);
     double a = 0.0;
     if (j < k) {
         const double th = theta[j];
-        for (int r = ty; r < n; r += 8) {
+        for (int r = r0 + ty; r < r1; r += 8) {
             const double y0 = Y0[(size_t)r * ld + j];
             const double v = e_over_sig * Y1[(size_t)r * ld + j] + (c - th) * y0;
             a += v * v;
@@ -157,8 +162,15 @@ residual_kernel(const double *__restrict__ Y0, const double *__restrict__ Y1, in
     if (ty == 0 && j < k) {
         double v = 0.0;
         for (int g = 0; g < 8; g++) v += s[g][tx];
-        res[j] = sqrt(v);
+        part[(size_t)blockIdx.y * k + j] = v;
     }
+}
+__global__ void residual_final_kernel(const double *__restrict__ part, int k, double *__restrict__ res) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    double v = 0.0;
+    for (int g = 0; g < RS_SLABS; g++) v += part[(size_t)g * k + j];
+    res[j] = sqrt(v);
 }
 
 // scores[:, j] = U[:, j] * sqrt(max(w_j, 0)), j < k; padding columns zero
@@ -372,6 +384,7 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
         TP_TRY(ctx->small1.reserve(sm)); TP_TRY(ctx->small2.reserve(sm)); TP_TRY(ctx->Jv.reserve(sm));
         TP_TRY(ctx->Jw.reserve((size_t)4 * b * sizeof(double)));
         TP_TRY(ctx->resid.reserve((size_t)(k + b) * sizeof(double)));
+        TP_TRY(ctx->part.reserve((size_t)RS_SLABS * k * sizeof(double)));
         TP_TRY(tp_pin_reserve(ctx, (size_t)(k + b + 8) * sizeof(double)));
         double *W = ctx->W.as<double>();
         double *G = ctx->G.as<double>(), *T = ctx->T.as<double>(), *Q = ctx->Q.as<double>();
@@ -529,8 +542,10 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
                 double rmax = 0.0;
                 for (int attempt = 0; attempt < 2; attempt++) {
                     TP_TRY(filter_step1());
-                    residual_kernel<<<(k + 31) / 32, 256, 0, st>>>(Y, F1, n, ldb, k, theta, bd.e / bd.sig1, bd.c, res);
-                    ctx->launches += 1;
+                    residual_partial_kernel<<<dim3((k + 31) / 32, RS_SLABS), 256, 0, st>>>(Y, F1, n, ldb, k, theta, bd.e / bd.sig1,
+                                                                                         bd.c, ctx->part.as<double>());
+                    residual_final_kernel<<<(k + 127) / 128, 128, 0, st>>>(ctx->part.as<double>(), k, res);
+                    ctx->launches += 2;
                     TP_CUDA(cudaMemcpyAsync(hbuf, res, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, st));
                     TP_TRY(tp_flags_enqueue(ctx));
                     TP_CUDA(tp_stream_sync(ctx));

@@ -39,6 +39,19 @@ def test_batch_entry_equals_one_call_at_a_time(ctx):
     assert ctx.call_batch([], inflight=2) == []
 
 
+def test_batch_of_slightly_different_sizes_many_in_flight(ctx):
+    """Eight host threads launching the same kernels with slightly different shared-memory sizes (bins 560..606): the
+    opt-in shared-memory limit of a kernel is process-wide state, and 'set my size, launch' used to race with another
+    thread's smaller size (cudaErrorInvalidValue in bench.py's end-to-end pass)."""
+    from tadpole_b200.synth import synth_hic
+    mats = [synth_hic(560 + 2 * i, seed=60 + i) for i in range(24)]
+    for rep in range(2):
+        got = ctx.call_batch(mats, inflight=8, tables=False)
+        assert not any(isinstance(g, Exception) for g in got), [str(g) for g in got if isinstance(g, Exception)][:1]
+    for i in (0, 11, 23):
+        _same_call(got[i], ctx.call(mats[i]))
+
+
 def test_batch_on_device_inputs(ctx):
     import torch
     from tadpole_b200.synth import synth_hic

@@ -58,3 +58,18 @@ def test_eigensolver(ctx, b):
     assert np.linalg.norm(v.T @ v - np.eye(b)) <= 1e-12 * b
     assert np.linalg.norm(t @ v - v * w) <= 1e-12 * wref[0] * b
     assert 1 <= sweeps <= 30
+
+
+@pytest.mark.parametrize("b,scale", [(256, 1.0), (256, 1e-30), (224, 1e12), (96, 1.0)])
+def test_eigensolver_fp32_mode(ctx, b, scale):
+    """Loose tolerances (>= 1e-4: the start Rayleigh-Ritz step, whose Ritz values only set the filter bounds) are solved by
+    the FP32 variant of the cluster Jacobi kernel, whatever the scale of the matrix (the factor is scaled by a power of two
+    on load).  Eigenvalues to ~1e-5 of the largest, eigenvectors orthogonal to ~1e-5."""
+    t = _spd(b, 1e3, seed=7 + b) * scale
+    t = 0.5 * (t + t.T)
+    w, v, sweeps = ctx.test_eig(t, tol=1e-2)
+    wref = np.linalg.eigvalsh(t)[::-1]
+    np.testing.assert_allclose(w, wref, rtol=0, atol=2e-4 * wref[0])
+    assert np.abs(v.T @ v - np.eye(b)).max() <= 5e-2
+    assert np.linalg.norm(t @ v - v * w, axis=0).max() <= 5e-2 * wref[0]
+    assert 1 <= sweeps <= 30
