@@ -2,7 +2,9 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <algorithm>
+#include <mutex>
 #include <numeric>
+#include <unordered_map>
 
 int tp_sweep_device(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stride, int *ncand_out);
 int tp_ch_device(tp_ctx *ctx, int min_clusters, int ncand, int ld_chs);
@@ -27,6 +29,21 @@ int tp_pin_reserve(tp_ctx *ctx, size_t bytes) {
     TP_CUDA(cudaMallocHost(&ctx->pin, bytes));
     ctx->pin_cap = bytes;
     return TP_OK;
+}
+
+cudaError_t tp_optin_smem_fn(const void *kernel, const tp_ctx *ctx) {
+    static std::mutex mu;
+    static std::unordered_map<const void *, unsigned> done;          // kernel -> devices it has been set on
+    const unsigned bit = 1u << (ctx->device & 31);
+    std::lock_guard<std::mutex> lock(mu);
+    unsigned &mask = done[kernel];
+    if (mask & bit) return cudaSuccess;
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, kernel);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin - (int)a.sharedSizeBytes);
+    if (e == cudaSuccess) mask |= bit;
+    return e;
 }
 
 int tp_flags_reset(tp_ctx *ctx) {

@@ -290,7 +290,7 @@ int tp_chol_inv_1cta(tp_ctx *ctx, double *G, double *Linv, int b, int ld, int *i
 static int launch_cholinv(tp_ctx *ctx, double *G, double *Linv, int b, int ld, int *info, int factor_only) {
     if (b > CI_MAXB) return tp_chol_inv_1cta(ctx, G, Linv, b, ld, info, factor_only);
     const size_t smem = (size_t)(CI_ROWS * CI_P + CI_ROWS * CI_PE + 2 * CI_W * CI_P + CI_W * CI_W) * sizeof(double);
-    TP_CUDA(cudaFuncSetAttribute(cholinv8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tp_smem_optin(ctx)));
+    TP_CUDA(tp_optin_smem(cholinv8_kernel, ctx));
     tp_prof_begin(ctx, PC_CHOL);
     long long *trace = nullptr;
     const bool tr = getenv("TADPOLE_CHOL_TRACE") != nullptr;

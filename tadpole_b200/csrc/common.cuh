@@ -173,11 +173,15 @@ enum { PC_ROWMEAN = 0, PC_COMPACT, PC_GEMM, PC_JACOBI, PC_SWEEP, PC_CH, PC_DIFFT
 void tp_prof_begin(tp_ctx *ctx, int cls);
 void tp_prof_end(tp_ctx *ctx);
 
-// Opt-in limit of dynamic shared memory handed to cudaFuncSetAttribute: ALWAYS the device maximum, never the size of the
-// launch at hand.  The attribute is per function and process-wide, and several host threads (tp_call_batch, the member
-// threads of a multi-device context) launch the same kernel with different sizes: "set my size, then launch" raced with
-// another thread setting a smaller size in between (cudaErrorInvalidValue at the launch).
-static inline int tp_smem_optin(const tp_ctx *ctx) { return ctx->max_smem_optin; }
+// Opt-in limit of dynamic shared memory of a kernel: ALWAYS the most the device allows (minus the kernel's static shared
+// memory), never the size of the launch at hand.  The attribute is per function and process-wide, and several host threads
+// (tp_call_batch, the member threads of a multi-device context) launch the same kernel with different sizes: "set my
+// size, then launch" raced with another thread setting a smaller size in between (cudaErrorInvalidValue at the launch).
+// Set once per kernel and device.
+cudaError_t tp_optin_smem_fn(const void *kernel, const tp_ctx *ctx);      // api.cu: once per (kernel, device)
+template <class K> static inline cudaError_t tp_optin_smem(K kernel, const tp_ctx *ctx) {
+    return tp_optin_smem_fn((const void *)kernel, ctx);
+}
 int tp_pin_reserve(tp_ctx *ctx, size_t bytes);
 // wait for everything queued on the context stream (spinning or sleeping, see sync_blocking)
 cudaError_t tp_stream_sync(tp_ctx *ctx);

@@ -583,7 +583,7 @@ int tp_sweep_device(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stri
     if (getenv("TADPOLE_SWEEP_TRACE")) { TP_TRY(trbuf.reserve(8 * sizeof(long long))); trace = trbuf.as<long long>(); }
 #define LAUNCH_SWEEP2(LT, LS, IS, TR)                                                                     \
     do {                                                                                                  \
-        TP_CUDA(cudaFuncSetAttribute(coniss_sweep_kernel<LT, LS, IS, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, tp_smem_optin(ctx))); \
+        TP_CUDA(tp_optin_smem(coniss_sweep_kernel<LT, LS, IS, TR>, ctx)); \
         tp_prof_begin(ctx, PC_SWEEP);                                                                     \
         coniss_sweep_kernel<LT, LS, IS, TR><<<nblocks, 32 * wpc, smem, st>>>(ctx->P.as<double>(), ldk, n, ctx->d0.as<double>(), ldd, \
                                                                  d_cands, ncand, (unsigned)cand_smem, ctx->seqdist.as<double>(), \

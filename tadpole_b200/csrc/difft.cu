@@ -163,7 +163,7 @@ static int difft_device(tp_ctx *ctx, const int *dx, size_t xstride, const int *d
     TP_TRY(ctx->dhash.reserve((size_t)(npairs + 1) * sizeof(int)));
     int *d_over = ctx->dhash.as<int>();
     TP_CUDA(cudaMemsetAsync(d_over, 0, sizeof(int), st));
-    TP_CUDA(cudaFuncSetAttribute(difft_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tp_smem_optin(ctx)));
+    TP_CUDA(tp_optin_smem(difft_kernel<false>, ctx));
     TP_MARK(ctx, EV_DIFFT0);
     tp_prof_begin(ctx, PC_DIFFT);
     difft_kernel<false><<<grid, DT_THREADS, smem, st>>>(dx, xstride, dy, L, npairs, dout, dtotals, smem_slots, nullptr,

@@ -174,7 +174,7 @@ template <bool A_KC, bool B_KC, int BM, int BN, int WM, int WN>
 static int launch_cfg(tp_ctx *ctx, const GemmArgs &g, double *partial, int splits, int kt_per_split) {
     constexpr size_t smem = (size_t)GEMM_STAGES * (tile_doubles<BM, A_KC>() + tile_doubles<BN, B_KC>()) * sizeof(double);
     auto kern = dgemm_kernel<A_KC, B_KC, BM, BN, WM, WN>;
-    TP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tp_smem_optin(ctx)));
+    TP_CUDA(tp_optin_smem(kern, ctx));
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, splits);
     tp_prof_begin(ctx, PC_GEMM);
     // algorithmic flops: 2 M N K, or M N (K + 1) ~ SYRK count when only one triangle is computed

@@ -303,7 +303,7 @@ int tp_igram(tp_ctx *ctx, const double *X, int n, int ld, double *C, int ldc, co
     p.n = n; p.kblocks = Kp / IG_BK; p.C = C; p.ldc = ldc; p.mean = mean; p.sd = sd; p.nrows = (double)n; p.raw = raw;
     p.row_begin = row_begin; p.row_end = row_end; p.ss = ss;
     const size_t smem = (size_t)IG_STAGES * IG_STAGE_BYTES + 1024;
-    TP_CUDA(cudaFuncSetAttribute(ig_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tp_smem_optin(ctx)));
+    TP_CUDA(tp_optin_smem(ig_gram_kernel, ctx));
     if (row_end > row_begin) {
         dim3 grid(rows_pad / IG_BN, (row_end - row_begin + IG_BM - 1) / IG_BM);
         tp_prof_begin(ctx, PC_IGEMM);
@@ -680,7 +680,7 @@ static int iop_apply_np(tp_ctx *ctx, const double *Yin, int b, int ldy, double *
     p.D = D; p.ldd = ldd; p.E1 = E1; p.lde1 = lde1; p.E2 = E2; p.lde2 = lde2;
     p.alpha = alpha; p.beta = beta; p.gamma = gamma; p.rowscale = rowscale; p.colscale = colscale; p.sym = 0; p.banded = 0; p.ss = SymShard{1, 1 << 30};
     const size_t smem = (size_t)IoCfg<NP, BN>::STAGES * IoCfg<NP, BN>::STAGE_BYTES + 1024;
-    TP_CUDA(cudaFuncSetAttribute(io_gemm_kernel<NP, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tp_smem_optin(ctx)));
+    TP_CUDA(tp_optin_smem(io_gemm_kernel<NP, BN>, ctx));
     dim3 grid(rows_padB / BN, (row_end - row_begin + IO_BM - 1) / IO_BM);
     if (ctx->prof) ctx->prof_imma_ops += 2.0 * (NP * (NP + 1) / 2) * (double)grid.x * grid.y * IO_BM * BN * (double)Kp;
     tp_prof_begin(ctx, PC_IGEMM);
@@ -736,7 +736,7 @@ int tp_igram_sliced(tp_ctx *ctx, const double *A, int n, int ld, double *M, int 
         p.alpha = 1.0; p.beta = 0.0; p.gamma = 0.0; p.rowscale = rowscale; p.colscale = rowscale;
         p.sym = sym; p.banded = 1; p.ss = ss;
         const size_t smem = (size_t)IoCfg<NP, IO_BN>::STAGES * IoCfg<NP, IO_BN>::STAGE_BYTES + 1024;
-        TP_CUDA(cudaFuncSetAttribute(io_gemm_kernel<NP, IO_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tp_smem_optin(ctx)));
+        TP_CUDA(tp_optin_smem(io_gemm_kernel<NP, IO_BN>, ctx));
         dim3 grid(rows_pad / IO_BN, (row_end - row_begin + IO_BM - 1) / IO_BM);
         if (ctx->prof) {
             double tiles = 0.0;

@@ -473,7 +473,7 @@ int tp_chol_inv_1cta(tp_ctx *ctx, double *G, double *Linv, int b, int ld, int *i
     const size_t chsm2 = (size_t)(nbw < 32 ? nbw : 32) * CH_PW * (CH_PW + 1) * sizeof(double);
     if (!factor_only && chsm2 > chsm) chsm = chsm2;
     TP_ARG(chsm <= (size_t)ctx->max_smem_optin, "tp_chol_inv: block too wide for the shared-memory panel");
-    TP_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tp_smem_optin(ctx)));
+    TP_CUDA(tp_optin_smem(chol_inv_kernel, ctx));
     tp_prof_begin(ctx, PC_CHOL);
     chol_inv_kernel<<<1, CH_THREADS, chsm, st>>>(G, Linv, b, ld, info, factor_only);
     tp_prof_end(ctx);

@@ -592,7 +592,7 @@ int tp_osj(tp_ctx *ctx, double *T, int b, int ld, double *w, double *Vs, int lds
         const size_t smem32 = (size_t)2 * H * BP * sizeof(float);
 #define OSJ32_LAUNCH(R)                                                                                         \
     case R:                                                                                                     \
-        TP_CUDA(cudaFuncSetAttribute(osj32_kernel<2 * R>, cudaFuncAttributeMaxDynamicSharedMemorySize, tp_smem_optin(ctx))); \
+        TP_CUDA(tp_optin_smem(osj32_kernel<2 * R>, ctx)); \
         osj32_kernel<2 * R><<<OSJ_CLUSTER, OSJ_THREADS, smem32, st>>>(Ac, b, BP, H, 30, tol, scale, cmax, wtmp, info); \
         break;
         switch (BP / 32) {
@@ -610,7 +610,7 @@ int tp_osj(tp_ctx *ctx, double *T, int b, int ld, double *w, double *Vs, int lds
     if (getenv("TADPOLE_OSJ_TRACE")) { TP_TRY(trbuf.reserve(OSJ_CLUSTER * 8 * sizeof(long long))); trace = trbuf.as<long long>(); }
 #define OSJ_LAUNCH(R)                                                                                         \
     case R:                                                                                                   \
-        TP_CUDA(cudaFuncSetAttribute(osj_kernel<2 * R>, cudaFuncAttributeMaxDynamicSharedMemorySize, tp_smem_optin(ctx))); \
+        TP_CUDA(tp_optin_smem(osj_kernel<2 * R>, ctx)); \
         osj_kernel<2 * R><<<OSJ_CLUSTER, OSJ_THREADS, smem, st>>>(Ac, b, BP, H, 30, otol, predict, cmax, wtmp, info, trace); \
         break;
     if (!f32) switch (BP / 32) {
