@@ -10,7 +10,7 @@ dev = [torch.as_tensor(m, device="cuda") for m in mats]
 torch.cuda.synchronize()
 ptrs = [d.data_ptr() for d in dev]
 ctx = Context(0)
-for s in (1, 2, 4, 6, 8, 12, 16, 24, 32):
+for s in [int(x) for x in os.environ.get('INFLIGHT', '1,2,4,6,8,12,16,24,32').split(',')]:
     ctx.call_batch(None, device_ptrs=ptrs, n=n, inflight=s, tables=False)
     ctx.call_batch(None, device_ptrs=ptrs * 10, n=n, inflight=s, tables=False)
     ms = ctx.last_batch_device_ms
