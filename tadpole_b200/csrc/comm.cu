@@ -37,7 +37,9 @@ static int nccl_bind() {
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
     void *h = nullptr;
     for (const char *nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_NOLOAD); if (h) break; }     // a copy already in the process
-    for (const char *nm : names) { if (h) break; h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); }
+    // RTLD_LOCAL: a copy loaded here must not satisfy the NCCL symbols of a library loaded later (torch imported after the
+    // first multi-device context would otherwise bind to the system's older libnccl and fail on symbols it lacks)
+    for (const char *nm : names) { if (h) break; h = dlopen(nm, RTLD_NOW | RTLD_LOCAL); }
     if (!h) { tp_set_error("NCCL not found (%s); multi-GPU calls need libnccl.so.2", dlerror()); return TP_ERR_CUDA; }
 #define BIND(f)                                                                  \
     do {                                                                         \
