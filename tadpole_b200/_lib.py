@@ -125,6 +125,17 @@ def load():
     return lib
 
 
+def _nccl_first_from_torch():
+    """The library binds NCCL at run time (dlopen) the first time a communicator is made.  If torch is going to be used in
+    this process too, its bundled NCCL must be the copy that gets loaded: the dynamic loader keeps ONE library per soname,
+    and torch cannot live with the system's older libnccl.so.2.  So import torch first when it is there (an R host has no
+    torch and binds the system NCCL)."""
+    try:
+        import torch  # noqa: F401
+    except ImportError:
+        pass
+
+
 def device_count():
     return int(load().tp_device_count())
 
@@ -150,6 +161,7 @@ class Context:
         self.lib = load()
         self._h = c_void_p()
         if isinstance(device, (list, tuple)):
+            _nccl_first_from_torch()
             devs = np.ascontiguousarray(device, dtype=np.int32)
             check(self.lib.tp_ctx_create_multi(_ip(devs), devs.size, ctypes.byref(self._h)))
             self.devices = [int(d) for d in devs]
@@ -296,11 +308,13 @@ class Context:
     # ---- multi-GPU ----
     def comm_unique_id(self):
         """128-byte NCCL unique id (call on one rank, ship the bytes to the others)."""
+        _nccl_first_from_torch()
         buf = ctypes.create_string_buffer(128)
         check(self.lib.tp_comm_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
         return buf.raw
 
     def comm_init(self, unique_id, rank, nranks, slot=0):
+        _nccl_first_from_torch()
         buf = ctypes.create_string_buffer(bytes(unique_id), 128)
         check(self.lib.tp_ctx_comm_init(self._h, ctypes.cast(buf, ctypes.c_void_p), int(rank), int(nranks), int(slot)))
 
