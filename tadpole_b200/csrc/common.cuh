@@ -135,6 +135,7 @@ struct tp_ctx {
     int nf = 0, ldx = 0;
     DevBuf ioA, ioB, ioscale;            // digit planes / scales of the sliced int8 operator of stage 3 (igemm.cu)
     int io_n = 0;
+    bool io_cmax_clean = false;          // the column-maximum scratch of the sliced operator is zero (io_colmax_kernel leaves it so)
     DevBuf X, C, colstat, islices;      // islices: int8 digit planes of X for the tcgen05 integer Gram (igemm.cu)
     bool have_X = false, have_C = false;
     // PCA

@@ -373,29 +373,39 @@ __global__ void io_rowmax_kernel(const double *__restrict__ A, int n, int ld, in
     if (lane == 0) { const int e = io_exponent(mx); expo[w] = e; scale[w] = ldexp(1.0, e - 6); }
 }
 
-// largest |entry| of every column of Y (n x b, ld): 16-row slabs (n / 16 CTAs: several waves of the 148 SMs, 16
-// independent coalesced loads in flight per thread), one atomicMax per column and slab on the IEEE bit pattern
-// (non-negative doubles order like unsigned integers; max is exact and order independent)
+// largest |entry| of every column of Y (n x b, ld) -> exponent and scale of the column.  At most two CTAs per SM walk the
+// 16-row slabs (16 independent coalesced loads in flight per thread), one atomicMax per column and CTA on the IEEE bit
+// pattern (non-negative doubles order like unsigned integers; max is exact and order independent); the CTA that finishes
+// last turns the maxima into exponents / scales and clears the scratch for the next application (no memset, no second
+// launch: five stream operations per operator application were three too many).
 #define IO_CM_ROWS 16
 __global__ void __launch_bounds__(256)
-io_colmax_kernel(const double *__restrict__ Y, int n, int b, int ld, unsigned long long *__restrict__ colmax_bits) {
-    const int r0 = blockIdx.x * IO_CM_ROWS;
+io_colmax_kernel(const double *__restrict__ Y, int n, int b, int ld, unsigned long long *__restrict__ colmax_bits,
+                 unsigned *__restrict__ ticket, int *__restrict__ expo, double *__restrict__ scale) {
+    __shared__ int s_last;
     for (int c = threadIdx.x; c < b; c += 256) {
-        double v[IO_CM_ROWS];
-#pragma unroll
-        for (int t = 0; t < IO_CM_ROWS; t++) v[t] = (r0 + t < n) ? Y[(size_t)(r0 + t) * ld + c] : 0.0;
         double mx = 0.0;
+        for (int r0 = blockIdx.x * IO_CM_ROWS; r0 < n; r0 += gridDim.x * IO_CM_ROWS) {
+            double v[IO_CM_ROWS];
 #pragma unroll
-        for (int t = 0; t < IO_CM_ROWS; t++) mx = fmax(mx, fabs(v[t]));
+            for (int t = 0; t < IO_CM_ROWS; t++) v[t] = (r0 + t < n) ? Y[(size_t)(r0 + t) * ld + c] : 0.0;
+#pragma unroll
+            for (int t = 0; t < IO_CM_ROWS; t++) mx = fmax(mx, fabs(v[t]));
+        }
         if (mx > 0.0 && isfinite(mx)) atomicMax(colmax_bits + c, (unsigned long long)__double_as_longlong(mx));
     }
-}
-__global__ void io_colscale_kernel(const unsigned long long *__restrict__ colmax_bits, int b, int *__restrict__ expo,
-                                   double *__restrict__ scale) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= b) return;
-    const int e = io_exponent(__longlong_as_double((long long)colmax_bits[c]));
-    expo[c] = e; scale[c] = ldexp(1.0, e - 6);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int c = threadIdx.x; c < b; c += 256) {
+        const int e = io_exponent(__longlong_as_double((long long)__ldcg(colmax_bits + c)));
+        expo[c] = e; scale[c] = ldexp(1.0, e - 6);
+        colmax_bits[c] = 0ull;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
 }
 
 template <int NP>
@@ -435,28 +445,47 @@ io_slice_rows_kernel(const double *__restrict__ A, int n, int ld, const int *__r
         *reinterpret_cast<int4 *>(P + s * plane + (size_t)row * Kp + k0) = *reinterpret_cast<const int4 *>(d[s]);
 }
 
-// planes P[s][j][k] of the COLUMNS of Y (n x b, ld): 32 x 32 tiles transposed through shared memory
+// planes P[s][j][k] of the COLUMNS of Y (n x b, ld): tiles of 128 k x 32 j transposed through shared memory.  A thread
+// converts four consecutive k of one column (loads coalesced along j) and packs their digits into one 32-bit word per
+// plane; the planes leave in 16-byte stores, eight threads to a 128-byte run along k.  (32 x 32 tiles with byte stores
+// in 32-byte runs ran at a sixth of the HBM rate.)
 template <int NP>
 __global__ void __launch_bounds__(256)
 io_slice_cols_kernel(const double *__restrict__ Y, int n, int b, int ld, const int *__restrict__ expo,
                      int8_t *__restrict__ P, int rows_pad, int Kp) {
-    __shared__ int8_t s[NP][32][33];
+    __shared__ unsigned s[NP][32][33];              // [plane][j][k / 4], pitch 33 words: conflict-free both ways
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int k0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
-    for (int kk = ty; kk < 32; kk += 8) {
-        const int k = k0 + kk, j = j0 + tx;
-        int8_t dd[NP];
-        io_digits<NP>((k < n && j < b) ? Y[(size_t)k * ld + j] : 0.0, j < b ? expo[j] : 0, dd);
+    const int k0 = blockIdx.x * 128, j0 = blockIdx.y * 32;
+    const int j = j0 + tx;
+    const int e = j < b ? expo[j] : 0;
 #pragma unroll
-        for (int p = 0; p < NP; p++) s[p][kk][tx] = dd[p];
+    for (int i = 0; i < 4; i++) {
+        const int kq = ty + 8 * i;                  // group of four k
+        unsigned w[NP];
+#pragma unroll
+        for (int p = 0; p < NP; p++) w[p] = 0u;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = k0 + 4 * kq + q;
+            int8_t dd[NP];
+            io_digits<NP>((k < n && j < b) ? Y[(size_t)k * ld + j] : 0.0, e, dd);
+#pragma unroll
+            for (int p = 0; p < NP; p++) w[p] |= (unsigned)(unsigned char)dd[p] << (8 * q);
+        }
+#pragma unroll
+        for (int p = 0; p < NP; p++) s[p][tx][kq] = w[p];
     }
     __syncthreads();
     const size_t plane = (size_t)rows_pad * Kp;
-    for (int jj = ty; jj < 32; jj += 8) {
-        const int j = j0 + jj, k = k0 + tx;
-        if (j < rows_pad && k < Kp)
-#pragma unroll
-            for (int p = 0; p < NP; p++) P[p * plane + (size_t)j * Kp + k] = s[p][tx][jj];
+    for (int item = threadIdx.x; item < NP * 256; item += 256) {
+        const int p = item >> 8, jj = (item >> 3) & 31, k16 = item & 7;
+        const int jo = j0 + jj, k = k0 + 16 * k16;
+        if (jo < rows_pad && k < Kp) {
+            int4 v;
+            v.x = (int)s[p][jj][4 * k16]; v.y = (int)s[p][jj][4 * k16 + 1];
+            v.z = (int)s[p][jj][4 * k16 + 2]; v.w = (int)s[p][jj][4 * k16 + 3];
+            *reinterpret_cast<int4 *>(P + p * plane + (size_t)jo * Kp + k) = v;
+        }
     }
 }
 
@@ -635,7 +664,7 @@ int tp_iop_prepare(tp_ctx *ctx, const double *S, int n, int ld) {
     const int rows_pad = round_up(n, IO_BM), Kp = round_up(n, 128);
     const size_t plane = (size_t)rows_pad * Kp;
     TP_TRY(ctx->ioA.reserve(IO_MAXNP * plane));
-    TP_TRY(ctx->ioscale.reserve((size_t)(n + 1024) * (sizeof(double) + sizeof(int)) * 2 + 1024 * sizeof(unsigned long long)));
+    TP_TRY(ctx->ioscale.reserve((size_t)(n + 1024) * (sizeof(double) + sizeof(int)) * 2 + 1024 * sizeof(unsigned long long) + 64));
     double *rowscale = ctx->ioscale.as<double>();
     int *rowexp = (int *)(rowscale + 2 * (n + 1024));
     tp_prof_begin(ctx, PC_ISLICE);
@@ -646,6 +675,7 @@ int tp_iop_prepare(tp_ctx *ctx, const double *S, int n, int ld) {
     ctx->launches += 2;
     TP_CUDA(cudaGetLastError());
     ctx->io_n = n;
+    ctx->io_cmax_clean = false;      // the scratch of the column maxima sits behind the n-dependent scale arrays: clear it once
     return TP_OK;
 }
 
@@ -665,11 +695,15 @@ static int iop_apply_np(tp_ctx *ctx, const double *Yin, int b, int ldy, double *
     int *rowexp = (int *)(rowscale + 2 * (n + 1024));
     int *colexp = rowexp + (n + 1024);
     tp_prof_begin(ctx, PC_ISLICE);
-    unsigned long long *cmax = (unsigned long long *)(colexp + (n + 1024));
-    TP_CUDA(cudaMemsetAsync(cmax, 0, (size_t)b * sizeof(unsigned long long), st));
-    io_colmax_kernel<<<(n + IO_CM_ROWS - 1) / IO_CM_ROWS, 256, 0, st>>>(Yin, n, b, ldy, cmax);
-    io_colscale_kernel<<<(b + 255) / 256, 256, 0, st>>>(cmax, b, colexp, colscale);
-    dim3 sg(Kp / 32, rows_padB / 32);
+    unsigned long long *cmax = (unsigned long long *)(colexp + (n + 1024));      // 1024 maxima (zero between uses) + the ticket
+    unsigned *ticket = (unsigned *)(cmax + 1024);
+    if (!ctx->io_cmax_clean) {
+        TP_CUDA(cudaMemsetAsync(cmax, 0, 1024 * sizeof(unsigned long long) + 16, st));
+        ctx->io_cmax_clean = true;
+    }
+    const int cm_grid = std::min((n + IO_CM_ROWS - 1) / IO_CM_ROWS, 2 * ctx->sm_count);
+    io_colmax_kernel<<<cm_grid, 256, 0, st>>>(Yin, n, b, ldy, cmax, ticket, colexp, colscale);
+    dim3 sg(Kp / 128, rows_padB / 32);
     io_slice_cols_kernel<NP><<<sg, 256, 0, st>>>(Yin, n, b, ldy, colexp, ctx->ioB.as<int8_t>(), rows_padB, Kp);
     tp_prof_end(ctx);
     CUtensorMap mapA, mapB;
@@ -686,7 +720,7 @@ static int iop_apply_np(tp_ctx *ctx, const double *Yin, int b, int ldy, double *
     tp_prof_begin(ctx, PC_IGEMM);
     io_gemm_kernel<NP, BN><<<grid, IG_THREADS, smem, st>>>(mapA, mapB, p);
     tp_prof_end(ctx);
-    ctx->launches += 4;
+    ctx->launches += 3;
     TP_CUDA(cudaGetLastError());
     return TP_OK;
 }
@@ -718,7 +752,7 @@ int tp_igram_sliced(tp_ctx *ctx, const double *A, int n, int ld, double *M, int 
     const int rows_pad = round_up(n, IO_BM), Kp = round_up(n, 128);
     const size_t plane = (size_t)rows_pad * Kp;
     TP_TRY(ctx->ioA.reserve(IO_MAXNP * plane));
-    TP_TRY(ctx->ioscale.reserve((size_t)(n + 1024) * (sizeof(double) + sizeof(int)) * 2 + 1024 * sizeof(unsigned long long)));
+    TP_TRY(ctx->ioscale.reserve((size_t)(n + 1024) * (sizeof(double) + sizeof(int)) * 2 + 1024 * sizeof(unsigned long long) + 64));
     double *rowscale = ctx->ioscale.as<double>();
     int *rowexp = (int *)(rowscale + 2 * (n + 1024));
     tp_prof_begin(ctx, PC_ISLICE);
