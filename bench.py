@@ -479,8 +479,10 @@ def run_b200(args, rank, world, local_rank):
                 continue
             if n == 2000:
                 for r in roofs.values():
-                    if r["traffic"] is None and r["kernel"] in traffic:
-                        r["traffic"] = traffic[r["kernel"]]
+                    key = r["kernel"].split(" ")[0] if r["kernel"].startswith("dgemm_kernel") else (
+                        "io_gemm_kernel" if r["kernel"].startswith("ig_gram_kernel + io_gemm_kernel") else r["kernel"])
+                    if r["traffic"] is None and key in traffic:
+                        r["traffic"] = traffic[key]
                         r["traffic_unit"] = f"bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/{fn})"
         top = max(roofs, key=lambda c: roofs[c]["share_of_step"])
         roof = roofs[top]
