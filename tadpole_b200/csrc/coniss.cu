@@ -456,7 +456,11 @@ ch_kernel(const double *__restrict__ P, const double *__restrict__ Qp, int ldk, 
     const int ncl = s_ncl;
     if (ncl < 1) return;
 
-    // Calinski-Harabasz on all k columns; level lev is reached by undoing the last lev - 1 merges.  The merge undone by
+    // Calinski-Harabasz on all k columns; level lev is reached by undoing the last lev - 1 merges, in MERGE-STEP order.
+    // cutree (tp_assemble*, and R's .find.groups) ranks the boundaries by (height, index) instead; the two orders differ only
+    // among merges whose heights are equal as doubles, i.e. whose increases vanish against the running total -- W, and
+    // with it every CH value, is the same to rounding whichever of those merges is undone first, and the tables the
+    // caller gets come from the (height, index) order.  The merge undone by
     // level lev lowers W by n_a n_b / (n_a + n_b) |c_a - c_b|^2: one warp per level (only levels the caller's row holds)
     const int nlev = min(ncl, ld_chs);
     for (int lev = 2 + warp; lev <= nlev; lev += CH_WARPS) {

@@ -512,8 +512,11 @@ int tp_pca(tp_ctx *ctx, int max_pcs, int *k_out) {
             random_block_kernel<<<(unsigned)(((size_t)n * ldb + 255) / 256), 256, 0, st>>>(Y, n, b, ldb);
             ctx->launches += 1;
             {   // start: orthonormalise the random block, one Rayleigh-Ritz step at low accuracy
+                // (one pass: an n x b block of uniform random numbers has condition number ~(sqrt(n) + sqrt(b)) / (sqrt(n) -
+                //  sqrt(b)) < 5 for n > 2 b, so Cholesky QR leaves cond^2 eps ~ 1e-15 of non-orthogonality; closer to square
+                //  the block is worse conditioned and gets the second pass)
                 int bad = 0;
-                TP_TRY(cholqr(2, &bad));
+                TP_TRY(cholqr(n > 2 * b ? 1 : 2, &bad));
                 TP_TRY(op.apply(Y, W, 1.0, nullptr, 0.0, nullptr, 0.0));
                 if (bad) TP_TRY(rr_general(1e-2)); else TP_TRY(rr_orthonormal(1e-2));      // only the Ritz VALUES of the start step are used (filter bounds)
             }
