@@ -130,6 +130,25 @@ def test_sweep_against_oracle_same_scores(ctx, synth_cache, n):
         assert np.isnan(sc[i - 1, oncl:]).all()
 
 
+def test_sweep_bitmap_neighbours(ctx, synth_cache, monkeypatch):
+    """Above ~18k bins the live-boundary links are one bit per boundary in shared memory instead of two link arrays; the
+    same code path forced at 601 bins must give the array path's result bit for bit, and the oracle's merge order."""
+    c = synth_cache(601)
+    pcs, k = c["pcs"], c["k"]
+    nf = pcs.shape[0]
+    ctx.set_scores(pcs)
+    ncl_a, sc_a = ctx.sweep(k)
+    ref = {i: ctx.dendro(i - 1, nf) for i in (1, 9, 77, k)}
+    monkeypatch.setenv("TADPOLE_SWEEP_LINKS", "bitmap")
+    ctx.set_scores(pcs)
+    ncl_b, sc_b = ctx.sweep(k)
+    assert np.array_equal(ncl_a, ncl_b) and np.array_equal(sc_a, sc_b, equal_nan=True)
+    for i, (seq, order) in ref.items():
+        seq_b, order_b = ctx.dendro(i - 1, nf)
+        assert np.array_equal(seq, seq_b) and np.array_equal(order, order_b)
+        assert np.array_equal(order_b, O.coniss_lw(pcs[:, :i])[1])
+
+
 def test_sweep_candidate_sharding(ctx, synth_cache):
     c = synth_cache(200)
     pcs, k = c["pcs"], c["k"]
