@@ -138,10 +138,8 @@ template <typename LinkT, bool SMEM> struct Links {
 // 200 one-warp CTAs would be spread over all 148 SMs, and their 25-40 KB of shared memory each would keep the
 // ~200 KB CTAs of the tcgen05 kernels of OTHER calls in flight on the same GPU off every SM for the whole sweep.
 // TRACE: cycles of one merge step by phase, summed over the merge loop of the first candidate of the list (the widest),
-// written to trace[0..5] = find + links of the steps whose boundary was not predicted, reciprocals, wait for the P rows +
-// dot products, shuffle reduce + scale, speculation for the next step (early tree repair, find, links, preload issue),
-// write back + tree repair + verification; trace[6] = steps, [7] = columns, [8] = steps whose boundary was predicted
-// (TADPOLE_SWEEP_TRACE; profiles/r02_coniss_merge_step.md)
+// written to trace[0..5] = find, links, P rows + dot products, shuffle reduce + scale, write back + level-1 re-reduce,
+// level-2 re-reduce; trace[6] = steps (TADPOLE_SWEEP_TRACE; profiles/r02_coniss_merge_step.md)
 template <typename LinkT, bool LINKS_SMEM, bool INV_SMEM, bool TRACE>
 __global__ void __launch_bounds__(256)
 coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
@@ -239,45 +237,46 @@ coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
     const double tie_abs = TIE_ABS * __ldg(qtot);       // qtot: sum of the squared norms of all score rows
     const double *Plane = P + lane;
     double total = 0.0;
-    long long tr_acc[6] = {0, 0, 0, 0, 0, 0}, tr_t = 0, tr_hits = 0;
+    long long tr_acc[6] = {0, 0, 0, 0, 0, 0}, tr_t = 0;
 #define CS_TR(ph) do { if (TRACE) { const long long t_ = clock64(); tr_acc[ph] += t_ - tr_t; tr_t = t_; } } while (0)
-
-    // ---- find the minimum; among increases equal to it, the lowest index ---------------------------
-    // The reference's scan keeps the first of EQUAL increases (strict '<').  Equal means equal in exact arithmetic:
-    // bins with identical score rows (zero-variance bins all map to one row of the correlation matrix, quirk Q9) give
-    // families of exactly tied increases, which Lance-Williams arithmetic on the distance matrix reproduces bit for bit
-    // while differences of prefix sums taken at different offsets differ in their last bits.  So an increase within
-    // TIE_REL (relative, two orders above the rounding of this kernel's arithmetic) + tie_abs (for exact zeros: identical
-    // adjacent rows) of the minimum counts as tied.  Two increases that close without being structurally equal are
-    // ordered by rounding noise in the reference too.
-    // Returns the boundary, its own increase (dj) and the tie threshold of the minimum (thr).
-    auto find_min = [&](int &j, double &dj, double &thr) {
+    for (int t = 0; t < n1; t++) {
+        if (TRACE) tr_t = clock64();
+        // ---- find the minimum; among increases equal to it, the lowest index ---------------------------
+        // The reference's scan keeps the first of EQUAL increases (strict '<').  Equal means equal in exact arithmetic:
+        // bins with identical score rows (zero-variance bins all map to one row of the correlation matrix, quirk Q9) give
+        // families of exactly tied increases, which Lance-Williams arithmetic on the distance matrix reproduces bit for bit
+        // while differences of prefix sums taken at different offsets differ in their last bits.  So an increase within
+        // TIE_REL (relative, two orders above the rounding of this kernel's arithmetic) + tie_abs (for exact zeros: identical
+        // adjacent rows) of the minimum counts as tied.  Two increases that close without being structurally equal are
+        // ordered by rounding noise in the reference too.
         double mn;
         int b2 = 0;
         if (B2p == 32) {
             const double v = lds_f64(sm2 + 8u * lane);
             mn = warp_min_nonneg(v);
-            thr = fma(mn, TIE_REL, mn) + tie_abs;
+            const double thr = fma(mn, TIE_REL, mn) + tie_abs;
             b2 = __ffs(__ballot_sync(0xffffffffu, v <= thr)) - 1;
         } else {
             double v = INF_D;
             for (int q = lane; q < B2p; q += 32) v = fmin(v, lds_f64(sm2 + 8u * q));
             mn = warp_min_nonneg(v);
-            thr = fma(mn, TIE_REL, mn) + tie_abs;
+            const double thr = fma(mn, TIE_REL, mn) + tie_abs;
             for (int q0 = 0; q0 < B2p; q0 += 32) {
                 unsigned bal = __ballot_sync(0xffffffffu, lds_f64(sm2 + 8u * (q0 + lane)) <= thr);
                 if (bal) { b2 = q0 + __ffs(bal) - 1; break; }
             }
         }
+        const double thr = fma(mn, TIE_REL, mn) + tie_abs;
         const unsigned bal1 = __ballot_sync(0xffffffffu, lds_f64(sm1 + 8u * ((b2 << 5) + lane)) <= thr);
         const int b1 = (b2 << 5) + __ffs(bal1) - 1;
         const double leaf = lds_f64(sd + 8u * ((b1 << 5) + lane));
         const unsigned bal0 = __ballot_sync(0xffffffffu, leaf <= thr);
-        j = (b1 << 5) + __ffs(bal0) - 1;
-        dj = __shfl_sync(0xffffffffu, leaf, j & 31);
-    };
-    // previous / next live boundary of j (-1 / n1: none) and theirs
-    auto neighbours = [&](int j, int &pj, int &nj, int &ppj, int &nnj) {
+        const int j = (b1 << 5) + __ffs(bal0) - 1;
+        mn = __shfl_sync(0xffffffffu, leaf, j & 31);          // the increase of the boundary that is merged
+
+        CS_TR(0);
+        // ---- neighbours ---------------------------------------------------------------------
+        int pj, nj, ppj, nnj;                    // previous / next live boundary (-1 / n1: none) and theirs
         if (LINKS_SMEM) {
             pj = lk.prv(j) - 1; nj = lk.nxt(j);
             ppj = pj >= 0 ? lk.prv(pj) - 1 : -1;
@@ -287,63 +286,6 @@ coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
             ppj = pj >= 0 ? bm_prev(pj) : -1;
             nnj = nj < n1 ? bm_next(nj) : n1;
         }
-    };
-    // re-reduce the leaf blocks k0, k1, k2 of the dSS array and the level-2 entries above them
-    auto repair = [&](int k0, int k1, int k2) {
-        // independent re-reductions issued back to back (ILP), then stored
-        const double x0 = lds_f64(sd + 8u * ((k0 << 5) + lane));
-        const double x1 = lds_f64(sd + 8u * ((k1 << 5) + lane));
-        const double x2 = lds_f64(sd + 8u * ((k2 << 5) + lane));
-        const double r0 = warp_min_nonneg(x0);
-        const double r1 = (k1 != k0) ? warp_min_nonneg(x1) : r0;
-        const double r2 = (k2 != k0) ? warp_min_nonneg(x2) : r0;
-        if (lane == 0) {
-            sts_f64(sm1 + 8u * k0, r0);
-            if (k1 != k0) sts_f64(sm1 + 8u * k1, r1);
-            if (k2 != k0) sts_f64(sm1 + 8u * k2, r2);
-        }
-        __syncwarp();
-        const int g0 = k0 >> 5, g1 = k1 >> 5, g2 = k2 >> 5;
-        const double y0 = warp_min_nonneg(lds_f64(sm1 + 8u * ((g0 << 5) + lane)));
-        if (lane == 0) sts_f64(sm2 + 8u * g0, y0);
-        if (g1 != g0) {
-            const double y1 = warp_min_nonneg(lds_f64(sm1 + 8u * ((g1 << 5) + lane)));
-            if (lane == 0) sts_f64(sm2 + 8u * g1, y1);
-        }
-        if (g2 != g0 && g2 != g1) {
-            const double y2 = warp_min_nonneg(lds_f64(sm1 + 8u * ((g2 << 5) + lane)));
-            if (lane == 0) sts_f64(sm2 + 8u * g2, y2);
-        }
-        __syncwarp();
-    };
-
-    // The merge loop.  A step is a dependent chain -- which boundary (tree), which rows (links), the rows themselves (one L2
-    // round trip, the largest single item), two reductions, tree repair (profiles/r02_coniss_merge_step.md) -- and the next
-    // step's boundary is normally known long before this step's arithmetic is done: the increases this merge creates are
-    // rarely the smallest left.  So while this step's rows are in flight the warp already takes boundary j and its two
-    // neighbours out of the tree (j for good, the neighbours until their new increases are known), finds the minimum of
-    // all OTHER boundaries (j2, with its tie threshold thr2), looks up j2's neighbours in the links as they will be after
-    // this merge, and starts loading j2's rows.  When the two new increases turn out above thr2, j2 IS the next step's
-    // boundary (the tie set of the minimum is unchanged) and that step starts with its tree descent, link look-ups and row
-    // loads already done; otherwise the preloaded rows are dropped and the next step proceeds the ordinary way.  The order
-    // of the merges and every value are those of the plain loop: only WHEN the rows are fetched changes.
-    int cj = 0, cpj = 0, cnj = 0, cppj = 0, cnnj = 0;
-    double cmn = 0.0;
-    bool have = false;                        // (cj ... cmn) describe this step; their first 32 x CS_CHUNK columns are in pv*
-    double pva[CS_CHUNK], pvb[CS_CHUNK], pvc[CS_CHUNK], pve[CS_CHUNK];
-#pragma unroll
-    for (int u = 0; u < CS_CHUNK; u++) pva[u] = pvb[u] = pvc[u] = pve[u] = 0.0;
-    for (int t = 0; t < n1; t++) {
-        if (TRACE) tr_t = clock64();
-        const bool pre = have;
-        if (!have) {
-            double thr;
-            find_min(cj, cmn, thr);
-            CS_TR(0);
-            neighbours(cj, cpj, cnj, cppj, cnnj);
-        }
-        const int j = cj, pj = cpj, nj = cnj, ppj = cppj, nnj = cnnj;
-        const double mn = cmn;
         const bool hasL = pj >= 0, hasR = nj < n1;
         // P rows: LL = [a, b), C = [b, c), RR = [c, e)
         const int a = ppj + 1, b = pj + 1, c = nj + 1, e = nnj + 1;
@@ -351,88 +293,27 @@ coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
         const double *Pc = Plane + (size_t)c * ldk, *Pe = Plane + (size_t)e * ldk;
         const int cC = c - b, cLL = b - a, cRR = e - c;
         const double iC = inv_of(cC), iLL = inv_of(cLL), iRR = inv_of(cRR);
-        if (TRACE) { asm volatile("" ::"d"(iC), "d"(iLL), "d"(iRR)); CS_TR(1); }
-        // the first 32 x CS_CHUNK columns of the four rows: preloaded by the previous step, or requested now
-        double va[CS_CHUNK], vb[CS_CHUNK], vc[CS_CHUNK], ve[CS_CHUNK];
-#pragma unroll
-        for (int u = 0; u < CS_CHUNK; u++) {
-            const int col = 32 * u;
-            if (pre) { va[u] = pva[u]; vb[u] = pvb[u]; vc[u] = pvc[u]; ve[u] = pve[u]; }
-            else if (col < ncol) {
-                const bool ok = col + lane < ncol;
-                vb[u] = ok ? __ldg(Pb + col) : 0.0;
-                vc[u] = ok ? __ldg(Pc + col) : 0.0;
-                va[u] = (ok && hasL) ? __ldg(Pa + col) : 0.0;
-                ve[u] = (ok && hasR) ? __ldg(Pe + col) : 0.0;
-            } else { va[u] = vb[u] = vc[u] = ve[u] = 0.0; }
-        }
-        // ---- boundary j dies; its neighbours leave the tree until their new increases are known ----------------------
-        if (lane == 0) {
-            sts_f64(sd + 8u * j, INF_D);
-            if (hasL) { sts_f64(sd + 8u * pj, INF_D); if (LINKS_SMEM) lk.set_nxt(pj, nj); }
-            if (hasR) { sts_f64(sd + 8u * nj, INF_D); if (LINKS_SMEM) lk.set_prv(nj, pj + 1); }
-            if (!LINKS_SMEM) sts_u32(sbits + 4u * (j >> 5), lds_u32(sbits + 4u * (j >> 5)) & ~(1u << (j & 31)));
-        }
-        __syncwarp();
-        const int k0 = j >> 5;
-        const int k1 = hasL ? (pj >> 5) : k0;
-        const int k2 = hasR ? (nj >> 5) : k0;
-        // ---- the next step, speculatively: the minimum of all other boundaries and its rows -------------------------
-        bool spec = t + 1 < n1;
-        int sj = 0, spj = 0, snj = 0, sppj = 0, snnj = 0;
-        double smn = 0.0, thr2 = 0.0;
-        if (spec) {
-            repair(k0, k1, k2);
-            find_min(sj, smn, thr2);
-            spec = smn < INF_D;                   // (nothing else alive: the last boundaries are this merge's neighbours)
-        }
-        if (spec) {
-            neighbours(sj, spj, snj, sppj, snnj);
-            const bool sL = spj >= 0, sR = snj < n1;
-            const double *Qa = Plane + (size_t)(sppj + 1) * ldk, *Qb = Plane + (size_t)(spj + 1) * ldk;
-            const double *Qc = Plane + (size_t)(snj + 1) * ldk, *Qe = Plane + (size_t)(snnj + 1) * ldk;
-#pragma unroll
-            for (int u = 0; u < CS_CHUNK; u++) {
-                const int col = 32 * u;
-                if (col < ncol) {
-                    const bool ok = col + lane < ncol;
-                    pvb[u] = ok ? __ldg(Qb + col) : 0.0;
-                    pvc[u] = ok ? __ldg(Qc + col) : 0.0;
-                    pva[u] = (ok && sL) ? __ldg(Qa + col) : 0.0;
-                    pve[u] = (ok && sR) ? __ldg(Qe + col) : 0.0;
-                }
-            }
-        }
-        if (TRACE) CS_TR(4);
-        // ---- this step's two dot products ---------------------------------------------------------------------------
         double accL = 0.0, accR = 0.0;
-#pragma unroll
-        for (int u = 0; u < CS_CHUNK; u++) {
-            if (32 * u >= ncol) break;
-            const double mC = (vc[u] - vb[u]) * iC;
-            const double tL = hasL ? (vb[u] - va[u]) * iLL - mC : 0.0;
-            const double tR = hasR ? mC - (ve[u] - vc[u]) * iRR : 0.0;
-            accL = fma(tL, tL, accL);
-            accR = fma(tR, tR, accR);
-        }
-        for (int c0 = 32 * CS_CHUNK; c0 < ncol; c0 += 32 * CS_CHUNK) {      // candidates wider than 256 columns
-            double wa[CS_CHUNK], wb[CS_CHUNK], wc[CS_CHUNK], we[CS_CHUNK];
+        if (TRACE) { asm volatile("" ::"d"(iC), "d"(iLL), "d"(iRR)); CS_TR(1); }
+        for (int c0 = 0; c0 < ncol; c0 += 32 * CS_CHUNK) {
+            double va[CS_CHUNK], vb[CS_CHUNK], vc[CS_CHUNK], ve[CS_CHUNK];
+            // all loads of the batch first: one L2 round trip per step instead of one per 32 columns
 #pragma unroll
             for (int u = 0; u < CS_CHUNK; u++) {
                 const int col = c0 + 32 * u;
                 if (col >= ncol) break;
                 const bool ok = col + lane < ncol;
-                wb[u] = ok ? __ldg(Pb + col) : 0.0;
-                wc[u] = ok ? __ldg(Pc + col) : 0.0;
-                wa[u] = (ok && hasL) ? __ldg(Pa + col) : 0.0;
-                we[u] = (ok && hasR) ? __ldg(Pe + col) : 0.0;
+                vb[u] = ok ? __ldg(Pb + col) : 0.0;
+                vc[u] = ok ? __ldg(Pc + col) : 0.0;
+                va[u] = (ok && hasL) ? __ldg(Pa + col) : 0.0;
+                ve[u] = (ok && hasR) ? __ldg(Pe + col) : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < CS_CHUNK; u++) {
                 if (c0 + 32 * u >= ncol) break;
-                const double mC = (wc[u] - wb[u]) * iC;
-                const double tL = hasL ? (wb[u] - wa[u]) * iLL - mC : 0.0;
-                const double tR = hasR ? mC - (we[u] - wc[u]) * iRR : 0.0;
+                const double mC = (vc[u] - vb[u]) * iC;
+                const double tL = hasL ? (vb[u] - va[u]) * iLL - mC : 0.0;
+                const double tR = hasR ? mC - (ve[u] - vc[u]) * iRR : 0.0;
                 accL = fma(tL, tL, accL);
                 accR = fma(tR, tR, accR);
             }
@@ -453,24 +334,49 @@ coniss_sweep_kernel(const double *__restrict__ P, int ldk, int n,
         accR *= (double)cC * (double)cRR * inv_of(cC + cRR);
 
         if (TRACE) { asm volatile("" ::"d"(accL), "d"(accR)); CS_TR(3); }
-        // ---- the neighbours come back with their new increases ---------------------------------------------------------
+        // ---- write back: boundary j dies, its neighbours get new increases ---------------
         if (lane == 0) {
-            if (hasL) sts_f64(sd + 8u * pj, accL);
-            if (hasR) sts_f64(sd + 8u * nj, accR);
+            sts_f64(sd + 8u * j, INF_D);
+            if (hasL) { sts_f64(sd + 8u * pj, accL); if (LINKS_SMEM) lk.set_nxt(pj, nj); }
+            if (hasR) { sts_f64(sd + 8u * nj, accR); if (LINKS_SMEM) lk.set_prv(nj, pj + 1); }
+            if (!LINKS_SMEM) sts_u32(sbits + 4u * (j >> 5), lds_u32(sbits + 4u * (j >> 5)) & ~(1u << (j & 31)));
         }
         __syncwarp();
-        repair(spec ? k1 : k0, k1, k2);
-        // the next boundary is the speculated one when neither new increase reaches the tie threshold of that minimum
-        have = spec && (!hasL || accL > thr2) && (!hasR || accR > thr2);
-        if (have) { cj = sj; cpj = spj; cnj = snj; cppj = sppj; cnnj = snnj; cmn = smn; }
-        if (TRACE) tr_hits += have;
+        const int k0 = j >> 5;
+        const int k1 = hasL ? (pj >> 5) : k0;
+        const int k2 = hasR ? (nj >> 5) : k0;
+        // independent re-reductions issued back to back (ILP), then stored
+        const double x0 = lds_f64(sd + 8u * ((k0 << 5) + lane));
+        const double x1 = lds_f64(sd + 8u * ((k1 << 5) + lane));
+        const double x2 = lds_f64(sd + 8u * ((k2 << 5) + lane));
+        const double r0 = warp_min_nonneg(x0);
+        const double r1 = (k1 != k0) ? warp_min_nonneg(x1) : r0;
+        const double r2 = (k2 != k0) ? warp_min_nonneg(x2) : r0;
+        if (lane == 0) {
+            sts_f64(sm1 + 8u * k0, r0);
+            if (k1 != k0) sts_f64(sm1 + 8u * k1, r1);
+            if (k2 != k0) sts_f64(sm1 + 8u * k2, r2);
+        }
+        __syncwarp();
+        CS_TR(4);
+        const int g0 = k0 >> 5, g1 = k1 >> 5, g2 = k2 >> 5;
+        const double y0 = warp_min_nonneg(lds_f64(sm1 + 8u * ((g0 << 5) + lane)));
+        if (lane == 0) sts_f64(sm2 + 8u * g0, y0);
+        if (g1 != g0) {
+            const double y1 = warp_min_nonneg(lds_f64(sm1 + 8u * ((g1 << 5) + lane)));
+            if (lane == 0) sts_f64(sm2 + 8u * g1, y1);
+        }
+        if (g2 != g0 && g2 != g1) {
+            const double y2 = warp_min_nonneg(lds_f64(sm1 + 8u * ((g2 << 5) + lane)));
+            if (lane == 0) sts_f64(sm2 + 8u * g2, y2);
+        }
+        __syncwarp();
         CS_TR(5);
     }
     if (TRACE && slot == 0 && lane == 0) {
         for (int p = 0; p < 6; p++) trace[p] = tr_acc[p];
         trace[6] = n1;
         trace[7] = ncol;
-        trace[8] = tr_hits;
     }
 #undef CS_TR
 }
@@ -678,7 +584,7 @@ int tp_sweep_device(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stri
     void *glinks = nullptr;
     long long *trace = nullptr;
     DevBuf trbuf;
-    if (getenv("TADPOLE_SWEEP_TRACE")) { TP_TRY(trbuf.reserve(16 * sizeof(long long))); trace = trbuf.as<long long>(); }
+    if (getenv("TADPOLE_SWEEP_TRACE")) { TP_TRY(trbuf.reserve(8 * sizeof(long long))); trace = trbuf.as<long long>(); }
 #define LAUNCH_SWEEP2(LT, LS, IS, TR)                                                                     \
     do {                                                                                                  \
         TP_CUDA(tp_optin_smem(coniss_sweep_kernel<LT, LS, IS, TR>, ctx)); \
@@ -701,15 +607,13 @@ int tp_sweep_device(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stri
     TP_CUDA(cudaGetLastError());
     TP_MARK(ctx, EV_SWEEP1);
     if (trace) {
-        long long h[16];
+        long long h[8];
         TP_CUDA(cudaStreamSynchronize(st));
         TP_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
-        static const char *ph[6] = {"find_links_unpredicted", "reciprocals", "rows_wait_dots", "reduce_scale", "speculate_next", "writeback_repair_verify"};
-        fprintf(stderr, "[sweep trace] n=%d cols=%lld wpc=%d links_smem=%d inv_smem=%d predicted %.1f%% of the steps; cycles per merge step:", n, h[7], wpc,
-                (int)links_smem, (int)inv_smem, 100.0 * (double)h[8] / (double)h[6]);
-        double tot = 0.0;
-        for (int p = 0; p < 6; p++) { fprintf(stderr, " %s %.0f", ph[p], (double)h[p] / (double)h[6]); tot += (double)h[p] / (double)h[6]; }
-        fprintf(stderr, " total %.0f\n", tot);
+        static const char *ph[6] = {"find", "links", "p_rows_dot", "reduce_scale", "writeback_l1", "l2"};
+        fprintf(stderr, "[sweep trace] n=%d cols=%lld wpc=%d links_smem=%d inv_smem=%d cycles per merge step:", n, h[7], wpc, (int)links_smem, (int)inv_smem);
+        for (int p = 0; p < 6; p++) fprintf(stderr, " %s %.0f", ph[p], (double)h[p] / (double)h[6]);
+        fprintf(stderr, "\n");
         trbuf.release();
     }
     ctx->have_sweep = true;
