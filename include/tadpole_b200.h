@@ -124,6 +124,19 @@ int tp_ingest_tsv_file(tp_ctx *ctx, const char *path, int sep, int *n_out);
 int tp_ingested(tp_ctx *ctx, const double **dev_out, int *n_out);
 int tp_get_ingested(tp_ctx *ctx, double *out);
 int tp_ingest_stats(tp_ctx *ctx, double *out4);
+/* Sparse input: the non-zero pixels of the UPPER triangle as (bin1, bin2, count) triplets, the
+ * layout `cooler dump` and HiC-Pro write -- at 25 000 bins a few hundred MB cross PCIe instead of the 2.6 GB upper
+ * triangle of the dense matrix.  The dense N x N matrix stage 1 reads is built in HBM (zero fill + one scatter pass) and
+ * is handed on exactly like an ingested TSV (tp_ingested, on_device = 1, colmajor = 0).  Pixels below the diagonal are
+ * ignored and counted in *below_out (the reference reads the upper triangle only: Matrix::forceSymmetric(uplo = 'U'),
+ * R/TADpole.R:20); pixels naming the same cell add up (Matrix::sparseMatrix(i, j, x)); a bin outside [index_base,
+ * index_base + n) is an error naming the entry.  tp_ingest_coo: host arrays.  tp_ingest_coo_file: three-column text
+ * "bin1 <sep> bin2 <sep> count" parsed on the device (counts through the same exact decimal -> binary64 conversion as
+ * matrix fields), a first line that is not such a row is taken as a header; n <= 0: n = largest bin + 1 - index_base. */
+int tp_ingest_coo(tp_ctx *ctx, const int32_t *bin1, const int32_t *bin2, const double *count, size_t nnz, int n,
+                  int index_base, unsigned long long *below_out);
+int tp_ingest_coo_file(tp_ctx *ctx, const char *path, int sep, int n, int index_base, int *n_out,
+                       unsigned long long *nnz_out, unsigned long long *below_out);
 /* host-only test hook: the field conversion the parse kernel runs; returns 0 (value in *out) or 1 (field is left to
  * the host's strtod); needs no GPU */
 int tp_test_parse_field(const char *s, int len, double *out);

@@ -665,6 +665,57 @@ def read_matrix_text(text, sep="\t"):
     return np.array(rows, dtype=np.float64)
 
 
+def coo_to_dense(bin1, bin2, count, n, index_base=0):
+    """The dense matrix behind a list of upper-triangle pixels (bin1, bin2, count) -- what the reference would have read
+    from the equivalent dense file (R/TADpole.R:17) once only its upper triangle counts (forceSymmetric(uplo='U'), :20):
+    pixels below the diagonal are dropped, pixels naming the same cell add up (Matrix::sparseMatrix), a bin outside
+    the matrix is an error.  Returns (matrix with a zero lower triangle, number of pixels dropped)."""
+    b1 = np.asarray(bin1, dtype=np.int64) - index_base
+    b2 = np.asarray(bin2, dtype=np.int64) - index_base
+    v = np.asarray(count, dtype=np.float64)
+    bad = np.flatnonzero((b1 < 0) | (b2 < 0) | (b1 >= n) | (b2 >= n))
+    if bad.size:
+        raise ValueError(f"entry {bad[0] + 1} is outside the {n} bins")
+    up = b1 <= b2
+    m = np.zeros((n, n))
+    np.add.at(m, (b1[up], b2[up]), v[up])
+    return m, int((~up).sum())
+
+
+def read_coo_text(text, sep="\t"):
+    """Three-column pixel text 'bin1 <sep> bin2 <sep> count' (cooler dump): (bin1, bin2, count) arrays; a first line
+    that is not such a row is a header.  Counts through float() (correctly rounded), NA / empty -> NaN."""
+    if isinstance(text, (bytes, bytearray)):
+        text = text.decode()
+    lines = text.replace("\r\n", "\n").rstrip("\n\r ").split("\n")
+    b1, b2, v = [], [], []
+    for i, ln in enumerate(lines):
+        f = ln.split(sep)
+        try:
+            if len(f) != 3:
+                raise ValueError
+            a, b = f[0].strip(), f[1].strip()
+            if not (a.isdigit() and b.isdigit() and a.isascii() and b.isascii()):
+                raise ValueError
+            c = f[2].strip()
+            x = float("nan") if c in ("", "NA") else float(c)
+        except ValueError:
+            if i == 0:
+                continue
+            raise ValueError(f"row {i + 1} is not 'bin1 <sep> bin2 <sep> count'")
+        b1.append(int(a)); b2.append(int(b)); v.append(x)
+    return np.array(b1, dtype=np.int64), np.array(b2, dtype=np.int64), np.array(v, dtype=np.float64)
+
+
+def dense_to_coo(mat):
+    """Test helper: the non-zero (or NaN) upper-triangle pixels of a matrix, row-major order."""
+    m = np.asarray(mat, dtype=np.float64)
+    iu = np.triu_indices(m.shape[0])
+    vals = m[iu]
+    sel = (vals != 0) | np.isnan(vals)
+    return iu[0][sel].astype(np.int32), iu[1][sel].astype(np.int32), vals[sel]
+
+
 def matrix_to_text(mat, fmt=None, sep="\t"):
     """Text of a matrix file as the reference expects it (test helper): integers print without a decimal point,
     other values with repr() (shortest round-trip form) unless fmt is given."""

@@ -56,8 +56,27 @@
 }
 
 # the numeric core of load_mat on the GPU: which bins stay (index lists; the matrix itself stays in HBM)
+# A contact matrix given by its upper-triangle pixels (cooler dump / HiC-Pro): accepted wherever a matrix file is.
+# sparse_counts(bin1, bin2, count, n_bins) from vectors, sparse_counts(path = ) for a three-column text file
+# (n_bins = NULL: largest bin + 1).  A Matrix::sparseMatrix is accepted directly by TADpole() / load_mat().
+sparse_counts <- function(bin1 = NULL, bin2 = NULL, count = NULL, n_bins = NULL, index_base = 0L, path = NULL) {
+    if (is.null(path)) stopifnot(!is.null(bin1), !is.null(bin2), !is.null(count), !is.null(n_bins),
+                                 length(bin1) == length(bin2), length(bin1) == length(count))
+    structure(list(bin1 = as.integer(bin1), bin2 = as.integer(bin2), count = as.numeric(count),
+                   n_bins = if (is.null(n_bins)) 0L else as.integer(n_bins), index_base = as.integer(index_base), path = path),
+              class = "tadpole_pixels")
+}
+
 .tp_load <- function(ctx, mat_file, bad_frac, centromere_search) {
-    if (is.character(mat_file)) {
+    if (inherits(mat_file, "sparseMatrix")) {                   # Matrix package: triplet form, 0-based slots i / j
+        t <- methods::as(mat_file, "TsparseMatrix")
+        mat_file <- sparse_counts(t@i, t@j, t@x, nrow(t), 0L)
+    }
+    if (inherits(mat_file, "tadpole_pixels")) {
+        if (!is.null(mat_file$path)) .Call(C_tp_ingest_coo_file, ctx, path.expand(mat_file$path), mat_file$n_bins, mat_file$index_base)
+        else .Call(C_tp_ingest_coo, ctx, mat_file$bin1, mat_file$bin2, mat_file$count, mat_file$n_bins, mat_file$index_base)
+        bad <- .Call(C_tp_filter, ctx, NULL, as.numeric(bad_frac))
+    } else if (is.character(mat_file)) {
         .Call(C_tp_ingest, ctx, path.expand(mat_file))          # the file's text is parsed on the GPU
         bad <- .Call(C_tp_filter, ctx, NULL, as.numeric(bad_frac))
     } else {

@@ -67,6 +67,39 @@ SEXP C_tp_ingest(SEXP ctx, SEXP path) {
     return ScalarInteger(n);
 }
 
+/* Upper-triangle pixels (bin1, bin2, count) -> the dense matrix in HBM (tp_ingest_coo): a Matrix::sparseMatrix, or the
+ * columns of a `cooler dump`, without the dense N x N matrix ever existing in R.  Returns c(N, pixels below the
+ * diagonal that were ignored). */
+SEXP C_tp_ingest_coo(SEXP ctx, SEXP bin1, SEXP bin2, SEXP count, SEXP n, SEXP index_base) {
+    if (!isInteger(bin1) || !isInteger(bin2) || !isReal(count) || XLENGTH(bin1) != XLENGTH(bin2) || XLENGTH(bin1) != XLENGTH(count))
+        error("TADpole: bin1, bin2 (integer) and count (numeric) of equal length are expected");
+    unsigned long long below = 0;
+    if (tp_ingest_coo(ctx_of(ctx), INTEGER(bin1), INTEGER(bin2), REAL(count), (size_t)XLENGTH(bin1), asInteger(n),
+                      asInteger(index_base), &below) != TP_OK)
+        error("%s", tp_last_error());
+    SEXP out = PROTECT(allocVector(REALSXP, 2));
+    REAL(out)[0] = (double)asInteger(n);
+    REAL(out)[1] = (double)below;
+    UNPROTECT(1);
+    return out;
+}
+
+/* the same from a three-column text file "bin1 <tab> bin2 <tab> count" parsed on the device; n <= 0: largest bin + 1.
+ * Returns c(N, pixels, pixels below the diagonal). */
+SEXP C_tp_ingest_coo_file(SEXP ctx, SEXP path, SEXP n, SEXP index_base) {
+    int nn = 0;
+    unsigned long long nnz = 0, below = 0;
+    if (tp_ingest_coo_file(ctx_of(ctx), CHAR(STRING_ELT(path, 0)), '\t', asInteger(n), asInteger(index_base), &nn, &nnz,
+                           &below) != TP_OK)
+        error("%s", tp_last_error());
+    SEXP out = PROTECT(allocVector(REALSXP, 3));
+    REAL(out)[0] = (double)nn;
+    REAL(out)[1] = (double)nnz;
+    REAL(out)[2] = (double)below;
+    UNPROTECT(1);
+    return out;
+}
+
 /* the ingested matrix as an R matrix (for the plots of load_mat, R/TADpole.R:24-53); symmetric use only needs the
  * upper triangle, so the row-major device matrix is handed back transposed in place of a copy loop */
 SEXP C_tp_ingested_matrix(SEXP ctx) {
@@ -423,6 +456,8 @@ static const R_CallMethodDef call_table[] = {
     {"C_tp_ctx", (DL_FUNC)&C_tp_ctx, 1},
     {"C_tp_ingest", (DL_FUNC)&C_tp_ingest, 2},
     {"C_tp_ingested_matrix", (DL_FUNC)&C_tp_ingested_matrix, 1},
+    {"C_tp_ingest_coo", (DL_FUNC)&C_tp_ingest_coo, 6},
+    {"C_tp_ingest_coo_file", (DL_FUNC)&C_tp_ingest_coo_file, 4},
     {"C_tp_filter", (DL_FUNC)&C_tp_filter, 3},
     {"C_tp_call_arm", (DL_FUNC)&C_tp_call_arm, 4},
     {"C_tp_recall", (DL_FUNC)&C_tp_recall, 4},

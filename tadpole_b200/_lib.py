@@ -25,6 +25,7 @@ EXPORTED = [
     "tp_difft_batch", "tp_assemble", "tp_assemble_levels", "tp_test_cholinv", "tp_test_eig", "tp_test_igram", "tp_test_mgram", "tp_test_symshard", "tp_test_ss_need", "tp_test_ss_tile",
     "tp_comm_unique_id", "tp_ctx_comm_init", "tp_ctx_comm_select", "tp_ctx_comm_info",
     "tp_ingest_tsv", "tp_ingest_tsv_file", "tp_ingested", "tp_get_ingested", "tp_ingest_stats", "tp_test_parse_field",
+    "tp_ingest_coo", "tp_ingest_coo_file",
     "tp_difft_null", "tp_recall",
     "tp_ctx_create_multi", "tp_device_count", "tp_ctx_devices", "tp_ctx_generation", "tp_ctx_dims", "tp_call_arms", "tp_call_batch",
     "tp_batch_size", "tp_batch_device_ms", "tp_batch_launches", "tp_batch_status", "tp_batch_error", "tp_batch_dims", "tp_batch_get", "tp_batch_free", "tp_find_groups",
@@ -84,6 +85,9 @@ def load():
         "tp_get_ingested": (c_int, [vp, dp]),
         "tp_ingest_stats": (c_int, [vp, dp]),
         "tp_test_parse_field": (c_int, [c_char_p, c_int, dp]),
+        "tp_ingest_coo": (c_int, [vp, ip, ip, dp, ctypes.c_size_t, c_int, c_int, POINTER(ctypes.c_ulonglong)]),
+        "tp_ingest_coo_file": (c_int, [vp, c_char_p, c_int, c_int, c_int, ip, POINTER(ctypes.c_ulonglong),
+                                       POINTER(ctypes.c_ulonglong)]),
         "tp_filter": (c_int, [vp, vp, c_int, c_int, c_int, c_double, u8p, dp, dp]),
         "tp_compact": (c_int, [vp, ip, c_int]),
         "tp_set_filtered": (c_int, [vp, dp, c_int]),
@@ -241,6 +245,30 @@ class Context:
         ptr = c_void_p()
         check(self.lib.tp_ingested(self._h, ctypes.byref(ptr), ctypes.byref(n)))
         return ptr.value, n.value
+
+    def ingest_coo(self, bin1=None, bin2=None, count=None, n=None, index_base=0, path=None, sep="\t"):
+        """Upper-triangle pixels (bin1, bin2, count) -> the dense matrix in HBM (tp_ingest_coo), or the same from a
+        three-column text file (tp_ingest_coo_file; n=None: largest bin + 1).  Returns (device_ptr, n); the number of
+        pixels below the diagonal that were ignored is left in self.last_coo_below."""
+        below = ctypes.c_ulonglong(0)
+        nn = c_int(0)
+        if path is not None:
+            nnz = ctypes.c_ulonglong(0)
+            check(self.lib.tp_ingest_coo_file(self._h, os.fsencode(path), ord(sep), int(n or 0), int(index_base),
+                                              ctypes.byref(nn), ctypes.byref(nnz), ctypes.byref(below)))
+            self.last_coo_nnz = int(nnz.value)
+        else:
+            b1 = np.ascontiguousarray(bin1, dtype=np.int32)
+            b2 = np.ascontiguousarray(bin2, dtype=np.int32)
+            v = np.ascontiguousarray(count, dtype=np.float64)
+            assert b1.ndim == 1 and b1.shape == b2.shape == v.shape, "bin1, bin2, count: equal-length vectors expected"
+            check(self.lib.tp_ingest_coo(self._h, _ip(b1), _ip(b2), _dp(v), b1.size, int(n), int(index_base),
+                                         ctypes.byref(below)))
+            self.last_coo_nnz = int(b1.size)
+        self.last_coo_below = int(below.value)
+        ptr = c_void_p()
+        check(self.lib.tp_ingested(self._h, ctypes.byref(ptr), ctypes.byref(nn)))
+        return ptr.value, nn.value
 
     def get_ingested(self, n):
         out = np.empty((n, n))

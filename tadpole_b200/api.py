@@ -41,6 +41,30 @@ def get_context(device=0):
     return ctx
 
 
+class SparseCounts:
+    """A contact matrix given by its non-zero upper-triangle pixels, the layout of `cooler dump` / HiC-Pro: either
+    SparseCounts(bin1, bin2, count, n_bins) from arrays (a scipy.sparse matrix goes through from_scipy) or
+    SparseCounts(path=..., n_bins=None) for a three-column text file.  Accepted wherever a matrix file is: the dense
+    matrix the reference would have read (R/TADpole.R:17) is built on the GPU, only the pixels cross PCIe."""
+
+    def __init__(self, bin1=None, bin2=None, count=None, n_bins=None, index_base=0, path=None, sep="\t"):
+        if path is None:
+            if bin1 is None or bin2 is None or count is None or n_bins is None:
+                raise ValueError("SparseCounts needs bin1, bin2, count and n_bins, or a path")
+        self.bin1, self.bin2, self.count = bin1, bin2, count
+        self.n_bins, self.index_base, self.path, self.sep = n_bins, int(index_base), path, sep
+
+    @classmethod
+    def from_scipy(cls, m):
+        m = m.tocoo()
+        if m.shape[0] != m.shape[1]:
+            raise ValueError("square matrix expected")
+        return cls(m.row, m.col, m.data, m.shape[0])
+
+    def _ingest(self, ctx):
+        return ctx.ingest_coo(self.bin1, self.bin2, self.count, self.n_bins, self.index_base, self.path, self.sep)
+
+
 def read_matrix(mat_file, ctx=None):
     """bigmemory::read.big.matrix(mat_file, type='double', sep='\\t') (R/TADpole.R:17): header-less
     tab-separated numeric matrix, as a numpy array.  The text is uploaded and parsed on the GPU
@@ -48,7 +72,10 @@ def read_matrix(mat_file, ctx=None):
     if isinstance(mat_file, np.ndarray):
         return mat_file
     ctx = ctx or get_context()
-    _, n = ctx.ingest_tsv(mat_file)
+    if isinstance(mat_file, SparseCounts):
+        _, n = mat_file._ingest(ctx)
+    else:
+        _, n = ctx.ingest_tsv(mat_file)
     return ctx.get_ingested(n)
 
 
@@ -57,6 +84,9 @@ def _matrix_args(mat_file, ctx):
     a file through the device-side parser -- the FP64 matrix of a file never exists on the host."""
     if isinstance(mat_file, np.ndarray):
         return dict(mat=mat_file)
+    if isinstance(mat_file, SparseCounts):
+        ptr, n = mat_file._ingest(ctx)
+        return dict(mat=None, device_ptr=ptr, n=n, colmajor=0)
     ptr, n = ctx.ingest_tsv(mat_file)
     return dict(mat=None, device_ptr=ptr, n=n, colmajor=0)
 

@@ -119,7 +119,7 @@ struct tp_ctx {
     int level_cap = 256;
 
     // input side (ingest.cu): text of the matrix file, row-end offsets, fields left to the host, pinned staging
-    DevBuf itext, icounts, irows, islow;
+    DevBuf itext, icounts, irows, islow, icoo;   // icoo: (count, bin1, bin2) triplets of a sparse input
     void *ipin[2] = {nullptr, nullptr};
     cudaEvent_t ipin_ev[2] = {nullptr, nullptr};
     int ingested_n = 0;                  // > 0: raw_own holds a matrix parsed on the device (row-major n x n)

@@ -218,6 +218,74 @@ __global__ void scatter_kernel(double *__restrict__ out, const long long *__rest
     if (i < m) out[idx[i]] = val[i];
 }
 
+// ---- sparse input: pixels (bin1, bin2, count) of the upper triangle -------------------------------------------------
+// status64[0]: lowest index of an entry whose bins are outside [0, n) (~0 = none); status64[1]: entries below the diagonal
+// (ignored: the reference reads the upper triangle only, Matrix::forceSymmetric(uplo = 'U'), R/TADpole.R:20);
+// status64[2]: lowest index (>= 1) of a text row that is not "int sep int sep number"; status64[3]: largest bin seen + 1;
+// status64[4]: row 0 is not such a row (a header line).
+__global__ void __launch_bounds__(256)
+coo_scatter_kernel(double *__restrict__ out, int n, const int *__restrict__ b1, const int *__restrict__ b2,
+                   const double *__restrict__ v, unsigned m, int base, unsigned long long first,
+                   unsigned long long *__restrict__ status64) {
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+    bool below = false;
+    if (e < m) {
+        const long long i = (long long)b1[e] - base, j = (long long)b2[e] - base;
+        if (i < 0 || j < 0 || i >= n || j >= n) atomicMin(status64, first + e);
+        else if (i > j) below = true;
+        else atomicAdd(out + (size_t)i * n + j, v[e]);      // duplicates add up, as Matrix::sparseMatrix(i, j, x) has them
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, below);
+    if (bal && (threadIdx.x & 31) == 0) atomicAdd(status64 + 1, (unsigned long long)__popc(bal));
+}
+
+// one text row per thread: "bin1 <sep> bin2 <sep> count"; the count goes through np_parse_field like a matrix field
+__global__ void __launch_bounds__(256)
+coo_parse_kernel(const unsigned char *__restrict__ text, const long long *__restrict__ row_end, unsigned nrows, unsigned sep,
+                 double *__restrict__ v, int *__restrict__ b1, int *__restrict__ b2, SlowTok *__restrict__ slow,
+                 unsigned *__restrict__ slow_count, unsigned slow_cap, unsigned long long *__restrict__ status64) {
+    const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    long long p = r ? row_end[r - 1] + 1 : 0;
+    const long long e = row_end[r];
+    bool ok = true;
+    int bins[2] = {0, 0};
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+        while (p < e && text[p] == ' ' && sep != ' ') p++;       // blanks around a bin, unless the blank separates
+        long long x = 0;
+        int nd = 0;
+        while (p < e && text[p] - '0' < 10u && nd < 10) { x = x * 10 + (text[p] - '0'); p++; nd++; }
+        while (p < e && text[p] == ' ' && sep != ' ') p++;
+        ok = ok && nd > 0 && nd < 10 && p < e && text[p] == sep;
+        bins[f] = (int)x;
+        p++;
+    }
+    long long q = p;
+    while (ok && q < e && text[q] != sep) q++;
+    ok = ok && q == e && p <= e;
+    if (!ok) {                                   // row 0 may be a header line (cooler dump --header): flagged apart
+        if (r == 0) status64[4] = 1; else atomicMin(status64 + 2, (unsigned long long)r);
+        b1[r] = b2[r] = 0; v[r] = 0.0;
+        return;
+    }
+    double val;
+    if (np_parse_field(text + p, (int)(e - p), d_pow10, d_pow5, &val) != NP_OK) {
+        const unsigned k = atomicAdd(slow_count, 1u);
+        if (k < slow_cap) { slow[k].off = p; slow[k].row = r; slow[k].col = 2; }
+        else atomicMin(status64 + 2, ~0ull - 1);                 // list overflow
+        val = 0.0;
+    }
+    b1[r] = bins[0]; b2[r] = bins[1]; v[r] = val;
+    const int mx = bins[0] > bins[1] ? bins[0] : bins[1];
+    atomicMax(status64 + 3, (unsigned long long)mx + 1);
+}
+
+__global__ void scatter_f64_kernel(double *__restrict__ out, const unsigned *__restrict__ idx, const double *__restrict__ val, int m) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) out[idx[i]] = val[i];
+}
+
 // ---- host side -----------------------------------------------------------------------------------------------------
 struct TextSource {
     const unsigned char *mem = nullptr;
@@ -236,11 +304,11 @@ struct TextSource {
     }
 };
 
-static int ingest_core(tp_ctx *ctx, const TextSource &src, int sep, int *n_out) {
-    TP_ARG(sep > 0 && sep < 128 && sep != '\n' && sep != '\r' && sep != '.' && sep != '-' && sep != '+', "tp_ingest_tsv: bad separator");
-    TP_CUDA(cudaSetDevice(ctx->device));
+// Upload the text (through the two pinned buffers) and count its rows: on return *text_out is the device copy with a
+// newline and IG_PAD readable bytes appended, offs[0..nb] the newline offsets per 16 KB tile (offs[nb] = rows).
+static int text_rows(tp_ctx *ctx, const TextSource &src, const char *who, unsigned char **text_out, size_t *nbytes_out,
+                     int *nb_out, long long **offs_out, long long *nrows_out) {
     cudaStream_t st = ctx->stream;
-    const auto t_begin = std::chrono::steady_clock::now();
     // drop trailing newlines / blanks: the last row ends at the single '\n' appended on the device
     size_t nbytes = src.size;
     {
@@ -254,8 +322,8 @@ static int ingest_core(tp_ctx *ctx, const TextSource &src, int sep, int *n_out) 
             if (j > 0) break;
         }
     }
-    TP_ARG(nbytes > 0, "tp_ingest_tsv: the input holds no data");
-    TP_ARG(nbytes < ((size_t)1 << 40), "tp_ingest_tsv: input too large");
+    if (nbytes == 0) { tp_set_error("%s: the input holds no data", who); return TP_ERR_ARG; }
+    if (nbytes >= ((size_t)1 << 40)) { tp_set_error("%s: input too large", who); return TP_ERR_ARG; }
     const long long limit = (long long)nbytes + 1;
     TP_TRY(ctx->itext.reserve(nbytes + IG_PAD + 16));
     unsigned char *text = ctx->itext.as<unsigned char>();
@@ -289,6 +357,47 @@ static int ingest_core(tp_ctx *ctx, const TextSource &src, int sep, int *n_out) 
     TP_CUDA(cudaMemcpyAsync(&nrows_ll, offs + nb, sizeof(long long), cudaMemcpyDeviceToHost, st));
     TP_CUDA(tp_stream_sync(ctx));
     ctx->launches += 2;
+    *text_out = text; *nbytes_out = nbytes; *nb_out = nb; *offs_out = offs; *nrows_out = nrows_ll;
+    return TP_OK;
+}
+
+// One field of the text that the device left to the host: [off, end of field) converted by strtod.
+static int host_field(const TextSource &src, size_t nbytes, size_t off, int sep, std::vector<char> &buf, double *out, const char *who,
+                      unsigned row, unsigned col) {
+    size_t len = 0;
+    for (;;) {                                   // find the end of the field
+        const size_t want = buf.size() - 1;
+        const size_t k = nbytes - off < want ? nbytes - off : want;
+        TP_TRY(src.fetch(off, k, buf.data()));
+        len = 0;
+        while (len < k && buf[len] != (char)sep && buf[len] != '\n') len++;
+        if (len < k || k == nbytes - off) break;
+        buf.resize(buf.size() * 2);
+    }
+    while (len > 0 && (buf[len - 1] == '\r' || buf[len - 1] == ' ')) len--;
+    buf[len] = 0;
+    char *endp = nullptr;
+    const double v = strtod(buf.data(), &endp);
+    if (endp == buf.data() || *endp != 0) {
+        if (len > 40) buf[40] = 0;
+        tp_set_error("%s: row %u, column %u: '%s' is not a number", who, row + 1, col + 1, buf.data());
+        return TP_ERR_ARG;
+    }
+    *out = v;
+    return TP_OK;
+}
+
+static int ingest_core(tp_ctx *ctx, const TextSource &src, int sep, int *n_out) {
+    TP_ARG(sep > 0 && sep < 128 && sep != '\n' && sep != '\r' && sep != '.' && sep != '-' && sep != '+', "tp_ingest_tsv: bad separator");
+    TP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const auto t_begin = std::chrono::steady_clock::now();
+    unsigned char *text = nullptr;
+    size_t nbytes = 0;
+    int nb = 0;
+    long long *offs = nullptr, nrows_ll = 0;
+    TP_TRY(text_rows(ctx, src, "tp_ingest_tsv", &text, &nbytes, &nb, &offs, &nrows_ll));
+    const long long limit = (long long)nbytes + 1;
     TP_ARG(nrows_ll >= 2, "tp_ingest_tsv: the matrix must have at least 2 rows");
     TP_ARG(nrows_ll <= 200000, "tp_ingest_tsv: more than 200000 rows");
     const int n = (int)nrows_ll;
@@ -329,26 +438,8 @@ static int ingest_core(tp_ctx *ctx, const TextSource &src, int sep, int *n_out) 
         std::vector<double> val(nslow);
         std::vector<char> buf(4096 + 1);
         for (unsigned i = 0; i < nslow; i++) {
-            const size_t off = (size_t)list[i].off;
-            size_t len = 0;
-            for (;;) {                                   // find the end of the field
-                const size_t want = buf.size() - 1;
-                const size_t k = nbytes - off < want ? nbytes - off : want;
-                TP_TRY(src.fetch(off, k, buf.data()));
-                len = 0;
-                while (len < k && buf[len] != (char)sep && buf[len] != '\n') len++;
-                if (len < k || k == nbytes - off) break;
-                buf.resize(buf.size() * 2);
-            }
-            while (len > 0 && (buf[len - 1] == '\r' || buf[len - 1] == ' ')) len--;
-            buf[len] = 0;
-            char *endp = nullptr;
-            const double v = strtod(buf.data(), &endp);
-            if (endp == buf.data() || *endp != 0) {
-                if (len > 40) buf[40] = 0;
-                tp_set_error("tp_ingest_tsv: row %u, column %u: '%s' is not a number", list[i].row + 1, list[i].col + 1, buf.data());
-                return TP_ERR_ARG;
-            }
+            double v = 0.0;
+            TP_TRY(host_field(src, nbytes, (size_t)list[i].off, sep, buf, &v, "tp_ingest_tsv", list[i].row, list[i].col));
             idx[i] = (long long)list[i].row * n + list[i].col;
             val[i] = v;
         }
@@ -406,6 +497,211 @@ extern "C" int tp_ingest_tsv_file(tp_ctx *ctx, const char *path, int sep, int *n
     const int rc = ingest_core(ctx, src, sep, n_out);
     close(src.fd);
     return rc;
+}
+
+// ---- sparse input, host side ------------------------------------------------------------------------------------------
+static int coo_status_init(tp_ctx *ctx, unsigned long long **status_out) {
+    TP_TRY(ctx->islow.reserve(((size_t)1 << 20) * sizeof(SlowTok) + 128));
+    unsigned long long *status64 = ctx->islow.as<unsigned long long>();          // 8 words, then the slow list
+    const unsigned long long init[8] = {~0ull, 0, ~0ull, 0, 0, 0, 0, 0};
+    TP_CUDA(cudaMemcpyAsync(status64, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    *status_out = status64;
+    return TP_OK;
+}
+
+static int coo_dense_alloc(tp_ctx *ctx, int n, double **out) {
+    TP_TRY(ctx->raw_own.reserve((size_t)n * n * sizeof(double)));
+    *out = ctx->raw_own.as<double>();
+    TP_CUDA(cudaMemsetAsync(*out, 0, (size_t)n * n * sizeof(double), ctx->stream));
+    return TP_OK;
+}
+
+static void coo_done(tp_ctx *ctx, double *out, int n, std::chrono::steady_clock::time_point t_begin, double bytes, double nslow) {
+    ctx->raw = out;
+    ctx->n = n;
+    ctx->colmajor = 0;
+    ctx->ingested_n = n;
+    ctx->generation++;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[EV_INGEST0], ctx->ev[EV_INGEST1]);
+    ctx->ingest_stats[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    ctx->ingest_stats[1] = ms;
+    ctx->ingest_stats[2] = bytes;
+    ctx->ingest_stats[3] = nslow;
+}
+
+extern "C" int tp_ingest_coo(tp_ctx *ctx, const int32_t *bin1, const int32_t *bin2, const double *count, size_t nnz, int n,
+                             int index_base, unsigned long long *below_out) {
+    TP_ARG(ctx && (nnz == 0 || (bin1 && bin2 && count)), "tp_ingest_coo: null argument");
+    TP_ARG(n >= 2 && n <= 200000, "tp_ingest_coo: the number of bins must be in 2..200000");
+    TP_ARG(index_base == 0 || index_base == 1, "tp_ingest_coo: index_base must be 0 or 1");
+    TP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const auto t_begin = std::chrono::steady_clock::now();
+    ctx->raw = nullptr; ctx->n = 0; ctx->ingested_n = 0;
+    ctx->have_X = ctx->have_C = ctx->have_scores = ctx->have_sweep = false;
+    unsigned long long *status64 = nullptr;
+    TP_TRY(coo_status_init(ctx, &status64));
+    double *out = nullptr;
+    TP_TRY(coo_dense_alloc(ctx, n, &out));
+    // 16 bytes per pixel cross PCIe, through the two pinned buffers (the caller's arrays are pageable)
+    const size_t CH = (size_t)32 << 20, M = CH / 16;
+    if (!ctx->ipin[0]) {
+        for (int b = 0; b < 2; b++) {
+            TP_CUDA(cudaMallocHost(&ctx->ipin[b], CH));
+            TP_CUDA(cudaEventCreateWithFlags(&ctx->ipin_ev[b], cudaEventDisableTiming));
+        }
+    }
+    TP_TRY(ctx->icoo.reserve(CH));
+    double *dv = ctx->icoo.as<double>();
+    int *d1 = (int *)(dv + M), *d2 = d1 + M;
+    TP_MARK(ctx, EV_INGEST0);
+    int c = 0;
+    for (size_t off = 0; off < nnz; off += M, c++) {
+        const int b = c & 1;
+        const size_t m = nnz - off < M ? nnz - off : M;
+        if (c >= 2) TP_CUDA(cudaEventSynchronize(ctx->ipin_ev[b]));
+        char *pin = (char *)ctx->ipin[b];
+        memcpy(pin, count + off, m * 8);
+        memcpy(pin + M * 8, bin1 + off, m * 4);
+        memcpy(pin + M * 12, bin2 + off, m * 4);
+        if (m == M) TP_CUDA(cudaMemcpyAsync(dv, pin, CH, cudaMemcpyHostToDevice, st));
+        else {
+            TP_CUDA(cudaMemcpyAsync(dv, pin, m * 8, cudaMemcpyHostToDevice, st));
+            TP_CUDA(cudaMemcpyAsync(d1, pin + M * 8, m * 4, cudaMemcpyHostToDevice, st));
+            TP_CUDA(cudaMemcpyAsync(d2, pin + M * 12, m * 4, cudaMemcpyHostToDevice, st));
+        }
+        TP_CUDA(cudaEventRecord(ctx->ipin_ev[b], st));
+        coo_scatter_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(out, n, d1, d2, dv, (unsigned)m, index_base,
+                                                                         (unsigned long long)off, status64);
+        ctx->launches += 1;
+    }
+    TP_CUDA(cudaGetLastError());
+    TP_MARK(ctx, EV_INGEST1);
+    unsigned long long hs[8];
+    TP_CUDA(cudaMemcpyAsync(hs, status64, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    TP_CUDA(tp_stream_sync(ctx));
+    if (hs[0] != ~0ull) {
+        tp_set_error("tp_ingest_coo: entry %llu is (%d, %d): outside the %d bins (index_base %d)", hs[0] + 1,
+                     bin1[hs[0]], bin2[hs[0]], n, index_base);
+        return TP_ERR_ARG;
+    }
+    if (below_out) *below_out = hs[1];
+    coo_done(ctx, out, n, t_begin, (double)nnz * 16.0, 0.0);
+    return TP_OK;
+}
+
+extern "C" int tp_ingest_coo_file(tp_ctx *ctx, const char *path, int sep, int n, int index_base, int *n_out,
+                                  unsigned long long *nnz_out, unsigned long long *below_out) {
+    TP_ARG(ctx && path, "tp_ingest_coo_file: null argument");
+    TP_ARG(sep > 0 && sep < 128 && sep != '\n' && sep != '\r' && sep != '.' && sep != '-' && sep != '+' && !(sep >= '0' && sep <= '9'),
+           "tp_ingest_coo_file: bad separator");
+    TP_ARG(n <= 200000, "tp_ingest_coo_file: more than 200000 bins");
+    TP_ARG(index_base == 0 || index_base == 1, "tp_ingest_coo_file: index_base must be 0 or 1");
+    TextSource src;
+    src.fd = open(path, O_RDONLY);
+    if (src.fd < 0) {
+        tp_set_error("tp_ingest_coo_file: cannot open '%s' (%s)", path, strerror(errno));
+        return TP_ERR_ARG;
+    }
+    struct Closer { int fd; ~Closer() { close(fd); } } closer{src.fd};
+    struct stat sb;
+    if (fstat(src.fd, &sb) != 0 || !S_ISREG(sb.st_mode)) {
+        tp_set_error("tp_ingest_coo_file: '%s' is not a regular file", path);
+        return TP_ERR_ARG;
+    }
+    src.size = (size_t)sb.st_size;
+#ifdef POSIX_FADV_SEQUENTIAL
+    posix_fadvise(src.fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+#endif
+    TP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const auto t_begin = std::chrono::steady_clock::now();
+    ctx->raw = nullptr; ctx->n = 0; ctx->ingested_n = 0;
+    ctx->have_X = ctx->have_C = ctx->have_scores = ctx->have_sweep = false;
+    unsigned char *text = nullptr;
+    size_t nbytes = 0;
+    int nb = 0;
+    long long *offs = nullptr, nrows = 0;
+    TP_TRY(text_rows(ctx, src, "tp_ingest_coo_file", &text, &nbytes, &nb, &offs, &nrows));
+    TP_ARG(nrows >= 1 && nrows < 0x7fffffffLL, "tp_ingest_coo_file: the file must hold between 1 and 2^31 - 2 rows");
+    const long long limit = (long long)nbytes + 1;
+    const unsigned slow_cap = 1u << 20;
+    unsigned long long *status64 = nullptr;
+    TP_TRY(coo_status_init(ctx, &status64));
+    unsigned *slow_count = (unsigned *)(status64 + 5);
+    SlowTok *slow = (SlowTok *)(status64 + 8);
+    TP_TRY(ctx->irows.reserve((size_t)nrows * sizeof(long long)));
+    TP_TRY(ctx->icoo.reserve((size_t)nrows * 16));
+    long long *row_end = ctx->irows.as<long long>();
+    double *dv = ctx->icoo.as<double>();
+    int *d1 = (int *)(dv + nrows), *d2 = d1 + nrows;
+    newline_pos_kernel<<<nb, IG_THREADS, 0, st>>>(text, limit, offs, row_end);
+    coo_parse_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(text, row_end, (unsigned)nrows, (unsigned)sep, dv, d1, d2, slow,
+                                                                    slow_count, slow_cap, status64);
+    TP_CUDA(cudaGetLastError());
+    ctx->launches += 2;
+    unsigned long long hs[8];
+    TP_CUDA(cudaMemcpyAsync(hs, status64, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    TP_CUDA(tp_stream_sync(ctx));
+    if (hs[2] == ~0ull - 1) {
+        tp_set_error("tp_ingest_coo_file: more than %u counts need the host conversion path", slow_cap);
+        return TP_ERR_ARG;
+    }
+    if (hs[2] != ~0ull) {
+        tp_set_error("tp_ingest_coo_file: row %llu is not 'bin1 <sep> bin2 <sep> count' with non-negative integer bins", hs[2] + 1);
+        return TP_ERR_ARG;
+    }
+    const unsigned first = hs[4] ? 1u : 0u;                     // a header line is skipped
+    TP_ARG((unsigned long long)nrows > first, "tp_ingest_coo_file: the file holds a header and no pixels");
+    const unsigned nslow = (unsigned)(hs[5] & 0xffffffffu);
+    if (nslow) {
+        std::vector<SlowTok> list(nslow);
+        TP_CUDA(cudaMemcpy(list.data(), slow, (size_t)nslow * sizeof(SlowTok), cudaMemcpyDeviceToHost));
+        std::vector<unsigned> idx(nslow);
+        std::vector<double> val(nslow);
+        std::vector<char> buf(4096 + 1);
+        for (unsigned i = 0; i < nslow; i++) {
+            TP_TRY(host_field(src, nbytes, (size_t)list[i].off, sep, buf, &val[i], "tp_ingest_coo_file", list[i].row, 2));
+            idx[i] = list[i].row;
+        }
+        unsigned *didx = (unsigned *)slow;
+        double *dval = (double *)(slow + ((size_t)nslow + 1) / 2 + 1);            // past the indices, 8-byte aligned
+        TP_CUDA(cudaMemcpyAsync(didx, idx.data(), (size_t)nslow * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+        TP_CUDA(cudaMemcpyAsync(dval, val.data(), (size_t)nslow * sizeof(double), cudaMemcpyHostToDevice, st));
+        scatter_f64_kernel<<<(nslow + 255) / 256, 256, 0, st>>>(dv, didx, dval, (int)nslow);
+        TP_CUDA(cudaGetLastError());
+        TP_CUDA(tp_stream_sync(ctx));
+        ctx->launches += 1;
+    }
+    if (n <= 0) {
+        const long long nn = (long long)hs[3] - index_base;
+        if (nn < 2 || nn > 200000) {
+            tp_set_error("tp_ingest_coo_file: the largest bin in the file gives %lld bins; 2..200000 are supported", nn);
+            return TP_ERR_ARG;
+        }
+        n = (int)nn;
+    }
+    TP_ARG(n >= 2, "tp_ingest_coo_file: the number of bins must be at least 2");
+    double *out = nullptr;
+    TP_TRY(coo_dense_alloc(ctx, n, &out));
+    const unsigned m = (unsigned)nrows - first;
+    coo_scatter_kernel<<<(m + 255) / 256, 256, 0, st>>>(out, n, d1 + first, d2 + first, dv + first, m, index_base, (unsigned long long)first,
+                                                        status64);
+    TP_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    TP_MARK(ctx, EV_INGEST1);
+    TP_CUDA(cudaMemcpyAsync(hs, status64, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    TP_CUDA(tp_stream_sync(ctx));
+    if (hs[0] != ~0ull) {
+        tp_set_error("tp_ingest_coo_file: row %llu names a bin outside the %d bins (index_base %d)", hs[0] + 1, n, index_base);
+        return TP_ERR_ARG;
+    }
+    if (n_out) *n_out = n;
+    if (nnz_out) *nnz_out = m;
+    if (below_out) *below_out = hs[1];
+    coo_done(ctx, out, n, t_begin, (double)nbytes, (double)nslow);
+    return TP_OK;
 }
 
 extern "C" int tp_ingested(tp_ctx *ctx, const double **dev_out, int *n_out) {

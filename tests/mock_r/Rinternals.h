@@ -49,10 +49,14 @@ int Rf_length(SEXP);
 int Rf_nrows(SEXP);
 int Rf_ncols(SEXP);
 int Rf_isReal(SEXP);
+int Rf_isInteger(SEXP);
+ptrdiff_t Rf_xlength(SEXP);
 #define length Rf_length
 #define nrows Rf_nrows
 #define ncols Rf_ncols
 #define isReal Rf_isReal
+#define isInteger Rf_isInteger
+#define XLENGTH Rf_xlength
 char *R_alloc(size_t n, int size);
 void Rf_error(const char *fmt, ...) __attribute__((noreturn));
 #define error Rf_error

@@ -79,6 +79,8 @@ int Rf_length(SEXP s) { return s->n; }
 int Rf_nrows(SEXP s) { return s->nrow; }
 int Rf_ncols(SEXP s) { return s->ncol; }
 int Rf_isReal(SEXP s) { return s->type == REALSXP; }
+int Rf_isInteger(SEXP s) { return s->type == INTSXP; }
+ptrdiff_t Rf_xlength(SEXP s) { return s->n; }
 char *R_alloc(size_t n, int size) {
     struct ralloc *r = (struct ralloc *)calloc(1, sizeof(*r) + n * (size_t)size + 16);
     r->next = rallocs; rallocs = r;

@@ -137,6 +137,29 @@ def test_ingest_through_the_shim(R, rctx, tmp_path):
         R.call("C_tp_filter", rctx, np.zeros((3, 4)), 0.01)
 
 
+def test_sparse_input_through_the_shim(R, rctx, tmp_path):
+    """sparse_counts() / a Matrix::sparseMatrix in R/tadpole.R: pixels in, the same bad columns and call as the matrix."""
+    from tadpole_b200.synth import synth_hic
+    m = synth_hic(300, seed=6)
+    b1, b2, v = O.dense_to_coo(m)
+    got = R.call("C_tp_ingest_coo", rctx, b1 + 1, b2 + 1, v, 300, 1)       # one-based, as R users would pass them
+    assert got[0] == 300 and got[1] == 0
+    assert np.array_equal(R.call("C_tp_ingested_matrix", rctx), np.triu(m))
+    bad = R.call("C_tp_filter", rctx, None, 0.01)
+    obad, _, _ = O.bad_columns(O.symmetrise_upper(m), 0.01)
+    assert np.array_equal(bad, obad)
+    path = tmp_path / "pixels.tsv"
+    path.write_text("".join(f"{a}\t{b}\t{int(c)}\n" for a, b, c in zip(b1.tolist(), b2.tolist(), v.tolist())))
+    got = R.call("C_tp_ingest_coo_file", rctx, str(path), 0, 0)
+    assert got[0] == 300 and got[1] == b1.size and got[2] == 0
+    assert np.array_equal(R.call("C_tp_filter", rctx, None, 0.01), obad)
+    from mock_r.driver import RError
+    with pytest.raises(RError, match="outside the 300 bins"):
+        R.call("C_tp_ingest_coo", rctx, b1, b2, v, 300, 1)                 # bin 0 with index_base 1
+    with pytest.raises(RError, match="equal length"):
+        R.call("C_tp_ingest_coo", rctx, b1, b2[:-1], v, 300, 0)
+
+
 def test_difft_and_null_through_the_shim(R, rctx, ctx):
     import json
     with open(os.path.join(ROOT, "tests", "golden", "difft_control_case.json")) as fh:

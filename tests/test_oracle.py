@@ -291,3 +291,28 @@ def test_oracle_against_r_golden(tmp_path):
         sc = np.array([[np.nan if v is None else v for v in row] for row in g["scores"]], dtype=float)
         assert sc.shape == ref.scores.shape and np.array_equal(np.isnan(sc), np.isnan(ref.scores))
         np.testing.assert_allclose(sc[~np.isnan(sc)], ref.scores[~np.isnan(sc)], rtol=1e-7)
+
+
+def test_coo_restatement_against_scipy():
+    """oracle.coo_to_dense (the checker of tp_ingest_coo) against scipy.sparse: duplicates add up, the lower triangle is
+    dropped, one-based bins; read_coo_text round trip with and without a header line."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(2)
+    n = 40
+    b1 = rng.integers(0, n, 3000); b2 = rng.integers(0, n, 3000)
+    v = rng.poisson(5.0, 3000).astype(float)
+    d, below = O.coo_to_dense(b1, b2, v, n)
+    full = sp.coo_matrix((v, (b1, b2)), shape=(n, n)).toarray()          # scipy sums duplicates too
+    assert np.array_equal(d, np.triu(full)) and below == int((b1 > b2).sum())
+    d1, _ = O.coo_to_dense(b1 + 1, b2 + 1, v, n, index_base=1)
+    assert np.array_equal(d1, d)
+    with pytest.raises(ValueError, match="entry 3"):
+        O.coo_to_dense([0, 1, n], [0, 1, 2], [1.0, 1.0, 1.0], n)
+    text = "".join(f"{a}\t{b}\t{int(c)}\n" for a, b, c in zip(b1, b2, v))
+    for t in (text, "bin1_id\tbin2_id\tcount\n" + text):
+        r1, r2, rv = O.read_coo_text(t)
+        assert np.array_equal(r1, b1) and np.array_equal(r2, b2) and np.array_equal(rv, v)
+    with pytest.raises(ValueError, match="row 2"):
+        O.read_coo_text("0\t1\t2\n1\t2\n")
+    m = np.triu(rng.poisson(0.3, (n, n)).astype(float))
+    assert np.array_equal(O.coo_to_dense(*O.dense_to_coo(m), n)[0], m)
