@@ -138,12 +138,14 @@ extern "C" int tp_ctx_destroy(tp_ctx *ctx) {
                       &ctx->Q, &ctx->Jw, &ctx->Jv, &ctx->Jt, &ctx->small1, &ctx->small2, &ctx->part, &ctx->resid,
                       &ctx->P, &ctx->Qp, &ctx->d0, &ctx->seqdist, &ctx->order, &ctx->ncl, &ctx->chs, &ctx->bsbuf,
                       &ctx->links, &ctx->harm, &ctx->status, &ctx->islices, &ctx->ioA, &ctx->ioB, &ctx->ioscale, &ctx->lx, &ctx->ly, &ctx->dout, &ctx->dhash, &ctx->lhash,
-                      &ctx->itext, &ctx->icounts, &ctx->irows, &ctx->islow};
+                      &ctx->itext, &ctx->icounts, &ctx->irows, &ctx->islow, &ctx->icoo, &ctx->raw_next};
     for (DevBuf *b : bufs) b->release();
     tp_comm_destroy_all(ctx);
     for (int i = 0; i < EV_COUNT; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
+    if (ctx->staged_ev) cudaEventDestroy(ctx->staged_ev);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     for (int b = 0; b < 2; b++) {
         if (ctx->ipin[b]) cudaFreeHost(ctx->ipin[b]);
         if (ctx->ipin_ev[b]) cudaEventDestroy(ctx->ipin_ev[b]);
@@ -672,6 +674,7 @@ static int call_from_compacted(tp_ctx *ctx, int max_pcs, int min_clusters, int *
     TP_TRY(tp_correlation(ctx));
     TP_TRY(tp_pca(ctx, max_pcs, &k));
     if (k_out) *k_out = k;
+    if (ctx->after_pca) ctx->after_pca();                // batch worker: the next matrix uploads under the sweep
     return sweep_and_select(ctx, min_clusters, n_pcs_out, n_clusters_out, scores_out, ld_scores, maxlev_out, seqdist_out);
 }
 
@@ -718,7 +721,9 @@ extern "C" int tp_call(tp_ctx *ctx, const double *mat, int n, int colmajor, int 
         });
     TP_CUDA(cudaSetDevice(ctx->device));
     TP_MARK(ctx, EV_TOTAL0);
-    TP_TRY(tp_filter(ctx, mat, n, colmajor, on_device, bad_frac, bad_out, nullptr, nullptr));
+    const int frc = tp_filter(ctx, mat, n, colmajor, on_device, bad_frac, bad_out, nullptr, nullptr);
+    if (ctx->after_filter) ctx->after_filter();          // batch worker: this call's upload is over
+    TP_TRY(frc);
     std::vector<int> keep;
     keep.reserve(n);
     for (int i = 0; i < n; i++) if (!bad_out[i]) keep.push_back(i);
@@ -820,13 +825,17 @@ extern "C" int tp_assemble_levels(const double *seqdist, int nf, const int *leve
     TP_ARG(nf >= 2, "tp_assemble_levels: bad sizes");
     TP_ARG(nbad <= 0 || bad, "tp_assemble_levels: null bad list");
     const int n1 = nf - 1;
-    // rank[b] = position of boundary b when sorted by (seqdist descending, index descending): level k cuts rank < k - 1
-    std::vector<int> idx(n1), rank(n1);
+    int kmax = 1;
+    for (int l = 0; l < nlev; l++) {
+        TP_ARG(levels[l] >= 1 && levels[l] <= nf, "tp_assemble_levels: level out of range");
+        kmax = std::max(kmax, levels[l]);
+    }
+    // idx[0 .. kmax-2] = the boundaries in (seqdist descending, index descending) order: level k cuts the first k - 1 of them
+    std::vector<int> idx(n1);
     std::iota(idx.begin(), idx.end(), 0);
-    std::sort(idx.begin(), idx.end(), [&](int a, int b) {
+    std::partial_sort(idx.begin(), idx.begin() + (kmax - 1), idx.end(), [&](int a, int b) {
         return seqdist[a] > seqdist[b] || (seqdist[a] == seqdist[b] && a > b);
     });
-    for (int i = 0; i < n1; i++) rank[idx[i]] = i;
     // positions of the good bins and of the bad bins in the merged order (good first on equal names), once
     const int nb = nbad > 0 ? nbad : 0;
     const int total = nbad >= 0 ? nf + nb : nf;
@@ -847,19 +856,26 @@ extern "C" int tp_assemble_levels(const double *seqdist, int nf, const int *leve
     // instead of materialising the label vector, its run-length encoding and the fixed vector per level.
     std::vector<int> pos(nf);
     for (int p = 0; p < total; p++) if (src[p] >= 0) pos[src[p]] = p;
-    int rows = 0;
+    // A level of kc clusters has exactly kc rows, so every level's slot is known; the levels are visited in ascending order
+    // of kc with the cut boundaries kept sorted by position (one insertion per added cut), which makes a level O(kc)
+    // instead of a pass over all bins.
     offsets_out[0] = 0;
-    for (int l = 0; l < nlev; l++) {
-        const int kc = levels[l];
-        TP_ARG(kc >= 1 && kc <= nf, "tp_assemble_levels: level out of range");
-        int g0 = 0;
-        for (int i = 0; i < nf; i++) {
-            if (i == n1 || rank[i] < kc - 1) {            // a cut after good bin i (or the last bin)
-                start_out[rows] = pos[g0] + 1; end_out[rows] = pos[i] + 1; rows++;
-                g0 = i + 1;
-            }
+    for (int l = 0; l < nlev; l++) offsets_out[l + 1] = offsets_out[l] + levels[l];
+    std::vector<int> ord(nlev);
+    std::iota(ord.begin(), ord.end(), 0);
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return levels[a] < levels[b]; });
+    std::vector<int> cuts;
+    cuts.reserve((size_t)kmax);
+    int have = 0;                                   // boundaries of idx[] already in cuts
+    for (int o = 0; o < nlev; o++) {
+        const int l = ord[o], kc = levels[l];
+        for (; have < kc - 1; have++) cuts.insert(std::upper_bound(cuts.begin(), cuts.end(), idx[have]), idx[have]);
+        int rows = offsets_out[l], g0 = 0;
+        for (int c = 0; c < kc - 1; c++) {            // a cut after good bin cuts[c]
+            start_out[rows] = pos[g0] + 1; end_out[rows] = pos[cuts[c]] + 1; rows++;
+            g0 = cuts[c] + 1;
         }
-        offsets_out[l + 1] = rows;
+        start_out[rows] = pos[g0] + 1; end_out[rows] = pos[n1] + 1;
     }
     return TP_OK;
 }

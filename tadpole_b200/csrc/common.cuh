@@ -127,6 +127,14 @@ struct tp_ctx {
 
     // stage 1 state
     DevBuf raw_own;              // uploaded copy of the caller's matrix (when it came from the host)
+    // batch pool (group.cu): the NEXT call's host matrix is uploaded on a second stream under this call's compute
+    // (tp_stage_input); tp_filter adopts it when it is handed the same host pointer
+    DevBuf raw_next;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t staged_ev = nullptr;
+    const double *staged_mat = nullptr;
+    int staged_n = 0, staged_colmajor = 0;
+    std::function<void()> after_filter, after_pca;      // hooks of the batch worker inside tp_call
     const double *raw = nullptr; // device pointer to the N x N input (raw_own.p or caller's)
     int n = 0;
     int colmajor = 0;
@@ -254,6 +262,7 @@ int tp_group_size(const tp_ctx *ctx);
 tp_ctx *tp_group_member(const tp_ctx *ctx, int rank);
 void tp_group_destroy(tp_ctx *leader);
 void tp_pool_destroy(tp_ctx *ctx);
+int tp_stage_input(tp_ctx *ctx, const double *mat, int n, int colmajor);   // filter.cu: upload under the running call
 int tp_flags_reset(tp_ctx *ctx);                 // zero the status words (stream ordered)
 int tp_flags_read(tp_ctx *ctx, int out[4]);      // copy them to the host (synchronises the stream)
 int tp_flags_enqueue(tp_ctx *ctx);               // async copy into ctx->pin_flags; valid after the next stream sync

@@ -169,6 +169,50 @@ static void launch_rowmean(tp_ctx *ctx, const double *A, int n, int upper, doubl
     rowmean_kernel<R><<<(n + R - 1) / R, FT_THREADS, 0, ctx->stream>>>(A, n, upper, rm, d0);
 }
 
+// Upper triangle of a host matrix -> dst, ~32 band copies (row bands from the diagonal to the right edge; column bands from
+// the top to the diagonal for R's layout).  R > 1: only the bands dealt to `rank` (boustrophedon: equal bytes per rank).
+static int upload_bands(int n) {
+    static const int forced = getenv("TADPOLE_UPLOAD_BANDS") ? atoi(getenv("TADPOLE_UPLOAD_BANDS")) : 0;     // experiments
+    const int nb = forced > 0 ? forced : 32;
+    return n / nb > 64 ? n / nb : 64;
+}
+
+static int upload_upper(double *dst, const double *mat, int n, int colmajor, cudaStream_t st, int R, int rank) {
+    const int band = upload_bands(n);
+    const size_t pitch = (size_t)n * sizeof(double);
+    auto owner_of = [&](int bi) { const int blk = bi / R, pos = bi % R; return (blk & 1) ? R - 1 - pos : pos; };
+    int bi = 0;
+    for (int r = 0; r < n; r += band, bi++) {
+        if (R > 1 && owner_of(bi) != rank) continue;
+        const int h = n - r < band ? n - r : band;
+        if (!colmajor)   // rows [r, r + h), columns [r, n)
+            TP_CUDA(cudaMemcpy2DAsync(dst + (size_t)r * n + r, pitch, mat + (size_t)r * n + r, pitch,
+                                      (size_t)(n - r) * sizeof(double), h, cudaMemcpyHostToDevice, st));
+        else             // columns [r, r + h), rows [0, r + h)
+            TP_CUDA(cudaMemcpy2DAsync(dst + (size_t)r * n, pitch, mat + (size_t)r * n, pitch,
+                                      (size_t)(r + h) * sizeof(double), h, cudaMemcpyHostToDevice, st));
+    }
+    return TP_OK;
+}
+
+// Batch pool: start the upload of the matrix of the NEXT call on the context's copy stream, into the second input buffer,
+// while the current call computes; tp_filter adopts it when it is handed the same (pointer, n, layout).
+int tp_stage_input(tp_ctx *ctx, const double *mat, int n, int colmajor) {
+    TP_ARG(ctx && mat && n >= 2, "tp_stage_input: bad arguments");
+    if (ctx->group || tp_nranks(ctx) > 1) return TP_OK;         // single-device contexts only
+    TP_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) {
+        TP_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        TP_CUDA(cudaEventCreateWithFlags(&ctx->staged_ev, cudaEventDisableTiming));
+    }
+    ctx->staged_mat = nullptr;
+    TP_TRY(ctx->raw_next.reserve((size_t)n * n * sizeof(double)));
+    TP_TRY(upload_upper(ctx->raw_next.as<double>(), mat, n, colmajor, ctx->copy_stream, 1, 0));
+    TP_CUDA(cudaEventRecord(ctx->staged_ev, ctx->copy_stream));
+    ctx->staged_mat = mat; ctx->staged_n = n; ctx->staged_colmajor = colmajor ? 1 : 0;
+    return TP_OK;
+}
+
 int tp_filter(tp_ctx *ctx, const double *mat, int n, int colmajor, int on_device, double bad_frac,
               uint8_t *bad_out, double *rowmeans_out, double *thr_out) {
     TP_ARG(ctx && mat && bad_out, "tp_filter: null argument");
@@ -195,6 +239,14 @@ int tp_filter(tp_ctx *ctx, const double *mat, int n, int colmajor, int on_device
         ctx->raw = dst;
     } else if (on_device) {
         ctx->raw = mat;
+    } else if (ctx->staged_mat == mat && ctx->staged_n == n && ctx->staged_colmajor == (colmajor ? 1 : 0) && R == 1) {
+        // the batch worker uploaded this matrix under the previous call's compute: swap the input buffers
+        ctx->ingested_n = 0;
+        ctx->staged_mat = nullptr;
+        std::swap(ctx->raw_own.p, ctx->raw_next.p);
+        std::swap(ctx->raw_own.cap, ctx->raw_next.cap);
+        TP_CUDA(cudaStreamWaitEvent(st, ctx->staged_ev, 0));
+        ctx->raw = ctx->raw_own.as<double>();
     } else {
         // Only the upper triangle is ever read (forceSymmetric(uplo = 'U')), so only it crosses PCIe: ~32 band copies
         // (row bands from the diagonal to the right edge; column bands from the top to the diagonal for R's layout),
@@ -205,21 +257,11 @@ int tp_filter(tp_ctx *ctx, const double *mat, int n, int colmajor, int on_device
         ctx->ingested_n = 0;                       // raw_own is about to be overwritten
         TP_TRY(ctx->raw_own.reserve(bytes));
         double *dst = ctx->raw_own.as<double>();
-        const int band = n / 32 > 64 ? n / 32 : 64;
-        const size_t pitch = (size_t)n * sizeof(double);
+        const int band = upload_bands(n);
         const bool share = R > 1 && n >= ctx->dist_min_n;
         auto owner_of = [&](int bi) { const int blk = bi / R, pos = bi % R; return (blk & 1) ? R - 1 - pos : pos; };
         int bi = 0;
-        for (int r = 0; r < n; r += band, bi++) {
-            if (share && owner_of(bi) != rank) continue;
-            const int h = n - r < band ? n - r : band;
-            if (!colmajor)   // rows [r, r + h), columns [r, n)
-                TP_CUDA(cudaMemcpy2DAsync(dst + (size_t)r * n + r, pitch, mat + (size_t)r * n + r, pitch,
-                                          (size_t)(n - r) * sizeof(double), h, cudaMemcpyHostToDevice, st));
-            else             // columns [r, r + h), rows [0, r + h)
-                TP_CUDA(cudaMemcpy2DAsync(dst + (size_t)r * n, pitch, mat + (size_t)r * n, pitch,
-                                          (size_t)(r + h) * sizeof(double), h, cudaMemcpyHostToDevice, st));
-        }
+        TP_TRY(upload_upper(dst, mat, n, colmajor, st, share ? R : 1, rank));
         if (share) {
             // the memory between the first and the last uploaded element of a band is one contiguous range
             TP_TRY(tp_comm_group_begin(ctx));

@@ -319,10 +319,10 @@ extern "C" int tp_call_batch(tp_ctx *ctx, int ncalls, const double *const *mats,
     TpPool *pool = ctx->pool;
     int per_dev = std::max(1, std::min(inflight, (ncalls + ndev - 1) / ndev));
     {   // every call in flight holds its own working set in HBM (raw + filtered + correlation + M + digit planes +
-        // blocks: ~48 bytes per matrix element, 30 GB at 25k bins): do not keep more in flight than the device has room for
+        // second input buffer + blocks: ~56 bytes per matrix element, 35 GB at 25k bins): do not keep more in flight than the device has room for
         size_t nmax = 0;
         for (int i = 0; i < ncalls; i++) nmax = std::max(nmax, (size_t)(n[i] > 0 ? n[i] : 0));
-        const double need = 48.0 * (double)nmax * (double)nmax + 64e6;
+        const double need = 56.0 * (double)nmax * (double)nmax + 64e6;
         for (int d = 0; d < ndev; d++) {
             size_t fr = 0, tot = 0;
             cudaSetDevice(pool->devices[d]);
@@ -330,7 +330,7 @@ extern "C" int tp_call_batch(tp_ctx *ctx, int ncalls, const double *const *mats,
             // memory the pool's contexts on this device already hold counts as available to them
             double have = 0.8 * (double)fr;
             for (tp_ctx *c : pool->ctxs[d])
-                for (const DevBuf *bf : {&c->raw_own, &c->X, &c->C, &c->M, &c->ioA, &c->ioB, &c->islices, &c->Y0, &c->Y1, &c->Y2, &c->W})
+                for (const DevBuf *bf : {&c->raw_own, &c->raw_next, &c->X, &c->C, &c->M, &c->ioA, &c->ioB, &c->islices, &c->Y0, &c->Y1, &c->Y2, &c->W})
                     have += (double)bf->cap;
             per_dev = std::max(1, std::min(per_dev, (int)(have / need)));
         }
@@ -370,23 +370,48 @@ extern "C" int tp_call_batch(tp_ctx *ctx, int ncalls, const double *const *mats,
         cudaEventRecord(ev_start[d], pool->ctxs[d][0]->stream);
     }
     std::atomic<int> next(0);
-    auto worker = [&](tp_ctx *c, cudaEvent_t done) {
+    // Host matrices: (1) the first uploads of the workers of one device go one after the other (ticket order), so the
+    // first call starts computing after ONE upload instead of after all of them sharing the PCIe link; (2) from then on a
+    // worker claims its next matrix while the current call is in the n_pcs sweep and uploads it on its copy stream into the
+    // second input buffer (tp_stage_input): the upload leaves the critical path of the call.
+    const bool prefetch = !on_device && !ctx->group && getenv("TADPOLE_BATCH_NOPREFETCH") == nullptr;
+    std::vector<std::mutex> first_upload((size_t)ndev);
+    auto worker = [&](tp_ctx *c, cudaEvent_t done, int d) {
         cudaSetDevice(c->device);
+        int claimed = -1;
+        bool holding = false;
+        c->after_filter = [&]() { if (holding) { first_upload[(size_t)d].unlock(); holding = false; } };
+        c->after_pca = [&]() {
+            if (!prefetch || claimed >= 0) return;
+            const int j = next.fetch_add(1);
+            if (j >= ncalls) return;
+            claimed = j;
+            if (mats[j] && n[j] >= 2) (void)tp_stage_input(c, mats[j], n[j], colmajor);    // a failure leaves the normal upload
+        };
+        bool first = true;
         for (;;) {
-            const int i = next.fetch_add(1);
+            int i = claimed;
+            claimed = -1;
+            if (i < 0) i = next.fetch_add(1);
             if (i >= ncalls) break;
+            if (first && !on_device) { first_upload[(size_t)d].lock(); holding = true; }
+            first = false;
             TpBatchItem &it = b->items[(size_t)i];
             it.rc = mats[i] ? batch_one(c, mats[i], n[i], colmajor, on_device, max_pcs, min_clusters, bad_frac, want_tables, it)
                             : (tp_set_error("tp_call_batch: matrix %d is null", i), (int)TP_ERR_ARG);
+            if (holding) { first_upload[(size_t)d].unlock(); holding = false; }
             if (it.rc != TP_OK) it.err = tp_last_error();
         }
+        c->after_filter = nullptr;
+        c->after_pca = nullptr;
+        c->staged_mat = nullptr;
         cudaEventRecord(done, c->stream);
     };
     std::vector<std::thread> threads;
     for (int s2 = 0; s2 < per_dev; s2++)
         for (int d = 0; d < ndev; d++)
-            if (!(s2 == 0 && d == 0)) threads.emplace_back(worker, pool->ctxs[d][s2], ev_end[(size_t)d * per_dev + s2]);
-    worker(pool->ctxs[0][0], ev_end[0]);
+            if (!(s2 == 0 && d == 0)) threads.emplace_back(worker, pool->ctxs[d][s2], ev_end[(size_t)d * per_dev + s2], d);
+    worker(pool->ctxs[0][0], ev_end[0], 0);
     for (std::thread &t : threads) t.join();
     for (int d = 0; d < ndev; d++) {
         cudaSetDevice(pool->devices[d]);
