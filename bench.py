@@ -56,8 +56,10 @@ def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--batch", type=int, default=16, help="calls per step (one tp_call_batch of that many different matrices)")
-    ap.add_argument("--streams", type=int, default=8, help="calls kept in flight per GPU by the library's own threads")
+    ap.add_argument("--batch", type=int, default=0, help="calls per step (one tp_call_batch of that many different matrices); "
+                                                         "0 = twice the calls in flight")
+    ap.add_argument("--streams", type=int, default=16, help="calls kept in flight per GPU by the library's own threads "
+                                                            "(fewer when the box has under a quarter of a CPU per thread)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bins", type=int, default=N_BINS)
@@ -317,7 +319,9 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    S, B, n = max(1, args.streams), max(1, args.batch), args.bins
+    # every call in flight has a library-owned host thread (asleep on an event most of the time): keep at most 4 per CPU
+    S = max(1, min(args.streams, max(8, 4 * (os.cpu_count() or 1) // max(world, 1))))
+    B, n = (args.batch if args.batch > 0 else 2 * S), args.bins
     ctx = Context(local_rank)
     # the library's batch threads wait for their streams most of the time; a spinning wait (the CUDA default) needs a core
     # each, so with several ranks on one host they sleep on blocking-sync events instead (tp_call_batch decides this for

@@ -574,9 +574,12 @@ int tp_sweep_device(tp_ctx *ctx, int min_clusters, int cand_begin, int cand_stri
     if (force && force[0] == 'a' && base + link_bytes <= limit) links_smem = true;
     const size_t cand_smem = round_up((int)(links_smem ? base + link_bytes : base + bitmap_bytes), 16);
     // the reciprocal table goes to shared memory while at least two candidates still fit beside it
-    const bool inv_smem = 2 * cand_smem + inv_bytes <= limit;
+    bool inv_smem = 2 * cand_smem + inv_bytes <= limit;
+    const char *e_inv = getenv("TADPOLE_SWEEP_INV"), *e_wpc = getenv("TADPOLE_SWEEP_WPC");       // experiments
+    if (e_inv && e_inv[0] == 'g') inv_smem = false;
     int wpc = (int)((limit - (inv_smem ? inv_bytes : 0)) / cand_smem);
-    wpc = wpc < 1 ? 1 : (wpc > 4 ? 4 : wpc);      // one warp per SM sub-partition: 8 slowed each merge chain by 19 %
+    const int wpc_cap = e_wpc && atoi(e_wpc) > 0 ? atoi(e_wpc) : 4;
+    wpc = wpc < 1 ? 1 : (wpc > wpc_cap ? wpc_cap : wpc);      // one warp per SM sub-partition: 8 slowed each merge chain by 19 %
     // (not more warps than needed to give every SM-sized group of candidates a CTA: a lone call still wants them spread)
     while (wpc > 1 && (ncand + wpc - 1) / wpc < 16) wpc--;
     const size_t smem = (size_t)wpc * cand_smem + (inv_smem ? inv_bytes : 0);
