@@ -145,6 +145,11 @@ extern "C" int tp_ctx_destroy(tp_ctx *ctx) {
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
     if (ctx->staged_ev) cudaEventDestroy(ctx->staged_ev);
+    for (tp_ctx::UploadLane &ln : ctx->lanes) {
+        if (ln.st) { cudaStreamSynchronize(ln.st); cudaStreamDestroy(ln.st); }
+        if (ln.done) cudaEventDestroy(ln.done);
+        for (int b = 0; b < 2; b++) { if (ln.pin[b]) cudaFreeHost(ln.pin[b]); if (ln.ev[b]) cudaEventDestroy(ln.ev[b]); }
+    }
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     for (int b = 0; b < 2; b++) {
         if (ctx->ipin[b]) cudaFreeHost(ctx->ipin[b]);
@@ -195,6 +200,7 @@ extern "C" int tp_ctx_set(tp_ctx *ctx, const char *key, double value) {
     else if (k == "mgram_min_n") ctx->mgram_min_n = (int)value;
     else if (k == "shard_sym") ctx->shard_sym = (int)value != 0;
     else if (k == "sync_blocking") ctx->sync_blocking = (int)value != 0;
+    else if (k == "upload_lanes") ctx->upload_lanes = (int)value < 0 ? 0 : ((int)value > 16 ? 16 : (int)value);
     else if (k == "iop_switch") ctx->iop_switch = value;
     else if (k == "io_bn32") ctx->io_bn32 = (int)value;
     else if (k == "iop_final") ctx->iop_final = ((int)value == 8) ? 8 : 0;

@@ -122,6 +122,10 @@ struct tp_ctx {
     DevBuf itext, icounts, irows, islow, icoo;   // icoo: (count, bin1, bin2) triplets of a sparse input
     void *ipin[2] = {nullptr, nullptr};
     cudaEvent_t ipin_ev[2] = {nullptr, nullptr};
+    // pageable host matrices (filter.cu, upload_upper): lanes of pinned staging filled by helper threads
+    struct UploadLane { cudaStream_t st = nullptr; void *pin[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr}; cudaEvent_t done = nullptr; };
+    std::vector<UploadLane> lanes;
+    int upload_lanes = 4;                // tunable: 0 = always the driver's own staging
     int ingested_n = 0;                  // > 0: raw_own holds a matrix parsed on the device (row-major n x n)
     double ingest_stats[4] = {};         // wall ms (read + upload + parse), parse kernels ms, text bytes, host-converted fields
 
@@ -262,6 +266,7 @@ int tp_group_size(const tp_ctx *ctx);
 tp_ctx *tp_group_member(const tp_ctx *ctx, int rank);
 void tp_group_destroy(tp_ctx *leader);
 void tp_pool_destroy(tp_ctx *ctx);
+int tp_upload_range(tp_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st);   // filter.cu: pageable -> lanes
 int tp_stage_input(tp_ctx *ctx, const double *mat, int n, int colmajor);   // filter.cu: upload under the running call
 int tp_flags_reset(tp_ctx *ctx);                 // zero the status words (stream ordered)
 int tp_flags_read(tp_ctx *ctx, int out[4]);      // copy them to the host (synchronises the stream)

@@ -544,35 +544,19 @@ extern "C" int tp_ingest_coo(tp_ctx *ctx, const int32_t *bin1, const int32_t *bi
     TP_TRY(coo_status_init(ctx, &status64));
     double *out = nullptr;
     TP_TRY(coo_dense_alloc(ctx, n, &out));
-    // 16 bytes per pixel cross PCIe, through the two pinned buffers (the caller's arrays are pageable)
-    const size_t CH = (size_t)32 << 20, M = CH / 16;
-    if (!ctx->ipin[0]) {
-        for (int b = 0; b < 2; b++) {
-            TP_CUDA(cudaMallocHost(&ctx->ipin[b], CH));
-            TP_CUDA(cudaEventCreateWithFlags(&ctx->ipin_ev[b], cudaEventDisableTiming));
-        }
-    }
-    TP_TRY(ctx->icoo.reserve(CH));
+    // 16 bytes per pixel cross PCIe: the three arrays go up whole (pageable arrays through the staging lanes of filter.cu),
+    // then one scatter pass per 2^30 pixels
+    TP_TRY(ctx->icoo.reserve(nnz * 16 + 16));
     double *dv = ctx->icoo.as<double>();
-    int *d1 = (int *)(dv + M), *d2 = d1 + M;
+    int *d1 = (int *)(dv + nnz), *d2 = d1 + nnz;
     TP_MARK(ctx, EV_INGEST0);
-    int c = 0;
-    for (size_t off = 0; off < nnz; off += M, c++) {
-        const int b = c & 1;
+    TP_TRY(tp_upload_range(ctx, dv, count, nnz * 8, st));
+    TP_TRY(tp_upload_range(ctx, d1, bin1, nnz * 4, st));
+    TP_TRY(tp_upload_range(ctx, d2, bin2, nnz * 4, st));
+    const size_t M = (size_t)1 << 30;
+    for (size_t off = 0; off < nnz; off += M) {
         const size_t m = nnz - off < M ? nnz - off : M;
-        if (c >= 2) TP_CUDA(cudaEventSynchronize(ctx->ipin_ev[b]));
-        char *pin = (char *)ctx->ipin[b];
-        memcpy(pin, count + off, m * 8);
-        memcpy(pin + M * 8, bin1 + off, m * 4);
-        memcpy(pin + M * 12, bin2 + off, m * 4);
-        if (m == M) TP_CUDA(cudaMemcpyAsync(dv, pin, CH, cudaMemcpyHostToDevice, st));
-        else {
-            TP_CUDA(cudaMemcpyAsync(dv, pin, m * 8, cudaMemcpyHostToDevice, st));
-            TP_CUDA(cudaMemcpyAsync(d1, pin + M * 8, m * 4, cudaMemcpyHostToDevice, st));
-            TP_CUDA(cudaMemcpyAsync(d2, pin + M * 12, m * 4, cudaMemcpyHostToDevice, st));
-        }
-        TP_CUDA(cudaEventRecord(ctx->ipin_ev[b], st));
-        coo_scatter_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(out, n, d1, d2, dv, (unsigned)m, index_base,
+        coo_scatter_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(out, n, d1 + off, d2 + off, dv + off, (unsigned)m, index_base,
                                                                          (unsigned long long)off, status64);
         ctx->launches += 1;
     }

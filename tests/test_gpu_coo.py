@@ -138,3 +138,23 @@ def test_tadpole_from_pixels_equals_tadpole_from_matrix(ctx, tmp_path):
     import scipy.sparse as sp
     got = TADpole(SparseCounts.from_scipy(sp.coo_matrix(np.triu(m))), max_pcs=40, ctx=ctx)
     assert np.array_equal(got.dendro.seqdist, ref.dendro.seqdist)
+
+
+def test_pixel_arrays_large_enough_for_the_staging_lanes(ctx):
+    """Arrays of 64 MB and more go up through the pinned staging lanes (filter.cu, tp_upload_range), three uploads back
+    to back re-using the lanes' buffers."""
+    n = 6000
+    rng = np.random.default_rng(13)
+    nnz = 9_000_000                                                    # 72 MB of counts, 36 MB per bin array
+    b1 = rng.integers(0, n, nnz).astype(np.int32)
+    b2 = rng.integers(0, n, nnz).astype(np.int32)
+    lo, hi = np.minimum(b1, b2), np.maximum(b1, b2)
+    v = rng.integers(1, 9, nnz).astype(float)
+    want = np.zeros((n, n))
+    np.add.at(want, (lo, hi), v)
+    for _ in range(2):
+        ctx.ingest_coo(lo, hi, v, n)
+        assert same(ctx.get_ingested(n), want)
+    v2 = np.concatenate([v, v])                                        # 144 MB / 72 MB / 72 MB: every array through the lanes
+    ctx.ingest_coo(np.concatenate([lo, lo]), np.concatenate([hi, hi]), v2, n)
+    assert same(ctx.get_ingested(n), 2 * want)
