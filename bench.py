@@ -327,9 +327,7 @@ def run_b200(args, rank, world, local_rank):
     # each, so with several ranks on one host they sleep on blocking-sync events instead (tp_call_batch decides this for
     # the threads of ONE process; it cannot see the other ranks)
     ncpu = os.cpu_count() or 1
-    sync_blocking = world * S > ncpu // 2
-    if sync_blocking:
-        ctx.set("sync_blocking", 1)
+    sync_blocking = world * S > ncpu // 2          # applied to the batch passes only; a single call at a time spins
 
     # synthetic inputs: B different matrices per rank; pinned host copies for e2e, device copies for value
     host = []
@@ -370,6 +368,8 @@ def run_b200(args, rank, world, local_rank):
     prof = ctx.profile(0)
     stage = ctx.timings()
     # ---- value: K steps of B device-resident calls, S in flight ------------------------------------
+    if sync_blocking:
+        ctx.set("sync_blocking", 1)
     barrier()
     ctx.call_batch(None, device_ptrs=ptrs * args.steps, n=n, inflight=S, tables=False, max_pcs=MAX_PCS)
     ms_thr, launches = ctx.last_batch_device_ms, ctx.last_batch_launches
@@ -388,6 +388,7 @@ def run_b200(args, rank, world, local_rank):
     d2h = int(n + tp.scores.size * 8 + (res["nf"] - 1) * 8) * B
     # one call at a time through the public API (what a plain TADpole() in a loop costs)
     from tadpole_b200 import TADpole
+    ctx.set("sync_blocking", 0)
     t0 = time.perf_counter()
     for i in range(lat_steps):
         TADpole(host_np[i % B], max_pcs=MAX_PCS, ctx=ctx)
