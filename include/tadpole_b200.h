@@ -77,7 +77,10 @@ long long tp_ctx_launches(tp_ctx *ctx);
  * "sync_blocking" (1: the host thread sleeps on a blocking-sync event while it waits for the GPU instead of spinning
  * in cudaStreamSynchronize; for hosts that run more calls in flight than they have cores),
  * "shard_sym" (0: ranks of a sharded call compute full-width row blocks of the symmetric products),
- * "mgram_min_n" (smallest nf whose M = Xc Xc^T is formed by the sliced int8 Gram; 0 = FP64 DMMA) */
+ * "mgram_min_n" (smallest nf whose M = Xc Xc^T is formed by the sliced int8 Gram; 0 = FP64 DMMA),
+ * "io_bn32" (operator applications on 32-column tiles: -1 auto, 0 never, 1 always),
+ * "upload_lanes" (helper threads that stage a pageable host matrix or pixel array of 64 MB and more through pinned
+ * buffers, default 4; 0 = leave pageable memory to the driver's own staging) */
 int tp_ctx_set(tp_ctx *ctx, const char *key, double value);
 /* The environment variable TADPOLE_TUNE="key=value,key=value" applies tp_ctx_set to every context at creation. */
 /* per-stage device milliseconds of the last tp_call / stage call, measured with CUDA events on
