@@ -168,6 +168,20 @@ def test_assemble_levels_matches_per_level_calls():
         for k in levels:
             ref, _ = _lib.assemble(seq, int(k), names, b)
             assert np.array_equal(got[int(k)], ref), (k, None if b is None else len(b))
+    # levels in any order, with repeats: every level's rows land in its own slot of the output
+    import ctypes
+    lib = _lib.load()
+    lv = np.array([120, 2, nf, 2, 17, 1, 120], dtype=np.int32)
+    cap = int(lv.sum()) + lv.size * (bad.size + 2)
+    start, end = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    off = np.zeros(lv.size + 1, np.int32)
+    ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+    assert lib.tp_assemble_levels(seq.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), nf, ip(lv), lv.size, ip(names), ip(bad),
+                                  bad.size, ip(start), ip(end), ip(off)) == 0
+    assert off.tolist() == [0] + np.cumsum(lv).tolist()
+    for i, k in enumerate(lv):
+        ref, _ = _lib.assemble(seq, int(k), names, bad)
+        assert np.array_equal(np.stack([start[off[i]:off[i + 1]], end[off[i]:off[i + 1]]], axis=1), ref), (i, k)
 
 
 @pytest.mark.parametrize("n,nranks", [(300, 2), (500, 4), (700, 8), (513, 3), (640, 5), (129, 2), (260, 4)])
