@@ -72,6 +72,14 @@ def parse():
     return ap.parse_args()
 
 
+def usable_cpus():
+    """CPUs this process may run on (a container's share, not the host's count)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
 def workload_text(bins):
     return (f"synthetic {bins}-bin Hi-C matrix, nested block TADs, power-law decay, max_pcs=200 "
             "(BASELINE.json configs[1]); one TADpole() call per matrix")
@@ -114,7 +122,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from tadpole_b200.synth import synth_hic
-    threads = os.cpu_count() or 1
+    threads = usable_cpus()
     mats = [synth_hic(args.bins, seed=1 + s) for s in range(min(4, max(1, args.steps)))]
     if args.warmup > 0:          # ONE untimed call whatever W is: page-in and thread start-up are all this path has to warm,
         cpu_full_call(mats[0], threads)      # and every further warm-up call would cost as much as a timed step
@@ -320,13 +328,13 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     # every call in flight has a library-owned host thread (asleep on an event most of the time): keep at most 4 per CPU
-    S = max(1, min(args.streams, max(8, 4 * (os.cpu_count() or 1) // max(world, 1))))
+    S = max(1, min(args.streams, max(8, 4 * usable_cpus() // max(world, 1))))
     B, n = (args.batch if args.batch > 0 else 2 * S), args.bins
     ctx = Context(local_rank)
     # the library's batch threads wait for their streams most of the time; a spinning wait (the CUDA default) needs a core
     # each, so with several ranks on one host they sleep on blocking-sync events instead (tp_call_batch decides this for
     # the threads of ONE process; it cannot see the other ranks)
-    ncpu = os.cpu_count() or 1
+    ncpu = usable_cpus()
     sync_blocking = world * S > ncpu // 2          # applied to the batch passes only; a single call at a time spins
 
     # synthetic inputs: B different matrices per rank; pinned host copies for e2e, device copies for value
@@ -527,7 +535,7 @@ def run_b200(args, rank, world, local_rank):
         if strong is not None:
             line["strong_scaling"] = strong
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = usable_cpus()
             sec, detail = cpu_full_call(host_np[0].copy(), threads)
             line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "oracle/ (numpy + C restatement; R unavailable): " + cpu_sample_text(detail, threads),
