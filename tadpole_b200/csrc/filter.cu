@@ -172,8 +172,7 @@ static void launch_rowmean(tp_ctx *ctx, const double *A, int n, int upper, doubl
     rowmean_kernel<R><<<(n + R - 1) / R, FT_THREADS, 0, ctx->stream>>>(A, n, upper, rm, d0);
 }
 
-// Upper triangle of a host matrix -> dst, ~32 band copies (row bands from the diagonal to the right edge; column bands from
-// the top to the diagonal for R's layout).  R > 1: only the bands dealt to `rank` (boustrophedon: equal bytes per rank).
+// rows (columns, for R's layout) per upload band: ~32 bands
 static int upload_bands(int n) {
     static const int forced = getenv("TADPOLE_UPLOAD_BANDS") ? atoi(getenv("TADPOLE_UPLOAD_BANDS")) : 0;     // experiments
     const int nb = forced > 0 ? forced : 32;
@@ -256,6 +255,8 @@ int tp_upload_range(tp_ctx *ctx, void *dst, const void *src, size_t bytes, cudaS
     return TP_OK;
 }
 
+// Upper triangle of a host matrix -> dst, ~32 band copies (row bands from the diagonal to the right edge; column bands from
+// the top to the diagonal for R's layout).  R > 1: only the bands dealt to `rank` (boustrophedon: equal bytes per rank).
 static int upload_upper(tp_ctx *ctx, double *dst, const double *mat, int n, int colmajor, cudaStream_t st, int R, int rank) {
     const int band = upload_bands(n);
     const size_t pitch = (size_t)n * sizeof(double);
